@@ -1,0 +1,66 @@
+"""ctypes binding of the C ABI declared in include/fepe_b200.h.
+
+The shared library is built in-tree by ``__graft_entry__.build()`` (nvcc, sm_100a) into
+``pytorch-deepfepe_b200/lib/libfepe_b200.so``.  There is NO fallback: if the library is missing
+or a call returns a non-zero status, a RuntimeError is raised.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(os.path.dirname(_HERE), "lib", "libfepe_b200.so")
+
+SAVED_DOUBLES = 64          # FEPE_SAVED_DOUBLES
+POSE_OUT_FLOATS = 32        # FEPE_POSE_OUT_FLOATS
+
+_lib = None
+
+_c_f = ctypes.c_float
+_c_i = ctypes.c_int
+_c_p = ctypes.c_void_p
+
+_SIGNATURES = {
+    "fepe_version": (ctypes.c_char_p, []),
+    "fepe_max_correspondences": (_c_i, []),
+    "fepe_fit_fwd": (_c_i, [_c_p, _c_p, _c_i, _c_i, _c_f, _c_f, _c_f, _c_f, _c_f,
+                            _c_p, _c_p, _c_p, _c_p, _c_p]),
+    "fepe_fit_bwd": (_c_i, [_c_p, _c_p, _c_i, _c_i, _c_f, _c_f, _c_f, _c_f, _c_f,
+                            _c_p, _c_p, _c_p, _c_p, _c_p, _c_p]),
+}
+
+_ERRORS = {-1: "FEPE_E_BADARG (null pointer, misaligned buffer or non-positive size)",
+           -2: "FEPE_E_TOOLARGE (N does not fit one shared-memory stage)",
+           -3: "FEPE_E_NODEVICE (no sm_100 CUDA device)"}
+
+
+def exported_symbols():
+    """Names include/fepe_b200.h declares; tests check the library exports every one."""
+    return list(_SIGNATURES)
+
+
+def lib() -> ctypes.CDLL:
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f"{LIB_PATH} is missing: build the CUDA library first (python -c 'import __graft_entry__ as g; "
+                "g.build()').  fepe_b200 has no CPU or PyTorch fallback.")
+        handle = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in _SIGNATURES.items():
+            if not hasattr(handle, name):
+                continue            # reported by tests/test_abi.py; calling it raises below
+            fn = getattr(handle, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = handle
+    return _lib
+
+
+def check(status: int, what: str) -> None:
+    if status == 0:
+        return
+    if status < 0:
+        raise RuntimeError(f"{what}: {_ERRORS.get(status, status)}")
+    raise RuntimeError(f"{what}: CUDA error {status}")

@@ -1,0 +1,40 @@
+// Host build of the product's math header (pytorch-deepfepe_b200/csrc/fepe_math.cuh) so that the
+// eigen / SVD routines can be checked against LAPACK on a machine without a GPU.  Test
+// infrastructure: built on the fly by tests/test_math_host.py with g++.
+#include "fepe_math.cuh"
+
+extern "C" {
+
+int shim_eig9(const double* g36, double* f, double* lambda) {
+    double ff[9];
+    double lam;
+    int it = fepe::eig9_smallest(g36, ff, lam);
+    for (int i = 0; i < 9; ++i) f[i] = ff[i];
+    *lambda = lam;
+    return it;
+}
+
+void shim_pinv(const double* g36, const double* f, double lambda, const double* rhs, double* z) {
+    double ff[9], rr[9], zz[9];
+    for (int i = 0; i < 9; ++i) { ff[i] = f[i]; rr[i] = rhs[i]; }
+    fepe::eig9_pinv_apply(g36, ff, lambda, rr, zz);
+    for (int i = 0; i < 9; ++i) z[i] = zz[i];
+}
+
+void shim_svd3(const double* A, double* U, double* S, double* V) {
+    double a[9], u[9], s[3], v[9];
+    for (int i = 0; i < 9; ++i) a[i] = A[i];
+    fepe::svd3(a, u, s, v);
+    for (int i = 0; i < 9; ++i) { U[i] = u[i]; V[i] = v[i]; }
+    for (int i = 0; i < 3; ++i) S[i] = s[i];
+}
+
+void shim_rank2(const double* F0, double* F2) {
+    double a[9], f2[9], u[9], s[3], v[9];
+    for (int i = 0; i < 9; ++i) a[i] = F0[i];
+    fepe::rank2_project(a, f2, u, s, v);
+    for (int i = 0; i < 9; ++i) F2[i] = f2[i];
+}
+
+int shim_g36_index(int r, int c) { return fepe::g36_index(r, c); }
+}

@@ -1,0 +1,140 @@
+"""GPU parity tests of the fused forward kernel (through the C ABI) against the CPU oracle and
+the committed reference outputs.  Tolerances: F within 1e-4 relative Frobenius (sign aligned) of
+the reference -- BASELINE.json's bar; residual / epipolar distances to 2e-5 absolute."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import fepe_oracle as O
+from fepe_b200 import ops, synth
+
+pytestmark = pytest.mark.gpu
+T = torch.from_numpy
+F_TOL = 1e-4
+
+
+def _run(d, want_saved=False, clamp_at=0.5):
+    m = T(d["matches_xy_ori"]).cuda()
+    w = T(d["weights"]).cuda()
+    F, res, epi, saved = ops.fit_forward(m, w, ops.hw_affine(d["image_size"]), clamp_at=clamp_at,
+                                         want_saved=want_saved)
+    torch.cuda.synchronize()
+    return F.cpu(), res.cpu(), epi.cpu(), (saved.cpu() if saved is not None else None)
+
+
+def _oracle(d, dtype=torch.float32, clamp_at=0.5):
+    p1, p2, _ = O.norm_hw(T(d["matches_xy_ori"]).to(dtype), d["image_size"])
+    Fr, rr = O.fit_weighted_svd(p1, p2, T(d["weights"]).to(dtype))
+    return Fr, rr, O.epi_residual(p1, p2, Fr, clamp_at), p1, p2
+
+
+def _compare(F, res, epi, Fr, rr, er, f_tol=F_TOL, r_tol=2e-5):
+    err = O.sign_aligned_rel_err(F, Fr)
+    assert float(err.max()) < f_tol, err
+    sgn = torch.sign((F.double() * Fr.double()).sum((1, 2))).view(-1, 1)
+    assert float((res.double() * sgn - rr.double()).abs().max()) < r_tol
+    assert float((epi.double() - er.double()).abs().max()) < max(5 * r_tol, 100 * float(err.max()))
+
+
+@pytest.mark.parametrize("i", range(7))
+def test_against_reference_golden(golden, i):
+    B, N, seed = (int(v) for v in golden[f"fit{i}_meta"])
+    d = synth.make_batch(B, N, seed, weight_mode=str(golden[f"fit{i}_mode"]))
+    F, res, epi, _ = _run(d)
+    _compare(F, res, epi, T(golden[f"fit{i}_F"]), T(golden[f"fit{i}_res"]), T(golden[f"fit{i}_epi"]))
+
+
+@pytest.mark.parametrize("mode", ["uniform", "softmax", "inlier"])
+@pytest.mark.parametrize("B,N", [(16, 1000), (8, 2000), (5, 333), (3, 37), (2, 8), (300, 64)])
+def test_against_oracle(mode, B, N):
+    d = synth.make_batch(B, N, seed=100 + N, weight_mode=mode)
+    F, res, epi, _ = _run(d)
+    Fr, rr, er, _, _ = _oracle(d)
+    _compare(F, res, epi, Fr, rr, er)
+
+
+def test_peaked_weights_against_fp64_truth():
+    """softmax(3 randn) weights: the fp32 reference itself is 1e-3 off the fp64 answer on some
+    pairs (ill conditioned), so parity is asserted against fp64 and the reference's own error is
+    printed beside ours."""
+    d = synth.make_batch(32, 1000, seed=7, weight_mode="peaked")
+    F, res, epi, _ = _run(d)
+    F64, r64, e64, _, _ = _oracle(d, torch.float64)
+    F32, _, _, _, _ = _oracle(d, torch.float32)
+    ours = O.sign_aligned_rel_err(F, F64)
+    ref = O.sign_aligned_rel_err(F32, F64)
+    print(f"peaked: ours vs fp64 max {float(ours.max()):.2e}; reference fp32 vs fp64 max {float(ref.max()):.2e}")
+    assert float(ours.max()) < max(F_TOL, 2 * float(ref.max()))
+
+
+def test_config2_full_size_and_saved_state():
+    d = synth.make_batch(256, 1000, seed=0, weight_mode="softmax")
+    F, res, epi, saved = _run(d, want_saved=True)
+    Fr, rr, er, _, _ = _oracle(d)
+    _compare(F, res, epi, Fr, rr, er)
+    f = saved[:, 6:15]
+    assert torch.allclose(f.norm(dim=1), torch.ones(256, dtype=torch.float64), atol=1e-12)
+    assert float(saved[:, 15].min()) >= 0.0                  # lambda >= 0
+    assert float(saved[:, 52].max()) <= 24                   # factorisations used
+    # rank 2: the third singular value of the normalised F is what the projection removed
+    assert float(torch.linalg.svdvals(F.double())[:, 2].max()) < 1e-6
+
+
+def test_properties_at_full_size():
+    d = synth.make_batch(64, 2000, seed=5, weight_mode="inlier", noise_px=0.0, outlier_frac=0.0)
+    F, res, epi, _ = _run(d)
+    # noise free: F reproduces the GT epipolar geometry -> residuals ~ 0
+    assert float(epi.abs().max()) < 1e-3
+    assert float(res.abs().max()) < 1e-6
+    # scaling all weights scales the residual, leaves F unchanged
+    d2 = dict(d)
+    d2["weights"] = d["weights"] * 3.0
+    F2, res2, _, _ = _run(d2)
+    assert float(O.sign_aligned_rel_err(F2, F).max()) < 1e-5
+    # permuting the correspondences permutes the residuals and leaves F unchanged
+    d = synth.make_batch(16, 1000, seed=6, weight_mode="softmax")
+    F, res, epi, _ = _run(d)
+    perm = np.random.default_rng(0).permutation(1000)
+    dp = dict(d)
+    dp["matches_xy_ori"] = d["matches_xy_ori"][:, perm]
+    dp["weights"] = d["weights"][:, :, perm]
+    Fp, resp, epip, _ = _run(dp)
+    assert float(O.sign_aligned_rel_err(Fp, F).max()) < 1e-5
+    assert float((resp - res[:, perm]).abs().max()) < 1e-6
+    assert float((epip - epi[:, perm]).abs().max()) < 1e-4
+
+
+def test_edge_cases():
+    # clamp value is honoured
+    d = synth.make_batch(4, 256, seed=9)
+    _, _, epi, _ = _run(d, clamp_at=0.02)
+    assert float(epi.max()) <= 0.02 + 1e-9
+    # zero weights: finite output, e9 convention
+    d["weights"] = np.zeros_like(d["weights"])
+    F, res, epi, _ = _run(d)
+    assert torch.isfinite(F).all() and float(res.abs().max()) == 0.0
+    # planar scene (config 1 geometry): F is not unique, but outputs are finite and consistent
+    d = synth.make_batch(1, 100, seed=31, planar=True, outlier_frac=0.0)
+    F, res, epi, _ = _run(d)
+    assert torch.isfinite(F).all() and torch.isfinite(res).all() and torch.isfinite(epi).all()
+    assert float(epi.max()) < 0.05
+    # empty batch
+    m = torch.empty(0, 16, 4, device="cuda")
+    w = torch.empty(0, 16, device="cuda")
+    F, res, epi, _ = ops.fit_forward(m, w)
+    assert F.shape == (0, 3, 3)
+    # too many correspondences for one shared-memory stage -> loud error
+    with pytest.raises(RuntimeError):
+        ops.fit_forward(torch.zeros(1, 20000, 4, device="cuda"), torch.zeros(1, 20000, device="cuda"))
+    with pytest.raises(RuntimeError):
+        ops.fit_forward(torch.zeros(1, 8, 4), torch.zeros(1, 8))          # CPU tensors: no fallback
+
+
+def test_identity_affine_equals_fit_forward_semantics():
+    d = synth.make_batch(8, 512, seed=12, weight_mode="softmax")
+    p1, p2, _ = O.norm_hw(T(d["matches_xy_ori"]), d["image_size"])
+    m = torch.cat((p1[:, :, :2], p2[:, :, :2]), 2).contiguous().cuda()
+    F, res, epi, _ = ops.fit_forward(m, T(d["weights"]).cuda())
+    torch.cuda.synchronize()
+    Fr, rr = O.fit_weighted_svd(p1, p2, T(d["weights"]))
+    _compare(F.cpu(), res.cpu(), epi.cpu(), Fr, rr, O.epi_residual(p1, p2, Fr))

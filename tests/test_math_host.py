@@ -1,0 +1,172 @@
+"""CPU checks of the product's device math (csrc/fepe_math.cuh compiled for the host with g++)
+against LAPACK: smallest eigenpair of the 9x9 Gram matrix, pseudo-inverse apply, 3x3 SVD."""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from fepe_b200 import synth
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+CSRC = os.path.join(ROOT, "pytorch-deepfepe_b200", "csrc")
+BUILD = os.path.join(ROOT, "tests", "_build")
+
+
+@pytest.fixture(scope="module")
+def shim():
+    os.makedirs(BUILD, exist_ok=True)
+    so = os.path.join(BUILD, "host_shim.so")
+    src = os.path.join(ROOT, "tests", "host_shim.cpp")
+    hdr = os.path.join(CSRC, "fepe_math.cuh")
+    if not os.path.exists(so) or os.path.getmtime(so) < max(os.path.getmtime(src), os.path.getmtime(hdr)):
+        subprocess.check_call(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-Wno-unknown-pragmas",
+                               "-x", "c++", "-I", CSRC, src, "-o", so])
+    lib = ctypes.CDLL(so)
+    dp = ctypes.POINTER(ctypes.c_double)
+    lib.shim_eig9.argtypes = [dp, dp, dp]
+    lib.shim_eig9.restype = ctypes.c_int
+    lib.shim_pinv.argtypes = [dp, dp, ctypes.c_double, dp, dp]
+    lib.shim_svd3.argtypes = [dp, dp, dp, dp]
+    lib.shim_rank2.argtypes = [dp, dp]
+    lib.shim_g36_index.argtypes = [ctypes.c_int, ctypes.c_int]
+    lib.shim_g36_index.restype = ctypes.c_int
+    return lib
+
+
+def _ptr(a):
+    return a.ctypes.data_as(ctypes.POINTER(ctypes.c_double))
+
+
+def gram36(a, b, s):
+    """a,b [N,3], s [N] -> 36 monomial sums in the kernel's order."""
+    pairs = [(0, 0), (0, 1), (0, 2), (1, 1), (1, 2), (2, 2)]
+    mA = np.stack([a[:, i] * a[:, j] for i, j in pairs], 1)
+    mB = np.stack([b[:, i] * b[:, j] for i, j in pairs], 1)
+    return np.einsum("n,nu,nv->uv", s, mA, mB).reshape(36).copy()
+
+
+def full_gram(lib, g36):
+    return np.array([[g36[lib.shim_g36_index(r, c)] for c in range(9)] for r in range(9)])
+
+
+def scene_gram(seed, mode, N=500, noise=0.5, outl=0.3, planar=False):
+    d = synth.make_batch(1, N, seed, weight_mode=mode, noise_px=noise, outlier_frac=outl, planar=planar)
+    m = d["matches_xy_ori"][0].astype(np.float64)
+    H, W = 376, 1241
+    x1 = np.stack([2 * m[:, 0] / W - 1, 2 * m[:, 1] / H - 1], 1)
+    x2 = np.stack([2 * m[:, 2] / W - 1, 2 * m[:, 3] / H - 1], 1)
+
+    def hart(x):
+        c = x.mean(0)
+        s = 1.4142 / np.linalg.norm(x - c, axis=1).mean()
+        return (x - c) * s
+    x1, x2 = hart(x1), hart(x2)
+    a = np.concatenate([x2, np.ones((N, 1))], 1)
+    b = np.concatenate([x1, np.ones((N, 1))], 1)
+    w = d["weights"][0, 0].astype(np.float64)
+    s = w * w / ((a * a).sum(1) * (b * b).sum(1))
+    P = np.einsum("nj,nk->njk", a, b).reshape(N, 9)
+    X = P / np.linalg.norm(P, axis=1, keepdims=True) * w[:, None]
+    return gram36(a, b, s), X
+
+
+def test_g36_layout_matches_kron(shim):
+    rng = np.random.default_rng(0)
+    a, b, s = rng.normal(size=(50, 3)), rng.normal(size=(50, 3)), rng.uniform(size=50)
+    g36 = gram36(a, b, s)
+    P = np.einsum("nj,nk->njk", a, b).reshape(50, 9)
+    G = (P * s[:, None]).T @ P
+    np.testing.assert_allclose(full_gram(shim, g36), G, rtol=1e-12, atol=1e-12)
+
+
+@pytest.mark.parametrize("mode", ["uniform", "softmax", "peaked", "inlier"])
+def test_eig9_on_scene_grams(shim, mode):
+    worst, its = 0.0, []
+    for seed in range(40):
+        g36, X = scene_gram(seed, mode, noise=0.5 if seed % 2 else 0.0, outl=0.3 if seed % 3 else 0.0)
+        f, lam = np.zeros(9), np.zeros(1)
+        its.append(shim.shim_eig9(_ptr(g36), _ptr(f), _ptr(lam)))
+        v_ref = np.linalg.svd(X)[2][-1]
+        err = min(np.linalg.norm(f - v_ref), np.linalg.norm(f + v_ref))
+        worst = max(worst, err)
+        assert abs(np.linalg.norm(f) - 1) < 1e-12
+        assert f[np.argmax(np.abs(f))] > 0
+        ev = np.linalg.eigvalsh(full_gram(shim, g36))
+        assert abs(lam[0] - ev[0]) <= 1e-11 * ev[-1]
+    # conditioning of the problem itself limits agreement with the SVD of X; 1e-7 is far below
+    # the 1e-4 parity budget
+    assert worst < 1e-7, worst
+    assert max(its) <= 16, its
+
+
+def test_eig9_random_spd_and_degenerate(shim):
+    rng = np.random.default_rng(1)
+    max_it = 0
+    for trial in range(300):
+        a, b = rng.normal(size=(30, 3)), rng.normal(size=(30, 3))
+        a[:, 2] = 1
+        b[:, 2] = 1
+        s = rng.uniform(size=30) ** (1 + trial % 5)
+        g36 = gram36(a, b, s) * 10.0 ** rng.integers(-12, 6)
+        G = full_gram(shim, g36)
+        ev, evec = np.linalg.eigh(G)
+        f, lam = np.zeros(9), np.zeros(1)
+        max_it = max(max_it, shim.shim_eig9(_ptr(g36), _ptr(f), _ptr(lam)))
+        gap = (ev[1] - ev[0]) / ev[-1]
+        err = min(np.linalg.norm(f - evec[:, 0]), np.linalg.norm(f + evec[:, 0]))
+        assert err < 1e-9 / max(gap, 1e-9) * 1e-3 + 1e-9, (trial, err, gap)
+        assert np.linalg.norm(G @ f - lam[0] * f) <= 1e-9 * ev[-1]
+    assert max_it <= 20
+    # degenerate inputs: zero matrix and NaN -> e9, no NaN out; planar scene -> finite unit vector
+    for g36 in (np.zeros(36), np.full(36, np.nan)):
+        f, lam = np.zeros(9), np.zeros(1)
+        shim.shim_eig9(_ptr(g36), _ptr(f), _ptr(lam))
+        np.testing.assert_array_equal(f, np.eye(9)[8])
+    g36, _ = scene_gram(3, "uniform", noise=0.0, outl=0.0, planar=True)
+    f, lam = np.zeros(9), np.zeros(1)
+    shim.shim_eig9(_ptr(g36), _ptr(f), _ptr(lam))
+    G = full_gram(shim, g36)
+    assert np.isfinite(f).all() and abs(np.linalg.norm(f) - 1) < 1e-12
+    assert np.linalg.norm(G @ f - lam[0] * f) <= 1e-10 * np.trace(G)
+
+
+def test_pinv_apply(shim):
+    for seed in range(10):
+        g36, _ = scene_gram(seed, "inlier")
+        G = full_gram(shim, g36)
+        ev, evec = np.linalg.eigh(G)
+        f, lam = np.zeros(9), np.zeros(1)
+        shim.shim_eig9(_ptr(g36), _ptr(f), _ptr(lam))
+        rhs = np.random.default_rng(seed).normal(size=9)
+        z = np.zeros(9)
+        shim.shim_pinv(_ptr(g36), _ptr(f), float(lam[0]), _ptr(rhs), _ptr(z))
+        M = sum(np.outer(evec[:, k], evec[:, k]) / (ev[k] - ev[0]) for k in range(1, 9))
+        np.testing.assert_allclose(z, M @ rhs, rtol=1e-6, atol=1e-6 * np.abs(M @ rhs).max())
+
+
+def test_svd3(shim):
+    rng = np.random.default_rng(2)
+    mats = [rng.normal(size=(3, 3)) for _ in range(200)]
+    # rank-2 (essential-like) and nearly rank-2, repeated singular values, tiny scale
+    for _ in range(50):
+        u, _, vt = np.linalg.svd(rng.normal(size=(3, 3)))
+        mats.append(u @ np.diag([1.0, 1.0, 0.0]) @ vt)
+        mats.append(u @ np.diag([1.0, 0.7, 1e-9]) @ vt * 1e-6)
+        mats.append(u @ np.diag([2.0, 2.0, 2.0]) @ vt)
+    for A in mats:
+        A = np.ascontiguousarray(A)
+        U, S, V = np.zeros((3, 3)), np.zeros(3), np.zeros((3, 3))
+        shim.shim_svd3(_ptr(A), _ptr(U), _ptr(S), _ptr(V))
+        sc = np.linalg.norm(A)
+        np.testing.assert_allclose(U @ np.diag(S) @ V.T, A, atol=1e-13 * sc)
+        np.testing.assert_allclose(U.T @ U, np.eye(3), atol=1e-12)
+        np.testing.assert_allclose(V.T @ V, np.eye(3), atol=1e-12)
+        np.testing.assert_allclose(S, np.linalg.svd(A, compute_uv=False), atol=1e-13 * sc)
+        assert S[0] >= S[1] >= S[2] >= 0
+        F2 = np.zeros((3, 3))
+        shim.shim_rank2(_ptr(A), _ptr(F2))
+        u, s, vt = np.linalg.svd(A)
+        if s[1] - s[2] > 1e-3 * s[0]:     # the projection is not unique for repeated singular values
+            np.testing.assert_allclose(F2, u @ np.diag([s[0], s[1], 0]) @ vt, atol=1e-12 * sc + 1e-300)
