@@ -1,0 +1,461 @@
+#!/usr/bin/env python
+"""bench.py -- image-pairs/sec of the weighted 8-point + pose path (F + R,t) on B200.
+
+Contract (one JSON line on rank 0):
+  python bench.py [--gpus N] [--steps K] [--warmup W]            ours (CUDA kernels via the C ABI)
+  python bench.py --impl reference [...]                         the reference's CPU algorithm (oracle port)
+  torchrun --nproc-per-node N bench.py --gpus N ...              one rank per GPU, weak scaling
+
+Workload (BASELINE.json configs[1]): one STEP = one batch of 256 image pairs x 1000 synthetic
+correspondences (KITTI-shaped intrinsics, 0.5 px noise, 30 % outliers) through
+  fepe_fit_fwd   (Hartley, Gram, eigenvector, rank 2, residual + epipolar residual)   and
+  fepe_pose_fwd  (E = K^T F K, E -> R,t, pose errors vs GT, F-loss on 100 virtual points).
+`value` is timed with the batches already resident in HBM: a ring of distinct batches larger than
+the 126 MB L2 is cycled so no step finds its inputs in cache.  `e2e` times the same step through
+the public host API with PINNED HOST buffers, H2D of the step's inputs and D2H of its results
+inside the timed region.  `roofline` is for the dominant kernel (fepe_fit_fwd_kernel) at this
+launch size; `roofline_saturating` is the same kernel at a batch that fills the machine
+(a 256-pair launch moves 7 MB, ~1 us of HBM time, and is latency bound by nature).
+"""
+from __future__ import annotations
+
+import argparse
+import contextlib
+import io
+import json
+import os
+import statistics
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for _p in (ROOT, os.path.join(ROOT, "pytorch-deepfepe_b200")):
+    if _p not in sys.path:
+        sys.path.insert(0, _p)
+
+import numpy as np
+import torch
+
+METRIC = "image_pairs_per_sec_F_Rt"
+UNIT = "pairs/s"
+L2_BYTES = 126 * 1024 * 1024
+CLAMP_EPI = 0.5      # in-model epipolar clamp (DeepFNet.py:479 default)
+CLAMP_LOSS = 0.02    # configs/kitti_corr_baseline.yaml:36
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=2000)
+    ap.add_argument("--warmup", type=int, default=50)
+    ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
+    ap.add_argument("--batch", type=int, default=256, help="pairs per step (config C2: 256)")
+    ap.add_argument("--ncorr", type=int, default=1000, help="correspondences per pair (C2: 1000)")
+    ap.add_argument("--sat-batch", type=int, default=32768, help="batch of the saturating roofline run")
+    ap.add_argument("--no-graph", action="store_true", help="launch eagerly instead of replaying CUDA graphs")
+    ap.add_argument("--no-extras", action="store_true", help="skip e2e / cpu_baseline / saturating legs")
+    ap.add_argument("--phases", action="store_true", help="print per-phase SM cycles of the fused kernel")
+    return ap.parse_args()
+
+
+# ------------------------------------------------------------------------------------------------
+def dist_env():
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    return rank, world, local
+
+
+class ClockSampler(threading.Thread):
+    """Polls NVML for SM clock / throttle reasons while the benchmark runs."""
+
+    def __init__(self, index: int, period_s: float = 0.02):
+        super().__init__(daemon=True)
+        self.index, self.period = index, period_s
+        self.samples = []          # (t, sm_mhz, reasons_bitmask, util)
+        self.stop_flag = False
+        self.sm_max = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.sm_max = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def run(self):
+        if self.nv is None:
+            return
+        nv = self.nv
+        while not self.stop_flag:
+            try:
+                clk = nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)
+                rs = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h) if hasattr(
+                    nv, "nvmlDeviceGetCurrentClocksEventReasons") else nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                util = nv.nvmlDeviceGetUtilizationRates(self.h).gpu
+                self.samples.append((time.time(), clk, rs, util))
+            except Exception:
+                pass
+            time.sleep(self.period)
+
+    def summary(self, t0: float, t1: float) -> dict:
+        if self.nv is None or not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.sm_max, "reasons": [], "window": "unavailable"}
+        inside = [s for s in self.samples if t0 <= s[0] <= t1]
+        window = "timed_region"
+        if len(inside) < 3:      # region shorter than the sampling period: use the loaded part of the run
+            inside = [s for s in self.samples if s[3] > 0] or self.samples
+            window = "whole_bench_under_load"
+        names = {0x2: "applications_clocks_setting", 0x4: "sw_power_cap", 0x8: "hw_slowdown",
+                 0x10: "sync_boost", 0x20: "sw_thermal_slowdown", 0x40: "hw_thermal_slowdown",
+                 0x80: "hw_power_brake_slowdown", 0x100: "display_clock_setting"}
+        mask = 0
+        for s in inside:
+            mask |= s[2]
+        reasons = [n for bit, n in names.items() if mask & bit]
+        return {"sm_mhz": statistics.median(s[1] for s in inside), "sm_max_mhz": self.sm_max,
+                "reasons": reasons, "window": window, "samples": len(inside)}
+
+
+def measured_peak_gbs():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(path) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs, copy kernel)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def ncu_traffic(batch: int, ncorr: int):
+    """dram bytes per launch of the dominant kernel from the committed ncu capture, if one matches."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            t = json.load(f)
+        return t.get(f"fit_fwd_B{batch}_N{ncorr}")
+    except Exception:
+        return None
+
+
+def fit_bytes(B: int, N: int) -> int:
+    # algorithmic bytes of one fused forward launch: 16 B coords + 4 B weight read, 4 B residual +
+    # 4 B epipolar residual written per correspondence, 36 B F per pair (28 N + 36)
+    return B * (28 * N + 36)
+
+
+# ------------------------------------------------------------------------------------------------
+def make_host_batches(n_batches: int, B: int, N: int, seed0: int):
+    from fepe_b200 import synth
+    return [synth.make_batch(B, N, seed=seed0 + i, weight_mode="softmax") for i in range(n_batches)]
+
+
+class DeviceBatch:
+    """One step's inputs resident on the device plus its caller-owned outputs."""
+
+    def __init__(self, d: dict, dev):
+        from fepe_b200 import _lib
+        t = lambda k: torch.from_numpy(np.ascontiguousarray(d[k])).to(dev)
+        self.m = t("matches_xy_ori")
+        self.w = t("weights").reshape(self.m.shape[0], -1).contiguous()
+        self.K, self.q, self.tt, self.Rt = t("Ks"), t("q_cam"), t("t_cam"), t("delta_Rtijs_4_4")
+        self.v1, self.v2 = t("pts1_virt"), t("pts2_virt")
+        B, N = self.m.shape[0], self.m.shape[1]
+        self.F = torch.empty(B, 3, 3, device=dev)
+        self.res = torch.empty(B, N, device=dev)
+        self.epi = torch.empty(B, N, device=dev)
+        self.pose = torch.empty(1, B, _lib.POSE_OUT_FLOATS, device=dev)
+
+
+def step_fit(db: DeviceBatch, aff):
+    from fepe_b200 import ops
+    ops.fit_forward(db.m, db.w, aff, clamp_at=CLAMP_EPI, out=(db.F, db.res, db.epi, None))
+
+
+def step_full(db: DeviceBatch, aff):
+    from fepe_b200 import ops
+    step_fit(db, aff)
+    ops.pose_forward(db.F, db.K, aff, db.q, db.tt, db.Rt, db.v1, db.v2, clamp_at=CLAMP_LOSS, out=db.pose)
+
+
+def capture(fn):
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        fn()
+    return g
+
+
+def timed_loop(callables, steps: int, warmup: int, barrier=None):
+    """CUDA-event time of `steps` calls cycling through `callables`; returns (seconds, t0_wall, t1_wall)."""
+    n = len(callables)
+    for i in range(warmup):
+        callables[i % n]()
+    torch.cuda.synchronize()
+    if barrier is not None:
+        barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    t0 = time.time()
+    e0.record()
+    for i in range(steps):
+        callables[(warmup + i) % n]()
+    e1.record()
+    torch.cuda.synchronize()
+    t1 = time.time()
+    if barrier is not None:
+        barrier()
+    return e0.elapsed_time(e1) * 1e-3, t0, t1
+
+
+# ------------------------------------------------------------------------------------------------
+def reference_step(d: dict):
+    """The reference's CPU algorithm for one batch (oracle port): Fit + epipolar residual + F-loss +
+    E + pose decomposition / errors.  Returns nothing; timed by the caller."""
+    from oracle import fepe_oracle as O
+    T = torch.from_numpy
+    with torch.no_grad():
+        p1, p2, Tn = O.norm_hw(T(d["matches_xy_ori"]), d["image_size"])
+        Fo, res = O.fit_weighted_svd(p1, p2, T(d["weights"]))
+        O.epi_residual(p1, p2, Fo, CLAMP_EPI)
+        _, _, E_layers = O.f_loss_layers([Fo], Tn, Tn, T(d["pts1_virt"]), T(d["pts2_virt"]), T(d["Ks"]), CLAMP_LOSS)
+        O.pose_errors(E_layers[0], T(d["q_cam"]), T(d["t_cam"]), T(d["delta_Rtijs_4_4"]))
+
+
+def slice_batch(d: dict, n: int) -> dict:
+    out = {}
+    for k, v in d.items():
+        out[k] = v[:n] if isinstance(v, np.ndarray) and v.ndim >= 1 and v.shape[0] == d["matches_xy_ori"].shape[0] else v
+    return out
+
+
+def run_reference(args):
+    rank, world, _ = dist_env()
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    B, N = args.batch, args.ncorr
+    base = make_host_batches(2, B, N, seed0=1000)
+    # calibrate the per-step sample so that the whole run stays within ~2 minutes
+    t = time.perf_counter()
+    reference_step(slice_batch(base[0], min(B, 32)))
+    per_pair = (time.perf_counter() - t) / min(B, 32)
+    budget = 120.0 / max(1, args.steps + args.warmup)
+    n_s = int(max(8, min(B, budget / max(per_pair, 1e-9))))
+    sample = [slice_batch(b, n_s) for b in base]
+    for i in range(args.warmup):
+        reference_step(sample[i % 2])
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        reference_step(sample[i % 2])
+    dt = time.perf_counter() - t0
+    value = n_s * args.steps / dt
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"C2: batch={B} pairs x N={N} corr, 30% outliers, Fit + epi residual + F-loss + E->R,t",
+                   "pairs_per_step_sample": n_s, "ncorr": N},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+                         "sample": f"{n_s} of the {B} pairs of a step, {args.steps} steps; oracle/fepe_oracle.py "
+                                   "(per-pair torch.svd loop like deepFEPE/models/DeepFNet.py:232-240) on host cores"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+def run_ours(args):
+    rank, world, local = dist_env()
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback "
+                         "(use --impl reference for the CPU baseline)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    use_dist = world > 1
+    if use_dist:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+        barrier = lambda: (dist.barrier(), torch.cuda.synchronize())
+    else:
+        barrier = None
+
+    import __graft_entry__ as entry
+    entry.build()
+    from fepe_b200 import ops, synth, _lib
+
+    B, N = args.batch, args.ncorr
+    aff = ops.hw_affine(synth.KITTI_IMAGE_SIZE)
+    per_batch_bytes = B * N * 20
+    ring_n = max(2, int(np.ceil(1.6 * L2_BYTES / per_batch_bytes)))
+    ring_n = min(ring_n, 96)
+    sampler = ClockSampler(local)
+    sampler.start()
+
+    host = make_host_batches(ring_n, B, N, seed0=10_000 * (rank + 1))
+    ring = [DeviceBatch(d, dev) for d in host]
+    for db in ring[:2]:
+        step_full(db, aff)          # first-use configuration happens outside any graph capture
+    torch.cuda.synchronize()
+
+    if args.no_graph:
+        full_calls = [(lambda db=db: step_full(db, aff)) for db in ring]
+        fit_calls = [(lambda db=db: step_fit(db, aff)) for db in ring]
+    else:
+        s = torch.cuda.Stream()
+        with torch.cuda.stream(s):
+            full_graphs = [capture(lambda db=db: step_full(db, aff)) for db in ring]
+            fit_graphs = [capture(lambda db=db: step_fit(db, aff)) for db in ring]
+        torch.cuda.synchronize()
+        full_calls = [g.replay for g in full_graphs]
+        fit_calls = [g.replay for g in fit_graphs]
+
+    # ---- the contract number: K steps, device timed, max over ranks -----------------------------
+    secs, t0, t1 = timed_loop(full_calls, args.steps, max(args.warmup, 3), barrier)
+    if use_dist:
+        tt = torch.tensor([secs], device=dev, dtype=torch.float64)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        secs = float(tt.item())
+    value = world * B * args.steps / secs
+
+    # ---- dominant kernel alone at this launch size ----------------------------------------------
+    fit_secs, _, _ = timed_loop(fit_calls, max(args.steps, 200), 10)
+    fit_us = fit_secs / max(args.steps, 200) * 1e6
+    peak, peak_src = measured_peak_gbs()
+    achieved = fit_bytes(B, N) / (fit_us * 1e-6) / 1e9
+    roofline = {"bound": "hbm", "kernel": "fepe_fit_fwd_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": ncu_traffic(B, N), "launch_us": fit_us,
+                "algorithmic_bytes_per_launch": fit_bytes(B, N), "peak_source": peak_src,
+                "note": "launch of one config batch; see roofline_saturating for the same kernel at a batch that "
+                        "fills the 148 SMs"}
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": secs / args.steps * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32 (Gram / eigen / SVD in f64)", "data": "synthetic",
+        "config": {"workload": f"C2: batch={B} pairs x N={N} corr, 30% outliers, Fit + epi residual + F-loss + E->R,t",
+                   "batch_per_gpu": B, "ncorr": N, "parallelism": f"pairs sharded over {world} GPU(s), no collective",
+                   "l2_policy": f"ring of {ring_n} distinct batches ({ring_n * per_batch_bytes / 2**20:.0f} MiB) > 126 MiB L2",
+                   "launch": "eager" if args.no_graph else "cuda_graph_replay"},
+        "gpu_launches": 2 * args.steps,
+        "roofline": roofline,
+    }
+
+    if not args.no_extras:
+        # ---- end to end through the host API: pinned host -> device -> results on host ------------
+        nbuf = 3
+        pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
+        keys = ["matches_xy_ori", "weights", "Ks", "q_cam", "t_cam", "delta_Rtijs_4_4", "pts1_virt", "pts2_virt"]
+        hbat = [{k: pin(d[k]) for k in keys} for d in host[:min(len(host), 8)]]
+        h2d = sum(v.numel() * v.element_size() for v in hbat[0].values())
+        streams = [torch.cuda.Stream() for _ in range(nbuf)]
+        dbuf = [{k: torch.empty_like(v, device=dev) for k, v in hbat[0].items()} for _ in range(nbuf)]
+        outs = [(torch.empty(B, 3, 3, device=dev), torch.empty(B, N, device=dev), torch.empty(B, N, device=dev),
+                 torch.empty(1, B, _lib.POSE_OUT_FLOATS, device=dev)) for _ in range(nbuf)]
+        hres = [(torch.empty(B, 3, 3).pin_memory(), torch.empty(1, B, _lib.POSE_OUT_FLOATS).pin_memory())
+                for _ in range(nbuf)]
+        d2h = hres[0][0].numel() * 4 + hres[0][1].numel() * 4
+
+        def e2e_step(i):
+            j = i % nbuf
+            st, hb, db_, o, hr = streams[j], hbat[i % len(hbat)], dbuf[j], outs[j], hres[j]
+            with torch.cuda.stream(st):
+                for k in keys:
+                    db_[k].copy_(hb[k], non_blocking=True)
+                ops.fit_forward(db_["matches_xy_ori"], db_["weights"], aff, clamp_at=CLAMP_EPI,
+                                out=(o[0], o[1], o[2], None))
+                ops.pose_forward(o[0], db_["Ks"], aff, db_["q_cam"], db_["t_cam"], db_["delta_Rtijs_4_4"],
+                                 db_["pts1_virt"], db_["pts2_virt"], clamp_at=CLAMP_LOSS, out=o[3])
+                hr[0].copy_(o[0], non_blocking=True)
+                hr[1].copy_(o[3], non_blocking=True)
+
+        e2e_steps = max(50, min(args.steps, 400))
+        for i in range(6):
+            e2e_step(i)
+        torch.cuda.synchronize()
+        if barrier is not None:
+            barrier()
+        tw0 = time.perf_counter()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(e2e_steps):
+            e2e_step(i)
+        for st in streams:
+            torch.cuda.current_stream().wait_stream(st)
+        e1.record()
+        torch.cuda.synchronize()
+        e2e_secs = max(e0.elapsed_time(e1) * 1e-3, time.perf_counter() - tw0)
+        if use_dist:
+            tt = torch.tensor([e2e_secs], device=dev, dtype=torch.float64)
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            e2e_secs = float(tt.item())
+        line["e2e"] = {"value": world * B * e2e_steps / e2e_secs, "unit": UNIT, "h2d_bytes_per_step": h2d,
+                       "d2h_bytes_per_step": d2h, "steps": e2e_steps, "ms_per_step": e2e_secs / e2e_steps * 1e3,
+                       "n_gpus": world, "how": f"{nbuf} streams, pinned host buffers, H2D + 2 kernels + D2H per step"}
+
+
+    if rank == 0 and not args.no_extras:
+        # ---- saturating batch for the same kernel (roofline of the kernel itself) ---------------
+        SB = args.sat_batch
+        reps = (SB + B * ring_n - 1) // (B * ring_n)
+        big_m = torch.cat([db.m for db in ring] * reps)[:SB].contiguous()
+        big_w = torch.cat([db.w for db in ring] * reps)[:SB].contiguous()
+        outF, outr, oute = torch.empty(SB, 3, 3, device=dev), torch.empty(SB, N, device=dev), torch.empty(SB, N, device=dev)
+        sat_call = lambda: ops.fit_forward(big_m, big_w, aff, clamp_at=CLAMP_EPI, out=(outF, outr, oute, None))
+        sat_secs, _, _ = timed_loop([sat_call], 10, 3)
+        sat_us = sat_secs / 10 * 1e6
+        sat_ach = fit_bytes(SB, N) / (sat_us * 1e-6) / 1e9
+        line["roofline_saturating"] = {
+            "bound": "hbm", "kernel": "fepe_fit_fwd_kernel", "batch": SB, "achieved": sat_ach, "peak": peak,
+            "unit": "GB/s", "frac": sat_ach / peak, "traffic": ncu_traffic(SB, N), "launch_us": sat_us,
+            "pairs_per_sec": SB / (sat_us * 1e-6),
+            "l2_policy": f"input {SB * N * 20 / 2**20:.0f} MiB per launch > L2"}
+        if args.phases:
+            sv = torch.empty(SB, _lib.SAVED_DOUBLES, dtype=torch.float64, device=dev)
+            ops.fit_forward(big_m, big_w, aff, clamp_at=CLAMP_EPI, out=(outF, outr, oute, sv))
+            torch.cuda.synchronize()
+            ph = sv[:, 56:61].mean(0).tolist()
+            line["phase_cycles_saturating"] = dict(zip(["wait", "hartley", "gram", "solve", "residual"], ph))
+            line["factorisations_mean"] = float(sv[:, 52].mean())
+        del big_m, big_w, outF, outr, oute
+
+        # ---- the reference's CPU algorithm on this box's host cores (bounded sample) ---------------
+        cores = os.cpu_count() or 1
+        torch.set_num_threads(cores)
+        sample = [slice_batch(host[0], min(B, 128)), slice_batch(host[1], min(B, 128))]
+        reference_step(sample[0])
+        n_done, tc0 = 0, time.perf_counter()
+        while time.perf_counter() - tc0 < 10.0 or n_done < 3:
+            reference_step(sample[n_done % 2])
+            n_done += 1
+        cpu_secs = time.perf_counter() - tc0
+        line["cpu_baseline"] = {"value": sample[0]["matches_xy_ori"].shape[0] * n_done / cpu_secs, "unit": UNIT,
+                                "cores": torch.get_num_threads(), "kind": "port",
+                                "sample": f"{n_done} x {sample[0]['matches_xy_ori'].shape[0]} pairs x N={N} of the same "
+                                          "workload through oracle/fepe_oracle.py (per-pair torch.svd loop, "
+                                          "deepFEPE/models/DeepFNet.py:232-240) in {:.1f} s".format(cpu_secs)}
+    if "e2e" not in line:
+        line["e2e"] = None
+
+    sampler.stop_flag = True
+    sampler.join(timeout=1.0)
+    line["clocks"] = sampler.summary(t0, t1)
+    if use_dist:
+        import torch.distributed as dist
+        dist.barrier()
+        dist.destroy_process_group()
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -31,9 +31,9 @@ extern "C" {
  *   [0..5]   raw means and Hartley scales (m1x,m1y,s1,m2x,m2y,s2)
  *   [6..14]  f, unit eigenvector (= vec of the normalised F before the rank-2 projection)
  *   [15]     lambda_min          [16..51] the 36 distinct Gram entries (fepe_math.cuh order)
- *   [52]     factorisations used [53..55] singular values of reshape(f)
+ *   [52]     factorisations used [53..55] v3, right singular vector of reshape(f) removed by rank 2
  *   [56..60] SM cycles this pair spent waiting for its copy / in Hartley / Gram / solve / residual
- *   [61..63] reserved */
+ *   [61],[62] of the solve cycles: Gram reduce / eigen iteration   [63] sigma_3 of reshape(f) */
 #define FEPE_SAVED_DOUBLES 64
 
 /* library / build identification: returns e.g. "fepe_b200 0.1 sm_100a" (host pointer, static). */
@@ -74,6 +74,30 @@ int fepe_fit_bwd(const float* matches, const float* weights, int B, int N,
                  float ax, float bx, float ay, float by, float clamp_at,
                  const double* saved, const float* gF, const float* gresid, const float* gepi,
                  float* gweights, void* stream);
+
+/* ---- pose / loss head -----------------------------------------------------------------------------
+ * Replaces, per layer and pair: E = K^T T2^T F T1 K (deepFEPE/train_good_utils.py:356-358), the host
+ * loop of get_Rt_loss (train_good_utils.py:96-188: E^T -> _get_M2s (dsac_tools/utils_F.py:478-498),
+ * _R_to_q (dsac_tools/utils_geo.py:58-86), L2 errors to the GT pose, min-select, rot12_to_angle_error /
+ * vector_angle metrics) and the per-pair F-loss over the virtual correspondences
+ * (train_good_utils.py:325-354; clamp_at = 0.02 in the shipped configs).
+ *
+ *   F        [L,B,9]   F of each layer in primed coordinates (fepe_fit_fwd output)
+ *   K        [B,9]     intrinsics;  (ax,bx,ay,by) the NormalizeAndExpand_HW transform (= outs['T1'] = ['T2'])
+ *   q_gt     [B,4]     qs_cam (w,x,y,z);  t_gt [B,3] ts_cam (normalised inside, F.normalize semantics)
+ *   Rt_scene [B,16]    delta_Rtijs_4_4 (scene motion) for the rotation-angle metric, or NULL
+ *   virt1/2  [B,V,3]   homogeneous pixel virtual correspondences, or both NULL (no F-loss)
+ *   out      [L,B,FEPE_POSE_OUT_FLOATS]:
+ *            [0..8] E   [9..17] selected R   [18..20] selected t   [21] q L2 error   [22] t L2 error
+ *            [23] rotation angle error (deg)  [24] translation angle error (deg)
+ *            [25] F-loss (mean clamped epipolar residual of the V virtual points)
+ *            [26],[27] which of the two candidates won for q / t   [28..30] singular values of E
+ */
+#define FEPE_POSE_OUT_FLOATS 32
+int fepe_pose_fwd(const float* F, const float* K, int L, int B, float ax, float bx, float ay, float by,
+                  const float* q_gt, const float* t_gt, const float* Rt_scene,
+                  const float* virt1, const float* virt2, int V, float clamp_at,
+                  float* out, void* stream);
 
 #ifdef __cplusplus
 }

@@ -22,7 +22,10 @@
 
 namespace fepe {
 
-constexpr int kMaxWarps = 10;                // 9 consumers + 1 producer
+#ifndef FEPE_WARPS
+#define FEPE_WARPS 10
+#endif
+constexpr int kMaxWarps = FEPE_WARPS;        // consumers + 1 producer
 constexpr int kThreads = kMaxWarps * 32;
 constexpr int kMaxStages = 16;
 constexpr int kScratchDoubles = 40;          // per consumer warp: 36 Gram entries (+pad)
@@ -45,6 +48,17 @@ struct FitParams {
     RingLayout ring;
 };
 
+__device__ __forceinline__ float approx_sqrt(float x) {   // MUFU-based, <= 2 ulp: ample for distances
+    float r;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+__device__ __forceinline__ float approx_rcp(float x) {
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+
 // Per-pair affine maps derived from the Hartley transforms (all warp-uniform registers).
 struct PairNorm {
     float m1x, m1y, m2x, m2y;   // raw means
@@ -55,26 +69,50 @@ struct PairNorm {
 __device__ __forceinline__ PairNorm hartley_passes(const float4* __restrict__ sp, int N, int lane,
                                                    float ax, float bx, float ay, float by) {
     PairNorm h;
-    float a = 0.f, b = 0.f, c = 0.f, d = 0.f;
-    for (int i = lane; i < N; i += 32) {
+    // four independent accumulation chains per lane: the loop is latency bound (LDS -> FADD) otherwise
+    float a[4] = {0.f, 0.f, 0.f, 0.f}, b[4] = {0.f, 0.f, 0.f, 0.f}, c[4] = {0.f, 0.f, 0.f, 0.f},
+          d[4] = {0.f, 0.f, 0.f, 0.f};
+    int i = lane;
+    for (; i + 96 < N; i += 128) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const float4 q = sp[i + 32 * u];
+            a[u] += q.x; b[u] += q.y; c[u] += q.z; d[u] += q.w;
+        }
+    }
+    for (; i < N; i += 32) {
         const float4 q = sp[i];
-        a += q.x; b += q.y; c += q.z; d += q.w;
+        a[0] += q.x; b[0] += q.y; c[0] += q.z; d[0] += q.w;
     }
     const float invN = 1.0f / static_cast<float>(N);
-    h.m1x = warp_sum(a) * invN; h.m1y = warp_sum(b) * invN;
-    h.m2x = warp_sum(c) * invN; h.m2y = warp_sum(d) * invN;
-    float d1 = 0.f, d2 = 0.f;
-    for (int i = lane; i < N; i += 32) {
-        const float4 q = sp[i];
-        const float u1 = ax * (q.x - h.m1x), v1 = ay * (q.y - h.m1y);
-        const float u2 = ax * (q.z - h.m2x), v2 = ay * (q.w - h.m2y);
-        d1 += sqrtf(fmaf(u1, u1, v1 * v1));
-        d2 += sqrtf(fmaf(u2, u2, v2 * v2));
+    h.m1x = warp_sum((a[0] + a[1]) + (a[2] + a[3])) * invN;
+    h.m1y = warp_sum((b[0] + b[1]) + (b[2] + b[3])) * invN;
+    h.m2x = warp_sum((c[0] + c[1]) + (c[2] + c[3])) * invN;
+    h.m2y = warp_sum((d[0] + d[1]) + (d[2] + d[3])) * invN;
+    float d1[4] = {0.f, 0.f, 0.f, 0.f}, d2[4] = {0.f, 0.f, 0.f, 0.f};
+    const float o1x = -ax * h.m1x, o1y = -ay * h.m1y, o2x = -ax * h.m2x, o2y = -ay * h.m2y;
+    i = lane;
+    for (; i + 96 < N; i += 128) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const float4 q = sp[i + 32 * u];
+            const float u1 = fmaf(ax, q.x, o1x), v1 = fmaf(ay, q.y, o1y);
+            const float u2 = fmaf(ax, q.z, o2x), v2 = fmaf(ay, q.w, o2y);
+            d1[u] += approx_sqrt(fmaf(u1, u1, v1 * v1));
+            d2[u] += approx_sqrt(fmaf(u2, u2, v2 * v2));
+        }
     }
-    d1 = warp_sum(d1) * invN;
-    d2 = warp_sum(d2) * invN;
-    h.s1 = 1.4142f / d1;
-    h.s2 = 1.4142f / d2;
+    for (; i < N; i += 32) {
+        const float4 q = sp[i];
+        const float u1 = fmaf(ax, q.x, o1x), v1 = fmaf(ay, q.y, o1y);
+        const float u2 = fmaf(ax, q.z, o2x), v2 = fmaf(ay, q.w, o2y);
+        d1[0] += approx_sqrt(fmaf(u1, u1, v1 * v1));
+        d2[0] += approx_sqrt(fmaf(u2, u2, v2 * v2));
+    }
+    const float md1 = warp_sum((d1[0] + d1[1]) + (d1[2] + d1[3])) * invN;
+    const float md2 = warp_sum((d2[0] + d2[1]) + (d2[2] + d2[3])) * invN;
+    h.s1 = 1.4142f / md1;
+    h.s2 = 1.4142f / md2;
     h.c1x = fmaf(ax, h.m1x, bx); h.c1y = fmaf(ay, h.m1y, by);
     h.c2x = fmaf(ax, h.m2x, bx); h.c2y = fmaf(ay, h.m2y, by);
     return h;
@@ -83,16 +121,20 @@ __device__ __forceinline__ PairNorm hartley_passes(const float4* __restrict__ sp
 struct PairSolution {
     double f[9];      // unit eigenvector of the smallest eigenvalue (= vec of the normalised F before rank 2)
     double lambda;
-    double S3[3];     // singular values of reshape(f)
+    double S3[3];     // v3: right singular vector of reshape(f) for its smallest singular value
+    double sigma3;    // that singular value (what the rank-2 projection removed)
     float Fo[9];      // T2^T F_ T1, fp32
     int iters;
+    long long cyc_eig;
 };
 
 __device__ __noinline__ void solve_pair(const double* __restrict__ gram, const PairNorm& h, PairSolution& sol) {
     double f[9], lambda;
+    const long long t0 = clock64();
     sol.iters = eig9_smallest(gram, f, lambda);
-    double F2[9], U3[9], S3[3], V3[9];
-    rank2_project(f, F2, U3, S3, V3);
+    sol.cyc_eig = clock64() - t0;
+    double F2[9], v3[3], sigma3;
+    rank2_project(f, F2, v3, sigma3);
     const double s1 = h.s1, s2 = h.s2;
     const double t1x = -s1 * h.c1x, t1y = -s1 * h.c1y, t2x = -s2 * h.c2x, t2y = -s2 * h.c2y;
     double A[9];
@@ -111,7 +153,8 @@ __device__ __noinline__ void solve_pair(const double* __restrict__ gram, const P
 #pragma unroll
     for (int i = 0; i < 9; ++i) sol.f[i] = f[i];
     sol.lambda = lambda;
-    sol.S3[0] = S3[0]; sol.S3[1] = S3[1]; sol.S3[2] = S3[2];
+    sol.S3[0] = v3[0]; sol.S3[1] = v3[1]; sol.S3[2] = v3[2];
+    sol.sigma3 = sigma3;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -182,6 +225,7 @@ __global__ void __launch_bounds__(kThreads, 1) fepe_fit_fwd_kernel(const FitPara
         const PairNorm h = hartley_passes(sp, N, lane, ax, bx, ay, by);
         // raw -> Hartley-normalised:  x~ = k * (x - m)
         const float k1x = h.s1 * ax, k1y = h.s1 * ay, k2x = h.s2 * ax, k2y = h.s2 * ay;
+        const float j1x = -k1x * h.m1x, j1y = -k1y * h.m1y, j2x = -k2x * h.m2x, j2y = -k2y * h.m2y;
 
         const long long tc2 = clock64();
         // ---- pass 3: the 36 distinct entries of G = sum_i s_i (a a^T) (x) (b b^T), fp64 ----
@@ -192,8 +236,8 @@ __global__ void __launch_bounds__(kThreads, 1) fepe_fit_fwd_kernel(const FitPara
         for (int i = lane; i < N; i += 32) {
             const float4 q = sp[i];
             const float wi = sw[i];
-            const float x1 = k1x * (q.x - h.m1x), y1 = k1y * (q.y - h.m1y);
-            const float x2 = k2x * (q.z - h.m2x), y2 = k2y * (q.w - h.m2y);
+            const float x1 = fmaf(k1x, q.x, j1x), y1 = fmaf(k1y, q.y, j1y);
+            const float x2 = fmaf(k2x, q.z, j2x), y2 = fmaf(k2y, q.w, j2y);
             const float nb = fmaf(x1, x1, fmaf(y1, y1, 1.0f));
             const float na = fmaf(x2, x2, fmaf(y2, y2, 1.0f));
             const float s = __fdividef(wi * wi, na * nb);   // (w / |p|)^2, |p|^2 = |a|^2 |b|^2 (2 ulp is ample)
@@ -219,6 +263,7 @@ __global__ void __launch_bounds__(kThreads, 1) fepe_fit_fwd_kernel(const FitPara
             if (cnt > 1) gram[base + 1] = acc[1];
         }
         __syncwarp();
+        const long long tc3b = clock64();
 
         // ---- smallest eigenvector, rank-2 projection, de-normalisation (every lane redundantly;
         //      the inputs are warp-uniform).  Kept out of line so that its fp64 working set does not
@@ -237,6 +282,7 @@ __global__ void __launch_bounds__(kThreads, 1) fepe_fit_fwd_kernel(const FitPara
                 sv[15] = sol.lambda;
                 sv[52] = static_cast<double>(sol.iters);
                 sv[53] = sol.S3[0]; sv[54] = sol.S3[1]; sv[55] = sol.S3[2];
+                sv[63] = sol.sigma3;
             }
             for (int i = lane; i < 36; i += 32) sv[16 + i] = gram[i];
         }
@@ -245,14 +291,15 @@ __global__ void __launch_bounds__(kThreads, 1) fepe_fit_fwd_kernel(const FitPara
         float ff[9];
 #pragma unroll
         for (int i = 0; i < 9; ++i) ff[i] = static_cast<float>(sol.f[i]);
-        float* r_out = p.resid + pair * static_cast<size_t>(N);
-        float* e_out = (p.epi != nullptr) ? p.epi + pair * static_cast<size_t>(N) : nullptr;
+        float* __restrict__ r_out = p.resid + pair * static_cast<size_t>(N);
+        float* __restrict__ e_out = (p.epi != nullptr) ? p.epi + pair * static_cast<size_t>(N) : nullptr;
         const float clamp_at = p.clamp_at;
+#pragma unroll 4
         for (int i = lane; i < N; i += 32) {
             const float4 q = sp[i];
             const float wi = sw[i];
-            const float x1 = k1x * (q.x - h.m1x), y1 = k1y * (q.y - h.m1y);
-            const float x2 = k2x * (q.z - h.m2x), y2 = k2y * (q.w - h.m2y);
+            const float x1 = fmaf(k1x, q.x, j1x), y1 = fmaf(k1y, q.y, j1y);
+            const float x2 = fmaf(k2x, q.z, j2x), y2 = fmaf(k2y, q.w, j2y);
             const float nb = fmaf(x1, x1, fmaf(y1, y1, 1.0f));
             const float na = fmaf(x2, x2, fmaf(y2, y2, 1.0f));
             const float r0 = fmaf(ff[0], x1, fmaf(ff[1], y1, ff[2]));
@@ -270,9 +317,9 @@ __global__ void __launch_bounds__(kThreads, 1) fepe_fit_fwd_kernel(const FitPara
                 const float l20 = fmaf(Fo[0], u1, fmaf(Fo[1], v1, Fo[2]));
                 const float l21 = fmaf(Fo[3], u1, fmaf(Fo[4], v1, Fo[5]));
                 const float dd = fmaf(l10, u1, fmaf(l11, v1, l12));
-                const float n1 = sqrtf(fmaf(l10, l10, l11 * l11)) + 1e-6f;
-                const float n2 = sqrtf(fmaf(l20, l20, l21 * l21)) + 1e-6f;
-                const float dist = fabsf(dd) * (__frcp_rn(n1) + __frcp_rn(n2));
+                const float n1 = approx_sqrt(fmaf(l10, l10, l11 * l11)) + 1e-6f;
+                const float n2 = approx_sqrt(fmaf(l20, l20, l21 * l21)) + 1e-6f;
+                const float dist = fabsf(dd) * (approx_rcp(n1) + approx_rcp(n2));
                 e_out[i] = fminf(dist, clamp_at);
             }
         }
@@ -287,6 +334,8 @@ __global__ void __launch_bounds__(kThreads, 1) fepe_fit_fwd_kernel(const FitPara
                 sv[58] = static_cast<double>(tc3 - tc2);   // Gram pass
                 sv[59] = static_cast<double>(tc4 - tc3);   // reduce + eigen + rank 2
                 sv[60] = static_cast<double>(tc5 - tc4);   // residual pass
+                sv[61] = static_cast<double>(tc3b - tc3);  // of which: warp reduce-scatter of the Gram
+                sv[62] = static_cast<double>(sol.cyc_eig); // of which: eigen iteration
             }
         }
     }
@@ -298,6 +347,8 @@ struct DeviceInfo {
     int ok = 0;
     int sms = 0;
     int smem_optin = 0;
+    int fwd_configured = 0;
+    int bwd_configured = 0;
 };
 
 static DeviceInfo& device_info() {
@@ -362,9 +413,13 @@ int fepe_fit_fwd(const float* matches, const float* weights, int B, int N, float
     p.matches = matches; p.weights = weights; p.B = B; p.N = N;
     p.ax = ax; p.bx = bx; p.ay = ay; p.by = by; p.clamp_at = clamp_at;
     p.F_out = F_out; p.resid = resid; p.epi = epi; p.saved = saved;
-    cudaError_t e = cudaFuncSetAttribute(fepe::fepe_fit_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         p.ring.total_bytes);
-    if (e != cudaSuccess) return static_cast<int>(e);
+    cudaError_t e = cudaSuccess;
+    if (!d.fwd_configured) {   // once per device, outside any stream capture that may follow
+        e = cudaFuncSetAttribute(fepe::fepe_fit_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 d.smem_optin);
+        if (e != cudaSuccess) return static_cast<int>(e);
+        d.fwd_configured = 1;
+    }
     const int grid = B < d.sms ? B : d.sms;
     fepe::fepe_fit_fwd_kernel<<<grid, fepe::kThreads, p.ring.total_bytes, static_cast<cudaStream_t>(stream)>>>(p);
     e = cudaGetLastError();

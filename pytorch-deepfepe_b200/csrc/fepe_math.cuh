@@ -22,6 +22,35 @@
 
 namespace fepe {
 
+// fp64 reciprocal / reciprocal square root for the latency-critical solvers: hardware seed
+// (MUFU.RCP64H / RSQ64H, ~2^-23) plus two Newton steps, no special-case handling (callers guarantee
+// finite non-zero arguments).  About half the latency of the IEEE division sequence.
+FEPE_HD double fast_rcp(double d) {
+#if defined(__CUDA_ARCH__)
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(d));
+    double e = fma(-d, r, 1.0);
+    r = fma(r, e, r);
+    e = fma(-d, r, 1.0);
+    return fma(r, e, r);
+#else
+    return 1.0 / d;
+#endif
+}
+FEPE_HD double fast_rsqrt(double x) {
+#if defined(__CUDA_ARCH__)
+    double r;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+    double h = 0.5 * x;
+    double e = fma(-h * r, r, 0.5);
+    r = fma(r, e, r);
+    e = fma(-h * r, r, 0.5);
+    return fma(r, e, r);
+#else
+    return 1.0 / sqrt(x);
+#endif
+}
+
 // ---------------------------------------------------------------------------------------------
 // Gram matrix storage.  A constraint row is p = a (x) b with a = (x2,y2,1), b = (x1,y1,1), so
 // p p^T = (a a^T) (x) (b b^T) has only 6 x 6 = 36 distinct entries.  g36[u*6+v] holds
@@ -35,48 +64,53 @@ FEPE_HD constexpr int g36_index(int r, int c) { return sym6(r / 3, c / 3) * 6 + 
 
 // LDL^T of M = G - mu*I (unit lower L, reciprocal pivots rd).  Returns the number of negative
 // pivots = number of eigenvalues of G below mu (Sylvester inertia).
-FEPE_HD int ldl9(const double* __restrict__ g36, double mu, double tiny, double (&L)[36], double (&rd)[9]) {
-    // L is stored strictly-lower packed: L(i,j), i>j, at i*(i-1)/2 + j
+// Right-looking (outer-product) form: once column j is scaled every trailing update is an
+// independent FMA, so the dependent chain per column is just reciprocal -> scale -> one FMA.
+FEPE_HD int ldl9(const double* __restrict__ g36, double mu, double tiny, double (&A)[45]) {
+    // A: lower triangle incl. diagonal, (i,j), i>=j at i*(i+1)/2 + j.  On exit the strictly lower part
+    // holds L and the diagonal holds the RECIPROCAL pivots.
+#pragma unroll
+    for (int i = 0; i < 9; ++i) {
+#pragma unroll
+        for (int j = 0; j <= i; ++j) A[i * (i + 1) / 2 + j] = g36[g36_index(i, j)] - ((i == j) ? mu : 0.0);
+    }
     int nneg = 0;
-    double d[9];
 #pragma unroll
     for (int j = 0; j < 9; ++j) {
-        double v[9];
-        double dj = g36[g36_index(j, j)] - mu;
-#pragma unroll
-        for (int k = 0; k < j; ++k) {
-            v[k] = L[j * (j - 1) / 2 + k] * d[k];
-            dj -= L[j * (j - 1) / 2 + k] * v[k];
-        }
+        double dj = A[j * (j + 1) / 2 + j];
         if (dj < 0.0) ++nneg;
         if (fabs(dj) < tiny) dj = (dj < 0.0) ? -tiny : tiny;
-        d[j] = dj;
-        const double r = 1.0 / dj;
-        rd[j] = r;
+        const double r = fast_rcp(dj);
+        A[j * (j + 1) / 2 + j] = r;
+        double t[9];
+#pragma unroll
+        for (int i = j + 1; i < 9; ++i) t[i] = A[i * (i + 1) / 2 + j] * r;      // l_ij
 #pragma unroll
         for (int i = j + 1; i < 9; ++i) {
-            double lij = g36[g36_index(i, j)];
 #pragma unroll
-            for (int k = 0; k < j; ++k) lij -= L[i * (i - 1) / 2 + k] * v[k];
-            L[i * (i - 1) / 2 + j] = lij * r;
+            for (int k = j + 1; k <= i; ++k)                                     // a_kj still unscaled here
+                A[i * (i + 1) / 2 + k] = fma(-t[i], A[k * (k + 1) / 2 + j], A[i * (i + 1) / 2 + k]);
         }
+#pragma unroll
+        for (int i = j + 1; i < 9; ++i) A[i * (i + 1) / 2 + j] = t[i];
     }
     return nneg;
 }
 
-// x <- M^{-1} x using the factorisation above.
-FEPE_HD void ldl9_solve(const double (&L)[36], const double (&rd)[9], double (&x)[9]) {
+// x <- M^{-1} x using the factorisation above (column-oriented substitutions: each finished
+// unknown is pushed into all later rows at once, keeping the dependent chain at one FMA per step).
+FEPE_HD void ldl9_solve(const double (&A)[45], double (&x)[9]) {
 #pragma unroll
-    for (int i = 1; i < 9; ++i) {
+    for (int k = 0; k < 8; ++k) {
 #pragma unroll
-        for (int k = 0; k < i; ++k) x[i] -= L[i * (i - 1) / 2 + k] * x[k];
+        for (int i = k + 1; i < 9; ++i) x[i] = fma(-A[i * (i + 1) / 2 + k], x[k], x[i]);
     }
 #pragma unroll
-    for (int i = 0; i < 9; ++i) x[i] *= rd[i];
+    for (int i = 0; i < 9; ++i) x[i] *= A[i * (i + 1) / 2 + i];
 #pragma unroll
-    for (int i = 7; i >= 0; --i) {
+    for (int k = 8; k >= 1; --k) {
 #pragma unroll
-        for (int k = i + 1; k < 9; ++k) x[i] -= L[k * (k - 1) / 2 + i] * x[k];
+        for (int i = 0; i < k; ++i) x[i] = fma(-A[k * (k + 1) / 2 + i], x[k], x[i]);
     }
 }
 
@@ -121,8 +155,8 @@ FEPE_HD int eig9_smallest(const double* __restrict__ g36, double (&f)[9], double
     double r_prev = -1.0;      // residual after the previous solve (none yet)
     int it = 0;
     for (; it < 24; ++it) {
-        double L[36], rd[9];
-        const int nneg = ldl9(g36, mu, tiny, L, rd);
+        double A[45];
+        const int nneg = ldl9(g36, mu, tiny, A);
         if (nneg > 0) {         // overshot lambda_min: go back half way to the last safe shift
             mu = 0.5 * (mu + lo);
             continue;
@@ -134,11 +168,11 @@ FEPE_HD int eig9_smallest(const double* __restrict__ g36, double (&f)[9], double
             double y[9];
 #pragma unroll
             for (int i = 0; i < 9; ++i) y[i] = x[i];
-            ldl9_solve(L, rd, y);
+            ldl9_solve(A, y);
             double nrm2 = 0.0;
 #pragma unroll
             for (int i = 0; i < 9; ++i) nrm2 += y[i] * y[i];
-            const double inv = 1.0 / sqrt(nrm2);
+            const double inv = fast_rsqrt(nrm2);
             // With x' = y/|y| and (G - mu I) y = x:  G x' = mu x' + x/|y|, hence
             //   rho = mu + (x'.x)/|y|   and   G x' - rho x' = (x - (x'.x) x')/|y|   (no mat-vec needed)
             double c = 0.0;
@@ -156,8 +190,8 @@ FEPE_HD int eig9_smallest(const double* __restrict__ g36, double (&f)[9], double
         if (r_prev >= 0.0) {
             const double q = r / r_prev;
             if (q < 1.0) {
-                const double gap = (rho - mu) * (1.0 / q - 1.0);
-                if (r <= 1e-9 * gap) { ++it; break; }
+                // r <= 1e-8 gap  with  gap = (rho - mu) (1/q - 1), written without the division
+                if (r * q <= 1e-8 * (rho - mu) * (1.0 - q)) { ++it; break; }
             }
             if (q >= 0.5 && r_prev <= 1e-9 * tr) { ++it; break; }   // stagnated at the rounding floor
         }
@@ -345,18 +379,112 @@ FEPE_HD double det3(const double (&A)[9]) {
            A[2] * (A[3] * A[7] - A[4] * A[6]);
 }
 
+// Smallest right singular vector of a 3x3 matrix: eigenvector of M = A^T A for its smallest
+// eigenvalue.  lambda_3 by Newton on the characteristic polynomial starting at 0 (monotone from
+// the left of the smallest root, quadratic when lambda_3 << lambda_2 as for any F worth fitting),
+// the vector as the largest column of adj(M - lambda_3 I).  ~1/10 of the latency of a Jacobi SVD.
+FEPE_HD void smallest_right_sv3(const double (&A)[9], double (&v)[3], double& sigma3) {
+    const double m00 = A[0] * A[0] + A[3] * A[3] + A[6] * A[6];
+    const double m01 = A[0] * A[1] + A[3] * A[4] + A[6] * A[7];
+    const double m02 = A[0] * A[2] + A[3] * A[5] + A[6] * A[8];
+    const double m11 = A[1] * A[1] + A[4] * A[4] + A[7] * A[7];
+    const double m12 = A[1] * A[2] + A[4] * A[5] + A[7] * A[8];
+    const double m22 = A[2] * A[2] + A[5] * A[5] + A[8] * A[8];
+    const double c2 = m00 + m11 + m22;
+    const double c1 = (m00 * m11 - m01 * m01) + (m00 * m22 - m02 * m02) + (m11 * m22 - m12 * m12);
+    const double det = m00 * (m11 * m22 - m12 * m12) - m01 * (m01 * m22 - m12 * m02) + m02 * (m01 * m12 - m11 * m02);
+    const double c0 = det > 0.0 ? det : 0.0;
+    double lam = 0.0;
+    if (c1 > 0.0) {
+        for (int it = 0; it < 16; ++it) {
+            const double q = ((lam - c2) * lam + c1) * lam - c0;
+            const double dq = (3.0 * lam - 2.0 * c2) * lam + c1;
+            if (!(dq > 0.0)) break;
+            const double step = -q * fast_rcp(dq);
+            if (!(step > 1e-17 * c2)) break;
+            lam += step;
+        }
+    }
+    const double a00 = m00 - lam, a11 = m11 - lam, a22 = m22 - lam;
+    // rows r0=(a00,m01,m02) r1=(m01,a11,m12) r2=(m02,m12,a22); null vector = cross product of two rows
+    const double x0 = m01 * m12 - m02 * a11, y0 = m02 * m01 - a00 * m12, z0 = a00 * a11 - m01 * m01;   // r0 x r1
+    const double x1 = m01 * a22 - m02 * m12, y1 = m02 * m02 - a00 * a22, z1 = a00 * m12 - m01 * m02;   // r0 x r2
+    const double x2 = a11 * a22 - m12 * m12, y2 = m12 * m02 - m01 * a22, z2 = m01 * m12 - a11 * m02;   // r1 x r2
+    const double n0 = x0 * x0 + y0 * y0 + z0 * z0, n1 = x1 * x1 + y1 * y1 + z1 * z1, n2 = x2 * x2 + y2 * y2 + z2 * z2;
+    double vx = x0, vy = y0, vz = z0, nn = n0;
+    if (n1 > nn) { vx = x1; vy = y1; vz = z1; nn = n1; }
+    if (n2 > nn) { vx = x2; vy = y2; vz = z2; nn = n2; }
+    if (!(nn > 0.0)) { vx = 0.0; vy = 0.0; vz = 1.0; nn = 1.0; }
+    const double inv = fast_rsqrt(nn);
+    v[0] = vx * inv; v[1] = vy * inv; v[2] = vz * inv;
+    const double w0 = A[0] * v[0] + A[1] * v[1] + A[2] * v[2];
+    const double w1 = A[3] * v[0] + A[4] * v[1] + A[5] * v[2];
+    const double w2 = A[6] * v[0] + A[7] * v[1] + A[8] * v[2];
+    sigma3 = sqrt(w0 * w0 + w1 * w1 + w2 * w2);
+}
+
 // Rank-2 projection of F0 = reshape(f): F0 - sigma3 u3 v3^T  (DeepFNet.py:236-237, S*[1,1,0]).
-// Since sigma3 u3 = F0 v3 this is F0 (I - v3 v3^T); only V is needed.
-FEPE_HD void rank2_project(const double (&F0)[9], double (&F2)[9], double (&U)[9], double (&S)[3], double (&V)[9]) {
-    svd3(F0, U, S, V);
-    const double v0 = V[2], v1 = V[5], v2 = V[8];
+// Since sigma3 u3 = F0 v3 this is F0 (I - v3 v3^T); only v3 is needed.
+FEPE_HD void rank2_project(const double (&F0)[9], double (&F2)[9], double (&v3)[3], double& sigma3) {
+    smallest_right_sv3(F0, v3, sigma3);
 #pragma unroll
     for (int r = 0; r < 3; ++r) {
-        const double w = F0[3 * r] * v0 + F0[3 * r + 1] * v1 + F0[3 * r + 2] * v2;
-        F2[3 * r] = F0[3 * r] - w * v0;
-        F2[3 * r + 1] = F0[3 * r + 1] - w * v1;
-        F2[3 * r + 2] = F0[3 * r + 2] - w * v2;
+        const double w = F0[3 * r] * v3[0] + F0[3 * r + 1] * v3[1] + F0[3 * r + 2] * v3[2];
+        F2[3 * r] = F0[3 * r] - w * v3[0];
+        F2[3 * r + 1] = F0[3 * r + 1] - w * v3[1];
+        F2[3 * r + 2] = F0[3 * r + 2] - w * v3[2];
     }
+}
+
+}  // namespace fepe
+
+namespace fepe {
+
+// ---------------------------------------------------------------------------------------------
+// Pose head pieces (deepFEPE/dsac_tools/utils_F.py:478-498 _get_M2s,
+// deepFEPE/dsac_tools/utils_geo.py:58-86 _R_to_q).
+// ---------------------------------------------------------------------------------------------
+
+// E = U S V^T -> R1 = U W V^T, R2 = U W^T V^T, t = u3.  U and V are completed to proper rotations
+// (u3 = u1 x u2, v3 = v1 x v2), which makes det(U W V^T) = +1 without the reference's "W = -W if
+// det < 0" test and yields the same SET {R1,R2}, {t,-t} whatever signs LAPACK would have picked.
+FEPE_HD void essential_decompose(const double (&E)[9], double (&R1)[9], double (&R2)[9], double (&t)[3],
+                                 double (&U)[9], double (&S)[3], double (&V)[9]) {
+    svd3(E, U, S, V);
+    U[2] = U[3] * U[7] - U[6] * U[4]; U[5] = U[6] * U[1] - U[0] * U[7]; U[8] = U[0] * U[4] - U[3] * U[1];
+    V[2] = V[3] * V[7] - V[6] * V[4]; V[5] = V[6] * V[1] - V[0] * V[7]; V[8] = V[0] * V[4] - V[3] * V[1];
+    // U W = [u2, -u1, u3],  U W^T = [-u2, u1, u3]   (columns)
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+            const double a = U[3 * i + 1] * V[3 * j] - U[3 * i] * V[3 * j + 1];
+            const double b = U[3 * i + 2] * V[3 * j + 2];
+            R1[3 * i + j] = a + b;
+            R2[3 * i + j] = b - a;
+        }
+    }
+    const double n = 1.0 / (sqrt(U[2] * U[2] + U[5] * U[5] + U[8] * U[8]) + 1e-300);
+    t[0] = U[2] * n; t[1] = U[5] * n; t[2] = U[8] * n;
+}
+
+// Trace-method quaternion (w,x,y,z) with w >= 0; same four branches as the reference (m = R^T).
+FEPE_HD void rot_to_quat(const double (&R)[9], double (&q)[4]) {
+    // m[i][j] = R[j][i]
+    const double m00 = R[0], m11 = R[4], m22 = R[8];
+    const double m01 = R[3], m10 = R[1], m02 = R[6], m20 = R[2], m12 = R[7], m21 = R[5];
+    double tr;
+    if (m22 < 0.0) {
+        if (m00 > m11) { tr = 1.0 + m00 - m11 - m22; q[0] = m12 - m21; q[1] = tr; q[2] = m01 + m10; q[3] = m20 + m02; }
+        else           { tr = 1.0 - m00 + m11 - m22; q[0] = m20 - m02; q[1] = m01 + m10; q[2] = tr; q[3] = m12 + m21; }
+    } else {
+        if (m00 < -m11) { tr = 1.0 - m00 - m11 + m22; q[0] = m01 - m10; q[1] = m20 + m02; q[2] = m12 + m21; q[3] = tr; }
+        else            { tr = 1.0 + m00 + m11 + m22; q[0] = tr; q[1] = m12 - m21; q[2] = m20 - m02; q[3] = m01 - m10; }
+    }
+    const double s = 0.5 / sqrt(tr);
+    const double sg = (q[0] < 0.0) ? -s : s;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) q[i] *= sg;
 }
 
 }  // namespace fepe

@@ -10,7 +10,7 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(os.path.dirname(_HERE), "lib", "libfepe_b200.so")
+LIB_PATH = os.environ.get("FEPE_B200_LIB") or os.path.join(os.path.dirname(_HERE), "lib", "libfepe_b200.so")
 
 SAVED_DOUBLES = 64          # FEPE_SAVED_DOUBLES
 POSE_OUT_FLOATS = 32        # FEPE_POSE_OUT_FLOATS
@@ -28,6 +28,8 @@ _SIGNATURES = {
                             _c_p, _c_p, _c_p, _c_p, _c_p]),
     "fepe_fit_bwd": (_c_i, [_c_p, _c_p, _c_i, _c_i, _c_f, _c_f, _c_f, _c_f, _c_f,
                             _c_p, _c_p, _c_p, _c_p, _c_p, _c_p]),
+    "fepe_pose_fwd": (_c_i, [_c_p, _c_p, _c_i, _c_i, _c_f, _c_f, _c_f, _c_f, _c_p, _c_p, _c_p, _c_p, _c_p,
+                             _c_i, _c_f, _c_p, _c_p]),
 }
 
 _ERRORS = {-1: "FEPE_E_BADARG (null pointer, misaligned buffer or non-positive size)",

@@ -33,7 +33,7 @@ def _stream_ptr() -> int:
 
 
 def fit_forward(matches: torch.Tensor, weights: torch.Tensor, affine=IDENTITY_AFFINE,
-                clamp_at: float = 0.5, want_epi: bool = True, want_saved: bool = False):
+                clamp_at: float = 0.5, want_epi: bool = True, want_saved: bool = False, out=None):
     """matches [B,N,4], weights [B,N] (or [B,1,N]) -> F [B,3,3], residual [B,N], epi [B,N]|None,
     saved [B,64] float64|None.  One launch of the fused kernel (include/fepe_b200.h: fepe_fit_fwd)."""
     matches = _check_cuda_f32(matches, "matches")
@@ -44,10 +44,13 @@ def fit_forward(matches: torch.Tensor, weights: torch.Tensor, affine=IDENTITY_AF
     weights = weights.reshape(B, N)
     dev = matches.device
     with torch.cuda.device(dev):
-        F = torch.empty(B, 3, 3, dtype=torch.float32, device=dev)
-        res = torch.empty(B, N, dtype=torch.float32, device=dev)
-        epi = torch.empty(B, N, dtype=torch.float32, device=dev) if want_epi else None
-        saved = torch.empty(B, _lib.SAVED_DOUBLES, dtype=torch.float64, device=dev) if want_saved else None
+        if out is not None:      # caller-owned output buffers (F, res, epi|None, saved|None), e.g. for graphs
+            F, res, epi, saved = out
+        else:
+            F = torch.empty(B, 3, 3, dtype=torch.float32, device=dev)
+            res = torch.empty(B, N, dtype=torch.float32, device=dev)
+            epi = torch.empty(B, N, dtype=torch.float32, device=dev) if want_epi else None
+            saved = torch.empty(B, _lib.SAVED_DOUBLES, dtype=torch.float64, device=dev) if want_saved else None
         st = _lib.lib().fepe_fit_fwd(matches.data_ptr(), weights.data_ptr(), B, N,
                                      affine[0], affine[1], affine[2], affine[3], float(clamp_at),
                                      F.data_ptr(), res.data_ptr(),
@@ -56,3 +59,34 @@ def fit_forward(matches: torch.Tensor, weights: torch.Tensor, affine=IDENTITY_AF
                                      _stream_ptr())
     _lib.check(st, "fepe_fit_fwd")
     return F, res, epi, saved
+
+
+def pose_forward(F: torch.Tensor, K: torch.Tensor, affine, q_gt: torch.Tensor, t_gt: torch.Tensor,
+                 Rt_scene: Optional[torch.Tensor] = None, virt1: Optional[torch.Tensor] = None,
+                 virt2: Optional[torch.Tensor] = None, clamp_at: float = 0.02,
+                 out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """F [L,B,3,3] or [B,3,3]; K [B,3,3]; q_gt [B,4(,1)]; t_gt [B,3(,1)]; Rt_scene [B,4,4];
+    virt1/2 [B,V,3].  Returns [L,B,32] (layout in include/fepe_b200.h: fepe_pose_fwd)."""
+    F = _check_cuda_f32(F, "F")
+    if F.dim() == 3:
+        F = F.unsqueeze(0)
+    L, B = F.shape[0], F.shape[1]
+    K = _check_cuda_f32(K, "K").reshape(B, 9)
+    q_gt = _check_cuda_f32(q_gt, "q_gt").reshape(B, 4)
+    t_gt = _check_cuda_f32(t_gt, "t_gt").reshape(B, 3)
+    rt = _check_cuda_f32(Rt_scene, "Rt_scene").reshape(B, 16) if Rt_scene is not None else None
+    V = 0
+    if virt1 is not None:
+        virt1 = _check_cuda_f32(virt1, "virt1")
+        virt2 = _check_cuda_f32(virt2, "virt2")
+        V = virt1.shape[1]
+    with torch.cuda.device(F.device):
+        if out is None:
+            out = torch.empty(L, B, _lib.POSE_OUT_FLOATS, dtype=torch.float32, device=F.device)
+        st = _lib.lib().fepe_pose_fwd(F.data_ptr(), K.data_ptr(), L, B, affine[0], affine[1], affine[2], affine[3],
+                                      q_gt.data_ptr(), t_gt.data_ptr(), rt.data_ptr() if rt is not None else None,
+                                      virt1.data_ptr() if virt1 is not None else None,
+                                      virt2.data_ptr() if virt2 is not None else None, V, float(clamp_at),
+                                      out.data_ptr(), _stream_ptr())
+    _lib.check(st, "fepe_pose_fwd")
+    return out

@@ -30,11 +30,29 @@ void shim_svd3(const double* A, double* U, double* S, double* V) {
 }
 
 void shim_rank2(const double* F0, double* F2) {
-    double a[9], f2[9], u[9], s[3], v[9];
+    double a[9], f2[9], v[3], s3;
     for (int i = 0; i < 9; ++i) a[i] = F0[i];
-    fepe::rank2_project(a, f2, u, s, v);
+    fepe::rank2_project(a, f2, v, s3);
     for (int i = 0; i < 9; ++i) F2[i] = f2[i];
 }
 
 int shim_g36_index(int r, int c) { return fepe::g36_index(r, c); }
+
+void shim_essential(const double* E, double* R1, double* R2, double* t, double* q1, double* q2) {
+    double e[9], r1[9], r2[9], tt[3], u[9], s[3], v[9], qa[4], qb[4];
+    for (int i = 0; i < 9; ++i) e[i] = E[i];
+    fepe::essential_decompose(e, r1, r2, tt, u, s, v);
+    fepe::rot_to_quat(r1, qa);
+    fepe::rot_to_quat(r2, qb);
+    for (int i = 0; i < 9; ++i) { R1[i] = r1[i]; R2[i] = r2[i]; }
+    for (int i = 0; i < 3; ++i) t[i] = tt[i];
+    for (int i = 0; i < 4; ++i) { q1[i] = qa[i]; q2[i] = qb[i]; }
+}
+
+void shim_quat(const double* R, double* q) {
+    double r[9], qq[4];
+    for (int i = 0; i < 9; ++i) r[i] = R[i];
+    fepe::rot_to_quat(r, qq);
+    for (int i = 0; i < 4; ++i) q[i] = qq[i];
+}
 }
