@@ -16,55 +16,9 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
-#include "../../include/fepe_b200.h"
-#include "fepe_common.cuh"
-#include "fepe_math.cuh"
+#include "fepe_fit.cuh"
 
 namespace fepe {
-
-#ifndef FEPE_WARPS
-#define FEPE_WARPS 10
-#endif
-constexpr int kMaxWarps = FEPE_WARPS;        // consumers + 1 producer
-constexpr int kThreads = kMaxWarps * 32;
-constexpr int kMaxStages = 16;
-constexpr int kScratchDoubles = 40;          // per consumer warp: 36 Gram entries (+pad)
-
-struct FitParams {
-    const float* matches;   // [B,N,4]
-    const float* weights;   // [B,N]
-    int B, N;
-    float ax, bx, ay, by;
-    float clamp_at;
-    float* F_out;           // [B,9]
-    float* resid;           // [B,N]
-    float* epi;             // [B,N] or null
-    double* saved;          // [B,FEPE_SAVED_DOUBLES] or null
-    // backward only
-    const float* gF;
-    const float* gresid;
-    const float* gepi;
-    float* gweights;
-    RingLayout ring;
-};
-
-__device__ __forceinline__ float approx_sqrt(float x) {   // MUFU-based, <= 2 ulp: ample for distances
-    float r;
-    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
-    return r;
-}
-__device__ __forceinline__ float approx_rcp(float x) {
-    float r;
-    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
-    return r;
-}
-
-// Per-pair affine maps derived from the Hartley transforms (all warp-uniform registers).
-struct PairNorm {
-    float m1x, m1y, m2x, m2y;   // raw means
-    float c1x, c1y, c2x, c2y;   // primed centroids  (ax*m+bx)
-    float s1, s2;               // Hartley scales 1.4142/meandist (literal as in DeepFNet.py:168)
-};
 
 __device__ __forceinline__ PairNorm hartley_passes(const float4* __restrict__ sp, int N, int lane,
                                                    float ax, float bx, float ay, float by) {
@@ -135,21 +89,7 @@ __device__ __noinline__ void solve_pair(const double* __restrict__ gram, const P
     sol.cyc_eig = clock64() - t0;
     double F2[9], v3[3], sigma3;
     rank2_project(f, F2, v3, sigma3);
-    const double s1 = h.s1, s2 = h.s2;
-    const double t1x = -s1 * h.c1x, t1y = -s1 * h.c1y, t2x = -s2 * h.c2x, t2y = -s2 * h.c2y;
-    double A[9];
-#pragma unroll
-    for (int r = 0; r < 3; ++r) {
-        A[3 * r] = F2[3 * r] * s1;
-        A[3 * r + 1] = F2[3 * r + 1] * s1;
-        A[3 * r + 2] = fma(F2[3 * r], t1x, fma(F2[3 * r + 1], t1y, F2[3 * r + 2]));
-    }
-#pragma unroll
-    for (int k = 0; k < 3; ++k) {
-        sol.Fo[k] = static_cast<float>(s2 * A[k]);
-        sol.Fo[3 + k] = static_cast<float>(s2 * A[3 + k]);
-        sol.Fo[6 + k] = static_cast<float>(fma(t2x, A[k], fma(t2y, A[3 + k], A[6 + k])));
-    }
+    denormalise_F(F2, h, sol.Fo);
 #pragma unroll
     for (int i = 0; i < 9; ++i) sol.f[i] = f[i];
     sol.lambda = lambda;
@@ -177,31 +117,11 @@ __global__ void __launch_bounds__(kThreads, 1) fepe_fit_fwd_kernel(const FitPara
     __syncthreads();
 
     const uint32_t pts_bytes = static_cast<uint32_t>(N) * 16u;
-    const uint32_t w_bytes = static_cast<uint32_t>(N) * 4u;
 
     if (warp == C) {
         // ---------------- producer warp ----------------
-        for (int j = 0; j < n_local; ++j) {
-            const int stage = j % S;
-            const uint32_t phase = static_cast<uint32_t>(j / S) & 1u;
-            mbar_wait(&empty[stage], phase ^ 1u);
-            const size_t pair = static_cast<size_t>(blockIdx.x) + static_cast<size_t>(j) * gridDim.x;
-            unsigned char* sb = smem + static_cast<size_t>(stage) * p.ring.stage_bytes;
-            const float* gp = p.matches + pair * static_cast<size_t>(N) * 4;
-            const float* gw = p.weights + pair * static_cast<size_t>(N);
-            const bool w_bulk = ((reinterpret_cast<uintptr_t>(gw) & 15u) == 0) && ((N & 3) == 0);
-            if (!w_bulk) {   // ragged N: the weight row is not 16-byte aligned, copy it by hand
-                float* sw = reinterpret_cast<float*>(sb + pts_bytes);
-                for (int i = lane; i < N; i += 32) sw[i] = __ldg(gw + i);
-                __syncwarp();
-            }
-            if (lane == 0) {
-                mbar_arrive_expect_tx(&full[stage], pts_bytes + (w_bulk ? w_bytes : 0u));
-                bulk_g2s(sb, gp, pts_bytes, &full[stage]);
-                if (w_bulk) bulk_g2s(sb + pts_bytes, gw, w_bytes, &full[stage]);
-            }
-            __syncwarp();
-        }
+        RingSources src{{p.matches, p.weights, nullptr, nullptr}, 2};
+        ring_producer(smem, p.ring, full, empty, src, N, n_local, lane);
         return;
     }
     if (warp > C) return;
@@ -341,52 +261,6 @@ __global__ void __launch_bounds__(kThreads, 1) fepe_fit_fwd_kernel(const FitPara
     }
 }
 
-// ------------------------------------------------------------------------------------------------
-// host side
-struct DeviceInfo {
-    int ok = 0;
-    int sms = 0;
-    int smem_optin = 0;
-    int fwd_configured = 0;
-    int bwd_configured = 0;
-};
-
-static DeviceInfo& device_info() {
-    static DeviceInfo info[64];
-    int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) {
-        static DeviceInfo bad;
-        return bad;
-    }
-    DeviceInfo& d = info[dev];
-    if (!d.ok) {
-        int major = 0;
-        cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev);
-        cudaDeviceGetAttribute(&d.sms, cudaDevAttrMultiProcessorCount, dev);
-        cudaDeviceGetAttribute(&d.smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
-        d.ok = (major == 10 && d.sms > 0) ? 1 : -1;
-    }
-    return d;
-}
-
-static bool make_ring(int N, int smem_limit, RingLayout& r) {
-    const int stage = ((N * 20 + 127) / 128) * 128;
-    const int fixed = 2 * kMaxStages * 8 + (kMaxWarps - 1) * kScratchDoubles * 8 + 256;
-    int S = (smem_limit - fixed) / stage;
-    if (S > kMaxStages) S = kMaxStages;
-    if (S < 2) return false;
-    int C = S - 1;                     // keep at least one stage of prefetch
-    if (S >= 6) C = S - 2;
-    if (C > kMaxWarps - 1) C = kMaxWarps - 1;
-    r.stages = S;
-    r.consumers = C;
-    r.stage_bytes = stage;
-    r.bar_off = S * stage;
-    r.scratch_off = r.bar_off + 2 * kMaxStages * 8;
-    r.total_bytes = r.scratch_off + (kMaxWarps - 1) * kScratchDoubles * 8;
-    return true;
-}
-
 }  // namespace fepe
 
 extern "C" {
@@ -409,7 +283,7 @@ int fepe_fit_fwd(const float* matches, const float* weights, int B, int N, float
     fepe::DeviceInfo& d = fepe::device_info();
     if (d.ok != 1) return FEPE_E_NODEVICE;
     fepe::FitParams p{};
-    if (!fepe::make_ring(N, d.smem_optin, p.ring)) return FEPE_E_TOOLARGE;
+    if (!fepe::make_ring(N, 20, d.smem_optin, p.ring)) return FEPE_E_TOOLARGE;
     p.matches = matches; p.weights = weights; p.B = B; p.N = N;
     p.ax = ax; p.bx = bx; p.ay = ay; p.by = by; p.clamp_at = clamp_at;
     p.F_out = F_out; p.resid = resid; p.epi = epi; p.saved = saved;

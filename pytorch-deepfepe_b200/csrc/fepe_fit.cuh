@@ -1,0 +1,173 @@
+// Shared pieces of the fused forward / backward streaming kernels: launch parameters, the per-pair
+// Hartley state, the shared-memory ring geometry and the host-side device bookkeeping.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/fepe_b200.h"
+#include "fepe_common.cuh"
+#include "fepe_math.cuh"
+
+namespace fepe {
+
+#ifndef FEPE_WARPS
+#define FEPE_WARPS 10
+#endif
+constexpr int kMaxWarps = FEPE_WARPS;        // consumers + 1 producer
+constexpr int kThreads = kMaxWarps * 32;
+constexpr int kMaxStages = 16;
+constexpr int kScratchDoubles = 40;          // per consumer warp: 36 Gram entries (+pad)
+
+struct FitParams {
+    const float* matches;   // [B,N,4]
+    const float* weights;   // [B,N]
+    int B, N;
+    float ax, bx, ay, by;
+    float clamp_at;
+    float* F_out;           // [B,9]
+    float* resid;           // [B,N]
+    float* epi;             // [B,N] or null
+    double* saved;          // [B,FEPE_SAVED_DOUBLES] or null
+    // backward only
+    const float* gF;
+    const float* gresid;
+    const float* gepi;
+    float* gweights;
+    RingLayout ring;
+};
+
+__device__ __forceinline__ float approx_sqrt(float x) {   // MUFU-based, <= 2 ulp: ample for distances
+    float r;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+__device__ __forceinline__ float approx_rcp(float x) {
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+
+// Per-pair affine maps derived from the Hartley transforms (all warp-uniform registers).
+struct PairNorm {
+    float m1x, m1y, m2x, m2y;   // raw means
+    float c1x, c1y, c2x, c2y;   // primed centroids  (ax*m+bx)
+    float s1, s2;               // Hartley scales 1.4142/meandist (literal as in DeepFNet.py:168)
+};
+
+
+// out = T2^T F2 T1 with T = [[s,0,-s cx],[0,s,-s cy],[0,0,1]] (DeepFNet.py:256), fp64 in, fp32 out.
+__device__ __forceinline__ void denormalise_F(const double (&F2)[9], const PairNorm& h, float (&Fo)[9]) {
+    const double s1 = h.s1, s2 = h.s2;
+    const double t1x = -s1 * h.c1x, t1y = -s1 * h.c1y, t2x = -s2 * h.c2x, t2y = -s2 * h.c2y;
+    double A[9];
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+        A[3 * r] = F2[3 * r] * s1;
+        A[3 * r + 1] = F2[3 * r + 1] * s1;
+        A[3 * r + 2] = fma(F2[3 * r], t1x, fma(F2[3 * r + 1], t1y, F2[3 * r + 2]));
+    }
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        Fo[k] = static_cast<float>(s2 * A[k]);
+        Fo[3 + k] = static_cast<float>(s2 * A[3 + k]);
+        Fo[6 + k] = static_cast<float>(fma(t2x, A[k], fma(t2y, A[3 + k], A[6 + k])));
+    }
+}
+
+// Producer warp of the pair ring: streams `n_arrays` per-pair arrays (array 0 = the [N,4] coordinates,
+// 16 B per correspondence; arrays 1.. = [N] fp32 rows) into the stages.  Rows that are not 16-byte
+// aligned (ragged N) are copied by the warp itself before the barrier is armed.
+struct RingSources {
+    const float* ptr[4];   // ptr[0]: [B,N,4]; ptr[1..]: [B,N] (may be null: that slot is zero filled)
+    int n_arrays;
+};
+
+__device__ __forceinline__ void ring_producer(unsigned char* smem, const RingLayout& ring, uint64_t* full,
+                                              uint64_t* empty, const RingSources& src, int N, int n_local, int lane) {
+    const int S = ring.stages;
+    const uint32_t pts_bytes = static_cast<uint32_t>(N) * 16u;
+    const uint32_t row_bytes = static_cast<uint32_t>(N) * 4u;
+    for (int j = 0; j < n_local; ++j) {
+        const int stage = j % S;
+        const uint32_t phase = static_cast<uint32_t>(j / S) & 1u;
+        mbar_wait(&empty[stage], phase ^ 1u);
+        const size_t pair = static_cast<size_t>(blockIdx.x) + static_cast<size_t>(j) * gridDim.x;
+        unsigned char* sb = smem + static_cast<size_t>(stage) * ring.stage_bytes;
+        uint32_t tx = pts_bytes;
+        uint32_t bulk_mask = 0;
+        for (int a = 1; a < src.n_arrays; ++a) {
+            float* dst = reinterpret_cast<float*>(sb + pts_bytes + static_cast<uint32_t>(a - 1) * row_bytes);
+            if (src.ptr[a] == nullptr) {
+                for (int i = lane; i < N; i += 32) dst[i] = 0.f;
+                continue;
+            }
+            const float* g = src.ptr[a] + pair * static_cast<size_t>(N);
+            if (((reinterpret_cast<uintptr_t>(g) & 15u) == 0) && ((N & 3) == 0)) {
+                bulk_mask |= 1u << a;
+                tx += row_bytes;
+            } else {
+                for (int i = lane; i < N; i += 32) dst[i] = __ldg(g + i);
+            }
+        }
+        __syncwarp();
+        if (lane == 0) {
+            mbar_arrive_expect_tx(&full[stage], tx);
+            bulk_g2s(sb, src.ptr[0] + pair * static_cast<size_t>(N) * 4, pts_bytes, &full[stage]);
+            for (int a = 1; a < src.n_arrays; ++a)
+                if (bulk_mask & (1u << a))
+                    bulk_g2s(sb + pts_bytes + static_cast<uint32_t>(a - 1) * row_bytes,
+                             src.ptr[a] + pair * static_cast<size_t>(N), row_bytes, &full[stage]);
+        }
+        __syncwarp();
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side (inline: one copy per translation unit is fine, the state is per process via statics
+// inside device_info())
+struct DeviceInfo {
+    int ok = 0;
+    int sms = 0;
+    int smem_optin = 0;
+    int fwd_configured = 0;
+    int bwd_configured = 0;
+};
+
+inline DeviceInfo& device_info() {
+    static DeviceInfo info[64];
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) {
+        static DeviceInfo bad;
+        return bad;
+    }
+    DeviceInfo& d = info[dev];
+    if (!d.ok) {
+        int major = 0;
+        cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev);
+        cudaDeviceGetAttribute(&d.sms, cudaDevAttrMultiProcessorCount, dev);
+        cudaDeviceGetAttribute(&d.smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+        d.ok = (major == 10 && d.sms > 0) ? 1 : -1;
+    }
+    return d;
+}
+
+inline bool make_ring(int N, int bytes_per_corr, int smem_limit, RingLayout& r) {
+    const int stage = ((N * bytes_per_corr + 127) / 128) * 128;
+    const int fixed = 2 * kMaxStages * 8 + (kMaxWarps - 1) * kScratchDoubles * 8 + 256;
+    int S = (smem_limit - fixed) / stage;
+    if (S > kMaxStages) S = kMaxStages;
+    if (S < 2) return false;
+    int C = S - 1;                     // keep at least one stage of prefetch
+    if (S >= 6) C = S - 2;
+    if (C > kMaxWarps - 1) C = kMaxWarps - 1;
+    r.stages = S;
+    r.consumers = C;
+    r.stage_bytes = stage;
+    r.bar_off = S * stage;
+    r.scratch_off = r.bar_off + 2 * kMaxStages * 8;
+    r.total_bytes = r.scratch_off + (kMaxWarps - 1) * kScratchDoubles * 8;
+    return true;
+}
+
+}  // namespace fepe

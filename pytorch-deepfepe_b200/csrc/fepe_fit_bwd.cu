@@ -1,0 +1,221 @@
+// Analytic backward of the fused weighted 8-point forward w.r.t. the correspondence weights.
+//
+// Replaces what autograd does in the reference when loss.backward() (Train_model_pipeline.py:595)
+// walks DeepFNet.py:198-256 and utils_F.py:400-413: SvdBackward of the N x 9 SVD (materialising U
+// [N,9] per pair per layer), SvdBackward of the 3x3 SVD, and ~40 elementwise / bmm nodes.
+//
+// With x_i = w_i p^_i, G = sum x_i x_i^T, (lambda, f) its smallest eigenpair, F2 = rank2(reshape f),
+// out = T2^T F2 T1, r_i = x_i . f, e_i = clamp(epi_i(out)):
+//   outbar = gF + sum_i ebar_i de_i/dout                                   (pass 1, 9 sums)
+//   F2bar  = T2 outbar T1^T ;  F0bar = rank2 adjoint (fepe_math.cuh)
+//   fbar   = vec(F0bar) + sum_i rbar_i x_i                                 (pass 1, 9 more sums)
+//   z      = (G - lambda I)^+ fbar                                         (one 9x9 solve, G saved by forward)
+//   wbar_i = -2 w_i (p^_i . z)(p^_i . f) + rbar_i (p^_i . f)               (pass 2)
+// The Hartley transforms depend on the coordinates only (Fit.normalize is called with unit weights,
+// DeepFNet.py:194-199), so they carry no weight gradient.  Same pair ring as the forward: one warp per
+// pair, the pair's coordinates, weights and the two upstream rows staged once (28 B / correspondence).
+#include "fepe_fit.cuh"
+
+namespace fepe {
+
+__global__ void __launch_bounds__(kThreads, 1) fepe_fit_bwd_kernel(const FitParams p) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int S = p.ring.stages;
+    const int C = p.ring.consumers;
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem + p.ring.bar_off);
+    uint64_t* empty = full + S;
+    const int N = p.N;
+    const int n_local = (p.B - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) /
+                        static_cast<int>(gridDim.x);
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < S; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+        fence_barrier_init();
+    }
+    __syncthreads();
+
+    if (warp == C) {
+        RingSources src{{p.matches, p.weights, p.gresid, p.gepi}, 4};
+        ring_producer(smem, p.ring, full, empty, src, N, n_local, lane);
+        return;
+    }
+    if (warp > C) return;
+
+    double* gram = reinterpret_cast<double*>(smem + p.ring.scratch_off) + warp * kScratchDoubles;
+    const float ax = p.ax, bx = p.bx, ay = p.ay, by = p.by;
+    const uint32_t pts_bytes = static_cast<uint32_t>(N) * 16u;
+    const uint32_t row_bytes = static_cast<uint32_t>(N) * 4u;
+    const bool has_gr = p.gresid != nullptr, has_ge = p.gepi != nullptr;
+
+    for (int j = warp; j < n_local; j += C) {
+        const int stage = j % S;
+        const uint32_t phase = static_cast<uint32_t>(j / S) & 1u;
+        const size_t pair = static_cast<size_t>(blockIdx.x) + static_cast<size_t>(j) * gridDim.x;
+        const unsigned char* sb = smem + static_cast<size_t>(stage) * p.ring.stage_bytes;
+        const float4* sp = reinterpret_cast<const float4*>(sb);
+        const float* sw = reinterpret_cast<const float*>(sb + pts_bytes);
+        const float* sgr = reinterpret_cast<const float*>(sb + pts_bytes + row_bytes);
+        const float* sge = reinterpret_cast<const float*>(sb + pts_bytes + 2 * row_bytes);
+
+        // ---- per-pair state saved by the forward (warp-uniform) ----
+        const double* sv = p.saved + pair * FEPE_SAVED_DOUBLES;
+        PairNorm h;
+        h.m1x = static_cast<float>(sv[0]); h.m1y = static_cast<float>(sv[1]); h.s1 = static_cast<float>(sv[2]);
+        h.m2x = static_cast<float>(sv[3]); h.m2y = static_cast<float>(sv[4]); h.s2 = static_cast<float>(sv[5]);
+        h.c1x = fmaf(ax, h.m1x, bx); h.c1y = fmaf(ay, h.m1y, by);
+        h.c2x = fmaf(ax, h.m2x, bx); h.c2y = fmaf(ay, h.m2y, by);
+        double f[9], v3[3];
+#pragma unroll
+        for (int i = 0; i < 9; ++i) f[i] = sv[6 + i];
+        const double lambda = sv[15];
+        v3[0] = sv[53]; v3[1] = sv[54]; v3[2] = sv[55];
+        for (int i = lane; i < 36; i += 32) gram[i] = sv[16 + i];
+        double F2[9];
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {
+            const double wv = f[3 * r] * v3[0] + f[3 * r + 1] * v3[1] + f[3 * r + 2] * v3[2];
+            F2[3 * r] = f[3 * r] - wv * v3[0]; F2[3 * r + 1] = f[3 * r + 1] - wv * v3[1]; F2[3 * r + 2] = f[3 * r + 2] - wv * v3[2];
+        }
+        float Fo[9], ff[9];
+        denormalise_F(F2, h, Fo);
+#pragma unroll
+        for (int i = 0; i < 9; ++i) ff[i] = static_cast<float>(f[i]);
+        const float k1x = h.s1 * ax, k1y = h.s1 * ay, k2x = h.s2 * ax, k2y = h.s2 * ay;
+        const float j1x = -k1x * h.m1x, j1y = -k1y * h.m1y, j2x = -k2x * h.m2x, j2y = -k2y * h.m2y;
+        const float clamp_at = p.clamp_at;
+
+        mbar_wait(&full[stage], phase);
+
+        // ---- pass 1: hsum = sum rbar_i x_i  and  ge = sum ebar_i d epi_i / d out ----
+        float hs[9], ge[9];
+#pragma unroll
+        for (int i = 0; i < 9; ++i) { hs[i] = 0.f; ge[i] = 0.f; }
+#pragma unroll 2
+        for (int i = lane; i < N; i += 32) {
+            const float4 q = sp[i];
+            if (has_gr) {
+                const float x1 = fmaf(k1x, q.x, j1x), y1 = fmaf(k1y, q.y, j1y);
+                const float x2 = fmaf(k2x, q.z, j2x), y2 = fmaf(k2y, q.w, j2y);
+                const float nb = fmaf(x1, x1, fmaf(y1, y1, 1.0f));
+                const float na = fmaf(x2, x2, fmaf(y2, y2, 1.0f));
+                const float c = sgr[i] * sw[i] * rsqrtf(na * nb);
+                const float c0 = c * x2, c1 = c * y2;
+                hs[0] = fmaf(c0, x1, hs[0]); hs[1] = fmaf(c0, y1, hs[1]); hs[2] += c0;
+                hs[3] = fmaf(c1, x1, hs[3]); hs[4] = fmaf(c1, y1, hs[4]); hs[5] += c1;
+                hs[6] = fmaf(c, x1, hs[6]);  hs[7] = fmaf(c, y1, hs[7]);  hs[8] += c;
+            }
+            if (has_ge) {
+                const float u1 = fmaf(ax, q.x, bx), v1 = fmaf(ay, q.y, by);
+                const float u2 = fmaf(ax, q.z, bx), v2 = fmaf(ay, q.w, by);
+                const float l10 = fmaf(u2, Fo[0], fmaf(v2, Fo[3], Fo[6]));
+                const float l11 = fmaf(u2, Fo[1], fmaf(v2, Fo[4], Fo[7]));
+                const float l12 = fmaf(u2, Fo[2], fmaf(v2, Fo[5], Fo[8]));
+                const float l20 = fmaf(Fo[0], u1, fmaf(Fo[1], v1, Fo[2]));
+                const float l21 = fmaf(Fo[3], u1, fmaf(Fo[4], v1, Fo[5]));
+                const float dd = fmaf(l10, u1, fmaf(l11, v1, l12));
+                const float m1 = sqrtf(fmaf(l10, l10, l11 * l11)), m2 = sqrtf(fmaf(l20, l20, l21 * l21));
+                const float i1 = 1.0f / (m1 + 1e-6f), i2 = 1.0f / (m2 + 1e-6f);
+                const float dist = fabsf(dd) * (i1 + i2);
+                // torch.clamp(max=c) passes the gradient where d <= c
+                const float g = (dist <= clamp_at) ? sge[i] : 0.f;
+                const float sg = (dd > 0.f) ? g : ((dd < 0.f) ? -g : 0.f);
+                const float S12 = sg * (i1 + i2);
+                const float a1 = -g * fabsf(dd) * i1 * i1 / fmaxf(m1, 1e-30f);   // d(1/(m1+eps)) = -i1^2 dm1, dm1 = l1.dl1/m1
+                const float a2 = -g * fabsf(dd) * i2 * i2 / fmaxf(m2, 1e-30f);
+                // d dd / dF_jk = x2_j x1_k ; d m1 / dF_jk = l1_k x2_j / m1 (k<2) ; d m2 / dF_jk = l2_j x1_k / m2 (j<2)
+                const float uk0 = fmaf(S12, u1, a1 * l10), uk1 = fmaf(S12, v1, a1 * l11), uk2 = S12;   // times x2_j
+                const float vj0 = a2 * l20, vj1 = a2 * l21;                                            // times x1_k
+                ge[0] += fmaf(u2, uk0, vj0 * u1); ge[1] += fmaf(u2, uk1, vj0 * v1); ge[2] += fmaf(u2, uk2, vj0);
+                ge[3] += fmaf(v2, uk0, vj1 * u1); ge[4] += fmaf(v2, uk1, vj1 * v1); ge[5] += fmaf(v2, uk2, vj1);
+                ge[6] += uk0;                     ge[7] += uk1;                     ge[8] += uk2;
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < 9; ++i) { hs[i] = warp_sum(hs[i]); ge[i] = warp_sum(ge[i]); }
+
+        // ---- small algebra (warp-uniform, every lane) ----
+        double ob[9];
+#pragma unroll
+        for (int i = 0; i < 9; ++i) ob[i] = static_cast<double>(ge[i]) + static_cast<double>(p.gF[pair * 9 + i]);
+        double Ab[9];
+        {
+            const double s1 = h.s1, s2 = h.s2;
+            const double t1x = -s1 * h.c1x, t1y = -s1 * h.c1y, t2x = -s2 * h.c2x, t2y = -s2 * h.c2y;
+            double X[9];   // T2 * outbar
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                X[k] = s2 * ob[k] + t2x * ob[6 + k];
+                X[3 + k] = s2 * ob[3 + k] + t2y * ob[6 + k];
+                X[6 + k] = ob[6 + k];
+            }
+#pragma unroll
+            for (int r = 0; r < 3; ++r) {   // ... * T1^T
+                Ab[3 * r] = X[3 * r] * s1 + X[3 * r + 2] * t1x;
+                Ab[3 * r + 1] = X[3 * r + 1] * s1 + X[3 * r + 2] * t1y;
+                Ab[3 * r + 2] = X[3 * r + 2];
+            }
+        }
+        double fb[9], z[9];
+        rank2_project_adjoint(f, v3, Ab, fb);
+#pragma unroll
+        for (int i = 0; i < 9; ++i) fb[i] += static_cast<double>(hs[i]);
+        __syncwarp();
+        eig9_pinv_apply(gram, f, lambda, fb, z);
+        float zf[9];
+#pragma unroll
+        for (int i = 0; i < 9; ++i) zf[i] = static_cast<float>(z[i]);
+
+        // ---- pass 2: wbar_i ----
+        float* __restrict__ gw_out = p.gweights + pair * static_cast<size_t>(N);
+#pragma unroll 2
+        for (int i = lane; i < N; i += 32) {
+            const float4 q = sp[i];
+            const float x1 = fmaf(k1x, q.x, j1x), y1 = fmaf(k1y, q.y, j1y);
+            const float x2 = fmaf(k2x, q.z, j2x), y2 = fmaf(k2y, q.w, j2y);
+            const float nb = fmaf(x1, x1, fmaf(y1, y1, 1.0f));
+            const float na = fmaf(x2, x2, fmaf(y2, y2, 1.0f));
+            const float inv = rsqrtf(na * nb);
+            const float f0 = fmaf(ff[0], x1, fmaf(ff[1], y1, ff[2]));
+            const float f1 = fmaf(ff[3], x1, fmaf(ff[4], y1, ff[5]));
+            const float f2 = fmaf(ff[6], x1, fmaf(ff[7], y1, ff[8]));
+            const float pf = fmaf(x2, f0, fmaf(y2, f1, f2)) * inv;
+            const float z0 = fmaf(zf[0], x1, fmaf(zf[1], y1, zf[2]));
+            const float z1 = fmaf(zf[3], x1, fmaf(zf[4], y1, zf[5]));
+            const float z2 = fmaf(zf[6], x1, fmaf(zf[7], y1, zf[8]));
+            const float pz = fmaf(x2, z0, fmaf(y2, z1, z2)) * inv;
+            const float gr = has_gr ? sgr[i] : 0.f;
+            gw_out[i] = fmaf(-2.0f * sw[i] * pz, pf, gr * pf);
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty[stage]);
+    }
+}
+
+}  // namespace fepe
+
+extern "C" int fepe_fit_bwd(const float* matches, const float* weights, int B, int N, float ax, float bx, float ay,
+                            float by, float clamp_at, const double* saved, const float* gF, const float* gresid,
+                            const float* gepi, float* gweights, void* stream) {
+    if (B == 0) return 0;
+    if (!matches || !weights || !saved || !gF || !gweights || B < 0 || N <= 0) return FEPE_E_BADARG;
+    if (reinterpret_cast<uintptr_t>(matches) & 15u) return FEPE_E_BADARG;
+    fepe::DeviceInfo& d = fepe::device_info();
+    if (d.ok != 1) return FEPE_E_NODEVICE;
+    fepe::FitParams p{};
+    if (!fepe::make_ring(N, 28, d.smem_optin, p.ring)) return FEPE_E_TOOLARGE;
+    p.matches = matches; p.weights = weights; p.B = B; p.N = N;
+    p.ax = ax; p.bx = bx; p.ay = ay; p.by = by; p.clamp_at = clamp_at;
+    p.saved = const_cast<double*>(saved);
+    p.gF = gF; p.gresid = gresid; p.gepi = gepi; p.gweights = gweights;
+    cudaError_t e = cudaSuccess;
+    if (!d.bwd_configured) {
+        e = cudaFuncSetAttribute(fepe::fepe_fit_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 d.smem_optin);
+        if (e != cudaSuccess) return static_cast<int>(e);
+        d.bwd_configured = 1;
+    }
+    const int grid = B < d.sms ? B : d.sms;
+    fepe::fepe_fit_bwd_kernel<<<grid, fepe::kThreads, p.ring.total_bytes, static_cast<cudaStream_t>(stream)>>>(p);
+    return static_cast<int>(cudaGetLastError());
+}

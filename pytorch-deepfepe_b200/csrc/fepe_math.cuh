@@ -487,4 +487,59 @@ FEPE_HD void rot_to_quat(const double (&R)[9], double (&q)[4]) {
     for (int i = 0; i < 4; ++i) q[i] *= sg;
 }
 
+// y = (M - mu I)^+ c on the complement of the unit eigenvector v (M symmetric 3x3 given by its six
+// entries, mu its eigenvalue for v): solve (M - mu I + tau v v^T) y' = c - v (v.c) by the adjugate.
+FEPE_HD void sym3_pinv_apply(double m00, double m01, double m02, double m11, double m12, double m22, double mu,
+                             const double (&v)[3], const double (&c)[3], double (&y)[3]) {
+    const double tau = (m00 + m11 + m22) * (1.0 / 3.0) + 1e-300;
+    const double a00 = m00 - mu + tau * v[0] * v[0], a01 = m01 + tau * v[0] * v[1], a02 = m02 + tau * v[0] * v[2];
+    const double a11 = m11 - mu + tau * v[1] * v[1], a12 = m12 + tau * v[1] * v[2], a22 = m22 - mu + tau * v[2] * v[2];
+    const double vc = v[0] * c[0] + v[1] * c[1] + v[2] * c[2];
+    const double r0 = c[0] - v[0] * vc, r1 = c[1] - v[1] * vc, r2 = c[2] - v[2] * vc;
+    const double k00 = a11 * a22 - a12 * a12, k01 = a02 * a12 - a01 * a22, k02 = a01 * a12 - a02 * a11;
+    const double k11 = a00 * a22 - a02 * a02, k12 = a01 * a02 - a00 * a12, k22 = a00 * a11 - a01 * a01;
+    const double det = a00 * k00 + a01 * k01 + a02 * k02;
+    const double id = 1.0 / ((fabs(det) > 1e-300) ? det : 1e-300);
+    const double y0 = (k00 * r0 + k01 * r1 + k02 * r2) * id;
+    const double y1 = (k01 * r0 + k11 * r1 + k12 * r2) * id;
+    const double y2 = (k02 * r0 + k12 * r1 + k22 * r2) * id;
+    const double vy = v[0] * y0 + v[1] * y1 + v[2] * y2;
+    y[0] = y0 - v[0] * vy; y[1] = y1 - v[1] * vy; y[2] = y2 - v[2] * vy;
+}
+
+// Adjoint of the rank-2 projection F2 = F0 (I - v v^T), v = v3(F0):  given Abar = dL/dF2 returns dL/dF0.
+//   dF2 = dF0 P - F0 (dv v^T + v dv^T),  dv = -(M - mu I)^+ (dF0^T F0 + F0^T dF0) v,  M = F0^T F0
+//   => F0bar = Abar P + (F0 v) y^T + (F0 y) v^T   with  y = (M - mu I)^+ (F0^T Abar v + Abar^T F0 v).
+FEPE_HD void rank2_project_adjoint(const double (&F0)[9], const double (&v)[3], const double (&Ab)[9],
+                                   double (&F0b)[9]) {
+    const double m00 = F0[0] * F0[0] + F0[3] * F0[3] + F0[6] * F0[6];
+    const double m01 = F0[0] * F0[1] + F0[3] * F0[4] + F0[6] * F0[7];
+    const double m02 = F0[0] * F0[2] + F0[3] * F0[5] + F0[6] * F0[8];
+    const double m11 = F0[1] * F0[1] + F0[4] * F0[4] + F0[7] * F0[7];
+    const double m12 = F0[1] * F0[2] + F0[4] * F0[5] + F0[7] * F0[8];
+    const double m22 = F0[2] * F0[2] + F0[5] * F0[5] + F0[8] * F0[8];
+    double Fv[3], Av[3];
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+        Fv[r] = F0[3 * r] * v[0] + F0[3 * r + 1] * v[1] + F0[3 * r + 2] * v[2];
+        Av[r] = Ab[3 * r] * v[0] + Ab[3 * r + 1] * v[1] + Ab[3 * r + 2] * v[2];
+    }
+    const double mu = Fv[0] * Fv[0] + Fv[1] * Fv[1] + Fv[2] * Fv[2];     // sigma3^2 = v^T M v
+    double c[3], y[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k)
+        c[k] = (F0[k] * Av[0] + F0[3 + k] * Av[1] + F0[6 + k] * Av[2]) +
+               (Ab[k] * Fv[0] + Ab[3 + k] * Fv[1] + Ab[6 + k] * Fv[2]);
+    sym3_pinv_apply(m00, m01, m02, m11, m12, m22, mu, v, c, y);
+    double Fy[3];
+#pragma unroll
+    for (int r = 0; r < 3; ++r) Fy[r] = F0[3 * r] * y[0] + F0[3 * r + 1] * y[1] + F0[3 * r + 2] * y[2];
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+#pragma unroll
+        for (int k = 0; k < 3; ++k)
+            F0b[3 * r + k] = Ab[3 * r + k] - Av[r] * v[k] + Fv[r] * y[k] + Fy[r] * v[k];
+    }
+}
+
 }  // namespace fepe

@@ -1,0 +1,150 @@
+"""DeepFNet / Fit / NormalizeAndExpand_HW with the reference's module surface
+(deepFEPE/models/DeepFNet.py) and the weighted 8-point path in hand-written CUDA.
+
+Drop-in contract: same constructor arguments, same ``forward(data_batch) -> dict``
+keys, same sub-module names (``input_weights``, ``update_weights``, ``norm_HW``, ``fit``) and hence the
+same state_dict keys, so ``deepFEPE/utils/loader.py:modelLoader``, ``Train_model_pipeline`` and
+``train_good_utils.get_all_loss_DeepF`` work unchanged on the returned dict.
+
+What differs from the reference, deliberately:
+  * ``if_cpu_svd`` is accepted and ignored -- there is no host round trip at all;
+  * the sign of the null vector f is canonical (largest entry positive) instead of LAPACK's arbitrary
+    one; F and the signed ``residual`` follow it, everything else is sign invariant;
+  * gradients flow to the WEIGHTS (hence to both MLPs); the gradient w.r.t. the coordinates
+    (``if_learn_offsets`` / trainable SuperPoint) is not implemented yet and raises;
+  * the broken reference options ``if_des``, ``if_tri_depth`` are rejected.
+"""
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from .. import ops
+from .ErrorEstimators import ErrorEstimator
+from .GoodCorresNet import GoodCorresNet
+
+
+class NormalizeAndExpand_HW(nn.Module):
+    """pixels -> [-1,1]^2 for both images (deepFEPE/models/DeepFNet.py:93-120)."""
+
+    def __init__(self, image_size, is_cuda=True, is_test=False):
+        super().__init__()
+        self.H, self.W = image_size[0], image_size[1]
+
+    def affine(self):
+        return ops.hw_affine((self.H, self.W))
+
+    def normalize(self, pts):
+        T = torch.tensor([[2. / self.W, 0., -1.], [0., 2. / self.H, -1.], [0., 0., 1.]],
+                         device=pts.device, dtype=pts.dtype).unsqueeze(0).expand(pts.size(0), -1, -1)
+        ones = torch.ones(pts.size(0), pts.size(1), 1, device=pts.device, dtype=pts.dtype)
+        return T @ torch.cat((pts, ones), 2).permute(0, 2, 1), T
+
+    def forward(self, pts):
+        pts1, T1 = self.normalize(pts[:, :, :2])
+        pts2, T2 = self.normalize(pts[:, :, 2:])
+        return pts1, pts2, T1, T2
+
+
+class Fit(nn.Module):
+    """Weighted 8-point fit (deepFEPE/models/DeepFNet.py:123-295): forward(pts1 [B,N,3], pts2 [B,N,3],
+    weights [B,1,N]) -> (F [B,3,3], residual [B,N]).  One launch of the fused kernel."""
+
+    def __init__(self, is_cuda=True, is_test=False, if_cpu_svd=False, normalize_SVD=True):
+        super().__init__()
+        if not normalize_SVD:
+            raise NotImplementedError("normalize_SVD=False is never used by the reference (DeepFNet.py:353)")
+
+    def forward(self, pts1, pts2, weights, if_print=False, matches_good_unique_num=None):
+        if pts1.requires_grad or pts2.requires_grad:
+            raise NotImplementedError("fepe_b200.Fit: gradient w.r.t. the coordinates is not implemented")
+        # the kernel takes (x1,y1,x2,y2) rows; homogeneous inputs are assumed to have z = 1 as in every
+        # call site of the reference (NormalizeAndExpand_HW keeps the third row [0,0,1])
+        matches = torch.cat((pts1[:, :, :2], pts2[:, :, :2]), 2).contiguous()
+        B, N = matches.shape[0], matches.shape[1]
+        out, residual, _ = ops.FitFunction.apply(matches, weights.reshape(B, N), 1.0, 0.0, 1.0, 0.0, 0.5)
+        return out, residual
+
+
+class DeepFNet(nn.Module):
+    def __init__(self, depth, image_size, if_quality, if_img_w=False, if_goodCorresArch=False, if_tri_depth=False,
+                 if_learn_offsets=False, if_des=False, des_size=None, quality_size=0, is_cuda=True, is_test=False,
+                 if_cpu_svd=False, **params):
+        super().__init__()
+        if if_des or if_tri_depth:
+            raise NotImplementedError("if_des / if_tri_depth are broken in the reference itself "
+                                      "(DeepFNet.py:484,508) and are not provided")
+        if if_learn_offsets:
+            raise NotImplementedError("if_learn_offsets needs the coordinate gradient of the fit, which this "
+                                      "build does not provide yet (DESIGN.md, 'next')")
+        if not if_quality:
+            quality_size = 0
+        self.if_quality = if_quality
+        self.if_img_w = if_img_w
+        self.if_goodCorresArch = if_goodCorresArch
+        self.if_learn_offsets = False
+        self.image_size = image_size
+        self.depth = depth
+        if if_goodCorresArch:
+            # the reference builds 4+Q / 6+Q channel nets here but feeds 7+Q channels (DeepFNet.py:337,487):
+            # the update net is given the channel count it actually receives
+            self.input_weights = GoodCorresNet(4 + quality_size, bn=False)
+            self.update_weights = GoodCorresNet(4 + quality_size + 3, bn=False)
+        else:
+            self.input_weights = ErrorEstimator(4 + quality_size)
+            self.update_weights = ErrorEstimator(4 + quality_size + 3)   # + weights, epi_res, residual
+        if is_test:
+            self.input_weights.eval()
+            self.update_weights.eval()
+        self.norm_HW = NormalizeAndExpand_HW(self.image_size, is_cuda, is_test)
+        self.fit = Fit(is_cuda, is_test, if_cpu_svd)
+
+    def get_input(self, data_batch, offsets=None, iter=None):
+        pts = data_batch['matches_xy_ori']
+        pts1, pts2, T1, T2 = self.norm_HW(pts)
+        pts1 = pts1.permute(0, 2, 1)
+        pts2 = pts2.permute(0, 2, 1)
+        feats = [(pts1[:, :, :2] + 1) / 2, (pts2[:, :, :2] + 1) / 2]
+        if self.if_quality:
+            feats.append(data_batch['quality'])
+        weight_in = torch.cat(feats, 2).permute(0, 2, 1)
+        return weight_in, pts1, pts2, T1, T2
+
+    def forward(self, data_batch):
+        matches = data_batch['matches_xy_ori']
+        if not matches.is_cuda:
+            raise RuntimeError("fepe_b200.DeepFNet needs CUDA tensors: there is no CPU path")
+        matches = matches.float().contiguous()
+        B, N = matches.shape[0], matches.shape[1]
+        aff = self.norm_HW.affine()
+        pts_normalized_in, pts1, pts2, T1, T2 = self.get_input(data_batch)
+
+        logits = self.input_weights(pts_normalized_in)
+        weights_pts = F.softmax(logits, dim=2)
+        weights_prod = weights_pts * data_batch['weights_im'] if self.if_img_w else weights_pts
+        _ = data_batch.get('matches_good_unique_nums'), data_batch.get('t_scene_scale')   # read, unused (:449,:453)
+
+        out_layers, epi_res_layers, residual_layers = [], [], []
+        weights_layers, logits_layers = [weights_prod], [logits]
+        for _it in range(self.depth - 1):
+            # fused: Fit.forward (:466) + compute_epi_residual(pts1, pts2, out) (:479), one kernel
+            out, residual, epi = ops.FitFunction.apply(matches, weights_prod.reshape(B, N), *aff, 0.5)
+            out_layers.append(out)
+            residual_layers.append(residual)
+            epi_res = epi.unsqueeze(1)
+            epi_res_layers.append(epi_res)
+            net_in = torch.cat((pts_normalized_in, weights_prod, epi_res, residual.unsqueeze(1)), 1)
+            logits = self.update_weights(net_in)
+            weights_pts = F.softmax(logits, dim=2)
+            weights_prod = weights_pts * data_batch['weights_im'] if self.if_img_w else weights_pts
+            weights_layers.append(weights_prod)
+            logits_layers.append(logits)
+
+        out, residual, _ = ops.FitFunction.apply(matches, weights_prod.reshape(B, N), *aff, 0.5)
+        residual_layers.append(residual)
+        out_layers.append(out)
+        return {
+            "logits": logits.squeeze(1), 'logits_layers': logits_layers, 'F_est': out,
+            'epi_res_layers': epi_res_layers, 'T1': T1, 'T2': T2, 'out_layers': out_layers,
+            'pts1': pts1, 'pts2': pts2, 'weights': weights_prod, 'residual_layers': residual_layers,
+            'weights_layers': weights_layers,
+        }

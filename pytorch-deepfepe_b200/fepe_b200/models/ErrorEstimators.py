@@ -1,0 +1,34 @@
+"""ErrorEstimator -- the per-correspondence weight network (deepFEPE/models/ErrorEstimators.py:14-68).
+
+Shared MLP over the N correspondences: five blocks of (1x1 Conv1d -> InstanceNorm1d(affine) ->
+LeakyReLU(0.01)) with 64/128/1024/512/256 channels and a final 1x1 Conv1d.  The nn.Sequential is laid
+out exactly like the reference's live branch (if_bn=False, :46-64) so checkpoints interchange:
+keys fw.{0,3,6,9,12,15}.{weight,bias} (convs) and fw.{1,4,7,10,13}.{weight,bias} (norm affine).
+
+The layers run through PyTorch's cuDNN/cuBLAS kernels in this round (library path); the tcgen05
+GEMM with fused InstanceNorm statistics is row "next" in DESIGN.md.
+"""
+import torch
+import torch.nn as nn
+
+
+class ErrorEstimator(nn.Module):
+    def __init__(self, input_size, output_size=1, if_bn=False):
+        super().__init__()
+        if if_bn:
+            raise NotImplementedError("ErrorEstimator(if_bn=True) is never constructed by the reference's "
+                                      "DeepFNet (DeepFNet.py:339-342) and is not provided")
+        chans = [input_size, 64, 128, 1024, 512, 256]
+        layers = []
+        for cin, cout in zip(chans[:-1], chans[1:]):
+            layers += [nn.Conv1d(cin, cout, kernel_size=1, bias=True),
+                       nn.InstanceNorm1d(cout, affine=True),
+                       nn.LeakyReLU(inplace=True)]
+        layers.append(nn.Conv1d(256, output_size, kernel_size=1, bias=True))
+        self.fw = nn.Sequential(*layers)
+
+    def forward(self, data):
+        # the reference computes these 1x1 convolutions in fp32 (torch 1.3 had no TF32); keep cuDNN from
+        # silently dropping to TF32 so that weights / logits match it to fp32 accuracy
+        with torch.backends.cudnn.flags(enabled=True, allow_tf32=False):
+            return self.fw(data)

@@ -90,3 +90,57 @@ def pose_forward(F: torch.Tensor, K: torch.Tensor, affine, q_gt: torch.Tensor, t
                                       out.data_ptr(), _stream_ptr())
     _lib.check(st, "fepe_pose_fwd")
     return out
+
+
+def fit_backward(matches: torch.Tensor, weights: torch.Tensor, saved: torch.Tensor, gF: torch.Tensor,
+                 gres: Optional[torch.Tensor], gepi: Optional[torch.Tensor], affine=IDENTITY_AFFINE,
+                 clamp_at: float = 0.5) -> torch.Tensor:
+    """d loss / d weights [B,N] from the upstream gradients of (F, residual, epi).  One launch of
+    fepe_fit_bwd (include/fepe_b200.h)."""
+    matches = _check_cuda_f32(matches, "matches")
+    weights = _check_cuda_f32(weights, "weights")
+    B, N, _ = matches.shape
+    weights = weights.reshape(B, N)
+    if saved is None or saved.dtype != torch.float64 or tuple(saved.shape) != (B, _lib.SAVED_DOUBLES):
+        raise RuntimeError("fepe_b200: `saved` must be the [B,64] float64 state returned by fit_forward(want_saved=True)")
+    gF = _check_cuda_f32(gF, "gF").reshape(B, 9)
+    gres = _check_cuda_f32(gres, "gres").reshape(B, N) if gres is not None else None
+    gepi = _check_cuda_f32(gepi, "gepi").reshape(B, N) if gepi is not None else None
+    with torch.cuda.device(matches.device):
+        gw = torch.empty(B, N, dtype=torch.float32, device=matches.device)
+        st = _lib.lib().fepe_fit_bwd(matches.data_ptr(), weights.data_ptr(), B, N,
+                                     affine[0], affine[1], affine[2], affine[3], float(clamp_at),
+                                     saved.contiguous().data_ptr(), gF.data_ptr(),
+                                     gres.data_ptr() if gres is not None else None,
+                                     gepi.data_ptr() if gepi is not None else None,
+                                     gw.data_ptr(), _stream_ptr())
+    _lib.check(st, "fepe_fit_bwd")
+    return gw
+
+
+class FitFunction(torch.autograd.Function):
+    """Differentiable (w.r.t. the weights) fused weighted 8-point fit.
+
+    forward(matches [B,N,4], weights [B,N], ax, bx, ay, by, clamp_at) -> F [B,3,3], residual [B,N], epi [B,N]
+    The gradient w.r.t. the coordinates is not produced (the reference only needs it with
+    if_learn_offsets / a trainable SuperPoint front-end; DESIGN.md lists it under "next")."""
+
+    @staticmethod
+    def forward(ctx, matches, weights, ax, bx, ay, by, clamp_at):
+        aff = (float(ax), float(bx), float(ay), float(by))
+        need = weights.requires_grad
+        F, res, epi, saved = fit_forward(matches, weights, aff, clamp_at, want_epi=True, want_saved=need)
+        ctx.aff, ctx.clamp_at = aff, float(clamp_at)
+        if need:
+            ctx.save_for_backward(matches, weights, saved)
+        ctx.mark_non_differentiable()
+        return F, res, epi
+
+    @staticmethod
+    def backward(ctx, gF, gres, gepi):
+        matches, weights, saved = ctx.saved_tensors
+        B, N = matches.shape[0], matches.shape[1]
+        gF = torch.zeros(B, 3, 3, device=matches.device) if gF is None else gF.contiguous()
+        gw = fit_backward(matches, weights, saved, gF, gres.contiguous() if gres is not None else None,
+                          gepi.contiguous() if gepi is not None else None, ctx.aff, ctx.clamp_at)
+        return None, gw.reshape(weights.shape), None, None, None, None, None

@@ -49,6 +49,14 @@ void shim_essential(const double* E, double* R1, double* R2, double* t, double* 
     for (int i = 0; i < 4; ++i) { q1[i] = qa[i]; q2[i] = qb[i]; }
 }
 
+void shim_rank2_adjoint(const double* F0, const double* Ab, double* F0b) {
+    double a[9], ab[9], f2[9], v[3], s3, out[9];
+    for (int i = 0; i < 9; ++i) { a[i] = F0[i]; ab[i] = Ab[i]; }
+    fepe::rank2_project(a, f2, v, s3);
+    fepe::rank2_project_adjoint(a, v, ab, out);
+    for (int i = 0; i < 9; ++i) F0b[i] = out[i];
+}
+
 void shim_quat(const double* R, double* q) {
     double r[9], qq[4];
     for (int i = 0; i < 9; ++i) r[i] = R[i];

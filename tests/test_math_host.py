@@ -34,6 +34,7 @@ def shim():
     lib.shim_g36_index.restype = ctypes.c_int
     lib.shim_essential.argtypes = [dp] * 6
     lib.shim_quat.argtypes = [dp, dp]
+    lib.shim_rank2_adjoint.argtypes = [dp, dp, dp]
     return lib
 
 
@@ -200,3 +201,24 @@ def test_quaternion_branches_device_code(shim, golden):
         out = np.zeros(4)
         shim.shim_quat(_ptr(np.ascontiguousarray(R.astype(np.float64))), _ptr(out))
         np.testing.assert_allclose(out, q[:, 0], atol=1e-6)
+
+
+def test_rank2_adjoint_matches_autograd_through_svd(shim):
+    """Backward of U diag(S*[1,1,0]) V^T (the reference differentiates through torch.svd,
+    deepFEPE/models/DeepFNet.py:236-237) against torch autograd in fp64."""
+    import torch
+    rng = np.random.default_rng(4)
+    for trial in range(30):
+        F0 = rng.normal(size=(3, 3))
+        if trial % 3 == 0:      # nearly rank 2, like a fitted fundamental matrix
+            u, s_, vt = np.linalg.svd(F0)
+            F0 = u @ np.diag([s_[0], s_[1], 1e-3 * s_[1]]) @ vt
+        F0 /= np.linalg.norm(F0)
+        Ab = rng.normal(size=(3, 3))
+        out = np.zeros((3, 3))
+        shim.shim_rank2_adjoint(_ptr(np.ascontiguousarray(F0)), _ptr(np.ascontiguousarray(Ab)), _ptr(out))
+        Ft = torch.tensor(F0, requires_grad=True)
+        U, S, V = torch.svd(Ft)
+        F2 = U @ torch.diag(S * torch.tensor([1.0, 1.0, 0.0], dtype=torch.float64)) @ V.t()
+        (F2 * torch.tensor(Ab)).sum().backward()
+        np.testing.assert_allclose(out, Ft.grad.numpy(), rtol=1e-7, atol=1e-9)

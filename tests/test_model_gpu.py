@@ -1,0 +1,91 @@
+"""GPU tests of the drop-in module surface: DeepFNet / Fit with the reference's constructor, dict keys
+and state_dict keys, forward vs the oracle's restatement of DeepFNet.forward, and gradients reaching
+both MLPs."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import fepe_oracle as O
+from fepe_b200 import synth
+from fepe_b200.models import DeepFNet, Fit, ErrorEstimator
+
+pytestmark = pytest.mark.gpu
+T = torch.from_numpy
+MODEL_KW = dict(depth=5, image_size=[376, 1241, 3], quality_size=0, if_quality=False, if_img_des_to_pointnet=False,
+                if_goodCorresArch=False, if_img_feat=False, if_cpu_svd=True, if_learn_offsets=False,
+                if_tri_depth=False, if_sample_loss=False)   # what train_good.py:176-189 passes
+
+
+def _batch(d):
+    return {"matches_xy_ori": T(d["matches_xy_ori"]).cuda(),
+            "matches_good_unique_nums": T(d["matches_good_unique_nums"]),
+            "t_scene_scale": torch.ones(d["matches_xy_ori"].shape[0], 1, 1).cuda(),
+            "Ks": T(d["Ks"]).cuda(), "K_invs": T(d["K_invs"]).cuda()}
+
+
+def test_state_dict_keys_match_reference(golden):
+    net = DeepFNet(**MODEL_KW)
+    assert sorted(net.state_dict().keys()) == sorted(golden["c1_state_keys"].tolist())
+
+
+def test_forward_matches_oracle_and_reference_layer0(golden):
+    torch.manual_seed(77)
+    net = DeepFNet(**MODEL_KW).cuda()       # same construction order / seed as the golden generator
+    o_init, o_upd = O.build_error_estimator(4), O.build_error_estimator(7)
+    o_init.load_state_dict(net.input_weights.fw.state_dict())
+    o_upd.load_state_dict(net.update_weights.fw.state_dict())
+    m = T(golden["c1b_matches"])
+    with torch.no_grad():
+        outs = net({"matches_xy_ori": m.cuda(), "matches_good_unique_nums": torch.tensor([160, 160]),
+                    "t_scene_scale": torch.ones(2, 1, 1).cuda()})
+        ref = O.deepf_forward(m, [376, 1241, 3], o_init.cpu(), o_upd.cpu(), depth=5)
+    for key in ("logits", "logits_layers", "F_est", "epi_res_layers", "T1", "T2", "out_layers", "pts1", "pts2",
+                "weights", "residual_layers", "weights_layers"):
+        assert key in outs
+    assert len(outs["out_layers"]) == 5 and len(outs["epi_res_layers"]) == 4
+    # layer 0 is independent of the arbitrary sign of f: compare with the reference's own output
+    np.testing.assert_allclose(outs["weights_layers"][0].cpu().numpy(), golden["c1b_w_layers"][0], rtol=2e-3, atol=1e-7)
+    err0 = O.sign_aligned_rel_err(outs["out_layers"][0].cpu(), T(golden["c1b_F_layers"][0]))
+    assert float(err0.max()) < 1e-3          # weights come from cuDNN vs CPU convs: ~1e-4 relative
+    np.testing.assert_allclose(outs["epi_res_layers"][0].cpu().numpy(), golden["c1b_epi_layers"][0], atol=2e-3)
+    assert outs["pts1"].shape == (2, 160, 3) and outs["T1"].shape == (2, 3, 3)
+    np.testing.assert_allclose(outs["pts1"].cpu().numpy(), ref["pts1"].numpy(), atol=1e-6)
+    for l in range(5):
+        assert torch.isfinite(outs["out_layers"][l]).all()
+        # rank 2 at every layer
+        assert float(torch.linalg.svdvals(outs["out_layers"][l].double())[:, 2].max()) < 1e-6
+
+
+def test_training_step_reaches_both_mlps():
+    torch.manual_seed(0)
+    net = DeepFNet(**MODEL_KW).cuda()
+    d = synth.make_batch(4, 512, seed=5)
+    outs = net(_batch(d))
+    # F-loss exactly as get_all_loss_DeepF builds it (train_good_utils.py:325-364) with torch ops
+    T1 = outs["T1"]
+    p1 = (T1 @ T(d["pts1_virt"]).cuda().permute(0, 2, 1)).permute(0, 2, 1)
+    p2 = (T1 @ T(d["pts2_virt"]).cuda().permute(0, 2, 1)).permute(0, 2, 1)
+    loss = sum(O.epi_residual(p1, p2, Fo, 0.02).mean() for Fo in outs["out_layers"]) / 5
+    loss.backward()
+    for name, prm in net.named_parameters():
+        assert prm.grad is not None and torch.isfinite(prm.grad).all(), name
+    assert float(net.input_weights.fw[0].weight.grad.abs().sum()) > 0
+    assert float(net.update_weights.fw[0].weight.grad.abs().sum()) > 0
+
+
+def test_fit_module_signature():
+    d = synth.make_batch(3, 200, seed=2)
+    p1, p2, _ = O.norm_hw(T(d["matches_xy_ori"]), d["image_size"])
+    fit = Fit(is_cuda=True, is_test=False, if_cpu_svd=True)
+    out, res = fit(p1.cuda(), p2.cuda(), T(d["weights"]).cuda())
+    Fr, rr = O.fit_weighted_svd(p1, p2, T(d["weights"]))
+    assert out.shape == (3, 3, 3) and res.shape == (3, 200)
+    assert float(O.sign_aligned_rel_err(out.cpu(), Fr).max()) < 1e-4
+
+
+def test_error_estimator_matches_reference_output(golden):
+    torch.manual_seed(1234)
+    ee = ErrorEstimator(4).cuda()
+    with torch.no_grad():
+        y = ee(T(golden["ee_x"]).cuda())
+    np.testing.assert_allclose(y.cpu().numpy(), golden["ee_y"], rtol=1e-3, atol=1e-4)
