@@ -221,6 +221,26 @@ def reference_step(d: dict):
         O.pose_errors(E_layers[0], T(d["q_cam"]), T(d["t_cam"]), T(d["delta_Rtijs_4_4"]))
 
 
+def pick_cpu_threads(d: dict) -> int:
+    """torch.svd on 1000x9 matrices does not scale with threads (on a 128-core host the default is ~20x
+    SLOWER than 8 threads): give the reference its best thread count among a few candidates."""
+    cores = os.cpu_count() or 1
+    probe = slice_batch(d, min(16, d["matches_xy_ori"].shape[0]))
+    best_n, best_t = 1, float("inf")
+    for n in sorted({1, 4, 8, 16, 32, cores}):
+        if n > cores:
+            continue
+        torch.set_num_threads(n)
+        reference_step(probe)
+        t = time.perf_counter()
+        reference_step(probe)
+        dt = time.perf_counter() - t
+        if dt < best_t:
+            best_n, best_t = n, dt
+    torch.set_num_threads(best_n)
+    return best_n
+
+
 def slice_batch(d: dict, n: int) -> dict:
     out = {}
     for k, v in d.items():
@@ -232,10 +252,9 @@ def run_reference(args):
     rank, world, _ = dist_env()
     if rank != 0:
         return
-    cores = os.cpu_count() or 1
-    torch.set_num_threads(cores)
     B, N = args.batch, args.ncorr
     base = make_host_batches(2, B, N, seed0=1000)
+    pick_cpu_threads(base[0])
     # calibrate the per-step sample so that the whole run stays within ~2 minutes
     t = time.perf_counter()
     reference_step(slice_batch(base[0], min(B, 32)))
@@ -257,6 +276,7 @@ def run_reference(args):
         "config": {"workload": f"C2: batch={B} pairs x N={N} corr, 30% outliers, Fit + epi residual + F-loss + E->R,t",
                    "pairs_per_step_sample": n_s, "ncorr": N},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+                         "host_cores": os.cpu_count(),
                          "sample": f"{n_s} of the {B} pairs of a step, {args.steps} steps; oracle/fepe_oracle.py "
                                    "(per-pair torch.svd loop like deepFEPE/models/DeepFNet.py:232-240) on host cores"},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -421,8 +441,7 @@ def run_ours(args):
         del big_m, big_w, outF, outr, oute
 
         # ---- the reference's CPU algorithm on this box's host cores (bounded sample) ---------------
-        cores = os.cpu_count() or 1
-        torch.set_num_threads(cores)
+        pick_cpu_threads(host[0])
         sample = [slice_batch(host[0], min(B, 128)), slice_batch(host[1], min(B, 128))]
         reference_step(sample[0])
         n_done, tc0 = 0, time.perf_counter()
@@ -431,7 +450,7 @@ def run_ours(args):
             n_done += 1
         cpu_secs = time.perf_counter() - tc0
         line["cpu_baseline"] = {"value": sample[0]["matches_xy_ori"].shape[0] * n_done / cpu_secs, "unit": UNIT,
-                                "cores": torch.get_num_threads(), "kind": "port",
+                                "cores": torch.get_num_threads(), "kind": "port", "host_cores": os.cpu_count(),
                                 "sample": f"{n_done} x {sample[0]['matches_xy_ori'].shape[0]} pairs x N={N} of the same "
                                           "workload through oracle/fepe_oracle.py (per-pair torch.svd loop, "
                                           "deepFEPE/models/DeepFNet.py:232-240) in {:.1f} s".format(cpu_secs)}
