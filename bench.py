@@ -364,31 +364,20 @@ def run_ours(args):
 
     if not args.no_extras:
         # ---- end to end through the host API: pinned host -> device -> results on host ------------
+        from fepe_b200.staging import StagedStep
         nbuf = 3
-        pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
-        keys = ["matches_xy_ori", "weights", "Ks", "q_cam", "t_cam", "delta_Rtijs_4_4", "pts1_virt", "pts2_virt"]
-        hbat = [{k: pin(d[k]) for k in keys} for d in host[:min(len(host), 8)]]
-        h2d = sum(v.numel() * v.element_size() for v in hbat[0].values())
+        V = host[0]["pts1_virt"].shape[1]
+        n_host = min(len(host), 8)
+        # one staging object per DISTINCT host batch would be the user's dataloader output; here nbuf device
+        # slots are fed round-robin from n_host pinned host batches
+        stages = [StagedStep(B, N, V, dev) for _ in range(nbuf)]
+        pinned = [stages[0].pack(d) for d in host[:n_host]]
+        h2d, d2h = stages[0].in_bytes, stages[0].out_bytes
         streams = [torch.cuda.Stream() for _ in range(nbuf)]
-        dbuf = [{k: torch.empty_like(v, device=dev) for k, v in hbat[0].items()} for _ in range(nbuf)]
-        outs = [(torch.empty(B, 3, 3, device=dev), torch.empty(B, N, device=dev), torch.empty(B, N, device=dev),
-                 torch.empty(1, B, _lib.POSE_OUT_FLOATS, device=dev)) for _ in range(nbuf)]
-        hres = [(torch.empty(B, 3, 3).pin_memory(), torch.empty(1, B, _lib.POSE_OUT_FLOATS).pin_memory())
-                for _ in range(nbuf)]
-        d2h = hres[0][0].numel() * 4 + hres[0][1].numel() * 4
 
         def e2e_step(i):
             j = i % nbuf
-            st, hb, db_, o, hr = streams[j], hbat[i % len(hbat)], dbuf[j], outs[j], hres[j]
-            with torch.cuda.stream(st):
-                for k in keys:
-                    db_[k].copy_(hb[k], non_blocking=True)
-                ops.fit_forward(db_["matches_xy_ori"], db_["weights"], aff, clamp_at=CLAMP_EPI,
-                                out=(o[0], o[1], o[2], None))
-                ops.pose_forward(o[0], db_["Ks"], aff, db_["q_cam"], db_["t_cam"], db_["delta_Rtijs_4_4"],
-                                 db_["pts1_virt"], db_["pts2_virt"], clamp_at=CLAMP_LOSS, out=o[3])
-                hr[0].copy_(o[0], non_blocking=True)
-                hr[1].copy_(o[3], non_blocking=True)
+            stages[j].run(streams[j], aff, CLAMP_EPI, CLAMP_LOSS, host=pinned[i % n_host])
 
         e2e_steps = max(50, min(args.steps, 400))
         for i in range(6):
@@ -412,7 +401,8 @@ def run_ours(args):
             e2e_secs = float(tt.item())
         line["e2e"] = {"value": world * B * e2e_steps / e2e_secs, "unit": UNIT, "h2d_bytes_per_step": h2d,
                        "d2h_bytes_per_step": d2h, "steps": e2e_steps, "ms_per_step": e2e_secs / e2e_steps * 1e3,
-                       "n_gpus": world, "how": f"{nbuf} streams, pinned host buffers, H2D + 2 kernels + D2H per step"}
+                       "n_gpus": world, "how": f"fepe_b200.staging.StagedStep: {nbuf} streams, one pinned H2D copy + "
+                                               "fepe_fit_fwd + fepe_pose_fwd + one D2H copy per step"}
 
 
     if rank == 0 and not args.no_extras:

@@ -15,88 +15,226 @@
 // streaming passes (Hartley sums, residuals, epipolar distances) are fp32 like the reference.
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 #include "fepe_fit.cuh"
 
 namespace fepe {
 
-__device__ __forceinline__ PairNorm hartley_passes(const float4* __restrict__ sp, int N, int lane,
-                                                   float ax, float bx, float ay, float by) {
-    PairNorm h;
-    // four independent accumulation chains per lane: the loop is latency bound (LDS -> FADD) otherwise
+// ------------------------------------------------------------------------------------------------
+// The four streaming passes over one pair's correspondences, resident in shared memory.  `start` /
+// `stride` select the correspondences this thread owns: (lane, 32) when one warp owns the pair (ring
+// kernel), (threadIdx.x, blockDim.x) when a whole CTA does (latency kernel).
+// ------------------------------------------------------------------------------------------------
+
+// pass 1: coordinate sums (4-way ILP: the loop is an LDS -> FADD latency chain otherwise)
+__device__ __forceinline__ void pass_sums(const float4* __restrict__ sp, int N, int start, int stride,
+                                          float (&out)[4]) {
     float a[4] = {0.f, 0.f, 0.f, 0.f}, b[4] = {0.f, 0.f, 0.f, 0.f}, c[4] = {0.f, 0.f, 0.f, 0.f},
           d[4] = {0.f, 0.f, 0.f, 0.f};
-    int i = lane;
-    for (; i + 96 < N; i += 128) {
+    int i = start;
+    for (; i + 3 * stride < N; i += 4 * stride) {
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
-            const float4 q = sp[i + 32 * u];
+            const float4 q = sp[i + stride * u];
             a[u] += q.x; b[u] += q.y; c[u] += q.z; d[u] += q.w;
         }
     }
-    for (; i < N; i += 32) {
+    for (; i < N; i += stride) {
         const float4 q = sp[i];
         a[0] += q.x; b[0] += q.y; c[0] += q.z; d[0] += q.w;
     }
-    const float invN = 1.0f / static_cast<float>(N);
-    h.m1x = warp_sum((a[0] + a[1]) + (a[2] + a[3])) * invN;
-    h.m1y = warp_sum((b[0] + b[1]) + (b[2] + b[3])) * invN;
-    h.m2x = warp_sum((c[0] + c[1]) + (c[2] + c[3])) * invN;
-    h.m2y = warp_sum((d[0] + d[1]) + (d[2] + d[3])) * invN;
+    out[0] = (a[0] + a[1]) + (a[2] + a[3]);
+    out[1] = (b[0] + b[1]) + (b[2] + b[3]);
+    out[2] = (c[0] + c[1]) + (c[2] + c[3]);
+    out[3] = (d[0] + d[1]) + (d[2] + d[3]);
+}
+
+// pass 2: summed distance to the centroid in primed coordinates, both images
+__device__ __forceinline__ void pass_dist(const float4* __restrict__ sp, int N, int start, int stride, float ax,
+                                          float ay, const PairNorm& h, float (&out)[2]) {
     float d1[4] = {0.f, 0.f, 0.f, 0.f}, d2[4] = {0.f, 0.f, 0.f, 0.f};
     const float o1x = -ax * h.m1x, o1y = -ay * h.m1y, o2x = -ax * h.m2x, o2y = -ay * h.m2y;
-    i = lane;
-    for (; i + 96 < N; i += 128) {
+    int i = start;
+    for (; i + 3 * stride < N; i += 4 * stride) {
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
-            const float4 q = sp[i + 32 * u];
+            const float4 q = sp[i + stride * u];
             const float u1 = fmaf(ax, q.x, o1x), v1 = fmaf(ay, q.y, o1y);
             const float u2 = fmaf(ax, q.z, o2x), v2 = fmaf(ay, q.w, o2y);
             d1[u] += approx_sqrt(fmaf(u1, u1, v1 * v1));
             d2[u] += approx_sqrt(fmaf(u2, u2, v2 * v2));
         }
     }
-    for (; i < N; i += 32) {
+    for (; i < N; i += stride) {
         const float4 q = sp[i];
         const float u1 = fmaf(ax, q.x, o1x), v1 = fmaf(ay, q.y, o1y);
         const float u2 = fmaf(ax, q.z, o2x), v2 = fmaf(ay, q.w, o2y);
         d1[0] += approx_sqrt(fmaf(u1, u1, v1 * v1));
         d2[0] += approx_sqrt(fmaf(u2, u2, v2 * v2));
     }
-    const float md1 = warp_sum((d1[0] + d1[1]) + (d1[2] + d1[3])) * invN;
-    const float md2 = warp_sum((d2[0] + d2[1]) + (d2[2] + d2[3])) * invN;
-    h.s1 = 1.4142f / md1;
-    h.s2 = 1.4142f / md2;
-    h.c1x = fmaf(ax, h.m1x, bx); h.c1y = fmaf(ay, h.m1y, by);
-    h.c2x = fmaf(ax, h.m2x, bx); h.c2y = fmaf(ay, h.m2y, by);
-    return h;
+    out[0] = (d1[0] + d1[1]) + (d1[2] + d1[3]);
+    out[1] = (d2[0] + d2[1]) + (d2[2] + d2[3]);
 }
 
-struct PairSolution {
-    double f[9];      // unit eigenvector of the smallest eigenvalue (= vec of the normalised F before rank 2)
-    double lambda;
-    double S3[3];     // v3: right singular vector of reshape(f) for its smallest singular value
-    double sigma3;    // that singular value (what the rank-2 projection removed)
-    float Fo[9];      // T2^T F_ T1, fp32
-    int iters;
-    long long cyc_eig;
-};
+__device__ __forceinline__ void finish_norm(PairNorm& h, const float (&sums)[4], const float (&dist)[2], int N,
+                                            float ax, float bx, float ay, float by, bool have_dist) {
+    const float invN = 1.0f / static_cast<float>(N);
+    if (!have_dist) {
+        h.m1x = sums[0] * invN; h.m1y = sums[1] * invN; h.m2x = sums[2] * invN; h.m2y = sums[3] * invN;
+        h.c1x = fmaf(ax, h.m1x, bx); h.c1y = fmaf(ay, h.m1y, by);
+        h.c2x = fmaf(ax, h.m2x, bx); h.c2y = fmaf(ay, h.m2y, by);
+    } else {
+        h.s1 = 1.4142f / (dist[0] * invN);       // the reference's literal (DeepFNet.py:168)
+        h.s2 = 1.4142f / (dist[1] * invN);
+    }
+}
 
-__device__ __noinline__ void solve_pair(const double* __restrict__ gram, const PairNorm& h, PairSolution& sol) {
+// raw -> Hartley-normalised coordinates: x~ = k x + j
+struct PairMap {
+    float k1x, k1y, k2x, k2y, j1x, j1y, j2x, j2y;
+};
+__device__ __forceinline__ PairMap make_map(const PairNorm& h, float ax, float ay) {
+    PairMap m;
+    m.k1x = h.s1 * ax; m.k1y = h.s1 * ay; m.k2x = h.s2 * ax; m.k2y = h.s2 * ay;
+    m.j1x = -m.k1x * h.m1x; m.j1y = -m.k1y * h.m1y; m.j2x = -m.k2x * h.m2x; m.j2y = -m.k2y * h.m2y;
+    return m;
+}
+
+// pass 3: the 36 distinct entries of G = sum_i s_i (a a^T) (x) (b b^T), fp64 accumulation
+__device__ __forceinline__ void pass_gram(const float4* __restrict__ sp, const float* __restrict__ sw, int N,
+                                          int start, int stride, const PairMap& m, double (&acc)[36]) {
+#pragma unroll
+    for (int i = 0; i < 36; ++i) acc[i] = 0.0;
+#pragma unroll 1
+    for (int i = start; i < N; i += stride) {
+        const float4 q = sp[i];
+        const float wi = sw[i];
+        const float x1 = fmaf(m.k1x, q.x, m.j1x), y1 = fmaf(m.k1y, q.y, m.j1y);
+        const float x2 = fmaf(m.k2x, q.z, m.j2x), y2 = fmaf(m.k2y, q.w, m.j2y);
+        const float nb = fmaf(x1, x1, fmaf(y1, y1, 1.0f));
+        const float na = fmaf(x2, x2, fmaf(y2, y2, 1.0f));
+        const float s = __fdividef(wi * wi, na * nb);   // (w / |p|)^2, |p|^2 = |a|^2 |b|^2 (2 ulp is ample)
+        const double dx1 = x1, dy1 = y1, dx2 = x2, dy2 = y2, ds = s;
+        const double b0 = dx1 * dx1, b1 = dx1 * dy1, b3 = dy1 * dy1;
+        const double t0 = ds * dx2, t1 = ds * dy2;
+        const double a[6] = {t0 * dx2, t0 * dy2, t0, t1 * dy2, t1, ds};
+#pragma unroll
+        for (int u = 0; u < 6; ++u) {
+            acc[u * 6 + 0] = fma(a[u], b0, acc[u * 6 + 0]);
+            acc[u * 6 + 1] = fma(a[u], b1, acc[u * 6 + 1]);
+            acc[u * 6 + 2] = fma(a[u], dx1, acc[u * 6 + 2]);
+            acc[u * 6 + 3] = fma(a[u], b3, acc[u * 6 + 3]);
+            acc[u * 6 + 4] = fma(a[u], dy1, acc[u * 6 + 4]);
+            acc[u * 6 + 5] += a[u];
+        }
+    }
+}
+
+// pass 4: residual r_i = w_i p^_i . f and the clamped symmetric epipolar distance with out = T2^T F_ T1
+__device__ __forceinline__ void pass_resid(const float4* __restrict__ sp, const float* __restrict__ sw, int N,
+                                           int start, int stride, const PairMap& m, const float (&ff)[9],
+                                           const float (&Fo)[9], float ax, float bx, float ay, float by,
+                                           float clamp_at, float* __restrict__ r_out, float* __restrict__ e_out) {
+#pragma unroll 2
+    for (int i = start; i < N; i += stride) {
+        const float4 q = sp[i];
+        const float wi = sw[i];
+        const float x1 = fmaf(m.k1x, q.x, m.j1x), y1 = fmaf(m.k1y, q.y, m.j1y);
+        const float x2 = fmaf(m.k2x, q.z, m.j2x), y2 = fmaf(m.k2y, q.w, m.j2y);
+        const float nb = fmaf(x1, x1, fmaf(y1, y1, 1.0f));
+        const float na = fmaf(x2, x2, fmaf(y2, y2, 1.0f));
+        const float r0 = fmaf(ff[0], x1, fmaf(ff[1], y1, ff[2]));
+        const float r1 = fmaf(ff[3], x1, fmaf(ff[4], y1, ff[5]));
+        const float r2 = fmaf(ff[6], x1, fmaf(ff[7], y1, ff[8]));
+        const float dot = fmaf(x2, r0, fmaf(y2, r1, r2));
+        __stcs(r_out + i, wi * dot * rsqrtf(na * nb));    // streaming store: do not displace L1 lines
+        if (e_out != nullptr) {
+            const float u1 = fmaf(ax, q.x, bx), v1 = fmaf(ay, q.y, by);
+            const float u2 = fmaf(ax, q.z, bx), v2 = fmaf(ay, q.w, by);
+            // l1 = x2^T F (line in image 1), l2 = F x1 (line in image 2), dd = x2^T F x1
+            const float l10 = fmaf(u2, Fo[0], fmaf(v2, Fo[3], Fo[6]));
+            const float l11 = fmaf(u2, Fo[1], fmaf(v2, Fo[4], Fo[7]));
+            const float l12 = fmaf(u2, Fo[2], fmaf(v2, Fo[5], Fo[8]));
+            const float l20 = fmaf(Fo[0], u1, fmaf(Fo[1], v1, Fo[2]));
+            const float l21 = fmaf(Fo[3], u1, fmaf(Fo[4], v1, Fo[5]));
+            const float dd = fmaf(l10, u1, fmaf(l11, v1, l12));
+            const float n1 = approx_sqrt(fmaf(l10, l10, l11 * l11)) + 1e-6f;
+            const float n2 = approx_sqrt(fmaf(l20, l20, l21 * l21)) + 1e-6f;
+            const float dist = fabsf(dd) * (approx_rcp(n1) + approx_rcp(n2));
+            __stcs(e_out + i, fminf(dist, clamp_at));
+        }
+    }
+}
+
+// Per-warp scratch in shared memory (kScratchDoubles doubles): the Gram entries on the way in, the
+// solution on the way out.  Going through shared memory instead of a local-memory struct matters: with
+// ~227 KB of shared memory per CTA only ~28 KB of L1 is left and local loads miss it half of the time.
+//   [0..35] g36   [36..44] f   [45] lambda   [46..48] v3   [49] sigma3   [50] rounds   [51] eig cycles
+//   [52..56] Fo as 9 floats (+pad)   [57..61] Hartley state as 10 floats
+constexpr int kSolF = 36, kSolLambda = 45, kSolV3 = 46, kSolSigma3 = 49, kSolRounds = 50, kSolCycles = 51,
+              kSolFo = 52, kSolNorm = 57;
+
+// Smallest eigenvector (multi-shift, all 32 lanes cooperate), rank-2 projection, de-normalisation.
+// Out of line so that its fp64 working set does not inflate the registers of the streaming loops.
+__device__ __noinline__ void solve_pair(double* __restrict__ scratch, int lane) {
+    PairNorm h;
+    {
+        const float* hn = reinterpret_cast<const float*>(scratch + kSolNorm);
+        h.m1x = hn[0]; h.m1y = hn[1]; h.m2x = hn[2]; h.m2y = hn[3]; h.c1x = hn[4]; h.c1y = hn[5];
+        h.c2x = hn[6]; h.c2y = hn[7]; h.s1 = hn[8]; h.s2 = hn[9];
+    }
     double f[9], lambda;
     const long long t0 = clock64();
-    sol.iters = eig9_smallest(gram, f, lambda);
-    sol.cyc_eig = clock64() - t0;
+    const int rounds = eig9_smallest_warp(scratch, f, lambda, lane);
+    const long long t1 = clock64();
     double F2[9], v3[3], sigma3;
     rank2_project(f, F2, v3, sigma3);
-    denormalise_F(F2, h, sol.Fo);
+    float Fo[9];
+    denormalise_F(F2, h, Fo);
+    if (lane == 0) {
 #pragma unroll
-    for (int i = 0; i < 9; ++i) sol.f[i] = f[i];
-    sol.lambda = lambda;
-    sol.S3[0] = v3[0]; sol.S3[1] = v3[1]; sol.S3[2] = v3[2];
-    sol.sigma3 = sigma3;
+        for (int i = 0; i < 9; ++i) scratch[kSolF + i] = f[i];
+        scratch[kSolLambda] = lambda;
+        scratch[kSolV3] = v3[0]; scratch[kSolV3 + 1] = v3[1]; scratch[kSolV3 + 2] = v3[2];
+        scratch[kSolSigma3] = sigma3;
+        scratch[kSolRounds] = static_cast<double>(rounds);
+        scratch[kSolCycles] = static_cast<double>(t1 - t0);
+        float* fo = reinterpret_cast<float*>(scratch + kSolFo);
+#pragma unroll
+        for (int i = 0; i < 9; ++i) fo[i] = Fo[i];
+    }
+    __syncwarp();
 }
 
+__device__ __forceinline__ void publish_norm(double* scratch, const PairNorm& h, int lane) {
+    if (lane == 0) {
+        float* hn = reinterpret_cast<float*>(scratch + kSolNorm);
+        hn[0] = h.m1x; hn[1] = h.m1y; hn[2] = h.m2x; hn[3] = h.m2y; hn[4] = h.c1x; hn[5] = h.c1y;
+        hn[6] = h.c2x; hn[7] = h.c2y; hn[8] = h.s1; hn[9] = h.s2;
+    }
+}
+
+__device__ __forceinline__ void store_pair_state(const FitParams& p, size_t pair, const PairNorm& h,
+                                                 const double* scratch, int lane) {
+    const float* fo = reinterpret_cast<const float*>(scratch + kSolFo);
+    if (lane < 9) p.F_out[pair * 9 + lane] = fo[lane];
+    if (p.saved != nullptr) {
+        double* sv = p.saved + pair * FEPE_SAVED_DOUBLES;
+        if (lane == 0) {
+            sv[0] = h.m1x; sv[1] = h.m1y; sv[2] = h.s1; sv[3] = h.m2x; sv[4] = h.m2y; sv[5] = h.s2;
+            sv[52] = scratch[kSolRounds];
+            sv[63] = scratch[kSolSigma3];
+        }
+        if (lane < 9) sv[6 + lane] = scratch[kSolF + lane];
+        if (lane == 9) sv[15] = scratch[kSolLambda];
+        if (lane >= 10 && lane < 13) sv[53 + lane - 10] = scratch[kSolV3 + lane - 10];
+        for (int i = lane; i < 36; i += 32) sv[16 + i] = scratch[i];
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Throughput kernel: persistent pair ring, one warp per pair (see fepe_common.cuh).
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kThreads, 1) fepe_fit_fwd_kernel(const FitParams p) {
     extern __shared__ __align__(128) unsigned char smem[];
@@ -142,39 +280,22 @@ __global__ void __launch_bounds__(kThreads, 1) fepe_fit_fwd_kernel(const FitPara
         const long long tc1 = clock64();
 
         // ---- passes 1+2: Hartley transforms of both images (Fit.normalize with unit weights) ----
-        const PairNorm h = hartley_passes(sp, N, lane, ax, bx, ay, by);
-        // raw -> Hartley-normalised:  x~ = k * (x - m)
-        const float k1x = h.s1 * ax, k1y = h.s1 * ay, k2x = h.s2 * ax, k2y = h.s2 * ay;
-        const float j1x = -k1x * h.m1x, j1y = -k1y * h.m1y, j2x = -k2x * h.m2x, j2y = -k2y * h.m2y;
+        PairNorm h;
+        float sums[4], dist[2] = {0.f, 0.f};
+        pass_sums(sp, N, lane, 32, sums);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) sums[k] = warp_sum(sums[k]);
+        finish_norm(h, sums, dist, N, ax, bx, ay, by, false);
+        pass_dist(sp, N, lane, 32, ax, ay, h, dist);
+        dist[0] = warp_sum(dist[0]);
+        dist[1] = warp_sum(dist[1]);
+        finish_norm(h, sums, dist, N, ax, bx, ay, by, true);
+        const PairMap m = make_map(h, ax, ay);
 
         const long long tc2 = clock64();
-        // ---- pass 3: the 36 distinct entries of G = sum_i s_i (a a^T) (x) (b b^T), fp64 ----
+        // ---- pass 3: Gram, then warp reduce-scatter into shared memory ----
         double acc[36];
-#pragma unroll
-        for (int i = 0; i < 36; ++i) acc[i] = 0.0;
-#pragma unroll 1
-        for (int i = lane; i < N; i += 32) {
-            const float4 q = sp[i];
-            const float wi = sw[i];
-            const float x1 = fmaf(k1x, q.x, j1x), y1 = fmaf(k1y, q.y, j1y);
-            const float x2 = fmaf(k2x, q.z, j2x), y2 = fmaf(k2y, q.w, j2y);
-            const float nb = fmaf(x1, x1, fmaf(y1, y1, 1.0f));
-            const float na = fmaf(x2, x2, fmaf(y2, y2, 1.0f));
-            const float s = __fdividef(wi * wi, na * nb);   // (w / |p|)^2, |p|^2 = |a|^2 |b|^2 (2 ulp is ample)
-            const double dx1 = x1, dy1 = y1, dx2 = x2, dy2 = y2, ds = s;
-            const double b0 = dx1 * dx1, b1 = dx1 * dy1, b3 = dy1 * dy1;
-            const double t0 = ds * dx2, t1 = ds * dy2;
-            const double a[6] = {t0 * dx2, t0 * dy2, t0, t1 * dy2, t1, ds};
-#pragma unroll
-            for (int u = 0; u < 6; ++u) {
-                acc[u * 6 + 0] = fma(a[u], b0, acc[u * 6 + 0]);
-                acc[u * 6 + 1] = fma(a[u], b1, acc[u * 6 + 1]);
-                acc[u * 6 + 2] = fma(a[u], dx1, acc[u * 6 + 2]);
-                acc[u * 6 + 3] = fma(a[u], b3, acc[u * 6 + 3]);
-                acc[u * 6 + 4] = fma(a[u], dy1, acc[u * 6 + 4]);
-                acc[u * 6 + 5] += a[u];
-            }
-        }
+        pass_gram(sp, sw, N, lane, 32, m, acc);
         const long long tc3 = clock64();
         {
             int base = 0, cnt = 36;
@@ -185,64 +306,23 @@ __global__ void __launch_bounds__(kThreads, 1) fepe_fit_fwd_kernel(const FitPara
         __syncwarp();
         const long long tc3b = clock64();
 
-        // ---- smallest eigenvector, rank-2 projection, de-normalisation (every lane redundantly;
-        //      the inputs are warp-uniform).  Kept out of line so that its fp64 working set does not
-        //      inflate the register allocation of the streaming loops.
-        PairSolution sol;
-        solve_pair(gram, h, sol);
-        const float* Fo = sol.Fo;
+        // ---- eigenvector, rank 2, de-normalisation ----
+        publish_norm(gram, h, lane);
+        __syncwarp();
+        solve_pair(gram, lane);
         const long long tc4 = clock64();
-        if (lane < 9) p.F_out[pair * 9 + lane] = Fo[lane];
-        if (p.saved != nullptr) {
-            double* sv = p.saved + pair * FEPE_SAVED_DOUBLES;
-            if (lane == 0) {
-                sv[0] = h.m1x; sv[1] = h.m1y; sv[2] = h.s1; sv[3] = h.m2x; sv[4] = h.m2y; sv[5] = h.s2;
-#pragma unroll
-                for (int i = 0; i < 9; ++i) sv[6 + i] = sol.f[i];
-                sv[15] = sol.lambda;
-                sv[52] = static_cast<double>(sol.iters);
-                sv[53] = sol.S3[0]; sv[54] = sol.S3[1]; sv[55] = sol.S3[2];
-                sv[63] = sol.sigma3;
-            }
-            for (int i = lane; i < 36; i += 32) sv[16 + i] = gram[i];
-        }
+        store_pair_state(p, pair, h, gram, lane);
 
-        // ---- pass 4: residual r_i = w_i p_hat_i . f and the clamped epipolar distance ----
-        float ff[9];
+        // ---- pass 4: residual and clamped epipolar distance ----
+        float ff[9], Fo[9];
 #pragma unroll
-        for (int i = 0; i < 9; ++i) ff[i] = static_cast<float>(sol.f[i]);
-        float* __restrict__ r_out = p.resid + pair * static_cast<size_t>(N);
-        float* __restrict__ e_out = (p.epi != nullptr) ? p.epi + pair * static_cast<size_t>(N) : nullptr;
-        const float clamp_at = p.clamp_at;
-#pragma unroll 4
-        for (int i = lane; i < N; i += 32) {
-            const float4 q = sp[i];
-            const float wi = sw[i];
-            const float x1 = fmaf(k1x, q.x, j1x), y1 = fmaf(k1y, q.y, j1y);
-            const float x2 = fmaf(k2x, q.z, j2x), y2 = fmaf(k2y, q.w, j2y);
-            const float nb = fmaf(x1, x1, fmaf(y1, y1, 1.0f));
-            const float na = fmaf(x2, x2, fmaf(y2, y2, 1.0f));
-            const float r0 = fmaf(ff[0], x1, fmaf(ff[1], y1, ff[2]));
-            const float r1 = fmaf(ff[3], x1, fmaf(ff[4], y1, ff[5]));
-            const float r2 = fmaf(ff[6], x1, fmaf(ff[7], y1, ff[8]));
-            const float dot = fmaf(x2, r0, fmaf(y2, r1, r2));
-            r_out[i] = wi * dot * rsqrtf(na * nb);
-            if (e_out != nullptr) {
-                const float u1 = fmaf(ax, q.x, bx), v1 = fmaf(ay, q.y, by);
-                const float u2 = fmaf(ax, q.z, bx), v2 = fmaf(ay, q.w, by);
-                // l1 = x2^T F (line in image 1), l2 = F x1 (line in image 2), dd = x2^T F x1
-                const float l10 = fmaf(u2, Fo[0], fmaf(v2, Fo[3], Fo[6]));
-                const float l11 = fmaf(u2, Fo[1], fmaf(v2, Fo[4], Fo[7]));
-                const float l12 = fmaf(u2, Fo[2], fmaf(v2, Fo[5], Fo[8]));
-                const float l20 = fmaf(Fo[0], u1, fmaf(Fo[1], v1, Fo[2]));
-                const float l21 = fmaf(Fo[3], u1, fmaf(Fo[4], v1, Fo[5]));
-                const float dd = fmaf(l10, u1, fmaf(l11, v1, l12));
-                const float n1 = approx_sqrt(fmaf(l10, l10, l11 * l11)) + 1e-6f;
-                const float n2 = approx_sqrt(fmaf(l20, l20, l21 * l21)) + 1e-6f;
-                const float dist = fabsf(dd) * (approx_rcp(n1) + approx_rcp(n2));
-                e_out[i] = fminf(dist, clamp_at);
-            }
+        for (int i = 0; i < 9; ++i) {
+            ff[i] = static_cast<float>(gram[kSolF + i]);
+            Fo[i] = reinterpret_cast<const float*>(gram + kSolFo)[i];
         }
+        pass_resid(sp, sw, N, lane, 32, m, ff, Fo, ax, bx, ay, by, p.clamp_at,
+                   p.resid + pair * static_cast<size_t>(N),
+                   (p.epi != nullptr) ? p.epi + pair * static_cast<size_t>(N) : nullptr);
         __syncwarp();
         if (lane == 0) {
             mbar_arrive(&empty[stage]);
@@ -255,10 +335,131 @@ __global__ void __launch_bounds__(kThreads, 1) fepe_fit_fwd_kernel(const FitPara
                 sv[59] = static_cast<double>(tc4 - tc3);   // reduce + eigen + rank 2
                 sv[60] = static_cast<double>(tc5 - tc4);   // residual pass
                 sv[61] = static_cast<double>(tc3b - tc3);  // of which: warp reduce-scatter of the Gram
-                sv[62] = static_cast<double>(sol.cyc_eig); // of which: eigen iteration
+                sv[62] = gram[kSolCycles];                 // of which: eigen iteration
             }
         }
     }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Latency kernel for small batches (B <= ~2 pairs per SM): one CTA of kSmallWarps warps per pair, the
+// correspondences split across all its threads, block-level reductions through shared memory, the
+// small solve on warp 0.  A 256-pair launch is bound by the latency of ONE pair, so the streaming
+// passes are spread over 4 warps instead of 1; two such CTAs fit an SM (registers), which covers
+// B = 256 on 148 SMs in a single wave.
+// ------------------------------------------------------------------------------------------------
+#ifndef FEPE_SMALL_WARPS
+#define FEPE_SMALL_WARPS 4
+#endif
+#ifndef FEPE_SMALL_MINBLOCKS
+#define FEPE_SMALL_MINBLOCKS 2
+#endif
+constexpr int kSmallWarps = FEPE_SMALL_WARPS;
+constexpr int kSmallThreads = kSmallWarps * 32;
+
+__global__ void __launch_bounds__(kSmallThreads, FEPE_SMALL_MINBLOCKS) fepe_fit_fwd_small_kernel(const FitParams p) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    __shared__ uint64_t full_bar;
+    __shared__ float red[kSmallWarps][4];
+    __shared__ double gram_w[kSmallWarps][36];
+    __shared__ double gram[kScratchDoubles];
+    __shared__ float sol_ff[9], sol_Fo[9];
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int tid = threadIdx.x;
+    const int N = p.N;
+    const size_t pair = blockIdx.x;
+    const uint32_t pts_bytes = static_cast<uint32_t>(N) * 16u;
+    const uint32_t w_bytes = static_cast<uint32_t>(N) * 4u;
+    const float4* sp = reinterpret_cast<const float4*>(smem);
+    float* sw = reinterpret_cast<float*>(smem + pts_bytes);
+    const float* gw = p.weights + pair * static_cast<size_t>(N);
+    const bool w_bulk = ((reinterpret_cast<uintptr_t>(gw) & 15u) == 0) && ((N & 3) == 0);
+    const float ax = p.ax, bx = p.bx, ay = p.ay, by = p.by;
+
+    if (tid == 0) {
+        mbar_init(&full_bar, 1);
+        fence_barrier_init();
+    }
+    __syncthreads();
+    if (tid == 0) {
+        mbar_arrive_expect_tx(&full_bar, pts_bytes + (w_bulk ? w_bytes : 0u));
+        bulk_g2s(smem, p.matches + pair * static_cast<size_t>(N) * 4, pts_bytes, &full_bar);
+        if (w_bulk) bulk_g2s(smem + pts_bytes, gw, w_bytes, &full_bar);
+    }
+    if (!w_bulk) {
+        for (int i = tid; i < N; i += kSmallThreads) sw[i] = __ldg(gw + i);
+    }
+    mbar_wait(&full_bar, 0);
+    __syncthreads();       // also orders the hand-copied weights
+
+    // ---- passes 1+2 with block reductions ----
+    PairNorm h;
+    float sums[4], dist[2] = {0.f, 0.f};
+    pass_sums(sp, N, tid, kSmallThreads, sums);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) sums[k] = warp_sum(sums[k]);
+    if (lane == 0) { red[warp][0] = sums[0]; red[warp][1] = sums[1]; red[warp][2] = sums[2]; red[warp][3] = sums[3]; }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        float t = 0.f;
+#pragma unroll
+        for (int w = 0; w < kSmallWarps; ++w) t += red[w][k];
+        sums[k] = t;
+    }
+    finish_norm(h, sums, dist, N, ax, bx, ay, by, false);
+    __syncthreads();
+    pass_dist(sp, N, tid, kSmallThreads, ax, ay, h, dist);
+    dist[0] = warp_sum(dist[0]);
+    dist[1] = warp_sum(dist[1]);
+    if (lane == 0) { red[warp][0] = dist[0]; red[warp][1] = dist[1]; }
+    __syncthreads();
+    dist[0] = 0.f; dist[1] = 0.f;
+#pragma unroll
+    for (int w = 0; w < kSmallWarps; ++w) { dist[0] += red[w][0]; dist[1] += red[w][1]; }
+    finish_norm(h, sums, dist, N, ax, bx, ay, by, true);
+    const PairMap m = make_map(h, ax, ay);
+
+    // ---- pass 3 ----
+    {
+        double acc[36];
+        pass_gram(sp, sw, N, tid, kSmallThreads, m, acc);
+        int base = 0, cnt = 36;
+        ReduceScatter<36, 16>::run(acc, lane, base, cnt);
+        if (cnt > 0) gram_w[warp][base] = acc[0];
+        if (cnt > 1) gram_w[warp][base + 1] = acc[1];
+    }
+    __syncthreads();
+    if (tid < 36) {
+        double t = 0.0;
+#pragma unroll
+        for (int w = 0; w < kSmallWarps; ++w) t += gram_w[w][tid];
+        gram[tid] = t;
+    }
+    __syncthreads();
+
+    // ---- solve on warp 0, broadcast through shared memory ----
+    if (warp == 0) {
+        publish_norm(gram, h, lane);
+        __syncwarp();
+        solve_pair(gram, lane);
+        store_pair_state(p, pair, h, gram, lane);
+        if (lane < 9) {
+            sol_ff[lane] = static_cast<float>(gram[kSolF + lane]);
+            sol_Fo[lane] = reinterpret_cast<const float*>(gram + kSolFo)[lane];
+        }
+    }
+    __syncthreads();
+    float ff[9], Fo[9];
+#pragma unroll
+    for (int i = 0; i < 9; ++i) { ff[i] = sol_ff[i]; Fo[i] = sol_Fo[i]; }
+
+    // ---- pass 4 ----
+    pass_resid(sp, sw, N, tid, kSmallThreads, m, ff, Fo, ax, bx, ay, by, p.clamp_at,
+               p.resid + pair * static_cast<size_t>(N),
+               (p.epi != nullptr) ? p.epi + pair * static_cast<size_t>(N) : nullptr);
 }
 
 }  // namespace fepe
@@ -293,6 +494,21 @@ int fepe_fit_fwd(const float* matches, const float* weights, int B, int N, float
                                  d.smem_optin);
         if (e != cudaSuccess) return static_cast<int>(e);
         d.fwd_configured = 1;
+    }
+    // Small batches are bound by the latency of one pair: spread each pair over a CTA of 4 warps.
+    const int small_bytes = ((N * 20 + 127) / 128) * 128;
+    const char* force = getenv("FEPE_FIT_KERNEL");     // "ring" | "small": development override
+    bool use_small = (B <= 2 * d.sms) && (small_bytes <= 56 * 1024);
+    if (force != nullptr) use_small = (force[0] == 's') && (small_bytes <= 56 * 1024);
+    if (use_small) {
+        if (!d.small_configured) {
+            e = cudaFuncSetAttribute(fepe::fepe_fit_fwd_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     56 * 1024);
+            if (e != cudaSuccess) return static_cast<int>(e);
+            d.small_configured = 1;
+        }
+        fepe::fepe_fit_fwd_small_kernel<<<B, fepe::kSmallThreads, small_bytes, static_cast<cudaStream_t>(stream)>>>(p);
+        return static_cast<int>(cudaGetLastError());
     }
     const int grid = B < d.sms ? B : d.sms;
     fepe::fepe_fit_fwd_kernel<<<grid, fepe::kThreads, p.ring.total_bytes, static_cast<cudaStream_t>(stream)>>>(p);

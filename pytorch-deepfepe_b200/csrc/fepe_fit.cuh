@@ -12,12 +12,12 @@
 namespace fepe {
 
 #ifndef FEPE_WARPS
-#define FEPE_WARPS 10
+#define FEPE_WARPS 8      // 7 consumers + 1 producer: 256 threads => 255 registers, the fp64 solver does not spill
 #endif
 constexpr int kMaxWarps = FEPE_WARPS;        // consumers + 1 producer
 constexpr int kThreads = kMaxWarps * 32;
 constexpr int kMaxStages = 16;
-constexpr int kScratchDoubles = 40;          // per consumer warp: 36 Gram entries (+pad)
+constexpr int kScratchDoubles = 64;          // per consumer warp: Gram entries in, solution out (fepe_fit.cu)
 
 struct FitParams {
     const float* matches;   // [B,N,4]
@@ -55,6 +55,54 @@ struct PairNorm {
     float s1, s2;               // Hartley scales 1.4142/meandist (literal as in DeepFNet.py:168)
 };
 
+
+// Warp driver of the multi-shift eigen-solver (scalar pieces and rationale in fepe_math.cuh).
+// All 32 lanes call it with the same g36; returns the number of rounds.
+__device__ __forceinline__ int eig9_smallest_warp(const double* __restrict__ g36, double (&f)[9], double& lambda,
+                                                  int lane) {
+    Eig9Bracket b;
+    if (!eig9_bracket_init(g36, b)) {
+#pragma unroll
+        for (int i = 0; i < 9; ++i) f[i] = (i == 8) ? 1.0 : 0.0;
+        lambda = 0.0;
+        return 0;
+    }
+    const double tiny = 1e-18 * b.tr;
+    double x[9];
+    eig9_start_vector(x);
+    double rho = 0.0;
+    int rounds = 0;
+    while (rounds < 10) {
+        const double mu = eig9_lane_shift(b, lane);
+        double xl[9];
+#pragma unroll
+        for (int i = 0; i < 9; ++i) xl[i] = x[i];
+        int nneg;
+        double rho_l, r_l, c_l;
+        eig9_lane_round(g36, mu, tiny, 2, xl, nneg, rho_l, r_l, c_l);
+        ++rounds;
+        const unsigned ok = __ballot_sync(0xffffffffu, nneg == 0);
+        const unsigned bad = ~ok;
+        const int first_fail = bad ? (__ffs(bad) - 1) : 32;      // shifts ascend with the lane index
+        const int best = first_fail - 1;
+        if (best < 0) {        // even the safe shift failed (G indefinite to rounding): move it further down
+            b.lo = b.lo * 64.0 - 1e-13 * b.tr;
+            b.lo_heur = b.lo;
+            continue;
+        }
+        const double mu_best = __shfl_sync(0xffffffffu, mu, best);
+        const double mu_fail = (first_fail < 32) ? __shfl_sync(0xffffffffu, mu, first_fail & 31) : -1.0;
+        rho = __shfl_sync(0xffffffffu, rho_l, best);
+        const double r = __shfl_sync(0xffffffffu, r_l, best);
+        const double c = __shfl_sync(0xffffffffu, c_l, best);
+#pragma unroll
+        for (int i = 0; i < 9; ++i) x[i] = __shfl_sync(0xffffffffu, xl[i], best);
+        if (eig9_bracket_update(b, mu_best, mu_fail, rho, r, c)) break;
+    }
+    canonical_sign9(x, f);
+    lambda = rho;
+    return rounds;
+}
 
 // out = T2^T F2 T1 with T = [[s,0,-s cx],[0,s,-s cy],[0,0,1]] (DeepFNet.py:256), fp64 in, fp32 out.
 __device__ __forceinline__ void denormalise_F(const double (&F2)[9], const PairNorm& h, float (&Fo)[9]) {
@@ -132,6 +180,7 @@ struct DeviceInfo {
     int smem_optin = 0;
     int fwd_configured = 0;
     int bwd_configured = 0;
+    int small_configured = 0;
 };
 
 inline DeviceInfo& device_info() {

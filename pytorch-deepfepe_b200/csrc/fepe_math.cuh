@@ -217,6 +217,136 @@ FEPE_HD int eig9_smallest(const double* __restrict__ g36, double (&f)[9], double
     return it;
 }
 
+// ---------------------------------------------------------------------------------------------
+// Multi-shift variant for a warp that owns ONE eigenproblem: the 32 lanes would otherwise run the
+// serial iteration above redundantly, so each lane factors G - mu_l I with its OWN shift instead.
+// The inertia counts bracket lambda_min 32-fold per round (guaranteed, no heuristics), every lane
+// also does its two inverse-iteration solves, and the lane with the largest shift still below
+// lambda_min supplies the next iterate.  Three rounds typically replace six sequential
+// factorisations.  The scalar pieces below are shared by the device driver (fepe_fit.cuh, uses
+// ballot/shuffle) and by the host emulation in tests/host_shim.cpp.
+// ---------------------------------------------------------------------------------------------
+struct Eig9Bracket {
+    double tr;        // trace(G)
+    double lo;        // largest shift known to be below lambda_min (inertia count 0)
+    double hi;        // upper limit for lambda_min (first failing shift, Rayleigh quotient, min diagonal)
+    double r_prev;    // residual of the previous round's best lane (<0: none)
+    double lo_heur;   // heuristic (unverified) lower end for lanes 1..31: max(lo, rho - r)
+    int round;
+};
+
+FEPE_HD bool eig9_bracket_init(const double* __restrict__ g36, Eig9Bracket& b) {
+    double tr = 0.0, dmin = 1e300;
+#pragma unroll
+    for (int r = 0; r < 9; ++r) {
+        const double d = g36[g36_index(r, r)];
+        tr += d;
+        dmin = d < dmin ? d : dmin;
+    }
+    b.tr = tr;
+    b.lo = -1e-14 * tr;
+    b.hi = dmin;                 // e_i^T G e_i >= lambda_min
+    b.r_prev = -1.0;
+    b.lo_heur = b.lo;
+    b.round = 0;
+    return (tr > 0.0) && (tr < 1e300);
+}
+
+// Shift of lane `lane` (0..31) for the current round; lane 0 always carries the known-safe shift.
+FEPE_HD double eig9_lane_shift(const Eig9Bracket& b, int lane) {
+    if (lane == 0) return b.lo;
+    if (b.round == 0) {
+        // geometric ladder from 1e-13 tr up to the upper limit: lambda_min can sit anywhere on 13 decades
+        const double a = 1e-13 * b.tr;
+        const double top = (b.hi > 2.0 * a) ? b.hi : 2.0 * a;
+        return a * exp2(log2(top / a) * (static_cast<double>(lane - 1) * (1.0 / 30.0)));
+    }
+    const double lo = (b.lo_heur > 0.0) ? b.lo_heur : 0.0;
+    return lo + (b.hi - lo) * (static_cast<double>(lane - 1) * (1.0 / 31.0)) * 0.999;
+}
+
+// One lane's work for a round: factor at `mu`, `nsolve` inverse-iteration solves starting from x.
+FEPE_HD void eig9_lane_round(const double* __restrict__ g36, double mu, double tiny, int nsolve, double (&x)[9],
+                             int& nneg, double& rho, double& r, double& contraction) {
+    double A[45];
+    nneg = ldl9(g36, mu, tiny, A);
+    rho = 0.0;
+    r = 0.0;
+    contraction = 1.0;     // r_last / r_previous under THIS shift = (lambda_9 - mu) / (lambda_8 - mu)
+    for (int rep = 0; rep < nsolve; ++rep) {
+        double y[9];
+#pragma unroll
+        for (int i = 0; i < 9; ++i) y[i] = x[i];
+        ldl9_solve(A, y);
+        double nrm2 = 0.0;
+#pragma unroll
+        for (int i = 0; i < 9; ++i) nrm2 += y[i] * y[i];
+        const double inv = fast_rsqrt(nrm2);
+        double c = 0.0;
+#pragma unroll
+        for (int i = 0; i < 9; ++i) { y[i] *= inv; c += y[i] * x[i]; }
+        double e2 = 0.0;
+#pragma unroll
+        for (int i = 0; i < 9; ++i) { const double e = x[i] - c * y[i]; e2 += e * e; x[i] = y[i]; }
+        rho = mu + c * inv;
+        const double r_new = sqrt(e2) * inv;
+        if (rep > 0) contraction = r_new / (r + 1e-300);
+        r = r_new;
+    }
+}
+
+// Fold the round's outcome into the bracket.  mu_best / rho / r come from the best lane (largest
+// shift with inertia 0), mu_fail is the smallest failing shift (or <0 when every lane passed).
+// Returns true when the eigenvector has converged (same rule as eig9_smallest).
+FEPE_HD bool eig9_bracket_update(Eig9Bracket& b, double mu_best, double mu_fail, double rho, double r, double c) {
+    bool done = false;
+    if (r <= 1e-17 * b.tr) done = true;
+    // eigenvector error ~ r / (lambda_8 - lambda_9); the gap follows from the contraction c the best lane
+    // observed between its two solves at the same shift: gap = (rho - mu)(1/c - 1).  Stop at r <= 1e-8 gap.
+    if (c < 1.0 && r * c <= 1e-8 * (rho - mu_best) * (1.0 - c)) done = true;
+    if (c >= 0.5 && r <= 1e-9 * b.tr) done = true;                 // stagnated at the rounding floor
+    b.r_prev = r;
+    b.lo = mu_best;
+    double hi = rho;                                  // Rayleigh quotient >= lambda_min
+    if (mu_fail >= 0.0 && mu_fail < hi) hi = mu_fail;
+    // rho - r is (heuristically) a lower bound: start the next ladder there when it beats the safe shift
+    const double cand = rho - r * 1.0000001 - 4e-16 * b.tr;
+    if (cand > b.lo && cand < hi) {
+        // keep lane 0 on the verified shift; lanes 1.. spread over [cand, hi)
+        b.lo_heur = cand;
+    } else {
+        b.lo_heur = b.lo;
+    }
+    b.hi = hi;
+    b.round += 1;
+    return done;
+}
+
+// Canonical sign: the entry of largest magnitude is made positive (LAPACK's sign is arbitrary).
+FEPE_HD void canonical_sign9(const double (&x)[9], double (&f)[9]) {
+    int imax = 0;
+    double amax = 0.0;
+#pragma unroll
+    for (int i = 0; i < 9; ++i) {
+        if (fabs(x[i]) > amax) { amax = fabs(x[i]); imax = i; }
+    }
+    double sgn = 1.0;
+#pragma unroll
+    for (int i = 0; i < 9; ++i) {
+        if (i == imax && x[i] < 0.0) sgn = -1.0;
+    }
+#pragma unroll
+    for (int i = 0; i < 9; ++i) f[i] = sgn * x[i];
+}
+
+FEPE_HD void eig9_start_vector(double (&x)[9]) {
+    const double x0[9] = {0.3713906763541037, -0.2228344058124622, 0.4456688116249244, 0.1485562705416415,
+                          -0.5199469468957452, 0.2971125410832830, -0.0742781352708207, 0.3342516087186933,
+                          0.3565350492999395};
+#pragma unroll
+    for (int i = 0; i < 9; ++i) x[i] = x0[i];
+}
+
 // z = (G - lambda I)^+ rhs restricted to the complement of f (used by the backward pass):
 // solve (G - lambda I + tau f f^T) y = rhs - f (f.rhs), then z = y - f (f.y).
 FEPE_HD void eig9_pinv_apply(const double* __restrict__ g36, const double (&f)[9], double lambda,
@@ -440,6 +570,77 @@ FEPE_HD void rank2_project(const double (&F0)[9], double (&F2)[9], double (&v3)[
 
 namespace fepe {
 
+// Direct 3x3 SVD built from two smallest-singular-vector solves and ONE plane rotation:
+//   v3 / u3 = smallest right / left singular vectors (characteristic-polynomial Newton + adjugate),
+//   the remaining 2-D problem A [b1 b2] (b1,b2 an orthonormal basis of v3's complement) is
+//   diagonalised exactly by a single Hestenes rotation.  Same output contract as svd3 (sorted S,
+//   U S V^T = A) at a fraction of the dependent-latency chain of the Jacobi sweeps; the pose head's
+//   inputs are essential matrices (sigma_3 ~ 0) but the routine is exact for any 3x3.
+FEPE_HD void svd3_direct(const double (&A)[9], double (&U)[9], double (&S)[3], double (&V)[9]) {
+    double v3[3], s3;
+    smallest_right_sv3(A, v3, s3);
+    // orthonormal complement of v3: cross with the axis least aligned with it
+    const double ax = fabs(v3[0]), ay = fabs(v3[1]), az = fabs(v3[2]);
+    double e0 = 0.0, e1 = 0.0, e2 = 0.0;
+    if (ax <= ay && ax <= az) e0 = 1.0; else if (ay <= az) e1 = 1.0; else e2 = 1.0;
+    double b1[3] = {v3[1] * e2 - v3[2] * e1, v3[2] * e0 - v3[0] * e2, v3[0] * e1 - v3[1] * e0};
+    const double n1 = fast_rsqrt(b1[0] * b1[0] + b1[1] * b1[1] + b1[2] * b1[2]);
+    b1[0] *= n1; b1[1] *= n1; b1[2] *= n1;
+    double b2[3] = {v3[1] * b1[2] - v3[2] * b1[1], v3[2] * b1[0] - v3[0] * b1[2], v3[0] * b1[1] - v3[1] * b1[0]};
+    double w1[3], w2[3];
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+        w1[r] = A[3 * r] * b1[0] + A[3 * r + 1] * b1[1] + A[3 * r + 2] * b1[2];
+        w2[r] = A[3 * r] * b2[0] + A[3 * r + 1] * b2[1] + A[3 * r + 2] * b2[2];
+    }
+    const double alpha = w1[0] * w1[0] + w1[1] * w1[1] + w1[2] * w1[2];
+    const double beta = w2[0] * w2[0] + w2[1] * w2[1] + w2[2] * w2[2];
+    const double gamma = w1[0] * w2[0] + w1[1] * w2[1] + w1[2] * w2[2];
+    double c = 1.0, s = 0.0;
+    if (gamma * gamma > 1e-32 * alpha * beta) {
+        const double zeta = (beta - alpha) / (2.0 * gamma);
+        const double t = ((zeta >= 0.0) ? 1.0 : -1.0) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
+        c = fast_rsqrt(1.0 + t * t);
+        s = c * t;
+    }
+    double p1[3], p2[3], q1[3], q2[3];
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+        p1[r] = c * w1[r] - s * w2[r]; p2[r] = s * w1[r] + c * w2[r];
+        q1[r] = c * b1[r] - s * b2[r]; q2[r] = s * b1[r] + c * b2[r];
+    }
+    double na = sqrt(p1[0] * p1[0] + p1[1] * p1[1] + p1[2] * p1[2]);
+    double nb = sqrt(p2[0] * p2[0] + p2[1] * p2[1] + p2[2] * p2[2]);
+    if (na < nb) {
+#pragma unroll
+        for (int r = 0; r < 3; ++r) { double tmp = p1[r]; p1[r] = p2[r]; p2[r] = tmp; tmp = q1[r]; q1[r] = q2[r]; q2[r] = tmp; }
+        const double tmp = na; na = nb; nb = tmp;
+    }
+    const double ia = 1.0 / (na + 1e-300), ib = 1.0 / (nb + 1e-300);
+    double u1[3], u2[3];
+#pragma unroll
+    for (int r = 0; r < 3; ++r) { u1[r] = p1[r] * ia; u2[r] = p2[r] * ib; }
+    // re-orthogonalise u2 against u1 (matters only when sigma_2 is itself tiny) and complete both bases
+    {
+        const double d = u1[0] * u2[0] + u1[1] * u2[1] + u1[2] * u2[2];
+        u2[0] -= d * u1[0]; u2[1] -= d * u1[1]; u2[2] -= d * u1[2];
+        const double n = fast_rsqrt(u2[0] * u2[0] + u2[1] * u2[1] + u2[2] * u2[2] + 1e-300);
+        u2[0] *= n; u2[1] *= n; u2[2] *= n;
+    }
+    double u3[3] = {u1[1] * u2[2] - u1[2] * u2[1], u1[2] * u2[0] - u1[0] * u2[2], u1[0] * u2[1] - u1[1] * u2[0]};
+    // sign of v3 so that u3^T A v3 = +sigma3 >= 0
+    const double t0 = A[0] * v3[0] + A[1] * v3[1] + A[2] * v3[2];
+    const double t1 = A[3] * v3[0] + A[4] * v3[1] + A[5] * v3[2];
+    const double t2 = A[6] * v3[0] + A[7] * v3[1] + A[8] * v3[2];
+    const double sg = (u3[0] * t0 + u3[1] * t1 + u3[2] * t2 < 0.0) ? -1.0 : 1.0;
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+        U[3 * r] = u1[r]; U[3 * r + 1] = u2[r]; U[3 * r + 2] = u3[r];
+        V[3 * r] = q1[r]; V[3 * r + 1] = q2[r]; V[3 * r + 2] = sg * v3[r];
+    }
+    S[0] = na; S[1] = nb; S[2] = s3;
+}
+
 // ---------------------------------------------------------------------------------------------
 // Pose head pieces (deepFEPE/dsac_tools/utils_F.py:478-498 _get_M2s,
 // deepFEPE/dsac_tools/utils_geo.py:58-86 _R_to_q).
@@ -450,7 +651,7 @@ namespace fepe {
 // det < 0" test and yields the same SET {R1,R2}, {t,-t} whatever signs LAPACK would have picked.
 FEPE_HD void essential_decompose(const double (&E)[9], double (&R1)[9], double (&R2)[9], double (&t)[3],
                                  double (&U)[9], double (&S)[3], double (&V)[9]) {
-    svd3(E, U, S, V);
+    svd3_direct(E, U, S, V);
     U[2] = U[3] * U[7] - U[6] * U[4]; U[5] = U[6] * U[1] - U[0] * U[7]; U[8] = U[0] * U[4] - U[3] * U[1];
     V[2] = V[3] * V[7] - V[6] * V[4]; V[5] = V[6] * V[1] - V[0] * V[7]; V[8] = V[0] * V[4] - V[3] * V[1];
     // U W = [u2, -u1, u3],  U W^T = [-u2, u1, u3]   (columns)

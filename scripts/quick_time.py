@@ -26,6 +26,13 @@ def timeit(B, N, iters=20, epi=True, saved=False):
           f"{bytes_/ms/1e6:8.1f} GB/s", flush=True)
 
 if __name__ == "__main__":
+    for kern in ("ring", "small"):
+        os.environ["FEPE_FIT_KERNEL"] = kern
+        print("kernel", kern)
+        timeit(256, 1000)
+        timeit(64, 2000)
+        timeit(148, 1000)
+    del os.environ["FEPE_FIT_KERNEL"]
     for B, N in [(256, 1000), (32768, 1000), (64, 2000), (16384, 2000)]:
         timeit(B, N)
 

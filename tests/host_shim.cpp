@@ -29,11 +29,60 @@ void shim_svd3(const double* A, double* U, double* S, double* V) {
     for (int i = 0; i < 3; ++i) S[i] = s[i];
 }
 
+void shim_svd3_direct(const double* A, double* U, double* S, double* V) {
+    double a[9], u[9], s[3], v[9];
+    for (int i = 0; i < 9; ++i) a[i] = A[i];
+    fepe::svd3_direct(a, u, s, v);
+    for (int i = 0; i < 9; ++i) { U[i] = u[i]; V[i] = v[i]; }
+    for (int i = 0; i < 3; ++i) S[i] = s[i];
+}
+
 void shim_rank2(const double* F0, double* F2) {
     double a[9], f2[9], v[3], s3;
     for (int i = 0; i < 9; ++i) a[i] = F0[i];
     fepe::rank2_project(a, f2, v, s3);
     for (int i = 0; i < 9; ++i) F2[i] = f2[i];
+}
+
+// Host emulation of the warp driver eig9_smallest_warp (fepe_fit.cuh): same scalar pieces, the
+// ballot / shuffle replaced by loops over 32 virtual lanes.
+int shim_eig9_multishift(const double* g36, double* f, double* lambda) {
+    fepe::Eig9Bracket b;
+    if (!fepe::eig9_bracket_init(g36, b)) {
+        for (int i = 0; i < 9; ++i) f[i] = (i == 8) ? 1.0 : 0.0;
+        *lambda = 0.0;
+        return 0;
+    }
+    const double tiny = 1e-18 * b.tr;
+    double x[9];
+    fepe::eig9_start_vector(x);
+    double rho = 0.0;
+    int rounds = 0;
+    while (rounds < 10) {
+        double mu[32], rho_l[32], r_l[32], c_l[32], xl[32][9];
+        int nneg[32];
+        for (int lane = 0; lane < 32; ++lane) {
+            mu[lane] = fepe::eig9_lane_shift(b, lane);
+            double xx[9];
+            for (int i = 0; i < 9; ++i) xx[i] = x[i];
+            fepe::eig9_lane_round(g36, mu[lane], tiny, 2, xx, nneg[lane], rho_l[lane], r_l[lane], c_l[lane]);
+            for (int i = 0; i < 9; ++i) xl[lane][i] = xx[i];
+        }
+        ++rounds;
+        int first_fail = 32;
+        for (int lane = 31; lane >= 0; --lane) if (nneg[lane] != 0) first_fail = lane;
+        const int best = first_fail - 1;
+        if (best < 0) { b.lo = b.lo * 64.0 - 1e-13 * b.tr; b.lo_heur = b.lo; continue; }
+        const double mu_fail = (first_fail < 32) ? mu[first_fail] : -1.0;
+        rho = rho_l[best];
+        for (int i = 0; i < 9; ++i) x[i] = xl[best][i];
+        if (fepe::eig9_bracket_update(b, mu[best], mu_fail, rho, r_l[best], c_l[best])) break;
+    }
+    double ff[9];
+    fepe::canonical_sign9(x, ff);
+    for (int i = 0; i < 9; ++i) f[i] = ff[i];
+    *lambda = rho;
+    return rounds;
 }
 
 int shim_g36_index(int r, int c) { return fepe::g36_index(r, c); }

@@ -44,9 +44,17 @@ def test_against_reference_golden(golden, i):
     _compare(F, res, epi, T(golden[f"fit{i}_F"]), T(golden[f"fit{i}_res"]), T(golden[f"fit{i}_epi"]))
 
 
+@pytest.fixture(params=["ring", "small"])
+def kernel(request, monkeypatch):
+    """Both forward kernels (persistent pair ring / one CTA per pair) must pass the same parity tests;
+    FEPE_FIT_KERNEL overrides the batch-size dispatch inside fepe_fit_fwd."""
+    monkeypatch.setenv("FEPE_FIT_KERNEL", request.param)
+    return request.param
+
+
 @pytest.mark.parametrize("mode", ["uniform", "softmax", "inlier"])
 @pytest.mark.parametrize("B,N", [(16, 1000), (8, 2000), (5, 333), (3, 37), (2, 12), (300, 64)])
-def test_against_oracle(mode, B, N):
+def test_against_oracle(mode, B, N, kernel):
     d = synth.make_batch(B, N, seed=100 + N, weight_mode=mode)
     F, res, epi, _ = _run(d)
     Fr, rr, er, _, _ = _oracle(d)
@@ -67,7 +75,7 @@ def test_peaked_weights_against_fp64_truth():
     assert float(ours.max()) < max(F_TOL, 2 * float(ref.max()))
 
 
-def test_config2_full_size_and_saved_state():
+def test_config2_full_size_and_saved_state(kernel):
     d = synth.make_batch(256, 1000, seed=0, weight_mode="softmax")
     F, res, epi, saved = _run(d, want_saved=True)
     Fr, rr, er, _, _ = _oracle(d)
@@ -104,7 +112,7 @@ def test_properties_at_full_size():
     assert float((epip - epi[:, perm]).abs().max()) < 1e-4
 
 
-def test_edge_cases():
+def test_edge_cases(kernel):
     # clamp value is honoured
     d = synth.make_batch(4, 256, seed=9)
     _, _, epi, _ = _run(d, clamp_at=0.02)

@@ -27,8 +27,11 @@ def shim():
     dp = ctypes.POINTER(ctypes.c_double)
     lib.shim_eig9.argtypes = [dp, dp, dp]
     lib.shim_eig9.restype = ctypes.c_int
+    lib.shim_eig9_multishift.argtypes = [dp, dp, dp]
+    lib.shim_eig9_multishift.restype = ctypes.c_int
     lib.shim_pinv.argtypes = [dp, dp, ctypes.c_double, dp, dp]
     lib.shim_svd3.argtypes = [dp, dp, dp, dp]
+    lib.shim_svd3_direct.argtypes = [dp, dp, dp, dp]
     lib.shim_rank2.argtypes = [dp, dp]
     lib.shim_g36_index.argtypes = [ctypes.c_int, ctypes.c_int]
     lib.shim_g36_index.restype = ctypes.c_int
@@ -84,13 +87,15 @@ def test_g36_layout_matches_kron(shim):
     np.testing.assert_allclose(full_gram(shim, g36), G, rtol=1e-12, atol=1e-12)
 
 
+@pytest.mark.parametrize("solver", ["shim_eig9", "shim_eig9_multishift"])
 @pytest.mark.parametrize("mode", ["uniform", "softmax", "peaked", "inlier"])
-def test_eig9_on_scene_grams(shim, mode):
+def test_eig9_on_scene_grams(shim, mode, solver):
     worst, its = 0.0, []
+    solve = getattr(shim, solver)
     for seed in range(40):
         g36, X = scene_gram(seed, mode, noise=0.5 if seed % 2 else 0.0, outl=0.3 if seed % 3 else 0.0)
         f, lam = np.zeros(9), np.zeros(1)
-        its.append(shim.shim_eig9(_ptr(g36), _ptr(f), _ptr(lam)))
+        its.append(solve(_ptr(g36), _ptr(f), _ptr(lam)))
         v_ref = np.linalg.svd(X)[2][-1]
         err = min(np.linalg.norm(f - v_ref), np.linalg.norm(f + v_ref))
         worst = max(worst, err)
@@ -104,7 +109,9 @@ def test_eig9_on_scene_grams(shim, mode):
     assert max(its) <= 16, its
 
 
-def test_eig9_random_spd_and_degenerate(shim):
+@pytest.mark.parametrize("solver", ["shim_eig9", "shim_eig9_multishift"])
+def test_eig9_random_spd_and_degenerate(shim, solver):
+    solve = getattr(shim, solver)
     rng = np.random.default_rng(1)
     max_it = 0
     for trial in range(300):
@@ -116,7 +123,7 @@ def test_eig9_random_spd_and_degenerate(shim):
         G = full_gram(shim, g36)
         ev, evec = np.linalg.eigh(G)
         f, lam = np.zeros(9), np.zeros(1)
-        max_it = max(max_it, shim.shim_eig9(_ptr(g36), _ptr(f), _ptr(lam)))
+        max_it = max(max_it, solve(_ptr(g36), _ptr(f), _ptr(lam)))
         gap = (ev[1] - ev[0]) / ev[-1]
         err = min(np.linalg.norm(f - evec[:, 0]), np.linalg.norm(f + evec[:, 0]))
         assert err < 1e-12 / max(gap, 1e-9) + 5e-8, (trial, err, gap)   # stop rule: r <= 1e-8 * gap
@@ -125,11 +132,11 @@ def test_eig9_random_spd_and_degenerate(shim):
     # degenerate inputs: zero matrix and NaN -> e9, no NaN out; planar scene -> finite unit vector
     for g36 in (np.zeros(36), np.full(36, np.nan)):
         f, lam = np.zeros(9), np.zeros(1)
-        shim.shim_eig9(_ptr(g36), _ptr(f), _ptr(lam))
+        solve(_ptr(g36), _ptr(f), _ptr(lam))
         np.testing.assert_array_equal(f, np.eye(9)[8])
     g36, _ = scene_gram(3, "uniform", noise=0.0, outl=0.0, planar=True)
     f, lam = np.zeros(9), np.zeros(1)
-    shim.shim_eig9(_ptr(g36), _ptr(f), _ptr(lam))
+    solve(_ptr(g36), _ptr(f), _ptr(lam))
     G = full_gram(shim, g36)
     assert np.isfinite(f).all() and abs(np.linalg.norm(f) - 1) < 1e-12
     assert np.linalg.norm(G @ f - lam[0] * f) <= 1e-10 * np.trace(G)
@@ -222,3 +229,25 @@ def test_rank2_adjoint_matches_autograd_through_svd(shim):
         F2 = U @ torch.diag(S * torch.tensor([1.0, 1.0, 0.0], dtype=torch.float64)) @ V.t()
         (F2 * torch.tensor(Ab)).sum().backward()
         np.testing.assert_allclose(out, Ft.grad.numpy(), rtol=1e-7, atol=1e-9)
+
+
+def test_svd3_direct(shim):
+    """The pose head's SVD: exact for essential-like (rank 2) inputs, and a valid SVD for generic ones
+    whose singular values are reasonably separated."""
+    rng = np.random.default_rng(5)
+    mats = []
+    for _ in range(100):
+        u, _, vt = np.linalg.svd(rng.normal(size=(3, 3)))
+        s1 = rng.uniform(0.5, 2.0)
+        mats.append((u @ np.diag([s1, s1 * rng.uniform(0.3, 0.999), 0.0]) @ vt, 1e-12))
+        mats.append((u @ np.diag([s1, s1 * rng.uniform(0.3, 0.999), 1e-7 * s1]) @ vt, 1e-11))
+        mats.append((u @ np.diag([s1, 0.6 * s1, 0.1 * s1]) @ vt * 1e3, 1e-10))
+    for A, tol in mats:
+        A = np.ascontiguousarray(A)
+        U, S, V = np.zeros((3, 3)), np.zeros(3), np.zeros((3, 3))
+        shim.shim_svd3_direct(_ptr(A), _ptr(U), _ptr(S), _ptr(V))
+        sc = np.linalg.norm(A)
+        np.testing.assert_allclose(U @ np.diag(S) @ V.T, A, atol=tol * sc * 10)
+        np.testing.assert_allclose(U.T @ U, np.eye(3), atol=1e-9)
+        np.testing.assert_allclose(V.T @ V, np.eye(3), atol=1e-9)
+        np.testing.assert_allclose(S, np.linalg.svd(A, compute_uv=False), atol=1e-9 * sc)
