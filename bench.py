@@ -344,11 +344,14 @@ def run_ours(args):
     fit_us = fit_secs / max(args.steps, 200) * 1e6
     peak, peak_src = measured_peak_gbs()
     achieved = fit_bytes(B, N) / (fit_us * 1e-6) / 1e9
-    roofline = {"bound": "hbm", "kernel": "fepe_fit_fwd_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
+    small = B <= 2 * torch.cuda.get_device_properties(dev).multi_processor_count and N * 20 <= 56 * 1024
+    fit_kernel = "fepe_fit_fwd_small_kernel" if small else "fepe_fit_fwd_kernel"
+    roofline = {"bound": "hbm", "kernel": fit_kernel, "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": ncu_traffic(B, N), "launch_us": fit_us,
                 "algorithmic_bytes_per_launch": fit_bytes(B, N), "peak_source": peak_src,
-                "note": "launch of one config batch; see roofline_saturating for the same kernel at a batch that "
-                        "fills the 148 SMs"}
+                "note": "launch of one config batch (fepe_fit_fwd dispatches batches of <= 2 pairs per SM to the "
+                        "one-CTA-per-pair latency kernel); roofline_saturating is the persistent ring kernel the same "
+                        "entry point uses for batches that fill the 148 SMs"}
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
@@ -405,7 +408,7 @@ def run_ours(args):
                                                "fepe_fit_fwd + fepe_pose_fwd + one D2H copy per step"}
 
 
-    if rank == 0 and not args.no_extras:
+    if rank == 0 and world == 1 and not args.no_extras:
         # ---- saturating batch for the same kernel (roofline of the kernel itself) ---------------
         SB = args.sat_batch
         reps = (SB + B * ring_n - 1) // (B * ring_n)

@@ -99,6 +99,27 @@ int fepe_pose_fwd(const float* F, const float* K, int L, int B, float ax, float 
                   const float* virt1, const float* virt2, int V, float clamp_at,
                   float* out, void* stream);
 
+/* ---- per-correspondence weight MLP on tensor cores (inference path) -----------------------------
+ * Replaces ErrorEstimator.forward (deepFEPE/models/ErrorEstimators.py:46-68: five Conv1d(k=1) ->
+ * InstanceNorm1d(affine) -> LeakyReLU(0.01) blocks and a final Conv1d) and the softmax over the N
+ * correspondences (deepFEPE/models/DeepFNet.py:443,512).  Activations are bf16 row-major [B*Npad, C]
+ * with Npad = N rounded up to 128 (padded rows are zero and excluded from the statistics); weights are
+ * bf16 [Co, Ci] (Conv1d weight squeezed); accumulation is fp32 in tensor memory (tcgen05.mma).
+ *   fepe_mlp_first  layer 1 from fp32 features X0 [B,N,Ci<=8]                -> Y [B*Npad,Co] + stats
+ *   fepe_mlp_gemm   Y = X W^T + b (K % 64 == 0, Co % 64 == 0)                 -> Y + stats [B,Co,2]
+ *   fepe_mlp_norm   X' = LeakyReLU(gamma (Y - mean) rstd + beta) from stats (biased variance, eps)
+ *   fepe_mlp_last   logits = X w + b (Co = 1), weights = softmax over the N rows of each pair
+ * `stats` must be zeroed by the caller before fepe_mlp_first / fepe_mlp_gemm (they accumulate with atomics).
+ */
+int fepe_mlp_first(const float* X0, const float* W, const float* bias, void* Y, float* stats, int B, int N, int Npad,
+                   int Ci, int Co, void* stream);
+int fepe_mlp_gemm(const void* X, const void* W, const float* bias, void* Y, float* stats, int B, int Npad,
+                  int Nvalid, int K, int Co, void* stream);
+int fepe_mlp_norm(const void* Y, const float* stats, const float* gamma, const float* beta, void* X, int B, int Npad,
+                  int Nvalid, int Co, float eps, float slope, void* stream);
+int fepe_mlp_last(const void* X, const float* W, float bias, float* logits, float* weights, int B, int N, int Npad,
+                  int Ci, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -101,24 +101,41 @@ __device__ __forceinline__ PairMap make_map(const PairNorm& h, float ax, float a
     return m;
 }
 
-// pass 3: the 36 distinct entries of G = sum_i s_i (a a^T) (x) (b b^T), fp64 accumulation
+// pass 3: the 36 distinct entries of G = sum_i s_i (a a^T) (x) (b b^T), fp64 accumulation.
+// Software pipelined by hand: the fp32 front end + the five F2F conversions of correspondence i+1 are
+// independent of the 44-instruction fp64 burst of correspondence i, so they are issued around it
+// (one warp per scheduler has nothing else to hide the LDS -> FFMA -> MUFU -> F2F chain behind).
+struct GramTerm {
+    double x1, y1, x2, y2, s;
+};
+__device__ __forceinline__ GramTerm gram_prepare(const float4 q, const float wi, const PairMap& m) {
+    const float x1 = fmaf(m.k1x, q.x, m.j1x), y1 = fmaf(m.k1y, q.y, m.j1y);
+    const float x2 = fmaf(m.k2x, q.z, m.j2x), y2 = fmaf(m.k2y, q.w, m.j2y);
+    const float nb = fmaf(x1, x1, fmaf(y1, y1, 1.0f));
+    const float na = fmaf(x2, x2, fmaf(y2, y2, 1.0f));
+    const float s = __fdividef(wi * wi, na * nb);   // (w / |p|)^2, |p|^2 = |a|^2 |b|^2 (2 ulp is ample)
+    GramTerm t;
+    t.x1 = x1; t.y1 = y1; t.x2 = x2; t.y2 = y2; t.s = s;
+    return t;
+}
 __device__ __forceinline__ void pass_gram(const float4* __restrict__ sp, const float* __restrict__ sw, int N,
                                           int start, int stride, const PairMap& m, double (&acc)[36]) {
 #pragma unroll
     for (int i = 0; i < 36; ++i) acc[i] = 0.0;
+    if (start >= N) return;
+    GramTerm cur = gram_prepare(sp[start], sw[start], m);
 #pragma unroll 1
     for (int i = start; i < N; i += stride) {
-        const float4 q = sp[i];
-        const float wi = sw[i];
-        const float x1 = fmaf(m.k1x, q.x, m.j1x), y1 = fmaf(m.k1y, q.y, m.j1y);
-        const float x2 = fmaf(m.k2x, q.z, m.j2x), y2 = fmaf(m.k2y, q.w, m.j2y);
-        const float nb = fmaf(x1, x1, fmaf(y1, y1, 1.0f));
-        const float na = fmaf(x2, x2, fmaf(y2, y2, 1.0f));
-        const float s = __fdividef(wi * wi, na * nb);   // (w / |p|)^2, |p|^2 = |a|^2 |b|^2 (2 ulp is ample)
-        const double dx1 = x1, dy1 = y1, dx2 = x2, dy2 = y2, ds = s;
-        const double b0 = dx1 * dx1, b1 = dx1 * dy1, b3 = dy1 * dy1;
-        const double t0 = ds * dx2, t1 = ds * dy2;
-        const double a[6] = {t0 * dx2, t0 * dy2, t0, t1 * dy2, t1, ds};
+        const int inext = i + stride;
+        const bool more = inext < N;
+        float4 qn = make_float4(0.f, 0.f, 0.f, 0.f);
+        float wn = 0.f;
+        if (more) { qn = sp[inext]; wn = sw[inext]; }
+        const double b0 = cur.x1 * cur.x1, b1 = cur.x1 * cur.y1, b3 = cur.y1 * cur.y1;
+        const double t0 = cur.s * cur.x2, t1 = cur.s * cur.y2;
+        const double a[6] = {t0 * cur.x2, t0 * cur.y2, t0, t1 * cur.y2, t1, cur.s};
+        const double dx1 = cur.x1, dy1 = cur.y1;
+        const GramTerm nxt = gram_prepare(qn, wn, m);
 #pragma unroll
         for (int u = 0; u < 6; ++u) {
             acc[u * 6 + 0] = fma(a[u], b0, acc[u * 6 + 0]);
@@ -128,6 +145,7 @@ __device__ __forceinline__ void pass_gram(const float4* __restrict__ sp, const f
             acc[u * 6 + 4] = fma(a[u], dy1, acc[u * 6 + 4]);
             acc[u * 6 + 5] += a[u];
         }
+        cur = nxt;
     }
 }
 
@@ -136,7 +154,7 @@ __device__ __forceinline__ void pass_resid(const float4* __restrict__ sp, const 
                                            int start, int stride, const PairMap& m, const float (&ff)[9],
                                            const float (&Fo)[9], float ax, float bx, float ay, float by,
                                            float clamp_at, float* __restrict__ r_out, float* __restrict__ e_out) {
-#pragma unroll 2
+#pragma unroll 4
     for (int i = start; i < N; i += stride) {
         const float4 q = sp[i];
         const float wi = sw[i];

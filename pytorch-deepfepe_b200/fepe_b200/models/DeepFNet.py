@@ -98,6 +98,13 @@ class DeepFNet(nn.Module):
         self.norm_HW = NormalizeAndExpand_HW(self.image_size, is_cuda, is_test)
         self.fit = Fit(is_cuda, is_test, if_cpu_svd)
 
+    def enable_tensor_core_mlp(self, flag: bool = True):
+        """Run both weight networks on the tcgen05 bf16 path when called under torch.no_grad() (inference)."""
+        for net in (self.input_weights, self.update_weights):
+            if isinstance(net, ErrorEstimator):
+                net.tensor_cores = bool(flag)
+        return self
+
     def get_input(self, data_batch, offsets=None, iter=None):
         pts = data_batch['matches_xy_ori']
         pts1, pts2, T1, T2 = self.norm_HW(pts)
@@ -109,6 +116,12 @@ class DeepFNet(nn.Module):
         weight_in = torch.cat(feats, 2).permute(0, 2, 1)
         return weight_in, pts1, pts2, T1, T2
 
+    @staticmethod
+    def _softmax(net, logits):
+        # the tensor-core path computes the softmax over N in its last kernel
+        sm = getattr(net, "last_softmax", None)
+        return sm if sm is not None else F.softmax(logits, dim=2)
+
     def forward(self, data_batch):
         matches = data_batch['matches_xy_ori']
         if not matches.is_cuda:
@@ -119,7 +132,7 @@ class DeepFNet(nn.Module):
         pts_normalized_in, pts1, pts2, T1, T2 = self.get_input(data_batch)
 
         logits = self.input_weights(pts_normalized_in)
-        weights_pts = F.softmax(logits, dim=2)
+        weights_pts = self._softmax(self.input_weights, logits)
         weights_prod = weights_pts * data_batch['weights_im'] if self.if_img_w else weights_pts
         _ = data_batch.get('matches_good_unique_nums'), data_batch.get('t_scene_scale')   # read, unused (:449,:453)
 
@@ -134,7 +147,7 @@ class DeepFNet(nn.Module):
             epi_res_layers.append(epi_res)
             net_in = torch.cat((pts_normalized_in, weights_prod, epi_res, residual.unsqueeze(1)), 1)
             logits = self.update_weights(net_in)
-            weights_pts = F.softmax(logits, dim=2)
+            weights_pts = self._softmax(self.update_weights, logits)
             weights_prod = weights_pts * data_batch['weights_im'] if self.if_img_w else weights_pts
             weights_layers.append(weights_prod)
             logits_layers.append(logits)
