@@ -56,6 +56,9 @@ def parse_args():
     ap.add_argument("--no-graph", action="store_true", help="launch eagerly instead of replaying CUDA graphs")
     ap.add_argument("--no-extras", action="store_true", help="skip e2e / cpu_baseline / saturating legs")
     ap.add_argument("--phases", action="store_true", help="print per-phase SM cycles of the fused kernel")
+    ap.add_argument("--workload", choices=["C2", "C4"], default="C2",
+                    help="C2 (default, the contract line): solver only.  C4: whole DeepFNet forward (depth 5, "
+                         "ErrorEstimator on tcgen05 + 5 fits), batch 512 x N=1000 -- an extra line, not the contract")
     return ap.parse_args()
 
 
@@ -461,10 +464,56 @@ def run_ours(args):
         print(json.dumps(line), flush=True)
 
 
+def run_c4(args):
+    """Config 4 of BASELINE.json: ErrorEstimator(4) + 4 x ErrorEstimator(7) + 5 fits + 4 epipolar residuals
+    (DeepFNet.forward, depth 5) on a batch of 512 pairs x 1000 correspondences, inference mode."""
+    rank, world, local = dist_env()
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    import __graft_entry__ as entry
+    entry.build()
+    from fepe_b200 import synth
+    from fepe_b200.models import DeepFNet
+    B, N = (512 if args.batch == 256 else args.batch), args.ncorr
+    torch.manual_seed(0)
+    net = DeepFNet(depth=5, image_size=list(synth.KITTI_IMAGE_SIZE), if_quality=False).cuda().eval()
+    net.enable_tensor_core_mlp(True)
+    host = make_host_batches(2, min(B, 128), N, seed0=77)
+    batches = [{"matches_xy_ori": torch.from_numpy(d["matches_xy_ori"]).to(dev).repeat((B + 127) // 128, 1, 1)[:B].contiguous()}
+               for d in host]
+    steps, warm = min(args.steps, 50), max(3, min(args.warmup, 10))
+    with torch.no_grad():
+        secs, t0, t1 = timed_loop([(lambda b=b: net(b)) for b in batches], steps, warm)
+        net.enable_tensor_core_mlp(False)
+        secs32, _, _ = timed_loop([(lambda b=b: net(b)) for b in batches], max(3, steps // 10), 2)
+    flop_per_pt = lambda cin: 2 * (cin * 64 + 64 * 128 + 128 * 1024 + 1024 * 512 + 512 * 256 + 256)
+    flops = B * N * (flop_per_pt(4) + 4 * flop_per_pt(7))
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            peak_tf = float(json.load(f)["bf16_tflops_sustained"])
+    except Exception:
+        peak_tf = 1400.0
+    line = {"metric": METRIC, "value": world * B * steps / secs, "unit": UNIT, "n_gpus": world, "steps": steps,
+            "warmup": warm, "ms_per_step": secs / steps * 1e3, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "bf16 MLP (fp32 accumulate) + f32/f64 solver", "data": "synthetic",
+            "config": {"workload": f"C4: DeepFNet forward depth 5 (5 ErrorEstimator evaluations on tcgen05 + 5 fused fits), "
+                                   f"batch={B} x N={N}, inference", "batch_per_gpu": B, "ncorr": N},
+            "roofline": {"bound": "tensor", "kernel": "fepe_mlp_gemm_kernel (whole step counted)",
+                         "achieved": flops / (secs / steps) / 1e12, "peak": peak_tf, "unit": "TFLOP/s",
+                         "frac": flops / (secs / steps) / 1e12 / peak_tf, "traffic": None,
+                         "note": "MLP flops of the step / step time: includes the memory-bound norm kernels and the fits"},
+            "fp32_cudnn_mlp_pairs_per_sec": world * B * max(3, steps // 10) / secs32,
+            "gpu_launches": steps * (5 * 16 + 5)}
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+
+
 def main():
     args = parse_args()
     if args.impl == "reference":
         run_reference(args)
+    elif args.workload == "C4":
+        run_c4(args)
     else:
         run_ours(args)
 

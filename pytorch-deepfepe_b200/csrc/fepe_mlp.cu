@@ -108,8 +108,8 @@ fepe_mlp_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
-    const int m0 = blockIdx.x * kGemmBM;
-    const int n0 = blockIdx.y * BN;
+    const int m0 = blockIdx.y * kGemmBM;     // n-tiles vary fastest: the CTAs sharing an A tile are co-scheduled
+    const int n0 = blockIdx.x * BN;
     const int num_kb = p.K / kGemmBK;
 
     if (threadIdx.x == 0) {
@@ -219,45 +219,68 @@ fepe_mlp_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
     }
 }
 
-// X'[m][c] = LeakyReLU(gamma[c] (Y[m][c] - mean[b][c]) rstd[b][c] + beta[c]); padded rows -> 0
-__global__ void fepe_mlp_norm_kernel(const __nv_bfloat16* __restrict__ Y, const float* __restrict__ stats,
-                                     const float* __restrict__ gamma, const float* __restrict__ beta,
-                                     __nv_bfloat16* __restrict__ X, int M, int Co, int Npad, int Nvalid, float eps,
-                                     float slope) {
-    const size_t idx2 = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;     // one bf16x2 per thread
-    const size_t total2 = static_cast<size_t>(M) * Co / 2;
-    if (idx2 >= total2) return;
-    const size_t e = idx2 * 2;
-    const int m = static_cast<int>(e / Co), c = static_cast<int>(e % Co);
-    const int b = m / Npad, r = m % Npad;
-    __nv_bfloat162 out = __floats2bfloat162_rn(0.f, 0.f);
-    if (r < Nvalid) {
-        const __nv_bfloat162 y = *reinterpret_cast<const __nv_bfloat162*>(Y + e);
-        const float invN = 1.0f / static_cast<float>(Nvalid);
-        float o[2];
-#pragma unroll
-        for (int k = 0; k < 2; ++k) {
-            const float s1 = stats[(static_cast<size_t>(b) * Co + c + k) * 2];
-            const float s2 = stats[(static_cast<size_t>(b) * Co + c + k) * 2 + 1];
-            const float mean = s1 * invN;
-            const float var = fmaxf(s2 * invN - mean * mean, 0.f);       // biased variance, like InstanceNorm1d
-            const float yv = (k == 0) ? __low2float(y) : __high2float(y);
-            const float t = (yv - mean) * rsqrtf(var + eps) * gamma[c + k] + beta[c + k];
-            o[k] = t > 0.f ? t : slope * t;
-        }
-        out = __floats2bfloat162_rn(o[0], o[1]);
+// X'[m][c] = LeakyReLU(gamma[c] (Y[m][c] - mean[b][c]) rstd[b][c] + beta[c]); padded rows -> 0.
+// One CTA per (pair, 128-row slab): the per-channel scale / shift are computed once into shared memory,
+// then every thread streams 16-byte vectors (8 bf16).
+__global__ void __launch_bounds__(256) fepe_mlp_norm_kernel(const __nv_bfloat16* __restrict__ Y,
+                                                            const float* __restrict__ stats,
+                                                            const float* __restrict__ gamma,
+                                                            const float* __restrict__ beta,
+                                                            __nv_bfloat16* __restrict__ X, int Co, int Npad, int Nvalid,
+                                                            float eps, float slope) {
+    extern __shared__ float sc[];            // [Co] scale, [Co] shift
+    float* sh = sc + Co;
+    const int b = blockIdx.y;
+    const int r0 = blockIdx.x * 128;
+    const float invN = 1.0f / static_cast<float>(Nvalid);
+    for (int c = threadIdx.x; c < Co; c += blockDim.x) {
+        const float s1 = stats[(static_cast<size_t>(b) * Co + c) * 2];
+        const float s2 = stats[(static_cast<size_t>(b) * Co + c) * 2 + 1];
+        const float mean = s1 * invN;
+        const float var = fmaxf(s2 * invN - mean * mean, 0.f);           // biased variance, like InstanceNorm1d
+        const float a = rsqrtf(var + eps) * gamma[c];
+        sc[c] = a;
+        sh[c] = beta[c] - mean * a;
     }
-    *reinterpret_cast<__nv_bfloat162*>(X + e) = out;
+    __syncthreads();
+    const int vec_per_row = Co / 8;
+    const size_t base = (static_cast<size_t>(b) * Npad + r0) * Co;
+    for (int idx = threadIdx.x; idx < 128 * vec_per_row; idx += blockDim.x) {
+        const int r = idx / vec_per_row, c = (idx % vec_per_row) * 8;
+        uint4 out = make_uint4(0u, 0u, 0u, 0u);
+        if (r0 + r < Nvalid) {
+            const uint4 in = *reinterpret_cast<const uint4*>(Y + base + static_cast<size_t>(r) * Co + c);
+            const uint32_t w[4] = {in.x, in.y, in.z, in.w};
+            uint32_t o[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const __nv_bfloat162 y = *reinterpret_cast<const __nv_bfloat162*>(&w[k]);
+                float t0 = fmaf(__low2float(y), sc[c + 2 * k], sh[c + 2 * k]);
+                float t1 = fmaf(__high2float(y), sc[c + 2 * k + 1], sh[c + 2 * k + 1]);
+                t0 = t0 > 0.f ? t0 : slope * t0;
+                t1 = t1 > 0.f ? t1 : slope * t1;
+                const __nv_bfloat162 v = __floats2bfloat162_rn(t0, t1);
+                o[k] = *reinterpret_cast<const uint32_t*>(&v);
+            }
+            out = make_uint4(o[0], o[1], o[2], o[3]);
+        }
+        *reinterpret_cast<uint4*>(X + base + static_cast<size_t>(r) * Co + c) = out;
+    }
 }
 
-// layer 1: X0 [B,N,Ci] fp32 (Ci <= 8) -> Y [B*Npad, 64] bf16 + stats.  One thread per (row, 2 channels).
-__global__ void fepe_mlp_first_kernel(const float* __restrict__ X0, const float* __restrict__ W,
-                                      const float* __restrict__ bias, __nv_bfloat16* __restrict__ Y,
-                                      float* __restrict__ stats, int B, int N, int Npad, int Ci, int Co) {
-    // block = 128 rows of one pair x all Co channels handled in a loop; blockDim = 128
+// layer 1: X0 [B,N,Ci] fp32 (Ci <= 8) -> Y [B*Npad, Co=64] bf16 + stats.  One CTA per (pair, 128-row slab):
+// thread = row computes its 64 outputs into a shared tile, then thread = channel sums the slab's column.
+__global__ void __launch_bounds__(128) fepe_mlp_first_kernel(const float* __restrict__ X0, const float* __restrict__ W,
+                                                             const float* __restrict__ bias,
+                                                             __nv_bfloat16* __restrict__ Y, float* __restrict__ stats,
+                                                             int B, int N, int Npad, int Ci, int Co) {
+    __shared__ __nv_bfloat16 tile[128][64 + 2];
+    __shared__ float w_s[64 * 8], b_s[64];
     const int b = blockIdx.y;
     const int r = blockIdx.x * 128 + threadIdx.x;
-    __shared__ float red[2][128];
+    for (int i = threadIdx.x; i < Co * Ci; i += 128) w_s[i] = W[i];
+    for (int i = threadIdx.x; i < Co; i += 128) b_s[i] = bias[i];
+    __syncthreads();
     float x[8];
     const bool valid = r < N;
 #pragma unroll
@@ -265,22 +288,28 @@ __global__ void fepe_mlp_first_kernel(const float* __restrict__ X0, const float*
     for (int c = 0; c < Co; ++c) {
         float y = 0.f;
         if (valid) {
-            y = bias[c];
+            y = b_s[c];
 #pragma unroll
             for (int k = 0; k < 8; ++k)
-                if (k < Ci) y = fmaf(W[c * Ci + k], x[k], y);
+                if (k < Ci) y = fmaf(w_s[c * Ci + k], x[k], y);
         }
-        const __nv_bfloat16 yb = __float2bfloat16(y);
-        if (r < Npad) Y[(static_cast<size_t>(b) * Npad + r) * Co + c] = yb;
-        const float yr = __bfloat162float(yb);
-        float s1 = warp_sum(yr), s2 = warp_sum(yr * yr);
-        if ((threadIdx.x & 31) == 0) { red[0][threadIdx.x >> 5] = s1; red[1][threadIdx.x >> 5] = s2; }
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            atomicAdd(stats + (static_cast<size_t>(b) * Co + c) * 2, red[0][0] + red[0][1] + red[0][2] + red[0][3]);
-            atomicAdd(stats + (static_cast<size_t>(b) * Co + c) * 2 + 1, red[1][0] + red[1][1] + red[1][2] + red[1][3]);
+        tile[threadIdx.x][c] = __float2bfloat16(y);
+    }
+    __syncthreads();
+    if (threadIdx.x < Co) {
+        float s1 = 0.f, s2 = 0.f;
+        for (int rr = 0; rr < 128; ++rr) {
+            const float y = __bfloat162float(tile[rr][threadIdx.x]);
+            s1 += y;
+            s2 = fmaf(y, y, s2);
         }
-        __syncthreads();
+        atomicAdd(stats + (static_cast<size_t>(b) * Co + threadIdx.x) * 2, s1);
+        atomicAdd(stats + (static_cast<size_t>(b) * Co + threadIdx.x) * 2 + 1, s2);
+    }
+    for (int idx = threadIdx.x; idx < 128 * (Co / 2); idx += 128) {
+        const int rr = idx / (Co / 2), c2 = (idx % (Co / 2)) * 2;
+        *reinterpret_cast<__nv_bfloat162*>(Y + (static_cast<size_t>(b) * Npad + blockIdx.x * 128 + rr) * Co + c2) =
+            *reinterpret_cast<const __nv_bfloat162*>(&tile[rr][c2]);
     }
 }
 
@@ -367,7 +396,7 @@ static int launch_gemm(const void* X, const void* W, const GemmParams& p, cudaSt
         if (e != cudaSuccess) return static_cast<int>(e);
         configured = true;
     }
-    dim3 grid(p.M / kGemmBM, p.Co / BN);
+    dim3 grid(p.Co / BN, p.M / kGemmBM);
     fepe_mlp_gemm_kernel<BN><<<grid, kGemmThreads, smem, stream>>>(ma, mw, p);
     return static_cast<int>(cudaGetLastError());
 }
@@ -389,17 +418,17 @@ int fepe_mlp_gemm(const void* X, const void* W, const float* bias, void* Y, floa
 
 int fepe_mlp_norm(const void* Y, const float* stats, const float* gamma, const float* beta, void* X, int B, int Npad,
                   int Nvalid, int Co, float eps, float slope, void* stream) {
-    if (!Y || !stats || !gamma || !beta || !X || B <= 0 || (Co & 1)) return FEPE_E_BADARG;
-    const size_t total2 = static_cast<size_t>(B) * Npad * Co / 2;
-    fepe::fepe_mlp_norm_kernel<<<static_cast<unsigned>((total2 + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-        static_cast<const __nv_bfloat16*>(Y), stats, gamma, beta, static_cast<__nv_bfloat16*>(X), B * Npad, Co, Npad,
-        Nvalid, eps, slope);
+    if (!Y || !stats || !gamma || !beta || !X || B <= 0 || (Co & 7) || (Npad % 128) != 0) return FEPE_E_BADARG;
+    dim3 grid(Npad / 128, B);
+    fepe::fepe_mlp_norm_kernel<<<grid, 256, 2 * Co * sizeof(float), static_cast<cudaStream_t>(stream)>>>(
+        static_cast<const __nv_bfloat16*>(Y), stats, gamma, beta, static_cast<__nv_bfloat16*>(X), Co, Npad, Nvalid, eps,
+        slope);
     return static_cast<int>(cudaGetLastError());
 }
 
 int fepe_mlp_first(const float* X0, const float* W, const float* bias, void* Y, float* stats, int B, int N, int Npad,
                    int Ci, int Co, void* stream) {
-    if (!X0 || !W || !bias || !Y || !stats || B <= 0 || Ci <= 0 || Ci > 8) return FEPE_E_BADARG;
+    if (!X0 || !W || !bias || !Y || !stats || B <= 0 || Ci <= 0 || Ci > 8 || Co != 64 || (Npad % 128) != 0) return FEPE_E_BADARG;
     dim3 grid(Npad / 128, B);
     fepe::fepe_mlp_first_kernel<<<grid, 128, 0, static_cast<cudaStream_t>(stream)>>>(
         X0, W, bias, static_cast<__nv_bfloat16*>(Y), stats, B, N, Npad, Ci, Co);
