@@ -56,9 +56,11 @@ def parse_args():
     ap.add_argument("--no-graph", action="store_true", help="launch eagerly instead of replaying CUDA graphs")
     ap.add_argument("--no-extras", action="store_true", help="skip e2e / cpu_baseline / saturating legs")
     ap.add_argument("--phases", action="store_true", help="print per-phase SM cycles of the fused kernel")
-    ap.add_argument("--workload", choices=["C2", "C4"], default="C2",
+    ap.add_argument("--workload", choices=["C2", "C4", "C5"], default="C2",
                     help="C2 (default, the contract line): solver only.  C4: whole DeepFNet forward (depth 5, "
-                         "ErrorEstimator on tcgen05 + 5 fits), batch 512 x N=1000 -- an extra line, not the contract")
+                         "ErrorEstimator on tcgen05 + 5 fits), batch 512 x N=1000.  C5: training step (forward, F-loss, backward "
+                         "through the analytic fit backward, one flattened NCCL all-reduce, Adam), 16 pairs per GPU.  "
+                         "C4 / C5 are extra lines, not the contract")
     return ap.parse_args()
 
 
@@ -508,12 +510,90 @@ def run_c4(args):
         print(json.dumps(line), flush=True)
 
 
+def run_c5(args):
+    """Config 5 of BASELINE.json: end-to-end training step (random keypoints stand in for SuperPoint), batch 128
+    over 8 GPUs = 16 pairs per GPU; the only collective is the flattened gradient all-reduce."""
+    rank, world, local = dist_env()
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    import torch.distributed as dist
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    import __graft_entry__ as entry
+    entry.build()
+    from fepe_b200 import synth, dist as fdist
+    from fepe_b200.models import DeepFNet
+    B, N = 16, args.ncorr
+    torch.manual_seed(0)
+    net = DeepFNet(depth=5, image_size=list(synth.KITTI_IMAGE_SIZE), if_quality=False).cuda()
+    opt = torch.optim.Adam(net.parameters(), lr=1e-4)          # configs/kitti_corr_baseline.yaml:62
+    d = synth.make_batch(B, N, seed=500 + rank)
+    T = lambda k: torch.from_numpy(d[k]).to(dev)
+    batch = {"matches_xy_ori": T("matches_xy_ori")}
+    v1, v2 = T("pts1_virt"), T("pts2_virt")
+
+    def epi(p1, p2, Fm, clamp):            # utils_F.compute_epi_residual with torch ops (loss glue stays the reference's)
+        l1, l2 = p2 @ Fm, p1 @ Fm.transpose(1, 2)
+        dd = (p1 * l1).sum(2)
+        dist_ = dd.abs() * (1 / (l1[:, :, :2].norm(2, 2) + 1e-6) + 1 / (l2[:, :, :2].norm(2, 2) + 1e-6))
+        return torch.clamp(dist_, max=clamp)
+
+    times = {"fwd": 0.0, "bwd": 0.0, "allreduce": 0.0}
+
+    def step():
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+        opt.zero_grad(set_to_none=True)
+        ev[0].record()
+        outs = net(batch)
+        T1 = outs["T1"]
+        p1 = (T1 @ v1.transpose(1, 2)).transpose(1, 2)
+        p2 = (T1 @ v2.transpose(1, 2)).transpose(1, 2)
+        loss = sum(epi(p1, p2, Fo, CLAMP_LOSS).mean() for Fo in outs["out_layers"]) / len(outs["out_layers"])
+        ev[1].record()
+        loss.backward()
+        ev[2].record()
+        fdist.allreduce_mean_grads_(list(net.parameters()))
+        ev[3].record()
+        opt.step()
+        return ev
+
+    steps, warm = min(args.steps, 30), max(3, min(args.warmup, 5))
+    for _ in range(warm):
+        step()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    evs = [step() for _ in range(steps)]
+    e1.record()
+    torch.cuda.synchronize()
+    secs = fdist.max_over_ranks(e0.elapsed_time(e1) * 1e-3, dev)
+    for ev in evs:
+        times["fwd"] += ev[0].elapsed_time(ev[1]); times["bwd"] += ev[1].elapsed_time(ev[2]); times["allreduce"] += ev[2].elapsed_time(ev[3])
+    line = {"metric": "training_pairs_per_sec", "value": world * B * steps / secs, "unit": UNIT, "n_gpus": world,
+            "steps": steps, "warmup": warm, "ms_per_step": secs / steps * 1e3, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32 MLP (PyTorch autograd) + f32/f64 solver kernels",
+            "data": "synthetic",
+            "config": {"workload": f"C5: DeepFNet training step, depth 5, {B} pairs/GPU x N={N}, F-loss, Adam, "
+                                   "one flattened gradient all-reduce (NCCL)", "global_batch": world * B},
+            "ms_breakdown": {k: v / steps for k, v in times.items()},
+            "grad_bytes_allreduced": sum(p.numel() for p in net.parameters()) * 4}
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+
+
 def main():
     args = parse_args()
     if args.impl == "reference":
         run_reference(args)
     elif args.workload == "C4":
         run_c4(args)
+    elif args.workload == "C5":
+        run_c5(args)
     else:
         run_ours(args)
 

@@ -276,8 +276,8 @@ __global__ void __launch_bounds__(kThreads, 1) fepe_fit_fwd_kernel(const FitPara
 
     if (warp == C) {
         // ---------------- producer warp ----------------
-        RingSources src{{p.matches, p.weights, nullptr, nullptr}, 2};
-        ring_producer(smem, p.ring, full, empty, src, N, n_local, lane);
+        ring_producer(smem, p.ring, full, empty, RingSources{{p.matches, p.weights, nullptr, nullptr}, 2}, N, n_local,
+                      lane);
         return;
     }
     if (warp > C) return;
@@ -290,11 +290,12 @@ __global__ void __launch_bounds__(kThreads, 1) fepe_fit_fwd_kernel(const FitPara
         const int stage = j % S;
         const uint32_t phase = static_cast<uint32_t>(j / S) & 1u;
         const size_t pair = static_cast<size_t>(blockIdx.x) + static_cast<size_t>(j) * gridDim.x;
-        const unsigned char* sb = smem + static_cast<size_t>(stage) * p.ring.stage_bytes;
+        unsigned char* sb = smem + static_cast<size_t>(stage) * p.ring.stage_bytes;
         const float4* sp = reinterpret_cast<const float4*>(sb);
         const float* sw = reinterpret_cast<const float*>(sb + pts_bytes);
         const long long tc0 = clock64();
         mbar_wait(&full[stage], phase);
+        ring_fill_ragged(sb, RingSources{{p.matches, p.weights, nullptr, nullptr}, 2}, pair, N, lane);
         const long long tc1 = clock64();
 
         // ---- passes 1+2: Hartley transforms of both images (Fit.normalize with unit weights) ----

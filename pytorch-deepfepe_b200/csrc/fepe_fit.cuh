@@ -123,16 +123,25 @@ __device__ __forceinline__ void denormalise_F(const double (&F2)[9], const PairN
     }
 }
 
-// Producer warp of the pair ring: streams `n_arrays` per-pair arrays (array 0 = the [N,4] coordinates,
-// 16 B per correspondence; arrays 1.. = [N] fp32 rows) into the stages.  Rows that are not 16-byte
-// aligned (ragged N) are copied by the warp itself before the barrier is armed.
+// Pair-ring data movement.  `n_arrays` per-pair arrays travel into a stage: array 0 = the [N,4]
+// coordinates (16 B per correspondence, always 16-byte aligned), arrays 1.. = [N] fp32 rows.  Rows whose
+// global address is 16-byte aligned (N % 4 == 0) go by bulk-async copy from the PRODUCER warp; ragged rows
+// are copied by the CONSUMER warp that owns the pair, after its full-barrier wait (ring_fill_ragged) --
+// writer and reader are then the same warp, ordered by __syncwarp, and no generic-proxy write ever has to
+// be published to another warp through an mbarrier (compute-sanitizer racecheck clean).
 struct RingSources {
-    const float* ptr[4];   // ptr[0]: [B,N,4]; ptr[1..]: [B,N] (may be null: that slot is zero filled)
+    const float* ptr[4];   // ptr[0]: [B,N,4]; ptr[1..]: [B,N] (null: that slot is never read)
     int n_arrays;
 };
 
+__device__ __forceinline__ bool ring_row_is_bulk(const float* base, size_t pair, int N) {
+    return base != nullptr && ((reinterpret_cast<uintptr_t>(base + pair * static_cast<size_t>(N)) & 15u) == 0) &&
+           ((N & 3) == 0);
+}
+
 __device__ __forceinline__ void ring_producer(unsigned char* smem, const RingLayout& ring, uint64_t* full,
                                               uint64_t* empty, const RingSources& src, int N, int n_local, int lane) {
+    if (lane != 0) return;
     const int S = ring.stages;
     const uint32_t pts_bytes = static_cast<uint32_t>(N) * 16u;
     const uint32_t row_bytes = static_cast<uint32_t>(N) * 4u;
@@ -143,32 +152,31 @@ __device__ __forceinline__ void ring_producer(unsigned char* smem, const RingLay
         const size_t pair = static_cast<size_t>(blockIdx.x) + static_cast<size_t>(j) * gridDim.x;
         unsigned char* sb = smem + static_cast<size_t>(stage) * ring.stage_bytes;
         uint32_t tx = pts_bytes;
-        uint32_t bulk_mask = 0;
-        for (int a = 1; a < src.n_arrays; ++a) {
-            float* dst = reinterpret_cast<float*>(sb + pts_bytes + static_cast<uint32_t>(a - 1) * row_bytes);
-            if (src.ptr[a] == nullptr) {
-                for (int i = lane; i < N; i += 32) dst[i] = 0.f;
-                continue;
-            }
-            const float* g = src.ptr[a] + pair * static_cast<size_t>(N);
-            if (((reinterpret_cast<uintptr_t>(g) & 15u) == 0) && ((N & 3) == 0)) {
-                bulk_mask |= 1u << a;
-                tx += row_bytes;
-            } else {
-                for (int i = lane; i < N; i += 32) dst[i] = __ldg(g + i);
-            }
-        }
-        __syncwarp();
-        if (lane == 0) {
-            mbar_arrive_expect_tx(&full[stage], tx);
-            bulk_g2s(sb, src.ptr[0] + pair * static_cast<size_t>(N) * 4, pts_bytes, &full[stage]);
-            for (int a = 1; a < src.n_arrays; ++a)
-                if (bulk_mask & (1u << a))
-                    bulk_g2s(sb + pts_bytes + static_cast<uint32_t>(a - 1) * row_bytes,
-                             src.ptr[a] + pair * static_cast<size_t>(N), row_bytes, &full[stage]);
-        }
-        __syncwarp();
+        for (int a = 1; a < src.n_arrays; ++a)
+            if (ring_row_is_bulk(src.ptr[a], pair, N)) tx += row_bytes;
+        mbar_arrive_expect_tx(&full[stage], tx);
+        bulk_g2s(sb, src.ptr[0] + pair * static_cast<size_t>(N) * 4, pts_bytes, &full[stage]);
+        for (int a = 1; a < src.n_arrays; ++a)
+            if (ring_row_is_bulk(src.ptr[a], pair, N))
+                bulk_g2s(sb + pts_bytes + static_cast<uint32_t>(a - 1) * row_bytes,
+                         src.ptr[a] + pair * static_cast<size_t>(N), row_bytes, &full[stage]);
     }
+}
+
+// Consumer side of the ragged case: called by the owning warp after mbar_wait(full).
+__device__ __forceinline__ void ring_fill_ragged(unsigned char* sb, const RingSources& src, size_t pair, int N,
+                                                 int lane) {
+    const uint32_t pts_bytes = static_cast<uint32_t>(N) * 16u;
+    const uint32_t row_bytes = static_cast<uint32_t>(N) * 4u;
+    bool any = false;
+    for (int a = 1; a < src.n_arrays; ++a) {
+        if (src.ptr[a] == nullptr || ring_row_is_bulk(src.ptr[a], pair, N)) continue;
+        float* dst = reinterpret_cast<float*>(sb + pts_bytes + static_cast<uint32_t>(a - 1) * row_bytes);
+        const float* g = src.ptr[a] + pair * static_cast<size_t>(N);
+        for (int i = lane; i < N; i += 32) dst[i] = __ldg(g + i);
+        any = true;
+    }
+    if (any) __syncwarp();
 }
 
 // ------------------------------------------------------------------------------------------------

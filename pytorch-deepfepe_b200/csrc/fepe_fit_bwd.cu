@@ -36,8 +36,8 @@ __global__ void __launch_bounds__(kThreads, 1) fepe_fit_bwd_kernel(const FitPara
     __syncthreads();
 
     if (warp == C) {
-        RingSources src{{p.matches, p.weights, p.gresid, p.gepi}, 4};
-        ring_producer(smem, p.ring, full, empty, src, N, n_local, lane);
+        ring_producer(smem, p.ring, full, empty, RingSources{{p.matches, p.weights, p.gresid, p.gepi}, 4}, N, n_local,
+                      lane);
         return;
     }
     if (warp > C) return;
@@ -52,7 +52,7 @@ __global__ void __launch_bounds__(kThreads, 1) fepe_fit_bwd_kernel(const FitPara
         const int stage = j % S;
         const uint32_t phase = static_cast<uint32_t>(j / S) & 1u;
         const size_t pair = static_cast<size_t>(blockIdx.x) + static_cast<size_t>(j) * gridDim.x;
-        const unsigned char* sb = smem + static_cast<size_t>(stage) * p.ring.stage_bytes;
+        unsigned char* sb = smem + static_cast<size_t>(stage) * p.ring.stage_bytes;
         const float4* sp = reinterpret_cast<const float4*>(sb);
         const float* sw = reinterpret_cast<const float*>(sb + pts_bytes);
         const float* sgr = reinterpret_cast<const float*>(sb + pts_bytes + row_bytes);
@@ -86,6 +86,7 @@ __global__ void __launch_bounds__(kThreads, 1) fepe_fit_bwd_kernel(const FitPara
         const float clamp_at = p.clamp_at;
 
         mbar_wait(&full[stage], phase);
+        ring_fill_ragged(sb, RingSources{{p.matches, p.weights, p.gresid, p.gepi}, 4}, pair, N, lane);
 
         // ---- pass 1: hsum = sum rbar_i x_i  and  ge = sum ebar_i d epi_i / d out ----
         float hs[9], ge[9];

@@ -19,6 +19,7 @@
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 #include "../../include/fepe_b200.h"
 #include "fepe_common.cuh"
@@ -27,7 +28,6 @@ namespace fepe {
 
 constexpr int kGemmBM = 128;
 constexpr int kGemmBK = 64;          // 64 bf16 = 128 B = one swizzle atom
-constexpr int kGemmStages = 4;
 constexpr int kGemmThreads = 256;
 
 __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
@@ -90,8 +90,11 @@ struct GemmParams {
     float* stats;          // [B, Co, 2] (sum, sum of squares), zeroed by the caller
 };
 
-template <int BN>
-__global__ void __launch_bounds__(kGemmThreads, 1)
+// STAGES = 4 with one CTA per SM, or STAGES = 2 with two CTAs per SM: in the second configuration the
+// epilogue of one CTA (TMEM -> bf16 tile -> statistics -> store) overlaps the main loop of the other, which is
+// what the thin layers (K = 64 / 128: two k-blocks of MMA, then a long epilogue) need.
+template <int BN, int STAGES>
+__global__ void __launch_bounds__(kGemmThreads, (STAGES <= 2) ? 2 : 1)
 fepe_mlp_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w,
                      const GemmParams p) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
@@ -100,10 +103,10 @@ fepe_mlp_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
     constexpr int kABytes = kGemmBM * kGemmBK * 2;       // 16 KB
     constexpr int kBBytes = BN * kGemmBK * 2;
     constexpr int kStageBytes = kABytes + kBBytes;
-    unsigned char* tile_y = smem + kGemmStages * kStageBytes;                     // [128][BN] bf16
+    unsigned char* tile_y = smem + STAGES * kStageBytes;                     // [128][BN] bf16
     uint64_t* full = reinterpret_cast<uint64_t*>(tile_y + kGemmBM * BN * 2);
-    uint64_t* empty = full + kGemmStages;
-    uint64_t* tmem_full = empty + kGemmStages;
+    uint64_t* empty = full + STAGES;
+    uint64_t* tmem_full = empty + STAGES;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
 
     const int warp = threadIdx.x >> 5;
@@ -113,7 +116,7 @@ fepe_mlp_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
     const int num_kb = p.K / kGemmBK;
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < kGemmStages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+        for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
         mbar_init(tmem_full, 1);
         fence_barrier_init();
     }
@@ -131,8 +134,8 @@ fepe_mlp_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
         // ---------------- TMA producer ----------------
         if (lane == 0) {
             for (int kb = 0; kb < num_kb; ++kb) {
-                const int s = kb % kGemmStages;
-                const uint32_t ph = static_cast<uint32_t>(kb / kGemmStages) & 1u;
+                const int s = kb % STAGES;
+                const uint32_t ph = static_cast<uint32_t>(kb / STAGES) & 1u;
                 mbar_wait(&empty[s], ph ^ 1u);
                 unsigned char* sa = smem + s * kStageBytes;
                 mbar_arrive_expect_tx(&full[s], kStageBytes);
@@ -147,8 +150,8 @@ fepe_mlp_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
         constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(BN >> 3) << 17) |
                                    (static_cast<uint32_t>(kGemmBM >> 4) << 24);
         for (int kb = 0; kb < num_kb; ++kb) {
-            const int s = kb % kGemmStages;
-            const uint32_t ph = static_cast<uint32_t>(kb / kGemmStages) & 1u;
+            const int s = kb % STAGES;
+            const uint32_t ph = static_cast<uint32_t>(kb / STAGES) & 1u;
             mbar_wait(&full[s], ph);
             tcgen05_fence_after();
             if (lane == 0) {                                 // one fixed thread issues every MMA and commit
@@ -195,9 +198,12 @@ fepe_mlp_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
     {
         const __nv_bfloat16* ty = reinterpret_cast<const __nv_bfloat16*>(tile_y);
         const int pair = m0 / p.Npad;
-        for (int col = threadIdx.x; col < BN; col += kGemmThreads) {
+        // every thread sums half a column (BN <= 128 columns x 2 halves = 256 threads)
+        for (int item = threadIdx.x; item < 2 * BN; item += kGemmThreads) {
+            const int col = item % BN, half = item / BN;
             float s1 = 0.f, s2 = 0.f;
-            for (int r = 0; r < kGemmBM; ++r) {
+#pragma unroll 8
+            for (int r = half * (kGemmBM / 2); r < (half + 1) * (kGemmBM / 2); ++r) {
                 const float y = __bfloat162float(ty[r * BN + ((col + 2 * r) % BN)]);
                 s1 += y;
                 s2 = fmaf(y, y, s2);
@@ -385,19 +391,20 @@ static bool make_map(CUtensorMap* map, const void* ptr, int rows, int K, int box
                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
-template <int BN>
+template <int BN, int STAGES>
 static int launch_gemm(const void* X, const void* W, const GemmParams& p, cudaStream_t stream) {
     CUtensorMap ma, mw;
     if (!make_map(&ma, X, p.M, p.K, kGemmBM) || !make_map(&mw, W, p.Co, p.K, BN)) return FEPE_E_NODEVICE;
-    constexpr int smem = kGemmStages * (kGemmBM * kGemmBK * 2 + BN * kGemmBK * 2) + kGemmBM * BN * 2 + 256 + 1024;
+    constexpr int smem = STAGES * (kGemmBM * kGemmBK * 2 + BN * kGemmBK * 2) + kGemmBM * BN * 2 + 256 + 1024;
     static bool configured = false;
     if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(fepe_mlp_gemm_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        cudaError_t e =
+            cudaFuncSetAttribute(fepe_mlp_gemm_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         if (e != cudaSuccess) return static_cast<int>(e);
         configured = true;
     }
     dim3 grid(p.Co / BN, p.M / kGemmBM);
-    fepe_mlp_gemm_kernel<BN><<<grid, kGemmThreads, smem, stream>>>(ma, mw, p);
+    fepe_mlp_gemm_kernel<BN, STAGES><<<grid, kGemmThreads, smem, stream>>>(ma, mw, p);
     return static_cast<int>(cudaGetLastError());
 }
 
@@ -412,8 +419,14 @@ int fepe_mlp_gemm(const void* X, const void* W, const float* bias, void* Y, floa
         (K % fepe::kGemmBK) != 0 || (Co % 64) != 0)
         return FEPE_E_BADARG;
     fepe::GemmParams p{B * Npad, K, Co, Npad, Nvalid, bias, static_cast<__nv_bfloat16*>(Y), stats};
-    if (Co % 128 == 0) return fepe::launch_gemm<128>(X, W, p, static_cast<cudaStream_t>(stream));
-    return fepe::launch_gemm<64>(X, W, p, static_cast<cudaStream_t>(stream));
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    // 2 stages / 2 CTAs per SM: the epilogue of one CTA overlaps the main loop of the other.  Measured faster
+    // than 4 stages / 1 CTA per SM on every layer (profiles/r1_mlp_timing.txt).  FEPE_MLP_STAGES=2|4 overrides.
+    int stages = 2;
+    if (const char* ev = getenv("FEPE_MLP_STAGES")) stages = (ev[0] == '2') ? 2 : 4;
+    if (Co % 128 == 0)
+        return stages == 2 ? fepe::launch_gemm<128, 2>(X, W, p, st) : fepe::launch_gemm<128, 4>(X, W, p, st);
+    return stages == 2 ? fepe::launch_gemm<64, 2>(X, W, p, st) : fepe::launch_gemm<64, 4>(X, W, p, st);
 }
 
 int fepe_mlp_norm(const void* Y, const float* stats, const float* gamma, const float* beta, void* X, int B, int Npad,

@@ -1,0 +1,25 @@
+"""compute-sanitizer target: every kernel once on small shapes (ragged and aligned N)."""
+import sys, os
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path[:0] = [ROOT, os.path.join(ROOT, "pytorch-deepfepe_b200")]
+import torch
+from fepe_b200 import ops, synth
+from fepe_b200.models import ErrorEstimator
+shapes = [(5, 333), (3, 37), (4, 1000)] if len(sys.argv) < 2 else [tuple(int(v) for v in a.split("x")) for a in sys.argv[1:]]
+for kern in ("ring", "small"):
+    os.environ["FEPE_FIT_KERNEL"] = kern
+    for B, N in shapes:
+        d = synth.make_batch(B, N, seed=1)
+        aff = ops.hw_affine(d["image_size"])
+        m = torch.from_numpy(d["matches_xy_ori"]).cuda()
+        w = torch.from_numpy(d["weights"]).cuda().requires_grad_(True)
+        F, r, e = ops.FitFunction.apply(m, w.reshape(B, N), *aff, 0.5)
+        (F.sum() + r.sum() + e.sum()).backward()
+        t = lambda k: torch.from_numpy(d[k]).cuda()
+        ops.pose_forward(F.detach(), t("Ks"), aff, t("q_cam"), t("t_cam"), t("delta_Rtijs_4_4"), t("pts1_virt"), t("pts2_virt"))
+ee = ErrorEstimator(4).cuda()
+ee.tensor_cores = True
+with torch.no_grad():
+    ee(torch.rand(2, 4, 333, device="cuda"))
+torch.cuda.synchronize()
+print("sanitizer target done")
