@@ -486,7 +486,7 @@ def run_c4(args):
     steps, warm = min(args.steps, 50), max(3, min(args.warmup, 10))
     with torch.no_grad():
         secs, t0, t1 = timed_loop([(lambda b=b: net(b)) for b in batches], steps, warm)
-        net.enable_tensor_core_mlp(False)
+        net.enable_tensor_core_mlp(False, False)
         secs32, _, _ = timed_loop([(lambda b=b: net(b)) for b in batches], max(3, steps // 10), 2)
     flop_per_pt = lambda cin: 2 * (cin * 64 + 64 * 128 + 128 * 1024 + 1024 * 512 + 512 * 256 + 256)
     flops = B * N * (flop_per_pt(4) + 4 * flop_per_pt(7))

@@ -106,7 +106,7 @@ int fepe_pose_fwd(const float* F, const float* K, int L, int B, float ax, float 
  * with Npad = N rounded up to 128 (padded rows are zero and excluded from the statistics); weights are
  * bf16 [Co, Ci] (Conv1d weight squeezed); accumulation is fp32 in tensor memory (tcgen05.mma).
  *   fepe_mlp_first  layer 1 from fp32 features X0 [B,N,Ci<=8]                -> Y [B*Npad,Co] + stats
- *   fepe_mlp_gemm   Y = X W^T + b (K % 64 == 0, Co % 64 == 0)                 -> Y + stats [B,Co,2]
+ *   fepe_mlp_gemm   Y = X W^T + b (K % 64 == 0, Co % 64 == 0)                 -> Y + stats [B,Co,2] (stats may be NULL)
  *   fepe_mlp_norm   X' = LeakyReLU(gamma (Y - mean) rstd + beta) from stats (biased variance, eps)
  *   fepe_mlp_last   logits = X w + b (Co = 1), weights = softmax over the N rows of each pair
  * `stats` must be zeroed by the caller before fepe_mlp_first / fepe_mlp_gemm (they accumulate with atomics).
@@ -119,6 +119,19 @@ int fepe_mlp_norm(const void* Y, const float* stats, const float* gamma, const f
                   int Nvalid, int Co, float eps, float slope, void* stream);
 int fepe_mlp_last(const void* X, const float* W, float bias, float* logits, float* weights, int B, int N, int Npad,
                   int Ci, void* stream);
+/* training path: weight gradient of one Conv1d(k=1): dW[Co,Ci] += dY[M,Co]^T X[M,Ci] on tcgen05 (bf16 operands read
+ * in place as MN-major tiles, fp32 accumulation, split over row slabs with atomics; dW zeroed by the caller). */
+int fepe_mlp_wgrad(const void* dY, const void* X, float* dW, int M, int Co, int Ci, void* stream);
+/* backward of InstanceNorm(affine) + LeakyReLU: from dX' (gradient of the block output), the saved block output
+ * X' (sign), the saved pre-norm Y and the forward statistics: A[B,Co,2] = (sum dZ, sum dZ Yhat) (zeroed by the
+ * caller; dgamma = sum_b A[..,1], dbeta = sum_b A[..,0]) and dY [B*Npad,Co] bf16 (padded rows zero).  The data
+ * gradient dX = dY W then is fepe_mlp_gemm with W^T as the weight operand and stats = NULL. */
+int fepe_mlp_normbwd(const void* dX, const void* Xp, const void* Y, const float* stats, const float* gamma, float* A,
+                     void* dY, int B, int Npad, int Nvalid, int Co, float eps, float slope, void* stream);
+int fepe_mlp_last_bwd(const float* dlogits, const void* X, const float* W, void* dX, float* dW, float* db, int B, int N,
+                      int Npad, int Ci, void* stream);
+int fepe_mlp_first_bwd(const void* dY, const float* X0, const float* W, float* dX0, float* dW, int B, int N, int Npad,
+                       int Ci, int Co, void* stream);
 
 #ifdef __cplusplus
 }

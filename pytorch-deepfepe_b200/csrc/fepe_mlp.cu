@@ -198,6 +198,7 @@ fepe_mlp_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
     {
         const __nv_bfloat16* ty = reinterpret_cast<const __nv_bfloat16*>(tile_y);
         const int pair = m0 / p.Npad;
+        if (p.stats != nullptr) {        // (the data-gradient GEMM of the backward pass needs no statistics)
         // every thread sums half a column (BN <= 128 columns x 2 halves = 256 threads)
         for (int item = threadIdx.x; item < 2 * BN; item += kGemmThreads) {
             const int col = item % BN, half = item / BN;
@@ -210,6 +211,7 @@ fepe_mlp_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
             }
             atomicAdd(p.stats + (static_cast<size_t>(pair) * p.Co + n0 + col) * 2, s1);
             atomicAdd(p.stats + (static_cast<size_t>(pair) * p.Co + n0 + col) * 2 + 1, s2);
+        }
         }
         // store: each row of the tile is BN*2 bytes contiguous in Y
         for (int idx = threadIdx.x; idx < kGemmBM * (BN / 2); idx += kGemmThreads) {
@@ -362,6 +364,301 @@ __global__ void fepe_mlp_last_kernel(const __nv_bfloat16* __restrict__ X, const 
 }
 
 // ------------------------------------------------------------------------------------------------
+// Backward of  X' = LeakyReLU(gamma * Yhat + beta),  Yhat = (Y - mean) rstd  (InstanceNorm over the N rows
+// of a pair).  With dZ = dX' * (X' > 0 ? 1 : slope):
+//   A1[b,c] = sum_n dZ,  A2[b,c] = sum_n dZ Yhat           (fepe_mlp_normbwd_reduce_kernel)
+//   dY = rstd gamma (dZ - A1/N - Yhat A2/N)                 (fepe_mlp_normbwd_apply_kernel)
+//   dgamma[c] = sum_b A2, dbeta[c] = sum_b A1 (host side, tiny);  the bias of the preceding conv gets an
+//   exactly zero gradient (sum_n dY = 0): InstanceNorm cancels it.
+// One CTA per (128-row slab, pair); a thread owns 8 fixed channels and walks rows, so sums stay in registers.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void unpack8(const uint4 v, float (&o)[8]) {
+    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const __nv_bfloat162 t = *reinterpret_cast<const __nv_bfloat162*>(&w[k]);
+        o[2 * k] = __low2float(t);
+        o[2 * k + 1] = __high2float(t);
+    }
+}
+
+__global__ void __launch_bounds__(256) fepe_mlp_normbwd_reduce_kernel(
+    const __nv_bfloat16* __restrict__ dX, const __nv_bfloat16* __restrict__ Xp, const __nv_bfloat16* __restrict__ Y,
+    const float* __restrict__ stats, float* __restrict__ A, int Co, int Npad, int Nvalid, float eps, float slope) {
+    extern __shared__ float sm[];            // [Co] mean, [Co] rstd, [2*Co] accumulators
+    float* mean = sm;
+    float* rstd = sm + Co;
+    float* acc = sm + 2 * Co;
+    const int b = blockIdx.y, r0 = blockIdx.x * 128;
+    const float invN = 1.0f / static_cast<float>(Nvalid);
+    for (int c = threadIdx.x; c < Co; c += 256) {
+        const float s1 = stats[(static_cast<size_t>(b) * Co + c) * 2], s2 = stats[(static_cast<size_t>(b) * Co + c) * 2 + 1];
+        const float mu = s1 * invN;
+        mean[c] = mu;
+        rstd[c] = rsqrtf(fmaxf(s2 * invN - mu * mu, 0.f) + eps);
+        acc[2 * c] = 0.f;
+        acc[2 * c + 1] = 0.f;
+    }
+    __syncthreads();
+    const int vpr = Co / 8;                          // vectors per row (divides 256)
+    const int v = threadIdx.x % vpr, rg = threadIdx.x / vpr, nrg = 256 / vpr;
+    const int c0 = v * 8;
+    float a1[8], a2[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { a1[k] = 0.f; a2[k] = 0.f; }
+    const size_t base = (static_cast<size_t>(b) * Npad + r0) * Co + c0;
+    for (int r = rg; r < 128 && r0 + r < Nvalid; r += nrg) {
+        float g[8], xp[8], y[8];
+        unpack8(*reinterpret_cast<const uint4*>(dX + base + static_cast<size_t>(r) * Co), g);
+        unpack8(*reinterpret_cast<const uint4*>(Xp + base + static_cast<size_t>(r) * Co), xp);
+        unpack8(*reinterpret_cast<const uint4*>(Y + base + static_cast<size_t>(r) * Co), y);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const float dz = xp[k] > 0.f ? g[k] : slope * g[k];
+            a1[k] += dz;
+            a2[k] = fmaf(dz, (y[k] - mean[c0 + k]) * rstd[c0 + k], a2[k]);
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { atomicAdd(&acc[2 * (c0 + k)], a1[k]); atomicAdd(&acc[2 * (c0 + k) + 1], a2[k]); }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 2 * Co; i += 256) atomicAdd(A + static_cast<size_t>(b) * Co * 2 + i, acc[i]);
+}
+
+__global__ void __launch_bounds__(256) fepe_mlp_normbwd_apply_kernel(
+    const __nv_bfloat16* __restrict__ dX, const __nv_bfloat16* __restrict__ Xp, const __nv_bfloat16* __restrict__ Y,
+    const float* __restrict__ stats, const float* __restrict__ A, const float* __restrict__ gamma,
+    __nv_bfloat16* __restrict__ dY, int Co, int Npad, int Nvalid, float eps, float slope) {
+    extern __shared__ float sm[];            // per channel: mean, rstd, k0 = rstd*gamma, k1 = A1/N, k2 = A2/N
+    float* mean = sm; float* rstd = sm + Co; float* k0 = sm + 2 * Co; float* k1 = sm + 3 * Co; float* k2 = sm + 4 * Co;
+    const int b = blockIdx.y, r0 = blockIdx.x * 128;
+    const float invN = 1.0f / static_cast<float>(Nvalid);
+    for (int c = threadIdx.x; c < Co; c += 256) {
+        const float s1 = stats[(static_cast<size_t>(b) * Co + c) * 2], s2 = stats[(static_cast<size_t>(b) * Co + c) * 2 + 1];
+        const float mu = s1 * invN;
+        const float rs = rsqrtf(fmaxf(s2 * invN - mu * mu, 0.f) + eps);
+        mean[c] = mu; rstd[c] = rs; k0[c] = rs * gamma[c];
+        k1[c] = A[(static_cast<size_t>(b) * Co + c) * 2] * invN;
+        k2[c] = A[(static_cast<size_t>(b) * Co + c) * 2 + 1] * invN;
+    }
+    __syncthreads();
+    const int vpr = Co / 8;
+    const size_t base = (static_cast<size_t>(b) * Npad + r0) * Co;
+    for (int idx = threadIdx.x; idx < 128 * vpr; idx += 256) {
+        const int r = idx / vpr, c0 = (idx % vpr) * 8;
+        uint4 out = make_uint4(0u, 0u, 0u, 0u);
+        if (r0 + r < Nvalid) {
+            float g[8], xp[8], y[8];
+            const size_t off = base + static_cast<size_t>(r) * Co + c0;
+            unpack8(*reinterpret_cast<const uint4*>(dX + off), g);
+            unpack8(*reinterpret_cast<const uint4*>(Xp + off), xp);
+            unpack8(*reinterpret_cast<const uint4*>(Y + off), y);
+            uint32_t o[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                float d[2];
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const int c = c0 + 2 * k + h;
+                    const float dz = xp[2 * k + h] > 0.f ? g[2 * k + h] : slope * g[2 * k + h];
+                    const float yh = (y[2 * k + h] - mean[c]) * rstd[c];
+                    d[h] = k0[c] * (dz - k1[c] - yh * k2[c]);
+                }
+                const __nv_bfloat162 t = __floats2bfloat162_rn(d[0], d[1]);
+                o[k] = *reinterpret_cast<const uint32_t*>(&t);
+            }
+            out = make_uint4(o[0], o[1], o[2], o[3]);
+        }
+        *reinterpret_cast<uint4*>(dY + base + static_cast<size_t>(r) * Co + c0) = out;
+    }
+}
+
+// Backward of the last layer  logit[m] = X[m,:] . w + b :  dX[m,k] = dl[m] w[k],  dw[k] += sum_m dl[m] X[m,k],
+// db += sum_m dl[m].  One CTA per (128-row slab, pair), thread = channel (Ci = 256).
+__global__ void __launch_bounds__(256) fepe_mlp_last_bwd_kernel(const float* __restrict__ dlogits,
+                                                                const __nv_bfloat16* __restrict__ X,
+                                                                const float* __restrict__ W,
+                                                                __nv_bfloat16* __restrict__ dX, float* __restrict__ dW,
+                                                                float* __restrict__ db, int N, int Npad, int Ci) {
+    __shared__ float dl[128];
+    const int b = blockIdx.y, r0 = blockIdx.x * 128;
+    if (threadIdx.x < 128) dl[threadIdx.x] = (r0 + threadIdx.x < N) ? dlogits[static_cast<size_t>(b) * N + r0 + threadIdx.x] : 0.f;
+    __syncthreads();
+    for (int k = threadIdx.x; k < Ci; k += 256) {
+        const float wk = W[k];
+        float acc = 0.f;
+        const size_t base = (static_cast<size_t>(b) * Npad + r0) * Ci + k;
+        for (int r = 0; r < 128; ++r) {
+            acc = fmaf(dl[r], __bfloat162float(X[base + static_cast<size_t>(r) * Ci]), acc);
+            dX[base + static_cast<size_t>(r) * Ci] = __float2bfloat16(dl[r] * wk);
+        }
+        atomicAdd(dW + k, acc);
+    }
+    if (threadIdx.x == 0) {
+        float s = 0.f;
+        for (int r = 0; r < 128; ++r) s += dl[r];
+        atomicAdd(db, s);
+    }
+}
+
+// Backward of the first layer (Ci <= 8, Co = 64): dX0[b,n,ci] = sum_c dY[m,c] W[c,ci] (fp32), dW[c,ci] += sum_m dY[m,c] X0[m,ci].
+__global__ void __launch_bounds__(128) fepe_mlp_first_bwd_kernel(const __nv_bfloat16* __restrict__ dY,
+                                                                 const float* __restrict__ X0,
+                                                                 const float* __restrict__ W, float* __restrict__ dX0,
+                                                                 float* __restrict__ dW, int N, int Npad, int Ci, int Co) {
+    __shared__ float w_s[64 * 8];
+    __shared__ float dy_s[128][64 + 1];
+    __shared__ float x_s[128][8];
+    const int b = blockIdx.y, r0 = blockIdx.x * 128, r = r0 + threadIdx.x;
+    for (int i = threadIdx.x; i < Co * Ci; i += 128) w_s[i] = W[i];
+    const bool valid = r < N;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) x_s[threadIdx.x][k] = (valid && k < Ci) ? X0[(static_cast<size_t>(b) * N + r) * Ci + k] : 0.f;
+    for (int c = 0; c < Co; ++c)
+        dy_s[threadIdx.x][c] = valid ? __bfloat162float(dY[(static_cast<size_t>(b) * Npad + r) * Co + c]) : 0.f;
+    __syncthreads();
+    if (valid) {
+        float g[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) g[k] = 0.f;
+        for (int c = 0; c < Co; ++c) {
+            const float d = dy_s[threadIdx.x][c];
+#pragma unroll
+            for (int k = 0; k < 8; ++k)
+                if (k < Ci) g[k] = fmaf(d, w_s[c * Ci + k], g[k]);
+        }
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+            if (k < Ci) dX0[(static_cast<size_t>(b) * N + r) * Ci + k] = g[k];
+    }
+    for (int o = threadIdx.x; o < Co * Ci; o += 128) {
+        const int c = o / Ci, k = o % Ci;
+        float acc = 0.f;
+        for (int rr = 0; rr < 128; ++rr) acc = fmaf(dy_s[rr][c], x_s[rr][k], acc);
+        atomicAdd(dW + o, acc);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Weight gradient: dW[Co,Ci] += dY[M,Co]^T . X[M,Ci]   (split over K = M slabs, fp32 atomics).
+// Both operands are "MN-major" for the tensor core: the GEMM-K index (the row m) is the strided one and
+// the M / N index (channel) is contiguous -- exactly the row-major activation tensors, so no transposed
+// copies exist.  A TMA box is 64 rows x 64 channels (128 B, SWIZZLE_128B); a 128-channel operand tile is
+// two such boxes 8192 B apart (the descriptor's leading-byte-offset), 8-row groups are 1024 B apart
+// (stride-byte-offset); one MMA consumes 16 rows = 2048 B.   (canonical layout: cute/atom/mma_traits_sm100.hpp,
+// LayoutType::B128 MN-major  ((8,n),(8,k)):((1,LBO),(8,SBO)) in 16-byte units.)
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint64_t umma_desc_mn_sw128(const void* smem_ptr) {
+    const uint64_t addr = static_cast<uint64_t>(smem_u32(smem_ptr));
+    return ((addr >> 4) & 0x3FFFull) | (static_cast<uint64_t>(8192 >> 4) << 16) | (static_cast<uint64_t>(1024 >> 4) << 32) |
+           (1ull << 46) | (2ull << 61);
+}
+
+struct WgradParams {
+    int M, Co, Ci;
+    int rows_per_slab;       // multiple of 64
+    float* dW;               // [Co, Ci] fp32, accumulated with atomics (zeroed by the caller)
+};
+
+template <int BN>
+__global__ void __launch_bounds__(kGemmThreads, 2)
+fepe_mlp_wgrad_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_constant__ CUtensorMap map_x,
+                      const WgradParams p) {
+    constexpr int STAGES = 3;
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    constexpr int kABytes = 64 * 128 * 2;                 // 64 rows x 128 channels (two 64x64 boxes)
+    constexpr int kBBytes = 64 * BN * 2;
+    constexpr int kStageBytes = kABytes + kBBytes;
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem + STAGES * kStageBytes);
+    uint64_t* empty = full + STAGES;
+    uint64_t* tmem_full = empty + STAGES;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int ci0 = blockIdx.x * BN;
+    const int co0 = blockIdx.y * 128;
+    const int row0 = blockIdx.z * p.rows_per_slab;
+    int rows = p.M - row0;
+    if (rows > p.rows_per_slab) rows = p.rows_per_slab;
+    const int num_kb = rows / 64;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+        mbar_init(tmem_full, 1);
+        fence_barrier_init();
+    }
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                     "r"(static_cast<uint32_t>(BN)));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    tcgen05_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            for (int kb = 0; kb < num_kb; ++kb) {
+                const int s = kb % STAGES;
+                const uint32_t ph = static_cast<uint32_t>(kb / STAGES) & 1u;
+                mbar_wait(&empty[s], ph ^ 1u);
+                unsigned char* sa = smem + s * kStageBytes;
+                mbar_arrive_expect_tx(&full[s], kStageBytes);
+                const int r = row0 + kb * 64;
+                tma_load_2d(sa, &map_dy, co0, r, &full[s]);
+                tma_load_2d(sa + 8192, &map_dy, co0 + 64, r, &full[s]);
+#pragma unroll
+                for (int j = 0; j < BN / 64; ++j) tma_load_2d(sa + kABytes + j * 8192, &map_x, ci0 + j * 64, r, &full[s]);
+            }
+        }
+    } else if (warp == 1) {
+        // D = f32, A = B = bf16, BOTH MN-major (bits 15, 16), N>>3 at bit 17, M>>4 at bit 24
+        constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) |
+                                   (static_cast<uint32_t>(BN >> 3) << 17) | (static_cast<uint32_t>(128 >> 4) << 24);
+        for (int kb = 0; kb < num_kb; ++kb) {
+            const int s = kb % STAGES;
+            const uint32_t ph = static_cast<uint32_t>(kb / STAGES) & 1u;
+            mbar_wait(&full[s], ph);
+            tcgen05_fence_after();
+            if (lane == 0) {
+                const unsigned char* sa = smem + s * kStageBytes;
+                const uint64_t da = umma_desc_mn_sw128(sa);
+                const uint64_t db = umma_desc_mn_sw128(sa + kABytes);
+#pragma unroll
+                for (int k = 0; k < 4; ++k)      // 16 rows = 2048 B per MMA
+                    umma_bf16(tmem_base, da + static_cast<uint64_t>(k * 128), db + static_cast<uint64_t>(k * 128), idesc,
+                              (kb | k) != 0 ? 1u : 0u);
+                tcgen05_commit(&empty[s]);
+                if (kb == num_kb - 1) tcgen05_commit(tmem_full);
+            }
+            __syncwarp();
+        }
+    } else if (warp >= 4 && num_kb > 0) {
+        const int q = warp & 3;
+        const int row = q * 32 + lane;                         // output row = channel co0 + row
+        mbar_wait(tmem_full, 0);
+        tcgen05_fence_after();
+        float* out = p.dW + static_cast<size_t>(co0 + row) * p.Ci + ci0;
+#pragma unroll 1
+        for (int c = 0; c < BN; c += 32) {
+            uint32_t v[32];
+            tmem_ld32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(c), v);
+#pragma unroll
+            for (int j = 0; j < 32; ++j) atomicAdd(out + c + j, __uint_as_float(v[j]));
+        }
+        tcgen05_fence_before();
+    }
+    __syncthreads();
+    if (warp == 2) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
+                     "r"(static_cast<uint32_t>(BN)));
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -378,7 +675,7 @@ static EncodeTiledFn get_encode() {
     return fn;
 }
 
-// 2-D bf16 row-major [rows, K] tensor, box = 64 (K) x box_rows, 128-byte swizzle
+// 2-D bf16 row-major [rows, K] tensor, box = 64 (contiguous dim) x box_rows, 128-byte swizzle
 static bool make_map(CUtensorMap* map, const void* ptr, int rows, int K, int box_rows) {
     EncodeTiledFn enc = get_encode();
     if (enc == nullptr) return false;
@@ -408,14 +705,79 @@ static int launch_gemm(const void* X, const void* W, const GemmParams& p, cudaSt
     return static_cast<int>(cudaGetLastError());
 }
 
+template <int BN>
+static int launch_wgrad(const void* dY, const void* X, const WgradParams& p, int slabs, cudaStream_t stream) {
+    CUtensorMap my, mx;
+    if (!make_map(&my, dY, p.M, p.Co, 64) || !make_map(&mx, X, p.M, p.Ci, 64)) return FEPE_E_NODEVICE;
+    constexpr int smem = 3 * (64 * 128 * 2 + 64 * BN * 2) + 256 + 1024;
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(fepe_mlp_wgrad_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e != cudaSuccess) return static_cast<int>(e);
+        configured = true;
+    }
+    dim3 grid(p.Ci / BN, p.Co / 128, slabs);
+    fepe_mlp_wgrad_kernel<BN><<<grid, kGemmThreads, smem, stream>>>(my, mx, p);
+    return static_cast<int>(cudaGetLastError());
+}
+
 }  // namespace fepe
 
 extern "C" {
 
+int fepe_mlp_normbwd(const void* dX, const void* Xp, const void* Y, const float* stats, const float* gamma, float* A,
+                     void* dY, int B, int Npad, int Nvalid, int Co, float eps, float slope, void* stream) {
+    if (!dX || !Xp || !Y || !stats || !gamma || !A || !dY || B <= 0 || (Co % 64) != 0 || (Npad % 128) != 0)
+        return FEPE_E_BADARG;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    dim3 grid(Npad / 128, B);
+    fepe::fepe_mlp_normbwd_reduce_kernel<<<grid, 256, 4 * Co * sizeof(float), st>>>(
+        static_cast<const __nv_bfloat16*>(dX), static_cast<const __nv_bfloat16*>(Xp), static_cast<const __nv_bfloat16*>(Y),
+        stats, A, Co, Npad, Nvalid, eps, slope);
+    fepe::fepe_mlp_normbwd_apply_kernel<<<grid, 256, 5 * Co * sizeof(float), st>>>(
+        static_cast<const __nv_bfloat16*>(dX), static_cast<const __nv_bfloat16*>(Xp), static_cast<const __nv_bfloat16*>(Y),
+        stats, A, gamma, static_cast<__nv_bfloat16*>(dY), Co, Npad, Nvalid, eps, slope);
+    return static_cast<int>(cudaGetLastError());
+}
+
+int fepe_mlp_last_bwd(const float* dlogits, const void* X, const float* W, void* dX, float* dW, float* db, int B, int N,
+                      int Npad, int Ci, void* stream) {
+    if (!dlogits || !X || !W || !dX || !dW || !db || B <= 0 || (Npad % 128) != 0) return FEPE_E_BADARG;
+    dim3 grid(Npad / 128, B);
+    fepe::fepe_mlp_last_bwd_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        dlogits, static_cast<const __nv_bfloat16*>(X), W, static_cast<__nv_bfloat16*>(dX), dW, db, N, Npad, Ci);
+    return static_cast<int>(cudaGetLastError());
+}
+
+int fepe_mlp_first_bwd(const void* dY, const float* X0, const float* W, float* dX0, float* dW, int B, int N, int Npad,
+                       int Ci, int Co, void* stream) {
+    if (!dY || !X0 || !W || !dX0 || !dW || B <= 0 || Ci <= 0 || Ci > 8 || Co != 64 || (Npad % 128) != 0) return FEPE_E_BADARG;
+    dim3 grid(Npad / 128, B);
+    fepe::fepe_mlp_first_bwd_kernel<<<grid, 128, 0, static_cast<cudaStream_t>(stream)>>>(
+        static_cast<const __nv_bfloat16*>(dY), X0, W, dX0, dW, N, Npad, Ci, Co);
+    return static_cast<int>(cudaGetLastError());
+}
+
+// dW[Co,Ci] += dY[M,Co]^T X[M,Ci]  (bf16 operands, fp32 accumulation; dW zeroed by the caller)
+int fepe_mlp_wgrad(const void* dY, const void* X, float* dW, int M, int Co, int Ci, void* stream) {
+    if (!dY || !X || !dW || M <= 0 || (M % 64) != 0 || (Co % 128) != 0 || (Ci % 64) != 0) return FEPE_E_BADARG;
+    const int bn = (Ci % 128 == 0) ? 128 : 64;
+    const int tiles = (Co / 128) * (Ci / bn);
+    int slabs = (592 + tiles - 1) / tiles;                    // ~4 waves of 148 SMs
+    const int max_slabs = M / 64;
+    if (slabs > max_slabs) slabs = max_slabs;
+    if (slabs < 1) slabs = 1;
+    int rows_per_slab = ((M + slabs - 1) / slabs + 63) / 64 * 64;
+    slabs = (M + rows_per_slab - 1) / rows_per_slab;
+    fepe::WgradParams p{M, Co, Ci, rows_per_slab, dW};
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    return bn == 128 ? fepe::launch_wgrad<128>(dY, X, p, slabs, st) : fepe::launch_wgrad<64>(dY, X, p, slabs, st);
+}
+
 // Y = X W^T + b (bf16 in / out, fp32 accumulate on tcgen05) with per-(pair, channel) statistics.
 int fepe_mlp_gemm(const void* X, const void* W, const float* bias, void* Y, float* stats, int B, int Npad,
                   int Nvalid, int K, int Co, void* stream) {
-    if (!X || !W || !bias || !Y || !stats || B <= 0 || Npad <= 0 || (Npad % fepe::kGemmBM) != 0 || Nvalid > Npad ||
+    if (!X || !W || !bias || !Y || B <= 0 || Npad <= 0 || (Npad % fepe::kGemmBM) != 0 || Nvalid > Npad ||
         (K % fepe::kGemmBK) != 0 || (Co % 64) != 0)
         return FEPE_E_BADARG;
     fepe::GemmParams p{B * Npad, K, Co, Npad, Nvalid, bias, static_cast<__nv_bfloat16*>(Y), stats};

@@ -1,9 +1,13 @@
 """Tensor-core (tcgen05) inference path of ErrorEstimator: drives the fepe_mlp_* entry points of the
 C ABI (include/fepe_b200.h).  bf16 activations and weights, fp32 accumulation and statistics.
 
-The training path keeps PyTorch's fp32 kernels (autograd); this path is used under torch.no_grad()
-when a module was switched on with ``ErrorEstimator.tensor_cores = True`` /
-``DeepFNet.enable_tensor_core_mlp()``.
+Inference (torch.no_grad()): ``TensorCoreMLP.__call__`` -- ping-pong activation buffers, softmax fused.
+Training: ``TensorCoreMLPFunction`` (torch.autograd.Function) -- the same forward kernels keeping every
+layer's pre-norm output Y and block output X', and a backward made of fepe_mlp_last_bwd, fepe_mlp_normbwd
+(InstanceNorm + LeakyReLU adjoint), fepe_mlp_wgrad (MN-major tcgen05 GEMM, dW = dY^T X), the data-gradient
+GEMM (fepe_mlp_gemm with W^T) and fepe_mlp_first_bwd.  Both are opt-in:
+``DeepFNet.enable_tensor_core_mlp(inference=True, training=False)``; fp32 PyTorch kernels stay the default
+and the parity reference.
 """
 from __future__ import annotations
 
@@ -88,3 +92,109 @@ class TensorCoreMLP:
             _lib.check(lib.fepe_mlp_last(xa.data_ptr(), self.w_last.data_ptr(), self.b_last, logits.data_ptr(),
                                          weights.data_ptr(), B, N, Npad, 256, st), "fepe_mlp_last")
         return logits, weights
+
+
+class TensorCoreMLPFunction(torch.autograd.Function):
+    """logits = ErrorEstimator(x) with bf16 tensor-core GEMMs in forward AND backward.
+
+    forward(x [B,Cin,N] fp32, w1,b1,g1,be1, ..., w5,b5,g5,be5, w6,b6) -> logits [B,1,N] fp32.
+    Parameter order = the module's own (conv weight [Co,Ci,1], conv bias, norm weight, norm bias) x 5, then the
+    last conv's weight and bias."""
+
+    @staticmethod
+    def forward(ctx, x, *params):
+        lib = _lib.lib()
+        B, Cin, N = x.shape
+        Npad = (N + 127) // 128 * 128
+        dev = x.device
+        st = torch.cuda.current_stream().cuda_stream
+        M = B * Npad
+        convw = [params[4 * i] for i in range(5)] + [params[20]]
+        convb = [params[4 * i + 1] for i in range(5)] + [params[21]]
+        gam = [params[4 * i + 2].detach().float().contiguous() for i in range(5)]
+        bet = [params[4 * i + 3].detach().float().contiguous() for i in range(5)]
+        x0 = x.detach().permute(0, 2, 1).contiguous().float()
+        w0 = convw[0].detach().reshape(64, Cin).float().contiguous()
+        wb = [None] + [convw[i].detach().reshape(_CH[i], _CH[i - 1]).to(torch.bfloat16).contiguous() for i in range(1, 5)]
+        bias = [b.detach().float().contiguous() for b in convb]
+        w_last = convw[5].detach().reshape(256).float().contiguous()
+        Ys = [torch.empty(M, c, dtype=torch.bfloat16, device=dev) for c in _CH]
+        Xs = [torch.empty(M, c, dtype=torch.bfloat16, device=dev) for c in _CH]
+        stats = [torch.zeros(B, c, 2, dtype=torch.float32, device=dev) for c in _CH]
+        eps, slope = 1e-5, 0.01
+        with torch.cuda.device(dev):
+            _lib.check(lib.fepe_mlp_first(x0.data_ptr(), w0.data_ptr(), bias[0].data_ptr(), Ys[0].data_ptr(),
+                                          stats[0].data_ptr(), B, N, Npad, Cin, 64, st), "fepe_mlp_first")
+            for i in range(5):
+                if i > 0:
+                    _lib.check(lib.fepe_mlp_gemm(Xs[i - 1].data_ptr(), wb[i].data_ptr(), bias[i].data_ptr(),
+                                                 Ys[i].data_ptr(), stats[i].data_ptr(), B, Npad, N, _CH[i - 1], _CH[i],
+                                                 st), "fepe_mlp_gemm")
+                _lib.check(lib.fepe_mlp_norm(Ys[i].data_ptr(), stats[i].data_ptr(), gam[i].data_ptr(), bet[i].data_ptr(),
+                                             Xs[i].data_ptr(), B, Npad, N, _CH[i], eps, slope, st), "fepe_mlp_norm")
+            logits = torch.empty(B, 1, N, dtype=torch.float32, device=dev)
+            scratch = torch.empty(B, 1, N, dtype=torch.float32, device=dev)
+            _lib.check(lib.fepe_mlp_last(Xs[4].data_ptr(), w_last.data_ptr(), float(bias[5].item()), logits.data_ptr(),
+                                         scratch.data_ptr(), B, N, Npad, 256, st), "fepe_mlp_last")
+        ctx.dims = (B, Cin, N, Npad)
+        ctx.saved = (x0, w0, wb, w_last, gam, Ys, Xs, stats)
+        ctx.param_shapes = [p.shape for p in params]
+        return logits
+
+    @staticmethod
+    def backward(ctx, dlogits):
+        lib = _lib.lib()
+        B, Cin, N, Npad = ctx.dims
+        x0, w0, wb, w_last, gam, Ys, Xs, stats = ctx.saved
+        dev = x0.device
+        st = torch.cuda.current_stream().cuda_stream
+        M = B * Npad
+        eps, slope = 1e-5, 0.01
+        dl = dlogits.detach().reshape(B, N).float().contiguous()
+        grads = [None] * 22
+        zeros_b = lambda c: torch.zeros(c, dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            dX = torch.empty(M, 256, dtype=torch.bfloat16, device=dev)
+            dw6, db6 = zeros_b(256), zeros_b(1)
+            _lib.check(lib.fepe_mlp_last_bwd(dl.data_ptr(), Xs[4].data_ptr(), w_last.data_ptr(), dX.data_ptr(),
+                                             dw6.data_ptr(), db6.data_ptr(), B, N, Npad, 256, st), "fepe_mlp_last_bwd")
+            grads[20], grads[21] = dw6.reshape(1, 256, 1), db6
+            for i in range(4, -1, -1):
+                c = _CH[i]
+                A = torch.zeros(B, c, 2, dtype=torch.float32, device=dev)
+                dY = torch.empty(M, c, dtype=torch.bfloat16, device=dev)
+                _lib.check(lib.fepe_mlp_normbwd(dX.data_ptr(), Xs[i].data_ptr(), Ys[i].data_ptr(), stats[i].data_ptr(),
+                                                gam[i].data_ptr(), A.data_ptr(), dY.data_ptr(), B, Npad, N, c, eps, slope,
+                                                st), "fepe_mlp_normbwd")
+                grads[4 * i + 2] = A[:, :, 1].sum(0)          # dgamma
+                grads[4 * i + 3] = A[:, :, 0].sum(0)          # dbeta
+                grads[4 * i + 1] = zeros_b(c)                  # conv bias before InstanceNorm: exactly zero gradient
+                if i > 0:
+                    ci = _CH[i - 1]
+                    dW = torch.zeros(c, ci, dtype=torch.float32, device=dev)
+                    _lib.check(lib.fepe_mlp_wgrad(dY.data_ptr(), Xs[i - 1].data_ptr(), dW.data_ptr(), M, c, ci, st),
+                               "fepe_mlp_wgrad")
+                    grads[4 * i] = dW.reshape(c, ci, 1)
+                    wt = wb[i].t().contiguous()                # [ci, c]: the data-gradient GEMM's "weight"
+                    dXn = torch.empty(M, ci, dtype=torch.bfloat16, device=dev)
+                    _lib.check(lib.fepe_mlp_gemm(dY.data_ptr(), wt.data_ptr(), zeros_b(ci).data_ptr(), dXn.data_ptr(),
+                                                 None, B, Npad, Npad, c, ci, st), "fepe_mlp_gemm(dgrad)")
+                    dX = dXn
+                else:
+                    dW = torch.zeros(64, Cin, dtype=torch.float32, device=dev)
+                    dx0 = torch.zeros(B, N, Cin, dtype=torch.float32, device=dev)
+                    _lib.check(lib.fepe_mlp_first_bwd(dY.data_ptr(), x0.data_ptr(), w0.data_ptr(), dx0.data_ptr(),
+                                                      dW.data_ptr(), B, N, Npad, Cin, 64, st), "fepe_mlp_first_bwd")
+                    grads[0] = dW.reshape(64, Cin, 1)
+                    gx = dx0.permute(0, 2, 1).contiguous()
+        return (gx,) + tuple(grads)
+
+
+def module_params(fw: nn.Sequential):
+    """The 22 parameters of an ErrorEstimator in the order TensorCoreMLPFunction expects."""
+    convs = [m for m in fw if isinstance(m, nn.Conv1d)]
+    norms = [m for m in fw if isinstance(m, nn.InstanceNorm1d)]
+    out = []
+    for i in range(5):
+        out += [convs[i].weight, convs[i].bias, norms[i].weight, norms[i].bias]
+    return out + [convs[5].weight, convs[5].bias]

@@ -98,11 +98,13 @@ class DeepFNet(nn.Module):
         self.norm_HW = NormalizeAndExpand_HW(self.image_size, is_cuda, is_test)
         self.fit = Fit(is_cuda, is_test, if_cpu_svd)
 
-    def enable_tensor_core_mlp(self, flag: bool = True):
-        """Run both weight networks on the tcgen05 bf16 path when called under torch.no_grad() (inference)."""
+    def enable_tensor_core_mlp(self, inference: bool = True, training: bool = False):
+        """Run both weight networks on the tcgen05 bf16 path: under torch.no_grad() (`inference`) and / or under
+        autograd with the tensor-core backward (`training`).  fp32 PyTorch kernels remain the default."""
         for net in (self.input_weights, self.update_weights):
             if isinstance(net, ErrorEstimator):
-                net.tensor_cores = bool(flag)
+                net.tensor_cores = bool(inference)
+                net.tensor_cores_training = bool(training)
         return self
 
     def get_input(self, data_batch, offsets=None, iter=None):

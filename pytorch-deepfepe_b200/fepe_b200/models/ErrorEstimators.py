@@ -27,6 +27,7 @@ class ErrorEstimator(nn.Module):
         layers.append(nn.Conv1d(256, output_size, kernel_size=1, bias=True))
         self.fw = nn.Sequential(*layers)
         self.tensor_cores = False       # opt-in: bf16 tcgen05 path under torch.no_grad() (fepe_b200/mlp_tc.py)
+        self.tensor_cores_training = False   # opt-in: tcgen05 forward AND backward under autograd
         self._tc = None
         self.last_softmax = None        # softmax over N of the last tensor-core evaluation (fused in its last kernel)
 
@@ -39,6 +40,10 @@ class ErrorEstimator(nn.Module):
             logits, self.last_softmax = self._tc(data.float())
             return logits
         self.last_softmax = None
+        if (self.tensor_cores_training and torch.is_grad_enabled() and data.is_cuda and self.fw[-1].out_channels == 1
+                and data.shape[1] <= 8):
+            from ..mlp_tc import TensorCoreMLPFunction, module_params
+            return TensorCoreMLPFunction.apply(data.float(), *module_params(self.fw))
         # the reference computes these 1x1 convolutions in fp32 (torch 1.3 had no TF32); keep cuDNN from
         # silently dropping to TF32 so that weights / logits match it to fp32 accuracy
         with torch.backends.cudnn.flags(enabled=True, allow_tf32=False):
