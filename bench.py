@@ -558,26 +558,37 @@ def run_c5(args):
         return ev
 
     steps, warm = min(args.steps, 30), max(3, min(args.warmup, 5))
-    for _ in range(warm):
-        step()
-    torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    evs = [step() for _ in range(steps)]
-    e1.record()
-    torch.cuda.synchronize()
-    secs = fdist.max_over_ranks(e0.elapsed_time(e1) * 1e-3, dev)
-    for ev in evs:
-        times["fwd"] += ev[0].elapsed_time(ev[1]); times["bwd"] += ev[1].elapsed_time(ev[2]); times["allreduce"] += ev[2].elapsed_time(ev[3])
+
+    def run(tc: bool):
+        net.enable_tensor_core_mlp(inference=False, training=tc)
+        for k in times:
+            times[k] = 0.0
+        for _ in range(warm):
+            step()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        evs = [step() for _ in range(steps)]
+        e1.record()
+        torch.cuda.synchronize()
+        secs_ = fdist.max_over_ranks(e0.elapsed_time(e1) * 1e-3, dev)
+        for ev in evs:
+            times["fwd"] += ev[0].elapsed_time(ev[1]); times["bwd"] += ev[1].elapsed_time(ev[2]); times["allreduce"] += ev[2].elapsed_time(ev[3])
+        return secs_, {k: v / steps for k, v in times.items()}
+
+    secs32, br32 = run(False)
+    secs, br = run(True)
     line = {"metric": "training_pairs_per_sec", "value": world * B * steps / secs, "unit": UNIT, "n_gpus": world,
             "steps": steps, "warmup": warm, "ms_per_step": secs / steps * 1e3, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f32 MLP (PyTorch autograd) + f32/f64 solver kernels",
+            "scaling": "weak", "vs_baseline": None, "dtype": "bf16 MLP forward+backward on tcgen05 (fp32 accumulate) + f32/f64 solver kernels",
             "data": "synthetic",
             "config": {"workload": f"C5: DeepFNet training step, depth 5, {B} pairs/GPU x N={N}, F-loss, Adam, "
                                    "one flattened gradient all-reduce (NCCL)", "global_batch": world * B},
-            "ms_breakdown": {k: v / steps for k, v in times.items()},
+            "ms_breakdown": br,
+            "fp32_autograd_mlp": {"value": world * B * steps / secs32, "ms_per_step": secs32 / steps * 1e3,
+                                  "ms_breakdown": br32},
             "grad_bytes_allreduced": sum(p.numel() for p in net.parameters()) * 4}
     if world > 1:
         dist.barrier()
