@@ -99,6 +99,15 @@ int fepe_pose_fwd(const float* F, const float* K, int L, int B, float ax, float 
                   const float* virt1, const float* virt2, int V, float clamp_at,
                   float* out, void* stream);
 
+/* Backward of fepe_pose_fwd: dL/dF [L,B,9] from the upstream gradients g_q, g_t, g_loss [L,B] (any may be NULL)
+ * of out[..,21], out[..,22], out[..,25]; `pose_out` is the forward output (it records which candidates won).
+ * Replaces autograd through torch.svd / _get_M2s / _R_to_q / _l2_error / compute_epi_residual on the host
+ * (train_good_utils.py:96-188, :325-354). */
+int fepe_pose_bwd(const float* F, const float* K, int L, int B, float ax, float bx, float ay, float by,
+                  const float* q_gt, const float* t_gt, const float* virt1, const float* virt2, int V, float clamp_at,
+                  const float* pose_out, const float* g_q, const float* g_t, const float* g_loss, float* dF,
+                  void* stream);
+
 /* ---- per-correspondence weight MLP on tensor cores (inference path) -----------------------------
  * Replaces ErrorEstimator.forward (deepFEPE/models/ErrorEstimators.py:46-68: five Conv1d(k=1) ->
  * InstanceNorm1d(affine) -> LeakyReLU(0.01) blocks and a final Conv1d) and the softmax over the N

@@ -743,4 +743,152 @@ FEPE_HD void rank2_project_adjoint(const double (&F0)[9], const double (&v)[3], 
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Adjoint of the pose head (what autograd does through torch.svd / _get_M2s / _R_to_q / _l2_error in the
+// reference, train_good_utils.py:96-188).  All 3x3 row-major, fp64.
+// ---------------------------------------------------------------------------------------------
+
+// dL/dA from dL/dU, dL/dV for A = U diag(S) V^T (square, S may carry a signed / zero last entry):
+//   dA = U [ (K o (U^T Ubar - Ubar^T U)) S + S (K o (V^T Vbar - Vbar^T V)) ] V^T,  K_ij = 1/(s_j^2 - s_i^2), i != j
+// (the formula PyTorch's svd_backward uses when Sbar = 0).  Nearly equal singular values make K huge -- as in
+// the reference; the denominators are only protected against an exact zero.
+FEPE_HD void svd3_adjoint(const double (&U)[9], const double (&S)[3], const double (&V)[9], const double (&Ub)[9],
+                          const double (&Vb)[9], double (&Ab)[9]) {
+    double P[9], Q[9], T[9];
+    mat3_mul_tn(U, Ub, P);      // U^T Ubar
+    mat3_mul_tn(V, Vb, Q);      // V^T Vbar
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+            double t = 0.0;
+            if (i != j) {
+                double den = S[j] * S[j] - S[i] * S[i];
+                if (fabs(den) < 1e-300) den = (den < 0.0) ? -1e-300 : 1e-300;
+                const double k = 1.0 / den;
+                t = k * (P[3 * i + j] - P[3 * j + i]) * S[j] + S[i] * k * (Q[3 * i + j] - Q[3 * j + i]);
+            }
+            T[3 * i + j] = t;
+        }
+    }
+    double UT[9];
+    mat3_mul(U, T, UT);
+    mat3_mul_nt(UT, V, Ab);
+}
+
+// Adjoint of rot_to_quat: given qbar (4) returns Rbar (9).  Same branch as the forward.
+FEPE_HD void rot_to_quat_adjoint(const double (&R)[9], const double (&qb)[4], double (&Rb)[9]) {
+    // m[i][j] = R[j][i];  v = branch-dependent linear forms of m, tr = the "t" entry, q = sg * 0.5 v / sqrt(tr)
+    const double m00 = R[0], m11 = R[4], m22 = R[8];
+    const double m01 = R[3], m10 = R[1], m02 = R[6], m20 = R[2], m12 = R[7], m21 = R[5];
+    double v[4], tr;
+    int branch;
+    if (m22 < 0.0) {
+        if (m00 > m11) { branch = 0; tr = 1.0 + m00 - m11 - m22; v[0] = m12 - m21; v[1] = tr; v[2] = m01 + m10; v[3] = m20 + m02; }
+        else           { branch = 1; tr = 1.0 - m00 + m11 - m22; v[0] = m20 - m02; v[1] = m01 + m10; v[2] = tr; v[3] = m12 + m21; }
+    } else {
+        if (m00 < -m11) { branch = 2; tr = 1.0 - m00 - m11 + m22; v[0] = m01 - m10; v[1] = m20 + m02; v[2] = m12 + m21; v[3] = tr; }
+        else            { branch = 3; tr = 1.0 + m00 + m11 + m22; v[0] = tr; v[1] = m12 - m21; v[2] = m20 - m02; v[3] = m01 - m10; }
+    }
+    const double isq = 1.0 / sqrt(tr);
+    const double sg = (v[0] < 0.0) ? -1.0 : 1.0;          // sign(q0) = sign(v0)
+    // q_i = sg * 0.5 * v_i * tr^-1/2  =>  vbar_i = sg 0.5 isq qbar_i ;  trbar = -sg 0.25 tr^-3/2 sum_i v_i qbar_i
+    double vb[4];
+    double dot = 0.0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { vb[i] = sg * 0.5 * isq * qb[i]; dot += v[i] * qb[i]; }
+    const double trb = -sg * 0.25 * isq * isq * isq * dot;
+    // accumulate mbar[i][j]
+    double mb[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};   // index 3*i+j for m_ij
+    const int I00 = 0, I01 = 1, I02 = 2, I10 = 3, I11 = 4, I12 = 5, I20 = 6, I21 = 7, I22 = 8;
+    double tb = trb;
+    if (branch == 0) {
+        tb += vb[1]; mb[I12] += vb[0]; mb[I21] -= vb[0]; mb[I01] += vb[2]; mb[I10] += vb[2]; mb[I20] += vb[3]; mb[I02] += vb[3];
+        mb[I00] += tb; mb[I11] -= tb; mb[I22] -= tb;
+    } else if (branch == 1) {
+        tb += vb[2]; mb[I20] += vb[0]; mb[I02] -= vb[0]; mb[I01] += vb[1]; mb[I10] += vb[1]; mb[I12] += vb[3]; mb[I21] += vb[3];
+        mb[I00] -= tb; mb[I11] += tb; mb[I22] -= tb;
+    } else if (branch == 2) {
+        tb += vb[3]; mb[I01] += vb[0]; mb[I10] -= vb[0]; mb[I20] += vb[1]; mb[I02] += vb[1]; mb[I12] += vb[2]; mb[I21] += vb[2];
+        mb[I00] -= tb; mb[I11] -= tb; mb[I22] += tb;
+    } else {
+        tb += vb[0]; mb[I12] += vb[1]; mb[I21] -= vb[1]; mb[I20] += vb[2]; mb[I02] -= vb[2]; mb[I01] += vb[3]; mb[I10] -= vb[3];
+        mb[I00] += tb; mb[I11] += tb; mb[I22] += tb;
+    }
+    // R = m^T
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int j = 0; j < 3; ++j) Rb[3 * i + j] = mb[3 * j + i];
+}
+
+// Adjoint of the whole head for one (layer, pair).  Inputs: E_cam (= E^T, what was decomposed), the GT pose, which
+// candidates won (q_first, t_first) and the upstream gradients of the two L2 errors.  Output: dL/dE_cam.
+FEPE_HD void pose_head_adjoint(const double (&Ec)[9], const double (&qg)[4], const double (&tg_unit)[3], bool q_first,
+                               bool t_first, double gq, double gt, double (&Ecb)[9]) {
+    double R1[9], R2[9], t[3], U[9], S[3], V[9];
+    essential_decompose(Ec, R1, R2, t, U, S, V);
+    // essential_decompose overwrote the third columns with u1 x u2 / v1 x v2: (U, S', V) is still a factorisation of
+    // Ec with a SIGNED third value S'_3 = u3^T Ec v3 = +-S_3, which is what the adjoint formula needs.
+    {
+        const double w0 = Ec[0] * V[2] + Ec[1] * V[5] + Ec[2] * V[8];
+        const double w1 = Ec[3] * V[2] + Ec[4] * V[5] + Ec[5] * V[8];
+        const double w2 = Ec[6] * V[2] + Ec[7] * V[5] + Ec[8] * V[8];
+        S[2] = U[2] * w0 + U[5] * w1 + U[8] * w2;
+    }
+    double Rb[9], ub3[3];
+#pragma unroll
+    for (int i = 0; i < 9; ++i) Rb[i] = 0.0;
+    {
+        double q[4], Rsel[9];
+#pragma unroll
+        for (int i = 0; i < 9; ++i) Rsel[i] = q_first ? R1[i] : R2[i];
+        rot_to_quat(Rsel, q);
+        double d[4], n2 = 0.0;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { d[i] = q[i] - qg[i]; n2 += d[i] * d[i]; }
+        const double n = sqrt(n2);
+        if (n > 0.0 && gq != 0.0) {
+            double qb[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) qb[i] = gq * d[i] / n;
+            rot_to_quat_adjoint(Rsel, qb, Rb);
+        }
+    }
+    {
+        const double sgn = t_first ? 1.0 : -1.0;
+        double d[3], n2 = 0.0;
+#pragma unroll
+        for (int i = 0; i < 3; ++i) { d[i] = sgn * t[i] - tg_unit[i]; n2 += d[i] * d[i]; }
+        const double n = sqrt(n2);
+        // t = u3 / |u3| with |u3| = 1:  u3bar = (I - t t^T) tbar
+        double tb[3] = {0.0, 0.0, 0.0};
+        if (n > 0.0 && gt != 0.0) {
+#pragma unroll
+            for (int i = 0; i < 3; ++i) tb[i] = sgn * gt * d[i] / n;
+        }
+        const double tt = t[0] * tb[0] + t[1] * tb[1] + t[2] * tb[2];
+#pragma unroll
+        for (int i = 0; i < 3; ++i) ub3[i] = tb[i] - t[i] * tt;
+    }
+    // R1 = U W V^T, R2 = U W^T V^T with U W = [u2, -u1, u3], U W^T = [-u2, u1, u3]:
+    //   R = sum_k c_k(U) v_k^T  =>  Ubar, Vbar below (s = +1 for R1, -1 for R2 on the first two columns)
+    const double s = q_first ? 1.0 : -1.0;
+    double Ub[9], Vb[9];
+    // G = Rbar (3x3).  R = s (u2 v1^T - u1 v2^T) + u3 v3^T
+    //   u1bar = -s G v2, u2bar = s G v1, u3bar = G v3 ;  v1bar = s G^T u2, v2bar = -s G^T u1, v3bar = G^T u3
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+        const double Gv1 = Rb[3 * r] * V[0] + Rb[3 * r + 1] * V[3] + Rb[3 * r + 2] * V[6];
+        const double Gv2 = Rb[3 * r] * V[1] + Rb[3 * r + 1] * V[4] + Rb[3 * r + 2] * V[7];
+        const double Gv3 = Rb[3 * r] * V[2] + Rb[3 * r + 1] * V[5] + Rb[3 * r + 2] * V[8];
+        Ub[3 * r] = -s * Gv2; Ub[3 * r + 1] = s * Gv1; Ub[3 * r + 2] = Gv3 + ub3[r];
+        const double Gtu1 = Rb[r] * U[0] + Rb[3 + r] * U[3] + Rb[6 + r] * U[6];
+        const double Gtu2 = Rb[r] * U[1] + Rb[3 + r] * U[4] + Rb[6 + r] * U[7];
+        const double Gtu3 = Rb[r] * U[2] + Rb[3 + r] * U[5] + Rb[6 + r] * U[8];
+        Vb[3 * r] = s * Gtu2; Vb[3 * r + 1] = -s * Gtu1; Vb[3 * r + 2] = Gtu3;
+    }
+    svd3_adjoint(U, S, V, Ub, Vb, Ecb);
+}
+
 }  // namespace fepe

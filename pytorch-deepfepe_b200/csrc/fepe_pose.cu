@@ -102,13 +102,16 @@ __global__ void __launch_bounds__(128) fepe_pose_fwd_kernel(const PoseParams p) 
         const double c = 0.5 * (D[0] + D[4] + D[8] - 1.0);
         const double s = 0.5 * sqrt((D[7] - D[5]) * (D[7] - D[5]) + (D[2] - D[6]) * (D[2] - D[6]) +
                                     (D[3] - D[1]) * (D[3] - D[1]));
-        r_ang = static_cast<float>(atan2(s, c) * 57.29577951308232);
+        // the arguments are fp64-accurate; fp32 atan2 of them is good to ~1e-5 deg and far cheaper than the fp64 routine
+        r_ang = atan2f(static_cast<float>(s), static_cast<float>(c)) * 57.29577951f;
     }
     res[23] = r_ang;
     {
+        // angle between unit vectors as atan2(|a x b|, a.b): no acos cancellation near 0, fp32 evaluation
         const double dot = tsg * (t[0] * tg[0] + t[1] * tg[1] + t[2] * tg[2]);
-        const double c = fmin(1.0, fmax(-1.0, dot));
-        res[24] = static_cast<float>(acos(c) * 57.29577951308232);
+        const double cx = t[1] * tg[2] - t[2] * tg[1], cy = t[2] * tg[0] - t[0] * tg[2], cz = t[0] * tg[1] - t[1] * tg[0];
+        const double sn = sqrt(cx * cx + cy * cy + cz * cz);
+        res[24] = atan2f(static_cast<float>(sn), static_cast<float>(dot)) * 57.29577951f;
     }
 
     // F-loss over the virtual correspondences (fp32 like the reference)
@@ -148,7 +151,116 @@ __global__ void __launch_bounds__(128) fepe_pose_fwd_kernel(const PoseParams p) 
     }
 }
 
+// Backward of the head: dL/dF from the upstream gradients of (q L2 error, t L2 error, F-loss) of every (layer, pair).
+// One THREAD per (layer, pair): pure register math (3x3 SVD adjoint, quaternion adjoint), 32 pairs per warp.
+struct PoseBwdParams {
+    const float* F;        // [L,B,9]
+    const float* K;        // [B,9]
+    const float* q_gt;     // [B,4]
+    const float* t_gt;     // [B,3]
+    const float* virt1;    // [B,V,3] or null
+    const float* virt2;
+    const float* pose_out; // [L,B,32] forward output (which candidates won)
+    const float* g_q;      // [L,B] or null
+    const float* g_t;      // [L,B] or null
+    const float* g_loss;   // [L,B] or null
+    int L, B, V;
+    float ax, bx, ay, by, clamp_at;
+    float* dF;             // [L,B,9]
+};
+
+__global__ void __launch_bounds__(64) fepe_pose_bwd_kernel(const PoseBwdParams p) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= p.L * p.B) return;
+    const int b = idx % p.B;
+    double F[9], K[9], M[9];
+#pragma unroll
+    for (int i = 0; i < 9; ++i) { F[i] = p.F[static_cast<size_t>(idx) * 9 + i]; K[i] = p.K[static_cast<size_t>(b) * 9 + i]; }
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+        M[j] = p.ax * K[j] + p.bx * K[6 + j];
+        M[3 + j] = p.ay * K[3 + j] + p.by * K[6 + j];
+        M[6 + j] = K[6 + j];
+    }
+    double dF[9];
+#pragma unroll
+    for (int i = 0; i < 9; ++i) dF[i] = 0.0;
+    const double gq = p.g_q ? static_cast<double>(p.g_q[idx]) : 0.0;
+    const double gt = p.g_t ? static_cast<double>(p.g_t[idx]) : 0.0;
+    if (gq != 0.0 || gt != 0.0) {
+        double FM[9], E[9];
+        mat3_mul(F, M, FM);
+        mat3_mul_tn(M, FM, E);
+        const double Ec[9] = {E[0], E[3], E[6], E[1], E[4], E[7], E[2], E[5], E[8]};
+        double qg[4], tg[3];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) qg[i] = p.q_gt[static_cast<size_t>(b) * 4 + i];
+#pragma unroll
+        for (int i = 0; i < 3; ++i) tg[i] = p.t_gt[static_cast<size_t>(b) * 3 + i];
+        const double n = sqrt(tg[0] * tg[0] + tg[1] * tg[1] + tg[2] * tg[2]);
+        const double inv = 1.0 / fmax(n, 1e-12);
+        tg[0] *= inv; tg[1] *= inv; tg[2] *= inv;
+        const float* po = p.pose_out + static_cast<size_t>(idx) * FEPE_POSE_OUT_FLOATS;
+        double Ecb[9];
+        pose_head_adjoint(Ec, qg, tg, po[26] == 0.f, po[27] == 0.f, gq, gt, Ecb);
+        // dE = Ecb^T ; dF = M dE M^T
+        const double Eb[9] = {Ecb[0], Ecb[3], Ecb[6], Ecb[1], Ecb[4], Ecb[7], Ecb[2], Ecb[5], Ecb[8]};
+        double ME[9];
+        mat3_mul(M, Eb, ME);
+        mat3_mul_nt(ME, M, dF);
+    }
+    const float gl = p.g_loss ? p.g_loss[idx] : 0.f;
+    if (gl != 0.f && p.virt1 != nullptr && p.V > 0) {
+        float Ff[9], acc[9];
+#pragma unroll
+        for (int i = 0; i < 9; ++i) { Ff[i] = static_cast<float>(F[i]); acc[i] = 0.f; }
+        const float* v1 = p.virt1 + static_cast<size_t>(b) * p.V * 3;
+        const float* v2 = p.virt2 + static_cast<size_t>(b) * p.V * 3;
+        for (int i = 0; i < p.V; ++i) {
+            const float z1 = v1[3 * i + 2], z2 = v2[3 * i + 2];
+            const float u1 = fmaf(p.ax, v1[3 * i], p.bx * z1), w1 = fmaf(p.ay, v1[3 * i + 1], p.by * z1);
+            const float u2 = fmaf(p.ax, v2[3 * i], p.bx * z2), w2 = fmaf(p.ay, v2[3 * i + 1], p.by * z2);
+            const float l10 = u2 * Ff[0] + w2 * Ff[3] + z2 * Ff[6];
+            const float l11 = u2 * Ff[1] + w2 * Ff[4] + z2 * Ff[7];
+            const float l12 = u2 * Ff[2] + w2 * Ff[5] + z2 * Ff[8];
+            const float l20 = Ff[0] * u1 + Ff[1] * w1 + Ff[2] * z1;
+            const float l21 = Ff[3] * u1 + Ff[4] * w1 + Ff[5] * z1;
+            const float dd = l10 * u1 + l11 * w1 + l12 * z1;
+            const float m1 = sqrtf(l10 * l10 + l11 * l11), m2 = sqrtf(l20 * l20 + l21 * l21);
+            const float i1 = 1.0f / (m1 + 1e-6f), i2 = 1.0f / (m2 + 1e-6f);
+            const float dist = fabsf(dd) * (i1 + i2);
+            if (dist > p.clamp_at) continue;                      // clamp(max=c): zero gradient above c
+            const float sg = (dd > 0.f) ? 1.f : ((dd < 0.f) ? -1.f : 0.f);
+            const float S12 = sg * (i1 + i2);
+            const float a1 = -fabsf(dd) * i1 * i1 / fmaxf(m1, 1e-30f);
+            const float a2 = -fabsf(dd) * i2 * i2 / fmaxf(m2, 1e-30f);
+            const float uk0 = S12 * u1 + a1 * l10, uk1 = S12 * w1 + a1 * l11, uk2 = S12 * z1;
+            const float vj0 = a2 * l20, vj1 = a2 * l21;
+            acc[0] += u2 * uk0 + vj0 * u1; acc[1] += u2 * uk1 + vj0 * w1; acc[2] += u2 * uk2 + vj0 * z1;
+            acc[3] += w2 * uk0 + vj1 * u1; acc[4] += w2 * uk1 + vj1 * w1; acc[5] += w2 * uk2 + vj1 * z1;
+            acc[6] += z2 * uk0;            acc[7] += z2 * uk1;            acc[8] += z2 * uk2;
+        }
+        const double sc = static_cast<double>(gl) / static_cast<double>(p.V);
+#pragma unroll
+        for (int i = 0; i < 9; ++i) dF[i] += sc * static_cast<double>(acc[i]);
+    }
+#pragma unroll
+    for (int i = 0; i < 9; ++i) p.dF[static_cast<size_t>(idx) * 9 + i] = static_cast<float>(dF[i]);
+}
+
 }  // namespace fepe
+
+extern "C" int fepe_pose_bwd(const float* F, const float* K, int L, int B, float ax, float bx, float ay, float by,
+                             const float* q_gt, const float* t_gt, const float* virt1, const float* virt2, int V,
+                             float clamp_at, const float* pose_out, const float* g_q, const float* g_t,
+                             const float* g_loss, float* dF, void* stream) {
+    if (L == 0 || B == 0) return 0;
+    if (!F || !K || !q_gt || !t_gt || !pose_out || !dF || L < 0 || B < 0 || V < 0) return FEPE_E_BADARG;
+    fepe::PoseBwdParams p{F, K, q_gt, t_gt, virt1, virt2, pose_out, g_q, g_t, g_loss, L, B, V, ax, bx, ay, by, clamp_at, dF};
+    const int n = L * B;
+    fepe::fepe_pose_bwd_kernel<<<(n + 63) / 64, 64, 0, static_cast<cudaStream_t>(stream)>>>(p);
+    return static_cast<int>(cudaGetLastError());
+}
 
 extern "C" int fepe_pose_fwd(const float* F, const float* K, int L, int B, float ax, float bx, float ay, float by,
                              const float* q_gt, const float* t_gt, const float* Rt_scene, const float* virt1,

@@ -144,3 +144,46 @@ class FitFunction(torch.autograd.Function):
         gw = fit_backward(matches, weights, saved, gF, gres.contiguous() if gres is not None else None,
                           gepi.contiguous() if gepi is not None else None, ctx.aff, ctx.clamp_at)
         return None, gw.reshape(weights.shape), None, None, None, None, None
+
+
+class PoseLossFunction(torch.autograd.Function):
+    """Differentiable pose / F-loss head on the device.
+
+    forward(F [L,B,3,3], K, q_gt, t_gt, Rt_scene, virt1, virt2, ax, bx, ay, by, clamp_at)
+        -> q_l2 [L,B], t_l2 [L,B], loss_F [L,B], out [L,B,32] (metrics, not differentiable)
+    backward: dL/dF by fepe_pose_bwd (3x3 SVD adjoint, quaternion adjoint, epipolar-residual adjoint)."""
+
+    @staticmethod
+    def forward(ctx, F, K, q_gt, t_gt, Rt_scene, virt1, virt2, ax, bx, ay, by, clamp_at):
+        aff = (float(ax), float(bx), float(ay), float(by))
+        if F.dim() == 3:
+            F = F.unsqueeze(0)
+        F = F.contiguous()
+        out = pose_forward(F, K, aff, q_gt, t_gt, Rt_scene, virt1, virt2, clamp_at)
+        ctx.aff, ctx.clamp_at = aff, float(clamp_at)
+        ctx.save_for_backward(F, K, q_gt, t_gt, virt1 if virt1 is not None else F.new_empty(0),
+                              virt2 if virt2 is not None else F.new_empty(0), out)
+        ctx.mark_non_differentiable(out)
+        return out[..., 21].clone(), out[..., 22].clone(), out[..., 25].clone(), out
+
+    @staticmethod
+    def backward(ctx, g_q, g_t, g_loss, _g_out):
+        F, K, q_gt, t_gt, virt1, virt2, out = ctx.saved_tensors
+        L, B = F.shape[0], F.shape[1]
+        has_v = virt1.numel() > 0
+        prep = lambda g: _check_cuda_f32(g, "grad").reshape(L, B) if g is not None else None
+        g_q, g_t, g_loss = prep(g_q), prep(g_t), prep(g_loss)
+        Kc = _check_cuda_f32(K, "K").reshape(B, 9)
+        qc = _check_cuda_f32(q_gt, "q_gt").reshape(B, 4)
+        tc = _check_cuda_f32(t_gt, "t_gt").reshape(B, 3)
+        v1 = _check_cuda_f32(virt1, "virt1") if has_v else None
+        v2 = _check_cuda_f32(virt2, "virt2") if has_v else None
+        with torch.cuda.device(F.device):
+            dF = torch.empty_like(F)
+            ptr = lambda t: t.data_ptr() if t is not None else None
+            st = _lib.lib().fepe_pose_bwd(F.data_ptr(), Kc.data_ptr(), L, B, ctx.aff[0], ctx.aff[1], ctx.aff[2], ctx.aff[3],
+                                          qc.data_ptr(), tc.data_ptr(), ptr(v1), ptr(v2), v1.shape[1] if has_v else 0,
+                                          ctx.clamp_at, out.data_ptr(), ptr(g_q), ptr(g_t), ptr(g_loss), dF.data_ptr(),
+                                          _stream_ptr())
+        _lib.check(st, "fepe_pose_bwd")
+        return (dF,) + (None,) * 11

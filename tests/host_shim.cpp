@@ -106,6 +106,16 @@ void shim_rank2_adjoint(const double* F0, const double* Ab, double* F0b) {
     for (int i = 0; i < 9; ++i) F0b[i] = out[i];
 }
 
+void shim_pose_adjoint(const double* Ec, const double* qg, const double* tg, int q_first, int t_first, double gq,
+                       double gt, double* Ecb) {
+    double e[9], q[4], t[3], out[9];
+    for (int i = 0; i < 9; ++i) e[i] = Ec[i];
+    for (int i = 0; i < 4; ++i) q[i] = qg[i];
+    for (int i = 0; i < 3; ++i) t[i] = tg[i];
+    fepe::pose_head_adjoint(e, q, t, q_first != 0, t_first != 0, gq, gt, out);
+    for (int i = 0; i < 9; ++i) Ecb[i] = out[i];
+}
+
 void shim_quat(const double* R, double* q) {
     double r[9], qq[4];
     for (int i = 0; i < 9; ++i) r[i] = R[i];

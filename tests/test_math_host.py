@@ -37,6 +37,7 @@ def shim():
     lib.shim_g36_index.restype = ctypes.c_int
     lib.shim_essential.argtypes = [dp] * 6
     lib.shim_quat.argtypes = [dp, dp]
+    lib.shim_pose_adjoint.argtypes = [dp, dp, dp, ctypes.c_int, ctypes.c_int, ctypes.c_double, ctypes.c_double, dp]
     lib.shim_rank2_adjoint.argtypes = [dp, dp, dp]
     return lib
 
@@ -251,3 +252,42 @@ def test_svd3_direct(shim):
         np.testing.assert_allclose(U.T @ U, np.eye(3), atol=1e-9)
         np.testing.assert_allclose(V.T @ V, np.eye(3), atol=1e-9)
         np.testing.assert_allclose(S, np.linalg.svd(A, compute_uv=False), atol=1e-9 * sc)
+
+
+def test_pose_head_adjoint_matches_autograd_through_the_oracle(shim):
+    """d(q_l2, t_l2)/dE against torch autograd (fp64) through the oracle's restatement of _get_M2s / _R_to_q / L2
+    errors / min-select (oracle.pose_errors)."""
+    import torch
+    from oracle import fepe_oracle as O
+    d = synth.make_batch(12, 64, seed=5, outlier_frac=0.0)
+    E0 = torch.from_numpy(d["E_gt"]).double()
+    rng = np.random.default_rng(0)
+    worst = 0.0
+    for b in range(12):
+        # estimated essential matrices are never exact: perturb the GT one (keeps s1 != s2)
+        E = (E0[b] + 0.05 * torch.from_numpy(rng.normal(size=(3, 3)))).requires_grad_(True)
+        qg = torch.from_numpy(d["q_cam"][b]).double()
+        tg = torch.from_numpy(d["t_cam"][b]).double()
+        Rt = torch.from_numpy(d["delta_Rtijs_4_4"][b:b + 1]).double()
+        q_l2, t_l2, _, _ = O.pose_errors(E.unsqueeze(0), qg.unsqueeze(0), tg.unsqueeze(0), Rt)
+        gq, gt = float(rng.normal()), float(rng.normal())
+        (gq * q_l2[0] + gt * t_l2[0]).backward()
+        ref = E.grad.numpy()                       # dL/dE ; the head decomposes E^T
+        Ec = np.ascontiguousarray(E.detach().numpy().T)
+        # which candidates win (same rule as the oracle)
+        Rs, ts = O.essential_decompose(E.detach().t())
+        qa, qb = O.rot_to_quat(Rs[0]), O.rot_to_quat(Rs[1])
+        tgu = (tg / tg.norm()).flatten()
+        # our decomposition returns the same SET; find which of OUR candidates equals the oracle's winner
+        R1, R2, t, q1, q2 = np.zeros((3, 3)), np.zeros((3, 3)), np.zeros(3), np.zeros(4), np.zeros(4)
+        shim.shim_essential(_ptr(Ec), _ptr(R1), _ptr(R2), _ptr(t), _ptr(q1), _ptr(q2))
+        qgn = qg.flatten().numpy()
+        q_first = np.linalg.norm(q1 - qgn) < np.linalg.norm(q2 - qgn)
+        t_first = np.linalg.norm(t - tgu.numpy()) < np.linalg.norm(-t - tgu.numpy())
+        out = np.zeros((3, 3))
+        shim.shim_pose_adjoint(_ptr(Ec), _ptr(np.ascontiguousarray(qgn)), _ptr(np.ascontiguousarray(tgu.numpy())),
+                               int(q_first), int(t_first), gq, gt, _ptr(out))
+        got = out.T                               # dL/dE = (dL/dE_cam)^T
+        err = np.linalg.norm(got - ref) / np.linalg.norm(ref)
+        worst = max(worst, err)
+    assert worst < 1e-6, worst

@@ -72,3 +72,38 @@ def test_gt_fundamental_gives_zero_pose_error():
     assert float(out[:, 21].max()) < 1e-4 and float(out[:, 22].max()) < 1e-3
     assert float(out[:, 23].max()) < 1e-2 and float(out[:, 24].max()) < 0.1
     assert float(out[:, 25].max()) < 1e-4      # "SHOULD BE ALL ZEROS" (utils_misc.py:174)
+
+
+def test_pose_loss_function_gradient_against_oracle_autograd():
+    """dL/dF of the device head vs torch autograd (fp64) through the oracle's F-loss + pose errors."""
+    B, L = 16, 2
+    d = synth.make_batch(B, 400, seed=11, weight_mode="inlier", outlier_frac=0.1)
+    aff = ops.hw_affine(d["image_size"])
+    F0, _, _, _ = ops.fit_forward(T(d["matches_xy_ori"]).cuda(), T(d["weights"]).cuda(), aff)
+    gen = torch.Generator("cuda").manual_seed(0)
+    Fl = torch.stack([F0, F0 + 2e-3 * torch.randn(F0.shape, device="cuda", generator=gen)]).requires_grad_(True)
+    cuda = lambda k: T(d[k]).cuda()
+    q, t, lf, out = ops.PoseLossFunction.apply(Fl, cuda("Ks"), cuda("q_cam"), cuda("t_cam"), cuda("delta_Rtijs_4_4"),
+                                                cuda("pts1_virt"), cuda("pts2_virt"), *aff, 0.02)
+    gq = torch.randn(L, B, device="cuda", generator=gen)
+    gt = torch.randn(L, B, device="cuda", generator=gen)
+    gl = torch.randn(L, B, device="cuda", generator=gen)
+    ((q * gq).sum() + (t * gt).sum() + (lf * gl).sum()).backward()
+    ours = Fl.grad.cpu().double()
+    # oracle in fp64
+    Fr = Fl.detach().cpu().double().requires_grad_(True)
+    _, _, Tn = O.norm_hw(T(d["matches_xy_ori"]).double(), d["image_size"])
+    loss = 0.0
+    for l in range(L):
+        _, losses, E_layers = O.f_loss_layers([Fr[l]], Tn, Tn, T(d["pts1_virt"]).double(), T(d["pts2_virt"]).double(),
+                                              T(d["Ks"]).double(), clamp_at=0.02)
+        ql, tl, _, _ = O.pose_errors(E_layers[0], T(d["q_cam"]).double(), T(d["t_cam"]).double(),
+                                     T(d["delta_Rtijs_4_4"]).double())
+        loss = loss + (ql * gq[l].cpu().double()).sum() + (tl * gt[l].cpu().double()).sum() \
+            + (losses[0].mean(1) * gl[l].cpu().double()).sum()
+    loss.backward()
+    ref = Fr.grad
+    rel = (ours - ref).flatten(2).norm(dim=2) / ref.flatten(2).norm(dim=2)
+    print("pose head dL/dF rel err: median %.2e max %.2e" % (float(rel.median()), float(rel.max())))
+    # fp32 F and fp32 virtual-point arithmetic on our side; SVD-adjoint denominators 1/(s1^2-s2^2) amplify that
+    assert float(rel.median()) < 1e-3 and float(rel.max()) < 5e-2
