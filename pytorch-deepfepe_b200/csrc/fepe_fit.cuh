@@ -227,4 +227,9 @@ inline bool make_ring(int N, int bytes_per_corr, int smem_limit, RingLayout& r) 
     return true;
 }
 
+// Split throughput pipeline (fepe_fit_split.cu); taken from kSplitMinPairsPerSM pairs per SM upwards (measured crossover)
+constexpr int kSplitMinPairsPerSM = 24;
+bool split_path_supported(const FitParams& p, const DeviceInfo& d);
+int launch_split(FitParams p, const DeviceInfo& d, cudaStream_t stream);
+
 }  // namespace fepe

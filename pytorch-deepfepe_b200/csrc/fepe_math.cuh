@@ -51,6 +51,15 @@ FEPE_HD double fast_rsqrt(double x) {
 #endif
 }
 
+// sqrt for non-negative arguments through the fast reciprocal square root (0 -> 0).
+FEPE_HD double fast_sqrt(double x) {
+#if defined(__CUDA_ARCH__)
+    return (x > 0.0) ? x * fast_rsqrt(x) : 0.0;
+#else
+    return sqrt(x);
+#endif
+}
+
 // ---------------------------------------------------------------------------------------------
 // Gram matrix storage.  A constraint row is p = a (x) b with a = (x2,y2,1), b = (x1,y1,1), so
 // p p^T = (a a^T) (x) (b b^T) has only 6 x 6 = 36 distinct entries.  g36[u*6+v] holds
@@ -62,11 +71,21 @@ FEPE_HD constexpr int sym6(int i, int j) {
 }
 FEPE_HD constexpr int g36_index(int r, int c) { return sym6(r / 3, c / 3) * 6 + sym6(r % 3, c % 3); }
 
+// View of one Gram matrix inside an [entry][problem] array (entry e of this problem at p[e * STRIDE]): lets
+// one LANE own one eigenproblem with bank-conflict-free shared-memory reads (fepe_fit_split.cu).
+template <int STRIDE>
+struct StridedG36 {
+    const double* p;
+    FEPE_HD double operator[](int e) const { return p[e * STRIDE]; }
+};
+
 // LDL^T of M = G - mu*I (unit lower L, reciprocal pivots rd).  Returns the number of negative
 // pivots = number of eigenvalues of G below mu (Sylvester inertia).
 // Right-looking (outer-product) form: once column j is scaled every trailing update is an
 // independent FMA, so the dependent chain per column is just reciprocal -> scale -> one FMA.
-FEPE_HD int ldl9(const double* __restrict__ g36, double mu, double tiny, double (&A)[45]) {
+// G36 is anything indexable by the g36 entry number: a plain pointer, or a strided view (StridedG36).
+template <class G36>
+FEPE_HD int ldl9(const G36& g36, double mu, double tiny, double (&A)[45]) {
     // A: lower triangle incl. diagonal, (i,j), i>=j at i*(i+1)/2 + j.  On exit the strictly lower part
     // holds L and the diagonal holds the RECIPROCAL pivots.
 #pragma unroll
@@ -134,7 +153,8 @@ FEPE_HD void gram9_matvec(const double* __restrict__ g36, const double (&x)[9], 
 // repeated lambda_8 ~ lambda_9 (degenerate scenes) cost no extra iterations.
 // Output: unit f, sign fixed so that the entry of largest magnitude is positive.  Returns the
 // number of factorisations used.
-FEPE_HD int eig9_smallest(const double* __restrict__ g36, double (&f)[9], double& lambda) {
+template <class G36>
+FEPE_HD int eig9_smallest(const G36& g36, double (&f)[9], double& lambda) {
     double tr = 0.0;
 #pragma unroll
     for (int r = 0; r < 9; ++r) tr += g36[g36_index(r, r)];
@@ -182,13 +202,13 @@ FEPE_HD int eig9_smallest(const double* __restrict__ g36, double (&f)[9], double
 #pragma unroll
             for (int i = 0; i < 9; ++i) { const double e = x[i] - c * y[i]; e2 += e * e; x[i] = y[i]; }
             rho = mu + c * inv;
-            r = sqrt(e2) * inv;
+            r = fast_sqrt(e2) * inv;
         }
         // Stop when the eigenVECTOR has converged: its error is ~ r / (lambda_8 - lambda_9) and the
         // gap is estimated from the observed contraction q = r/r_prev = (lambda_9-mu)/(lambda_8-mu).
         if (r <= 1e-17 * tr) { ++it; break; }
         if (r_prev >= 0.0) {
-            const double q = r / r_prev;
+            const double q = (r_prev > 0.0) ? r * fast_rcp(r_prev) : 2.0;
             if (q < 1.0) {
                 // r <= 1e-8 gap  with  gap = (rho - mu) (1/q - 1), written without the division
                 if (r * q <= 1e-8 * (rho - mu) * (1.0 - q)) { ++it; break; }
@@ -259,7 +279,12 @@ FEPE_HD double eig9_lane_shift(const Eig9Bracket& b, int lane) {
         // geometric ladder from 1e-13 tr up to the upper limit: lambda_min can sit anywhere on 13 decades
         const double a = 1e-13 * b.tr;
         const double top = (b.hi > 2.0 * a) ? b.hi : 2.0 * a;
+#if defined(__CUDA_ARCH__)
+        // fp32 transcendentals: the ladder only has to be ascending, not accurate
+        return a * static_cast<double>(exp2f(log2f(static_cast<float>(top * fast_rcp(a))) * (static_cast<float>(lane - 1) * (1.0f / 30.0f))));
+#else
         return a * exp2(log2(top / a) * (static_cast<double>(lane - 1) * (1.0 / 30.0)));
+#endif
     }
     const double lo = (b.lo_heur > 0.0) ? b.lo_heur : 0.0;
     return lo + (b.hi - lo) * (static_cast<double>(lane - 1) * (1.0 / 31.0)) * 0.999;
@@ -289,8 +314,8 @@ FEPE_HD void eig9_lane_round(const double* __restrict__ g36, double mu, double t
 #pragma unroll
         for (int i = 0; i < 9; ++i) { const double e = x[i] - c * y[i]; e2 += e * e; x[i] = y[i]; }
         rho = mu + c * inv;
-        const double r_new = sqrt(e2) * inv;
-        if (rep > 0) contraction = r_new / (r + 1e-300);
+        const double r_new = fast_sqrt(e2) * inv;
+        if (rep > 0) contraction = r_new * fast_rcp(r + 1e-300);
         r = r_new;
     }
 }
@@ -550,7 +575,7 @@ FEPE_HD void smallest_right_sv3(const double (&A)[9], double (&v)[3], double& si
     const double w0 = A[0] * v[0] + A[1] * v[1] + A[2] * v[2];
     const double w1 = A[3] * v[0] + A[4] * v[1] + A[5] * v[2];
     const double w2 = A[6] * v[0] + A[7] * v[1] + A[8] * v[2];
-    sigma3 = sqrt(w0 * w0 + w1 * w1 + w2 * w2);
+    sigma3 = fast_sqrt(w0 * w0 + w1 * w1 + w2 * w2);
 }
 
 // Rank-2 projection of F0 = reshape(f): F0 - sigma3 u3 v3^T  (DeepFNet.py:236-237, S*[1,1,0]).
@@ -598,8 +623,8 @@ FEPE_HD void svd3_direct(const double (&A)[9], double (&U)[9], double (&S)[3], d
     const double gamma = w1[0] * w2[0] + w1[1] * w2[1] + w1[2] * w2[2];
     double c = 1.0, s = 0.0;
     if (gamma * gamma > 1e-32 * alpha * beta) {
-        const double zeta = (beta - alpha) / (2.0 * gamma);
-        const double t = ((zeta >= 0.0) ? 1.0 : -1.0) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
+        const double zeta = (beta - alpha) * fast_rcp(2.0 * gamma);
+        const double t = ((zeta >= 0.0) ? 1.0 : -1.0) * fast_rcp(fabs(zeta) + fast_sqrt(1.0 + zeta * zeta));
         c = fast_rsqrt(1.0 + t * t);
         s = c * t;
     }
@@ -609,14 +634,14 @@ FEPE_HD void svd3_direct(const double (&A)[9], double (&U)[9], double (&S)[3], d
         p1[r] = c * w1[r] - s * w2[r]; p2[r] = s * w1[r] + c * w2[r];
         q1[r] = c * b1[r] - s * b2[r]; q2[r] = s * b1[r] + c * b2[r];
     }
-    double na = sqrt(p1[0] * p1[0] + p1[1] * p1[1] + p1[2] * p1[2]);
-    double nb = sqrt(p2[0] * p2[0] + p2[1] * p2[1] + p2[2] * p2[2]);
+    double na = fast_sqrt(p1[0] * p1[0] + p1[1] * p1[1] + p1[2] * p1[2]);
+    double nb = fast_sqrt(p2[0] * p2[0] + p2[1] * p2[1] + p2[2] * p2[2]);
     if (na < nb) {
 #pragma unroll
         for (int r = 0; r < 3; ++r) { double tmp = p1[r]; p1[r] = p2[r]; p2[r] = tmp; tmp = q1[r]; q1[r] = q2[r]; q2[r] = tmp; }
         const double tmp = na; na = nb; nb = tmp;
     }
-    const double ia = 1.0 / (na + 1e-300), ib = 1.0 / (nb + 1e-300);
+    const double ia = fast_rcp(na + 1e-300), ib = fast_rcp(nb + 1e-300);
     double u1[3], u2[3];
 #pragma unroll
     for (int r = 0; r < 3; ++r) { u1[r] = p1[r] * ia; u2[r] = p2[r] * ib; }
@@ -665,7 +690,7 @@ FEPE_HD void essential_decompose(const double (&E)[9], double (&R1)[9], double (
             R2[3 * i + j] = b - a;
         }
     }
-    const double n = 1.0 / (sqrt(U[2] * U[2] + U[5] * U[5] + U[8] * U[8]) + 1e-300);
+    const double n = fast_rsqrt(U[2] * U[2] + U[5] * U[5] + U[8] * U[8] + 1e-300);
     t[0] = U[2] * n; t[1] = U[5] * n; t[2] = U[8] * n;
 }
 
@@ -682,7 +707,7 @@ FEPE_HD void rot_to_quat(const double (&R)[9], double (&q)[4]) {
         if (m00 < -m11) { tr = 1.0 - m00 - m11 + m22; q[0] = m01 - m10; q[1] = m20 + m02; q[2] = m12 + m21; q[3] = tr; }
         else            { tr = 1.0 + m00 + m11 + m22; q[0] = tr; q[1] = m12 - m21; q[2] = m20 - m02; q[3] = m01 - m10; }
     }
-    const double s = 0.5 / sqrt(tr);
+    const double s = 0.5 * fast_rsqrt(tr);     // tr >= 1 on every branch
     const double sg = (q[0] < 0.0) ? -s : s;
 #pragma unroll
     for (int i = 0; i < 4; ++i) q[i] *= sg;

@@ -13,6 +13,7 @@
 // pair: negligible next to the streaming kernel, it just has to stay on the device.
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 #include "../../include/fepe_b200.h"
 #include "fepe_math.cuh"
@@ -32,16 +33,91 @@ struct PoseParams {
     float* out;           // [L,B,FEPE_POSE_OUT_FLOATS]
 };
 
+constexpr int kVirtPerLane = 4;     // virtual correspondences held in registers per lane (V <= 128 in one trip)
+
+__device__ __forceinline__ float virt_term(const float (&Ff)[9], float ax, float bx, float ay, float by, float clamp_at,
+                                           float x1, float y1, float z1, float x2, float y2, float z2) {
+    const float u1 = fmaf(ax, x1, bx * z1), w1 = fmaf(ay, y1, by * z1);
+    const float u2 = fmaf(ax, x2, bx * z2), w2 = fmaf(ay, y2, by * z2);
+    const float l10 = u2 * Ff[0] + w2 * Ff[3] + z2 * Ff[6];
+    const float l11 = u2 * Ff[1] + w2 * Ff[4] + z2 * Ff[7];
+    const float l12 = u2 * Ff[2] + w2 * Ff[5] + z2 * Ff[8];
+    const float l20 = Ff[0] * u1 + Ff[1] * w1 + Ff[2] * z1;
+    const float l21 = Ff[3] * u1 + Ff[4] * w1 + Ff[5] * z1;
+    const float dd = l10 * u1 + l11 * w1 + l12 * z1;
+    const float d = fabsf(dd) * (1.0f / (sqrtf(l10 * l10 + l11 * l11) + 1e-6f) +
+                                 1.0f / (sqrtf(l20 * l20 + l21 * l21) + 1e-6f));
+    return fminf(d, clamp_at);
+}
+
 __global__ void __launch_bounds__(128) fepe_pose_fwd_kernel(const PoseParams p) {
     const int idx = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;   // one warp per (layer, pair)
     const int lane = threadIdx.x & 31;
     if (idx >= p.L * p.B) return;
     const int b = idx % p.B;
-    float* o = p.out + static_cast<size_t>(idx) * FEPE_POSE_OUT_FLOATS;
+    float* __restrict__ o = p.out + static_cast<size_t>(idx) * FEPE_POSE_OUT_FLOATS;
+
+    // Every global load of the item is issued here, before any arithmetic: the kernel is one dependent chain per
+    // warp, so a load that sits behind the SVD costs a full memory round trip of latency.
+    const float* __restrict__ gK = p.K + static_cast<size_t>(b) * 9;
+    const float* __restrict__ gq = p.q_gt + static_cast<size_t>(b) * 4;
+    const float* __restrict__ gt = p.t_gt + static_cast<size_t>(b) * 3;
+    float Kf[9], qgf[4], tgf[3], rtf[9] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int i = 0; i < 9; ++i) Kf[i] = __ldg(gK + i);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) qgf[i] = __ldg(gq + i);
+#pragma unroll
+    for (int i = 0; i < 3; ++i) tgf[i] = __ldg(gt + i);
+    if (p.Rt != nullptr) {
+        const float* __restrict__ rt = p.Rt + static_cast<size_t>(b) * 16;
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {
+#pragma unroll
+            for (int c = 0; c < 3; ++c) rtf[3 * r + c] = __ldg(rt + 4 * r + c);
+        }
+    }
+    const bool has_virt = (p.virt1 != nullptr) && (p.V > 0);
+    const float* __restrict__ v1 = has_virt ? p.virt1 + static_cast<size_t>(b) * p.V * 3 : nullptr;
+    const float* __restrict__ v2 = has_virt ? p.virt2 + static_cast<size_t>(b) * p.V * 3 : nullptr;
+    float va[kVirtPerLane][3], vb[kVirtPerLane][3];
+#pragma unroll
+    for (int u = 0; u < kVirtPerLane; ++u) {
+        const int i = lane + 32 * u;
+        const bool live = has_virt && i < p.V;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            va[u][c] = live ? __ldg(v1 + 3 * i + c) : 0.f;
+            vb[u][c] = live ? __ldg(v2 + 3 * i + c) : 0.f;
+        }
+    }
+#if __CUDA_ARCH__ >= 900
+    asm volatile("griddepcontrol.wait;" ::: "memory");   // F comes from the preceding kernel of the stream (PDL)
+#endif
+    float Ff[9];
+#pragma unroll
+    for (int i = 0; i < 9; ++i) Ff[i] = p.F[static_cast<size_t>(idx) * 9 + i];
+
+    // F-loss over the virtual correspondences (fp32 like the reference); independent of the SVD chain below
+    float loss = 0.f;
+    if (has_virt) {
+#pragma unroll
+        for (int u = 0; u < kVirtPerLane; ++u) {
+            if (lane + 32 * u < p.V)
+                loss += virt_term(Ff, p.ax, p.bx, p.ay, p.by, p.clamp_at, va[u][0], va[u][1], va[u][2], vb[u][0],
+                                  vb[u][1], vb[u][2]);
+        }
+        for (int i = lane + 32 * kVirtPerLane; i < p.V; i += 32)
+            loss += virt_term(Ff, p.ax, p.bx, p.ay, p.by, p.clamp_at, v1[3 * i], v1[3 * i + 1], v1[3 * i + 2], v2[3 * i],
+                              v2[3 * i + 1], v2[3 * i + 2]);
+#pragma unroll
+        for (int o2 = 16; o2 > 0; o2 >>= 1) loss += __shfl_xor_sync(0xffffffffu, loss, o2);
+        loss /= static_cast<float>(p.V);
+    }
 
     double F[9], K[9];
 #pragma unroll
-    for (int i = 0; i < 9; ++i) { F[i] = p.F[static_cast<size_t>(idx) * 9 + i]; K[i] = p.K[static_cast<size_t>(b) * 9 + i]; }
+    for (int i = 0; i < 9; ++i) { F[i] = Ff[i]; K[i] = Kf[i]; }
     // M = T K with T = [[ax,0,bx],[0,ay,by],[0,0,1]];  E = M^T F M
     double M[9];
 #pragma unroll
@@ -53,7 +129,6 @@ __global__ void __launch_bounds__(128) fepe_pose_fwd_kernel(const PoseParams p) 
     double FM[9], E[9];
     mat3_mul(F, M, FM);
     mat3_mul_tn(M, FM, E);
-    if (lane < 9) o[lane] = static_cast<float>(E[lane]);
 
     // decompose E^T
     double Et[9] = {E[0], E[3], E[6], E[1], E[4], E[7], E[2], E[5], E[8]};
@@ -64,12 +139,12 @@ __global__ void __launch_bounds__(128) fepe_pose_fwd_kernel(const PoseParams p) 
     rot_to_quat(R2, q2);
     double qg[4], tg[3];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) qg[i] = p.q_gt[static_cast<size_t>(b) * 4 + i];
+    for (int i = 0; i < 4; ++i) qg[i] = qgf[i];
 #pragma unroll
-    for (int i = 0; i < 3; ++i) tg[i] = p.t_gt[static_cast<size_t>(b) * 3 + i];
+    for (int i = 0; i < 3; ++i) tg[i] = tgf[i];
     {   // F.normalize(t_gt, p=2, dim=0): x / max(|x|, 1e-12)
-        const double n = sqrt(tg[0] * tg[0] + tg[1] * tg[1] + tg[2] * tg[2]);
-        const double inv = 1.0 / fmax(n, 1e-12);
+        const double n2 = tg[0] * tg[0] + tg[1] * tg[1] + tg[2] * tg[2];
+        const double inv = (n2 > 1e-24) ? fast_rsqrt(n2) : 1e12;
         tg[0] *= inv; tg[1] *= inv; tg[2] *= inv;
     }
     double eq1 = 0, eq2 = 0, et1 = 0, et2 = 0;
@@ -77,31 +152,31 @@ __global__ void __launch_bounds__(128) fepe_pose_fwd_kernel(const PoseParams p) 
     for (int i = 0; i < 4; ++i) { eq1 += (q1[i] - qg[i]) * (q1[i] - qg[i]); eq2 += (q2[i] - qg[i]) * (q2[i] - qg[i]); }
 #pragma unroll
     for (int i = 0; i < 3; ++i) { et1 += (t[i] - tg[i]) * (t[i] - tg[i]); et2 += (-t[i] - tg[i]) * (-t[i] - tg[i]); }
-    eq1 = sqrt(eq1); eq2 = sqrt(eq2); et1 = sqrt(et1); et2 = sqrt(et2);
-    const bool q_first = eq1 < eq2;     // strict, like the reference's q12_error[0] < q12_error[1]
+    const bool q_first = eq1 < eq2;     // strict, like the reference's q12_error[0] < q12_error[1] (sqrt is monotone)
     const bool t_first = et1 < et2;
     const double tsg = t_first ? 1.0 : -1.0;
     float res[FEPE_POSE_OUT_FLOATS];      // lane-uniform results, written once at the end
 #pragma unroll
-    for (int i = 0; i < 9; ++i) res[9 + i] = static_cast<float>(q_first ? R1[i] : R2[i]);
+    for (int i = 0; i < 9; ++i) res[i] = static_cast<float>(E[i]);
+    double Re[9];
+#pragma unroll
+    for (int i = 0; i < 9; ++i) { Re[i] = q_first ? R1[i] : R2[i]; res[9 + i] = static_cast<float>(Re[i]); }
 #pragma unroll
     for (int i = 0; i < 3; ++i) res[18 + i] = static_cast<float>(tsg * t[i]);
-    res[21] = static_cast<float>(q_first ? eq1 : eq2);
-    res[22] = static_cast<float>(t_first ? et1 : et2);
+    res[21] = static_cast<float>(fast_sqrt(q_first ? eq1 : eq2));
+    res[22] = static_cast<float>(fast_sqrt(t_first ? et1 : et2));
 
     // angular metrics
     float r_ang = 0.f;
     if (p.Rt != nullptr) {
         // R_gt = inverse(Rt)[:3,:3] = R_scene^T ; angle of R_est R_gt^T = R_est R_scene
-        const float* rt = p.Rt + static_cast<size_t>(b) * 16;
-        double Rs[9] = {rt[0], rt[1], rt[2], rt[4], rt[5], rt[6], rt[8], rt[9], rt[10]};
-        double Re[9], D[9];
+        double Rs[9], D[9];
 #pragma unroll
-        for (int i = 0; i < 9; ++i) Re[i] = q_first ? R1[i] : R2[i];
+        for (int i = 0; i < 9; ++i) Rs[i] = rtf[i];
         mat3_mul(Re, Rs, D);
         const double c = 0.5 * (D[0] + D[4] + D[8] - 1.0);
-        const double s = 0.5 * sqrt((D[7] - D[5]) * (D[7] - D[5]) + (D[2] - D[6]) * (D[2] - D[6]) +
-                                    (D[3] - D[1]) * (D[3] - D[1]));
+        const double s = 0.5 * fast_sqrt((D[7] - D[5]) * (D[7] - D[5]) + (D[2] - D[6]) * (D[2] - D[6]) +
+                                         (D[3] - D[1]) * (D[3] - D[1]));
         // the arguments are fp64-accurate; fp32 atan2 of them is good to ~1e-5 deg and far cheaper than the fp64 routine
         r_ang = atan2f(static_cast<float>(s), static_cast<float>(c)) * 57.29577951f;
     }
@@ -110,45 +185,18 @@ __global__ void __launch_bounds__(128) fepe_pose_fwd_kernel(const PoseParams p) 
         // angle between unit vectors as atan2(|a x b|, a.b): no acos cancellation near 0, fp32 evaluation
         const double dot = tsg * (t[0] * tg[0] + t[1] * tg[1] + t[2] * tg[2]);
         const double cx = t[1] * tg[2] - t[2] * tg[1], cy = t[2] * tg[0] - t[0] * tg[2], cz = t[0] * tg[1] - t[1] * tg[0];
-        const double sn = sqrt(cx * cx + cy * cy + cz * cz);
+        const double sn = fast_sqrt(cx * cx + cy * cy + cz * cz);
         res[24] = atan2f(static_cast<float>(sn), static_cast<float>(dot)) * 57.29577951f;
-    }
-
-    // F-loss over the virtual correspondences (fp32 like the reference)
-    float loss = 0.f;
-    if (p.virt1 != nullptr && p.V > 0) {
-        float Ff[9];
-#pragma unroll
-        for (int i = 0; i < 9; ++i) Ff[i] = static_cast<float>(F[i]);
-        const float* v1 = p.virt1 + static_cast<size_t>(b) * p.V * 3;
-        const float* v2 = p.virt2 + static_cast<size_t>(b) * p.V * 3;
-        for (int i = lane; i < p.V; i += 32) {
-            const float z1 = v1[3 * i + 2], z2 = v2[3 * i + 2];
-            const float u1 = fmaf(p.ax, v1[3 * i], p.bx * z1), w1 = fmaf(p.ay, v1[3 * i + 1], p.by * z1);
-            const float u2 = fmaf(p.ax, v2[3 * i], p.bx * z2), w2 = fmaf(p.ay, v2[3 * i + 1], p.by * z2);
-            const float l10 = u2 * Ff[0] + w2 * Ff[3] + z2 * Ff[6];
-            const float l11 = u2 * Ff[1] + w2 * Ff[4] + z2 * Ff[7];
-            const float l12 = u2 * Ff[2] + w2 * Ff[5] + z2 * Ff[8];
-            const float l20 = Ff[0] * u1 + Ff[1] * w1 + Ff[2] * z1;
-            const float l21 = Ff[3] * u1 + Ff[4] * w1 + Ff[5] * z1;
-            const float dd = l10 * u1 + l11 * w1 + l12 * z1;
-            const float d = fabsf(dd) * (1.0f / (sqrtf(l10 * l10 + l11 * l11) + 1e-6f) +
-                                         1.0f / (sqrtf(l20 * l20 + l21 * l21) + 1e-6f));
-            loss += fminf(d, p.clamp_at);
-        }
-#pragma unroll
-        for (int o2 = 16; o2 > 0; o2 >>= 1) loss += __shfl_xor_sync(0xffffffffu, loss, o2);
-        loss /= static_cast<float>(p.V);
     }
     res[25] = loss;
     res[26] = q_first ? 0.f : 1.f;
     res[27] = t_first ? 0.f : 1.f;
     res[28] = static_cast<float>(S[0]); res[29] = static_cast<float>(S[1]); res[30] = static_cast<float>(S[2]);
     res[31] = 0.f;
+    float mine = 0.f;                     // one coalesced 128-byte store per item
 #pragma unroll
-    for (int i = 9; i < FEPE_POSE_OUT_FLOATS; ++i) {
-        if (lane == i) o[i] = res[i];
-    }
+    for (int i = 0; i < FEPE_POSE_OUT_FLOATS; ++i) mine = (lane == i) ? res[i] : mine;
+    o[lane] = mine;
 }
 
 // Backward of the head: dL/dF from the upstream gradients of (q L2 error, t L2 error, F-loss) of every (layer, pair).
@@ -270,6 +318,20 @@ extern "C" int fepe_pose_fwd(const float* F, const float* K, int L, int B, float
     if ((virt1 == nullptr) != (virt2 == nullptr)) return FEPE_E_BADARG;
     fepe::PoseParams p{F, K, q_gt, t_gt, Rt_scene, virt1, virt2, L, B, V, ax, bx, ay, by, clamp_at, out};
     const int n = L * B;
-    fepe::fepe_pose_fwd_kernel<<<(n + 3) / 4, 128, 0, static_cast<cudaStream_t>(stream)>>>(p);
-    return static_cast<int>(cudaGetLastError());
+    // Programmatic dependent launch: the grid may be scheduled while the preceding kernel of the stream (normally
+    // fepe_fit_fwd, which produces F) is still running; the kernel fetches everything that does not depend on F and
+    // then blocks in griddepcontrol.wait until that kernel has completed and its writes are visible.  Disable with
+    // FEPE_POSE_PDL=0.
+    static const bool pdl = []() { const char* e = getenv("FEPE_POSE_PDL"); return e == nullptr || e[0] != '0'; }();
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((n + 3) / 4);
+    cfg.blockDim = dim3(128);
+    cfg.dynamicSmemBytes = 0;
+    cfg.stream = static_cast<cudaStream_t>(stream);
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl ? 1 : 0;
+    return static_cast<int>(cudaLaunchKernelEx(&cfg, fepe::fepe_pose_fwd_kernel, p));
 }
