@@ -179,8 +179,9 @@ def step_fit(db: DeviceBatch, aff):
 
 def step_full(db: DeviceBatch, aff):
     from fepe_b200 import ops
-    step_fit(db, aff)
-    ops.pose_forward(db.F, db.K, aff, db.q, db.tt, db.Rt, db.v1, db.v2, clamp_at=CLAMP_LOSS, out=db.pose)
+    # one call of the C ABI (fepe_fit_pose_fwd); at the config batch it is ONE kernel (pose head fused into the fit)
+    ops.fit_pose_forward(db.m, db.w, aff, db.K, db.q, db.tt, db.Rt, db.v1, db.v2, clamp_at=CLAMP_EPI,
+                         virt_clamp_at=CLAMP_LOSS, out=(db.F, db.res, db.epi, None, db.pose[0]))
 
 
 def capture(fn):
@@ -354,9 +355,10 @@ def run_ours(args):
     roofline = {"bound": "hbm", "kernel": fit_kernel, "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": ncu_traffic(B, N), "launch_us": fit_us,
                 "algorithmic_bytes_per_launch": fit_bytes(B, N), "peak_source": peak_src,
-                "note": "launch of one config batch (fepe_fit_fwd dispatches batches of <= 2 pairs per SM to the "
-                        "one-CTA-per-pair latency kernel); roofline_saturating is the persistent ring kernel the same "
-                        "entry point uses for batches that fill the 148 SMs"}
+                "note": "launch of one config batch (batches of <= 2 pairs per SM go to the one-CTA-per-pair latency "
+                        "kernel; in the timed step the pose head is fused into it, fepe_fit_pose_fwd); "
+                        "roofline_saturating is the split pipeline the same entry point uses for batches that fill "
+                        "the 148 SMs many times over"}
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
@@ -366,7 +368,7 @@ def run_ours(args):
                    "batch_per_gpu": B, "ncorr": N, "parallelism": f"pairs sharded over {world} GPU(s), no collective",
                    "l2_policy": f"ring of {ring_n} distinct batches ({ring_n * per_batch_bytes / 2**20:.0f} MiB) > 126 MiB L2",
                    "launch": "eager" if args.no_graph else "cuda_graph_replay"},
-        "gpu_launches": 2 * args.steps,
+        "gpu_launches": args.steps * (1 if B <= 2 * torch.cuda.get_device_properties(0).multi_processor_count else 2),
         "roofline": roofline,
     }
 

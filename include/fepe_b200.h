@@ -99,6 +99,17 @@ int fepe_pose_fwd(const float* F, const float* K, int L, int B, float ax, float 
                   const float* virt1, const float* virt2, int V, float clamp_at,
                   float* out, void* stream);
 
+/* fepe_fit_fwd followed by fepe_pose_fwd (L = 1) on the fitted F of every pair, as ONE call: the evaluation path
+ * "F and R,t per image pair" (train_good_utils.py:298 get_all_loss_DeepF + :64 get_Rt_loss on the last layer).  For
+ * batches that take the one-CTA-per-pair latency kernel the pose head runs inside that kernel (one launch, F never
+ * leaves the SM in between); larger batches run the two kernels back to back.  Arguments as in the two calls;
+ * `clamp_at` clamps the epipolar residual rows, `virt_clamp_at` the F-loss of the virtual correspondences. */
+int fepe_fit_pose_fwd(const float* matches, const float* weights, int B, int N, float ax, float bx, float ay,
+                      float by, float clamp_at, float* F_out, float* resid, float* epi, double* saved,
+                      const float* K, const float* q_gt, const float* t_gt, const float* Rt_scene,
+                      const float* virt1, const float* virt2, int V, float virt_clamp_at, float* pose_out,
+                      void* stream);
+
 /* Backward of fepe_pose_fwd: dL/dF [L,B,9] from the upstream gradients g_q, g_t, g_loss [L,B] (any may be NULL)
  * of out[..,21], out[..,22], out[..,25]; `pose_out` is the forward output (it records which candidates won).
  * Replaces autograd through torch.svd / _get_M2s / _R_to_q / _l2_error / compute_epi_residual on the host

@@ -19,6 +19,7 @@
 
 #include "fepe_fit.cuh"
 #include "fepe_fit_passes.cuh"
+#include "fepe_pose_head.cuh"
 
 namespace fepe {
 
@@ -205,6 +206,71 @@ __global__ void __launch_bounds__(kThreads, 1) fepe_fit_fwd_kernel(const FitPara
 // passes are spread over 4 warps instead of 1; two such CTAs fit an SM (registers), which covers
 // B = 256 on 148 SMs in a single wave.
 // ------------------------------------------------------------------------------------------------
+// Multi-shift eigen-solver spread over ALL warps of a CTA (latency kernel): NW*32 shifts per round instead of 32,
+// so lambda_min is bracketed NW*32-fold per round and fewer rounds are needed (host emulation:
+// tests/host_shim.cpp shim_eig9_multishift_n).  Every thread calls it with the same g36 (shared memory) and gets the
+// same f / lambda back; `okm` (NW words) and `xch` (16 doubles) are shared-memory exchange buffers.
+template <int NW>
+__device__ __forceinline__ int eig9_smallest_cta(const double* __restrict__ g36, double (&f)[9], double& lambda,
+                                                 int warp, int lane, unsigned* okm, double* xch) {
+    Eig9Bracket b;
+    if (!eig9_bracket_init(g36, b)) {
+#pragma unroll
+        for (int i = 0; i < 9; ++i) f[i] = (i == 8) ? 1.0 : 0.0;
+        lambda = 0.0;
+        return 0;
+    }
+    const double tiny = 1e-18 * b.tr;
+    const int L = warp * 32 + lane;
+    double x[9];
+    eig9_start_vector(x);
+    double rho = 0.0;
+    int rounds = 0;
+    while (rounds < 10) {
+        const double mu = eig9_lane_shift(b, L, NW * 32);
+        double xl[9];
+#pragma unroll
+        for (int i = 0; i < 9; ++i) xl[i] = x[i];
+        int nneg;
+        double rho_l, r_l, c_l;
+        eig9_lane_round(g36, mu, tiny, 2, xl, nneg, rho_l, r_l, c_l);
+        ++rounds;
+        const unsigned ok = __ballot_sync(0xffffffffu, nneg == 0);
+        if (lane == 0) okm[warp] = ok;
+        __syncthreads();
+        int first_fail = NW * 32;                           // shifts ascend with the CTA-wide lane index
+#pragma unroll
+        for (int w = NW - 1; w >= 0; --w) {
+            const unsigned bad = ~okm[w];
+            if (bad) first_fail = w * 32 + __ffs(bad) - 1;
+        }
+        const int best = first_fail - 1;
+        if (best < 0) {        // even the safe shift failed (G indefinite to rounding): move it further down
+            b.lo = b.lo * 64.0 - 1e-13 * b.tr;
+            b.lo_heur = b.lo;
+            __syncthreads();   // okm is rewritten next round
+            continue;
+        }
+        if (L == best) {
+            xch[0] = mu; xch[1] = rho_l; xch[2] = r_l; xch[3] = c_l;
+#pragma unroll
+            for (int i = 0; i < 9; ++i) xch[4 + i] = xl[i];
+        }
+        if (L == first_fail) xch[13] = mu;
+        __syncthreads();
+        const double mu_best = xch[0];
+        const double mu_fail = (first_fail < NW * 32) ? xch[13] : -1.0;
+        rho = xch[1];
+        const double r = xch[2], c = xch[3];
+#pragma unroll
+        for (int i = 0; i < 9; ++i) x[i] = xch[4 + i];
+        if (eig9_bracket_update(b, mu_best, mu_fail, rho, r, c)) break;
+    }
+    canonical_sign9(x, f);
+    lambda = rho;
+    return rounds;
+}
+
 #ifndef FEPE_SMALL_WARPS
 #define FEPE_SMALL_WARPS 4
 #endif
@@ -214,13 +280,20 @@ __global__ void __launch_bounds__(kThreads, 1) fepe_fit_fwd_kernel(const FitPara
 constexpr int kSmallWarps = FEPE_SMALL_WARPS;
 constexpr int kSmallThreads = kSmallWarps * 32;
 
-__global__ void __launch_bounds__(kSmallThreads, FEPE_SMALL_MINBLOCKS) fepe_fit_fwd_small_kernel(const FitParams p) {
+// POSE: the pose / loss head of the pair (fepe_pose_head.cuh, L = 1) runs on the last warp of the CTA while the
+// other warps write the residual rows -- F never leaves the SM before E -> R,t is done (fepe_fit_pose_fwd).
+template <bool POSE>
+__global__ void __launch_bounds__(kSmallThreads, FEPE_SMALL_MINBLOCKS) fepe_fit_fwd_small_kernel(const FitParams p,
+                                                                                               const PoseParams pp) {
     extern __shared__ __align__(128) unsigned char smem[];
     __shared__ uint64_t full_bar;
     __shared__ float red[kSmallWarps][4];
     __shared__ double gram_w[kSmallWarps][36];
     __shared__ double gram[kScratchDoubles];
-    __shared__ float sol_ff[9], sol_Fo[9];
+    __shared__ unsigned eig_ok[kSmallWarps];
+    __shared__ double eig_xch[16];
+    __shared__ float pose_in[POSE ? 32 : 1];                                // K(9) q(4) t(3) R_scene(9)
+    __shared__ float pose_virt[POSE ? 2 * kVirtPerLane * 3 * 32 : 1];      // [img][u][c][lane]
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -235,6 +308,7 @@ __global__ void __launch_bounds__(kSmallThreads, FEPE_SMALL_MINBLOCKS) fepe_fit_
     const bool w_bulk = ((reinterpret_cast<uintptr_t>(gw) & 15u) == 0) && ((N & 3) == 0);
     const float ax = p.ax, bx = p.bx, ay = p.ay, by = p.by;
 
+    const long long ts0 = clock64();
     if (tid == 0) {
         mbar_init(&full_bar, 1);
         fence_barrier_init();
@@ -249,13 +323,44 @@ __global__ void __launch_bounds__(kSmallThreads, FEPE_SMALL_MINBLOCKS) fepe_fit_
     if (!w_bulk) {
         for (int i = tid; i < N; i += kSmallThreads) sw[i] = __ldg(gw + i);
     }
+    if constexpr (POSE) {
+        // the pose head's inputs are fetched now, behind the bulk copy, and parked in shared memory
+        if (warp == kSmallWarps - 1) {
+            float v = 0.f;
+            if (lane < 9) v = __ldg(pp.K + pair * 9 + lane);
+            else if (lane < 13) v = __ldg(pp.q_gt + pair * 4 + (lane - 9));
+            else if (lane < 16) v = __ldg(pp.t_gt + pair * 3 + (lane - 13));
+            else if (lane < 25 && pp.Rt != nullptr) v = __ldg(pp.Rt + pair * 16 + 4 * ((lane - 16) / 3) + (lane - 16) % 3);
+            pose_in[lane] = v;
+            const bool has_virt = (pp.virt1 != nullptr) && (pp.V > 0);
+#pragma unroll
+            for (int u = 0; u < kVirtPerLane; ++u) {
+                const int i = lane + 32 * u;
+                const bool live = has_virt && i < pp.V;
+#pragma unroll
+                for (int c = 0; c < 3; ++c) {
+                    pose_virt[((0 * kVirtPerLane + u) * 3 + c) * 32 + lane] = live ? __ldg(pp.virt1 + (pair * pp.V + i) * 3 + c) : 0.f;
+                    pose_virt[((1 * kVirtPerLane + u) * 3 + c) * 32 + lane] = live ? __ldg(pp.virt2 + (pair * pp.V + i) * 3 + c) : 0.f;
+                }
+            }
+        }
+    }
     mbar_wait(&full_bar, 0);
     __syncthreads();       // also orders the hand-copied weights
+    const long long ts1 = clock64();
 
     // ---- passes 1+2 with block reductions ----
     PairNorm h;
     float sums[4], dist[2] = {0.f, 0.f};
-    pass_sums(sp, N, tid, kSmallThreads, sums);
+    constexpr int kTile = 8;
+    const bool tiled = N <= kTile * kSmallThreads;       // register-tile passes: one round of loads, 8-way ILP
+    if (tiled) {
+        float4 q[kTile];
+        tile_load(sp, N, tid, kSmallThreads, q);
+        tile_sums(q, sums);
+    } else {
+        pass_sums(sp, N, tid, kSmallThreads, sums);
+    }
 #pragma unroll
     for (int k = 0; k < 4; ++k) sums[k] = warp_sum(sums[k]);
     if (lane == 0) { red[warp][0] = sums[0]; red[warp][1] = sums[1]; red[warp][2] = sums[2]; red[warp][3] = sums[3]; }
@@ -269,7 +374,13 @@ __global__ void __launch_bounds__(kSmallThreads, FEPE_SMALL_MINBLOCKS) fepe_fit_
     }
     finish_norm(h, sums, dist, N, ax, bx, ay, by, false);
     __syncthreads();
-    pass_dist(sp, N, tid, kSmallThreads, ax, ay, h, dist);
+    if (tiled) {
+        float4 q[kTile];
+        tile_load(sp, N, tid, kSmallThreads, q);
+        tile_dist(q, N, tid, kSmallThreads, ax, ay, h, dist);
+    } else {
+        pass_dist(sp, N, tid, kSmallThreads, ax, ay, h, dist);
+    }
     dist[0] = warp_sum(dist[0]);
     dist[1] = warp_sum(dist[1]);
     if (lane == 0) { red[warp][0] = dist[0]; red[warp][1] = dist[1]; }
@@ -279,6 +390,7 @@ __global__ void __launch_bounds__(kSmallThreads, FEPE_SMALL_MINBLOCKS) fepe_fit_
     for (int w = 0; w < kSmallWarps; ++w) { dist[0] += red[w][0]; dist[1] += red[w][1]; }
     finish_norm(h, sums, dist, N, ax, bx, ay, by, true);
     const PairMap m = make_map(h, ax, ay);
+    const long long ts2 = clock64();
 
     // ---- pass 3 ----
     {
@@ -298,26 +410,93 @@ __global__ void __launch_bounds__(kSmallThreads, FEPE_SMALL_MINBLOCKS) fepe_fit_
     }
     __syncthreads();
 
-    // ---- solve on warp 0, broadcast through shared memory ----
-    if (warp == 0) {
-        publish_norm(gram, h, lane);
-        __syncwarp();
-        solve_pair(gram, lane);
-        store_pair_state(p, pair, h, gram, lane);
-        if (lane < 9) {
-            sol_ff[lane] = static_cast<float>(gram[kSolF + lane]);
-            sol_Fo[lane] = reinterpret_cast<const float*>(gram + kSolFo)[lane];
+    const long long ts3 = clock64();
+    // ---- eigenvector on all warps (4 x 32 shifts per round), the small uniform tail redundantly on every thread ----
+    float ff[9], Fo[9];
+    {
+        double f[9], lambda;
+        const long long te0 = clock64();
+        const int rounds = eig9_smallest_cta<kSmallWarps>(gram, f, lambda, warp, lane, eig_ok, eig_xch);
+        const long long te1 = clock64();
+        double F2[9], v3[3], sigma3;
+        rank2_project(f, F2, v3, sigma3);
+        denormalise_F(F2, h, Fo);
+#pragma unroll
+        for (int i = 0; i < 9; ++i) ff[i] = static_cast<float>(f[i]);
+        if (warp == 0) {
+            if (lane == 0) {
+#pragma unroll
+                for (int i = 0; i < 9; ++i) gram[kSolF + i] = f[i];
+                gram[kSolLambda] = lambda;
+                gram[kSolV3] = v3[0]; gram[kSolV3 + 1] = v3[1]; gram[kSolV3 + 2] = v3[2];
+                gram[kSolSigma3] = sigma3;
+                gram[kSolRounds] = static_cast<double>(rounds);
+                gram[kSolCycles] = static_cast<double>(te1 - te0);
+                float* fo = reinterpret_cast<float*>(gram + kSolFo);
+#pragma unroll
+                for (int i = 0; i < 9; ++i) fo[i] = Fo[i];
+            }
+            __syncwarp();
+            store_pair_state(p, pair, h, gram, lane);
         }
     }
-    __syncthreads();
-    float ff[9], Fo[9];
-#pragma unroll
-    for (int i = 0; i < 9; ++i) { ff[i] = sol_ff[i]; Fo[i] = sol_Fo[i]; }
+    const long long ts4 = clock64();
 
-    // ---- pass 4 ----
-    pass_resid(sp, sw, N, tid, kSmallThreads, m, ff, Fo, ax, bx, ay, by, p.clamp_at,
-               p.resid + pair * static_cast<size_t>(N),
-               (p.epi != nullptr) ? p.epi + pair * static_cast<size_t>(N) : nullptr);
+    // ---- pass 4 (and, fused, the pose head on the last warp) ----
+    if constexpr (POSE) {
+        if (warp == kSmallWarps - 1) {
+            float Kf[9], qgf[4], tgf[3], rtf[9];
+#pragma unroll
+            for (int i = 0; i < 9; ++i) { Kf[i] = pose_in[i]; rtf[i] = pose_in[16 + i]; }
+#pragma unroll
+            for (int i = 0; i < 4; ++i) qgf[i] = pose_in[9 + i];
+#pragma unroll
+            for (int i = 0; i < 3; ++i) tgf[i] = pose_in[13 + i];
+            float loss = 0.f;
+            if (pp.virt1 != nullptr && pp.V > 0) {
+#pragma unroll
+                for (int u = 0; u < kVirtPerLane; ++u) {
+                    if (lane + 32 * u < pp.V)
+                        loss += virt_term(Fo, ax, bx, ay, by, pp.clamp_at,
+                                          pose_virt[((0 * kVirtPerLane + u) * 3 + 0) * 32 + lane],
+                                          pose_virt[((0 * kVirtPerLane + u) * 3 + 1) * 32 + lane],
+                                          pose_virt[((0 * kVirtPerLane + u) * 3 + 2) * 32 + lane],
+                                          pose_virt[((1 * kVirtPerLane + u) * 3 + 0) * 32 + lane],
+                                          pose_virt[((1 * kVirtPerLane + u) * 3 + 1) * 32 + lane],
+                                          pose_virt[((1 * kVirtPerLane + u) * 3 + 2) * 32 + lane]);
+                }
+                const float* v1 = pp.virt1 + pair * pp.V * 3;
+                const float* v2 = pp.virt2 + pair * pp.V * 3;
+                for (int i = lane + 32 * kVirtPerLane; i < pp.V; i += 32)
+                    loss += virt_term(Fo, ax, bx, ay, by, pp.clamp_at, v1[3 * i], v1[3 * i + 1], v1[3 * i + 2],
+                                      v2[3 * i], v2[3 * i + 1], v2[3 * i + 2]);
+#pragma unroll
+                for (int o2 = 16; o2 > 0; o2 >>= 1) loss += __shfl_xor_sync(0xffffffffu, loss, o2);
+                loss /= static_cast<float>(pp.V);
+            }
+            pose_head(Fo, Kf, qgf, tgf, pp.Rt != nullptr, rtf, loss, ax, bx, ay, by, lane,
+                      pp.out + pair * FEPE_POSE_OUT_FLOATS);
+        } else {
+            pass_resid(sp, sw, N, tid, kSmallThreads - 32, m, ff, Fo, ax, bx, ay, by, p.clamp_at,
+                       p.resid + pair * static_cast<size_t>(N),
+                       (p.epi != nullptr) ? p.epi + pair * static_cast<size_t>(N) : nullptr);
+        }
+    } else {
+        pass_resid(sp, sw, N, tid, kSmallThreads, m, ff, Fo, ax, bx, ay, by, p.clamp_at,
+                   p.resid + pair * static_cast<size_t>(N),
+                   (p.epi != nullptr) ? p.epi + pair * static_cast<size_t>(N) : nullptr);
+    }
+    if (tid == 0 && p.saved != nullptr) {      // per-phase SM cycles of this pair (diagnostics)
+        double* sv = p.saved + pair * FEPE_SAVED_DOUBLES;
+        const long long ts5 = clock64();
+        sv[56] = static_cast<double>(ts1 - ts0);   // bulk copy
+        sv[57] = static_cast<double>(ts2 - ts1);   // Hartley passes
+        sv[58] = static_cast<double>(ts3 - ts2);   // Gram pass + reduction
+        sv[59] = static_cast<double>(ts4 - ts3);   // eigen + rank 2
+        sv[60] = static_cast<double>(ts5 - ts4);   // residual pass
+        sv[61] = 0.0;
+        sv[62] = gram[kSolCycles];
+    }
 }
 
 }  // namespace fepe
@@ -333,9 +512,11 @@ int fepe_max_correspondences(void) {
     return ((d.smem_optin - fixed) / 2 / 128) * 128 / 20;
 }
 
-int fepe_fit_fwd(const float* matches, const float* weights, int B, int N, float ax, float bx, float ay,
-                 float by, float clamp_at, float* F_out, float* resid, float* epi, double* saved,
-                 void* stream) {
+// `pose` != nullptr: also run the pose / loss head of every pair (L = 1); fused into the latency kernel when the
+// batch takes that path, otherwise as a second launch (fepe_pose_fwd) on the same stream.
+static int fit_fwd_impl(const float* matches, const float* weights, int B, int N, float ax, float bx, float ay,
+                        float by, float clamp_at, float* F_out, float* resid, float* epi, double* saved,
+                        const fepe::PoseParams* pose, void* stream) {
     if (B == 0) return 0;
     if (!matches || !weights || !F_out || !resid || B < 0 || N <= 0) return FEPE_E_BADARG;
     if (reinterpret_cast<uintptr_t>(matches) & 15u) return FEPE_E_BADARG;
@@ -361,21 +542,57 @@ int fepe_fit_fwd(const float* matches, const float* weights, int B, int N, float
     // Batches that fill the machine several times over go through the split pipeline (fepe_fit_split.cu).
     bool use_split = !use_small && (B >= fepe::kSplitMinPairsPerSM * d.sms) && fepe::split_path_supported(p, d);
     if (force != nullptr) use_split = (force[0] == 's') && (force[1] == 'p') && fepe::split_path_supported(p, d);
+    if (use_small && pose != nullptr) {
+        if (!d.small_pose_configured) {
+            e = cudaFuncSetAttribute(fepe::fepe_fit_fwd_small_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     56 * 1024);
+            if (e != cudaSuccess) return static_cast<int>(e);
+            d.small_pose_configured = 1;
+        }
+        fepe::fepe_fit_fwd_small_kernel<true><<<B, fepe::kSmallThreads, small_bytes, static_cast<cudaStream_t>(stream)>>>(p, *pose);
+        return static_cast<int>(cudaGetLastError());
+    }
+    if (pose != nullptr) {      // two launches: any forward path, then the stand-alone head on its F
+        const int st = fit_fwd_impl(matches, weights, B, N, ax, bx, ay, by, clamp_at, F_out, resid, epi, saved, nullptr,
+                                    stream);
+        if (st != 0) return st;
+        return fepe_pose_fwd(F_out, pose->K, 1, B, ax, bx, ay, by, pose->q_gt, pose->t_gt, pose->Rt, pose->virt1,
+                             pose->virt2, pose->V, pose->clamp_at, pose->out, stream);
+    }
     if (use_split) return fepe::launch_split(p, d, static_cast<cudaStream_t>(stream));
     if (use_small) {
         if (!d.small_configured) {
-            e = cudaFuncSetAttribute(fepe::fepe_fit_fwd_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+            e = cudaFuncSetAttribute(fepe::fepe_fit_fwd_small_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      56 * 1024);
             if (e != cudaSuccess) return static_cast<int>(e);
             d.small_configured = 1;
         }
-        fepe::fepe_fit_fwd_small_kernel<<<B, fepe::kSmallThreads, small_bytes, static_cast<cudaStream_t>(stream)>>>(p);
+        fepe::fepe_fit_fwd_small_kernel<false><<<B, fepe::kSmallThreads, small_bytes, static_cast<cudaStream_t>(stream)>>>(p, fepe::PoseParams{});
         return static_cast<int>(cudaGetLastError());
     }
     const int grid = B < d.sms ? B : d.sms;
     fepe::fepe_fit_fwd_kernel<<<grid, fepe::kThreads, p.ring.total_bytes, static_cast<cudaStream_t>(stream)>>>(p);
     e = cudaGetLastError();
     return static_cast<int>(e);
+}
+
+int fepe_fit_fwd(const float* matches, const float* weights, int B, int N, float ax, float bx, float ay,
+                 float by, float clamp_at, float* F_out, float* resid, float* epi, double* saved,
+                 void* stream) {
+    return fit_fwd_impl(matches, weights, B, N, ax, bx, ay, by, clamp_at, F_out, resid, epi, saved, nullptr, stream);
+}
+
+int fepe_fit_pose_fwd(const float* matches, const float* weights, int B, int N, float ax, float bx, float ay,
+                      float by, float clamp_at, float* F_out, float* resid, float* epi, double* saved,
+                      const float* K, const float* q_gt, const float* t_gt, const float* Rt_scene,
+                      const float* virt1, const float* virt2, int V, float virt_clamp_at, float* pose_out,
+                      void* stream) {
+    if (B == 0) return 0;
+    if (!K || !q_gt || !t_gt || !pose_out || V < 0) return FEPE_E_BADARG;
+    if ((virt1 == nullptr) != (virt2 == nullptr)) return FEPE_E_BADARG;
+    const fepe::PoseParams pose{F_out, K, q_gt, t_gt, Rt_scene, virt1, virt2, 1, B, V, ax, bx, ay, by, virt_clamp_at,
+                                pose_out};
+    return fit_fwd_impl(matches, weights, B, N, ax, bx, ay, by, clamp_at, F_out, resid, epi, saved, &pose, stream);
 }
 
 }  // extern "C"

@@ -189,6 +189,7 @@ struct DeviceInfo {
     int fwd_configured = 0;
     int bwd_configured = 0;
     int small_configured = 0;
+    int small_pose_configured = 0;
 };
 
 inline DeviceInfo& device_info() {

@@ -272,8 +272,8 @@ FEPE_HD bool eig9_bracket_init(const double* __restrict__ g36, Eig9Bracket& b) {
     return (tr > 0.0) && (tr < 1e300);
 }
 
-// Shift of lane `lane` (0..31) for the current round; lane 0 always carries the known-safe shift.
-FEPE_HD double eig9_lane_shift(const Eig9Bracket& b, int lane) {
+// Shift of lane `lane` (0..nlanes-1) for the current round; lane 0 always carries the known-safe shift.
+FEPE_HD double eig9_lane_shift(const Eig9Bracket& b, int lane, int nlanes = 32) {
     if (lane == 0) return b.lo;
     if (b.round == 0) {
         // geometric ladder from 1e-13 tr up to the upper limit: lambda_min can sit anywhere on 13 decades
@@ -281,13 +281,14 @@ FEPE_HD double eig9_lane_shift(const Eig9Bracket& b, int lane) {
         const double top = (b.hi > 2.0 * a) ? b.hi : 2.0 * a;
 #if defined(__CUDA_ARCH__)
         // fp32 transcendentals: the ladder only has to be ascending, not accurate
-        return a * static_cast<double>(exp2f(log2f(static_cast<float>(top * fast_rcp(a))) * (static_cast<float>(lane - 1) * (1.0f / 30.0f))));
+        return a * static_cast<double>(exp2f(log2f(static_cast<float>(top * fast_rcp(a))) *
+                                             (static_cast<float>(lane - 1) / static_cast<float>(nlanes - 2))));
 #else
-        return a * exp2(log2(top / a) * (static_cast<double>(lane - 1) * (1.0 / 30.0)));
+        return a * exp2(log2(top / a) * (static_cast<double>(lane - 1) / static_cast<double>(nlanes - 2)));
 #endif
     }
     const double lo = (b.lo_heur > 0.0) ? b.lo_heur : 0.0;
-    return lo + (b.hi - lo) * (static_cast<double>(lane - 1) * (1.0 / 31.0)) * 0.999;
+    return lo + (b.hi - lo) * (static_cast<double>(lane - 1) / static_cast<double>(nlanes - 1)) * 0.999;
 }
 
 // One lane's work for a round: factor at `mu`, `nsolve` inverse-iteration solves starting from x.

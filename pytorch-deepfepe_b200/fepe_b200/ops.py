@@ -92,6 +92,52 @@ def pose_forward(F: torch.Tensor, K: torch.Tensor, affine, q_gt: torch.Tensor, t
     return out
 
 
+def fit_pose_forward(matches: torch.Tensor, weights: torch.Tensor, affine, K: torch.Tensor, q_gt: torch.Tensor,
+                     t_gt: torch.Tensor, Rt_scene: Optional[torch.Tensor] = None, virt1: Optional[torch.Tensor] = None,
+                     virt2: Optional[torch.Tensor] = None, clamp_at: float = 0.5, virt_clamp_at: float = 0.02,
+                     want_epi: bool = True, want_saved: bool = False, out=None):
+    """fit_forward + pose_forward (one layer) as ONE call of the C ABI (include/fepe_b200.h: fepe_fit_pose_fwd):
+    a single kernel for batches of up to two pairs per SM.  Returns (F, residual, epi|None, saved|None, pose [B,32]);
+    `out` may carry caller-owned buffers in that order."""
+    matches = _check_cuda_f32(matches, "matches")
+    weights = _check_cuda_f32(weights, "weights")
+    B, N, four = matches.shape
+    if four != 4:
+        raise RuntimeError("fepe_b200: matches must be [B,N,4] (x1,y1,x2,y2)")
+    weights = weights.reshape(B, N)
+    dev = matches.device
+    K = _check_cuda_f32(K, "K").reshape(B, 9)
+    q_gt = _check_cuda_f32(q_gt, "q_gt").reshape(B, 4)
+    t_gt = _check_cuda_f32(t_gt, "t_gt").reshape(B, 3)
+    rt = _check_cuda_f32(Rt_scene, "Rt_scene").reshape(B, 16) if Rt_scene is not None else None
+    V = 0
+    if virt1 is not None:
+        virt1 = _check_cuda_f32(virt1, "virt1")
+        virt2 = _check_cuda_f32(virt2, "virt2")
+        V = virt1.shape[1]
+    with torch.cuda.device(dev):
+        if out is not None:
+            F, res, epi, saved, pose = out
+        else:
+            F = torch.empty(B, 3, 3, dtype=torch.float32, device=dev)
+            res = torch.empty(B, N, dtype=torch.float32, device=dev)
+            epi = torch.empty(B, N, dtype=torch.float32, device=dev) if want_epi else None
+            saved = torch.empty(B, _lib.SAVED_DOUBLES, dtype=torch.float64, device=dev) if want_saved else None
+            pose = torch.empty(B, _lib.POSE_OUT_FLOATS, dtype=torch.float32, device=dev)
+        st = _lib.lib().fepe_fit_pose_fwd(matches.data_ptr(), weights.data_ptr(), B, N,
+                                          affine[0], affine[1], affine[2], affine[3], float(clamp_at),
+                                          F.data_ptr(), res.data_ptr(),
+                                          epi.data_ptr() if epi is not None else None,
+                                          saved.data_ptr() if saved is not None else None,
+                                          K.data_ptr(), q_gt.data_ptr(), t_gt.data_ptr(),
+                                          rt.data_ptr() if rt is not None else None,
+                                          virt1.data_ptr() if virt1 is not None else None,
+                                          virt2.data_ptr() if virt2 is not None else None, V, float(virt_clamp_at),
+                                          pose.data_ptr(), _stream_ptr())
+    _lib.check(st, "fepe_fit_pose_fwd")
+    return F, res, epi, saved, pose
+
+
 def fit_backward(matches: torch.Tensor, weights: torch.Tensor, saved: torch.Tensor, gF: torch.Tensor,
                  gres: Optional[torch.Tensor], gepi: Optional[torch.Tensor], affine=IDENTITY_AFFINE,
                  clamp_at: float = 0.5) -> torch.Tensor:

@@ -55,17 +55,16 @@ class StagedStep:
         return buf
 
     def run(self, stream, affine, clamp_epi: float = 0.5, clamp_loss: float = 0.02, host: torch.Tensor = None) -> None:
-        """H2D (1 copy) -> fepe_fit_fwd -> fepe_pose_fwd -> D2H (1 copy), all on `stream`.
+        """H2D (1 copy) -> fepe_fit_pose_fwd (fit + pose head) -> D2H (1 copy), all on `stream`.
         `host` is a buffer made by pack(); default: this object's own pinned buffer."""
         with torch.cuda.stream(stream):
             self.d_in.copy_(host if host is not None else self.h_in, non_blocking=True)
             v = lambda k: self._view(self.d_in, k)
             F = self.d_out[:self.B * 9].view(self.B, 3, 3)
             pose = self.d_out[self.B * 9:].view(1, self.B, _lib.POSE_OUT_FLOATS)
-            ops.fit_forward(v("matches_xy_ori"), v("weights"), affine, clamp_at=clamp_epi,
-                            out=(F, self.d_res, self.d_epi, None))
-            ops.pose_forward(F, v("Ks"), affine, v("q_cam"), v("t_cam"), v("delta_Rtijs_4_4"), v("pts1_virt"),
-                             v("pts2_virt"), clamp_at=clamp_loss, out=pose)
+            ops.fit_pose_forward(v("matches_xy_ori"), v("weights"), affine, v("Ks"), v("q_cam"), v("t_cam"),
+                                 v("delta_Rtijs_4_4"), v("pts1_virt"), v("pts2_virt"), clamp_at=clamp_epi,
+                                 virt_clamp_at=clamp_loss, out=(F, self.d_res, self.d_epi, None, pose[0]))
             self.h_out.copy_(self.d_out, non_blocking=True)
 
     def results(self):

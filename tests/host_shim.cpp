@@ -44,11 +44,12 @@ void shim_rank2(const double* F0, double* F2) {
     for (int i = 0; i < 9; ++i) F2[i] = f2[i];
 }
 
-// Host emulation of the warp driver eig9_smallest_warp (fepe_fit.cuh): same scalar pieces, the
-// ballot / shuffle replaced by loops over 32 virtual lanes.
-int shim_eig9_multishift(const double* g36, double* f, double* lambda) {
+// Host emulation of the multi-shift drivers eig9_smallest_warp (fepe_fit.cuh, 32 lanes) and eig9_smallest_cta
+// (fepe_fit.cu, 128 lanes): same scalar pieces, the ballot / shuffle / shared-memory exchange replaced by
+// loops over `nlanes` virtual lanes.
+int shim_eig9_multishift_n(const double* g36, double* f, double* lambda, int nlanes) {
     fepe::Eig9Bracket b;
-    if (!fepe::eig9_bracket_init(g36, b)) {
+    if (nlanes < 3 || nlanes > 128 || !fepe::eig9_bracket_init(g36, b)) {
         for (int i = 0; i < 9; ++i) f[i] = (i == 8) ? 1.0 : 0.0;
         *lambda = 0.0;
         return 0;
@@ -59,21 +60,21 @@ int shim_eig9_multishift(const double* g36, double* f, double* lambda) {
     double rho = 0.0;
     int rounds = 0;
     while (rounds < 10) {
-        double mu[32], rho_l[32], r_l[32], c_l[32], xl[32][9];
-        int nneg[32];
-        for (int lane = 0; lane < 32; ++lane) {
-            mu[lane] = fepe::eig9_lane_shift(b, lane);
+        double mu[128], rho_l[128], r_l[128], c_l[128], xl[128][9];
+        int nneg[128];
+        for (int lane = 0; lane < nlanes; ++lane) {
+            mu[lane] = fepe::eig9_lane_shift(b, lane, nlanes);
             double xx[9];
             for (int i = 0; i < 9; ++i) xx[i] = x[i];
             fepe::eig9_lane_round(g36, mu[lane], tiny, 2, xx, nneg[lane], rho_l[lane], r_l[lane], c_l[lane]);
             for (int i = 0; i < 9; ++i) xl[lane][i] = xx[i];
         }
         ++rounds;
-        int first_fail = 32;
-        for (int lane = 31; lane >= 0; --lane) if (nneg[lane] != 0) first_fail = lane;
+        int first_fail = nlanes;
+        for (int lane = nlanes - 1; lane >= 0; --lane) if (nneg[lane] != 0) first_fail = lane;
         const int best = first_fail - 1;
         if (best < 0) { b.lo = b.lo * 64.0 - 1e-13 * b.tr; b.lo_heur = b.lo; continue; }
-        const double mu_fail = (first_fail < 32) ? mu[first_fail] : -1.0;
+        const double mu_fail = (first_fail < nlanes) ? mu[first_fail] : -1.0;
         rho = rho_l[best];
         for (int i = 0; i < 9; ++i) x[i] = xl[best][i];
         if (fepe::eig9_bracket_update(b, mu[best], mu_fail, rho, r_l[best], c_l[best])) break;
@@ -83,6 +84,12 @@ int shim_eig9_multishift(const double* g36, double* f, double* lambda) {
     for (int i = 0; i < 9; ++i) f[i] = ff[i];
     *lambda = rho;
     return rounds;
+}
+int shim_eig9_multishift(const double* g36, double* f, double* lambda) {
+    return shim_eig9_multishift_n(g36, f, lambda, 32);
+}
+int shim_eig9_multishift128(const double* g36, double* f, double* lambda) {
+    return shim_eig9_multishift_n(g36, f, lambda, 128);
 }
 
 int shim_g36_index(int r, int c) { return fepe::g36_index(r, c); }

@@ -29,6 +29,8 @@ def shim():
     lib.shim_eig9.restype = ctypes.c_int
     lib.shim_eig9_multishift.argtypes = [dp, dp, dp]
     lib.shim_eig9_multishift.restype = ctypes.c_int
+    lib.shim_eig9_multishift128.argtypes = [dp, dp, dp]
+    lib.shim_eig9_multishift128.restype = ctypes.c_int
     lib.shim_pinv.argtypes = [dp, dp, ctypes.c_double, dp, dp]
     lib.shim_svd3.argtypes = [dp, dp, dp, dp]
     lib.shim_svd3_direct.argtypes = [dp, dp, dp, dp]
@@ -88,7 +90,7 @@ def test_g36_layout_matches_kron(shim):
     np.testing.assert_allclose(full_gram(shim, g36), G, rtol=1e-12, atol=1e-12)
 
 
-@pytest.mark.parametrize("solver", ["shim_eig9", "shim_eig9_multishift"])
+@pytest.mark.parametrize("solver", ["shim_eig9", "shim_eig9_multishift", "shim_eig9_multishift128"])
 @pytest.mark.parametrize("mode", ["uniform", "softmax", "peaked", "inlier"])
 def test_eig9_on_scene_grams(shim, mode, solver):
     worst, its = 0.0, []
@@ -108,9 +110,10 @@ def test_eig9_on_scene_grams(shim, mode, solver):
     # the 1e-4 parity budget
     assert worst < 2e-7, worst
     assert max(its) <= 16, its
+    print(solver, mode, 'mean rounds / factorisations', np.mean(its), 'max', max(its))
 
 
-@pytest.mark.parametrize("solver", ["shim_eig9", "shim_eig9_multishift"])
+@pytest.mark.parametrize("solver", ["shim_eig9", "shim_eig9_multishift", "shim_eig9_multishift128"])
 def test_eig9_random_spd_and_degenerate(shim, solver):
     solve = getattr(shim, solver)
     rng = np.random.default_rng(1)

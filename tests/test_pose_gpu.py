@@ -107,3 +107,24 @@ def test_pose_loss_function_gradient_against_oracle_autograd():
     print("pose head dL/dF rel err: median %.2e max %.2e" % (float(rel.median()), float(rel.max())))
     # fp32 F and fp32 virtual-point arithmetic on our side; SVD-adjoint denominators 1/(s1^2-s2^2) amplify that
     assert float(rel.median()) < 1e-3 and float(rel.max()) < 5e-2
+
+
+@pytest.mark.parametrize("B,N,with_virt,with_rt", [(256, 1000, True, True), (40, 333, True, False), (7, 64, False, True),
+                                                   (600, 200, True, True)])
+def test_fused_fit_pose_equals_two_calls(B, N, with_virt, with_rt):
+    """fepe_fit_pose_fwd (pose head inside the latency kernel for B <= 2 pairs per SM, two launches above) against
+    fepe_fit_fwd + fepe_pose_fwd on the same inputs."""
+    d = synth.make_batch(B, N, seed=91 + N, weight_mode="softmax", outlier_frac=0.3)
+    aff = ops.hw_affine(d["image_size"])
+    g = lambda k: T(d[k]).cuda()
+    m, w = g("matches_xy_ori"), g("weights")
+    v1, v2 = (g("pts1_virt"), g("pts2_virt")) if with_virt else (None, None)
+    rt = g("delta_Rtijs_4_4") if with_rt else None
+    F0, r0, e0, s0 = ops.fit_forward(m, w, aff, want_saved=True)
+    p0 = ops.pose_forward(F0, g("Ks"), aff, g("q_cam"), g("t_cam"), rt, v1, v2, clamp_at=0.02)[0]
+    F1, r1, e1, s1, p1 = ops.fit_pose_forward(m, w, aff, g("Ks"), g("q_cam"), g("t_cam"), rt, v1, v2,
+                                              virt_clamp_at=0.02, want_saved=True)
+    torch.cuda.synchronize()
+    assert torch.equal(F0, F1) and torch.equal(r0, r1) and torch.equal(e0, e1)
+    assert torch.equal(s0[:, :56], s1[:, :56])
+    np.testing.assert_allclose(p1.cpu().numpy(), p0.cpu().numpy(), rtol=1e-6, atol=1e-6)
