@@ -75,6 +75,18 @@ int fepe_fit_bwd(const float* matches, const float* weights, int B, int N,
                  const double* saved, const float* gF, const float* gresid, const float* gepi,
                  float* gweights, void* stream);
 
+/* Same, plus the gradient w.r.t. the COORDINATES: gmatches [B,N,4] (16-byte aligned) receives
+ * d loss / d (x1,y1,x2,y2) of every correspondence, through compute_epi_residual's direct dependence
+ * (utils_F.py:400-413), the constraint rows and their L2 normalisation (DeepFNet.py:203-212), both Hartley
+ * transforms including their mean and mean-distance terms (Fit.normalize, DeepFNet.py:148-179; T enters
+ * out = T2^T F_ T1 as well, :256) and the affine (ax,bx,ay,by).  The reference needs it when learned offsets
+ * are added to the matches (if_learn_offsets, DeepFNet.py:373,489-505) or the keypoint front-end is trained
+ * (Train_model_pipeline.py:384).  gmatches == NULL is fepe_fit_bwd.  */
+int fepe_fit_bwd_coords(const float* matches, const float* weights, int B, int N,
+                        float ax, float bx, float ay, float by, float clamp_at,
+                        const double* saved, const float* gF, const float* gresid, const float* gepi,
+                        float* gweights, float* gmatches, void* stream);
+
 /* ---- pose / loss head -----------------------------------------------------------------------------
  * Replaces, per layer and pair: E = K^T T2^T F T1 K (deepFEPE/train_good_utils.py:356-358), the host
  * loop of get_Rt_loss (train_good_utils.py:96-188: E^T -> _get_M2s (dsac_tools/utils_F.py:478-498),

@@ -34,6 +34,7 @@ struct FitParams {
     const float* gresid;
     const float* gepi;
     float* gweights;
+    float* gmatches;        // [B,N,4] or null (coordinate gradient)
     RingLayout ring;
 };
 

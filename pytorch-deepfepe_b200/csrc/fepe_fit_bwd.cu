@@ -14,10 +14,19 @@
 // The Hartley transforms depend on the coordinates only (Fit.normalize is called with unit weights,
 // DeepFNet.py:194-199), so they carry no weight gradient.  Same pair ring as the forward: one warp per
 // pair, the pair's coordinates, weights and the two upstream rows staged once (28 B / correspondence).
+//
+// Coordinate gradient (`gmatches` != null; the reference needs it with if_learn_offsets, DeepFNet.py:373,489-505,
+// or a trainable keypoint front-end): pass 2 also forms the adjoint of every constraint row w.r.t. the
+// Hartley-normalised coordinates and of the epipolar distance w.r.t. the primed ones (fepe_fit_adjoint.cuh), parks
+// the four partial gradients of correspondence i in the four dead row slots of the stage (weight, rbar, ebar and
+// one spare row: 32 B / correspondence staged) and accumulates the ten sums the adjoint of Fit.normalize needs;
+// pass 3 adds the mean / mean-distance terms and writes [N,4] once.  No read-modify-write of global memory.
 #include "fepe_fit.cuh"
+#include "fepe_fit_adjoint.cuh"
 
 namespace fepe {
 
+template <bool COORDS>
 __global__ void __launch_bounds__(kThreads, 1) fepe_fit_bwd_kernel(const FitParams p) {
     extern __shared__ __align__(128) unsigned char smem[];
     const int warp = threadIdx.x >> 5;
@@ -54,9 +63,10 @@ __global__ void __launch_bounds__(kThreads, 1) fepe_fit_bwd_kernel(const FitPara
         const size_t pair = static_cast<size_t>(blockIdx.x) + static_cast<size_t>(j) * gridDim.x;
         unsigned char* sb = smem + static_cast<size_t>(stage) * p.ring.stage_bytes;
         const float4* sp = reinterpret_cast<const float4*>(sb);
-        const float* sw = reinterpret_cast<const float*>(sb + pts_bytes);
-        const float* sgr = reinterpret_cast<const float*>(sb + pts_bytes + row_bytes);
-        const float* sge = reinterpret_cast<const float*>(sb + pts_bytes + 2 * row_bytes);
+        float* sw = reinterpret_cast<float*>(sb + pts_bytes);
+        float* sgr = reinterpret_cast<float*>(sb + pts_bytes + row_bytes);
+        float* sge = reinterpret_cast<float*>(sb + pts_bytes + 2 * row_bytes);
+        float* sx4 = reinterpret_cast<float*>(sb + pts_bytes + 3 * row_bytes);   // spare row (coordinate gradient only)
 
         // ---- per-pair state saved by the forward (warp-uniform) ----
         const double* sv = p.saved + pair * FEPE_SAVED_DOUBLES;
@@ -167,27 +177,97 @@ __global__ void __launch_bounds__(kThreads, 1) fepe_fit_bwd_kernel(const FitPara
 #pragma unroll
         for (int i = 0; i < 9; ++i) zf[i] = static_cast<float>(z[i]);
 
-        // ---- pass 2: wbar_i ----
+        // ---- pass 2: wbar_i (and the partial coordinate gradient) ----
         float* __restrict__ gw_out = p.gweights + pair * static_cast<size_t>(N);
+        if constexpr (!COORDS) {
 #pragma unroll 2
-        for (int i = lane; i < N; i += 32) {
-            const float4 q = sp[i];
-            const float x1 = fmaf(k1x, q.x, j1x), y1 = fmaf(k1y, q.y, j1y);
-            const float x2 = fmaf(k2x, q.z, j2x), y2 = fmaf(k2y, q.w, j2y);
-            const float nb = fmaf(x1, x1, fmaf(y1, y1, 1.0f));
-            const float na = fmaf(x2, x2, fmaf(y2, y2, 1.0f));
-            const float inv = rsqrtf(na * nb);
-            const float f0 = fmaf(ff[0], x1, fmaf(ff[1], y1, ff[2]));
-            const float f1 = fmaf(ff[3], x1, fmaf(ff[4], y1, ff[5]));
-            const float f2 = fmaf(ff[6], x1, fmaf(ff[7], y1, ff[8]));
-            const float pf = fmaf(x2, f0, fmaf(y2, f1, f2)) * inv;
-            const float z0 = fmaf(zf[0], x1, fmaf(zf[1], y1, zf[2]));
-            const float z1 = fmaf(zf[3], x1, fmaf(zf[4], y1, zf[5]));
-            const float z2 = fmaf(zf[6], x1, fmaf(zf[7], y1, zf[8]));
-            const float pz = fmaf(x2, z0, fmaf(y2, z1, z2)) * inv;
-            const float gr = has_gr ? sgr[i] : 0.f;
-            gw_out[i] = fmaf(-2.0f * sw[i] * pz, pf, gr * pf);
+            for (int i = lane; i < N; i += 32) {
+                const float4 q = sp[i];
+                const float x1 = fmaf(k1x, q.x, j1x), y1 = fmaf(k1y, q.y, j1y);
+                const float x2 = fmaf(k2x, q.z, j2x), y2 = fmaf(k2y, q.w, j2y);
+                const float nb = fmaf(x1, x1, fmaf(y1, y1, 1.0f));
+                const float na = fmaf(x2, x2, fmaf(y2, y2, 1.0f));
+                const float inv = rsqrtf(na * nb);
+                const float f0 = fmaf(ff[0], x1, fmaf(ff[1], y1, ff[2]));
+                const float f1 = fmaf(ff[3], x1, fmaf(ff[4], y1, ff[5]));
+                const float f2 = fmaf(ff[6], x1, fmaf(ff[7], y1, ff[8]));
+                const float pf = fmaf(x2, f0, fmaf(y2, f1, f2)) * inv;
+                const float z0 = fmaf(zf[0], x1, fmaf(zf[1], y1, zf[2]));
+                const float z1 = fmaf(zf[3], x1, fmaf(zf[4], y1, zf[5]));
+                const float z2 = fmaf(zf[6], x1, fmaf(zf[7], y1, zf[8]));
+                const float pz = fmaf(x2, z0, fmaf(y2, z1, z2)) * inv;
+                const float gr = has_gr ? sgr[i] : 0.f;
+                gw_out[i] = fmaf(-2.0f * sw[i] * pz, pf, gr * pf);
+            }
+        } else {
+            // sums for the adjoint of Fit.normalize: [0..1] sum x~bar, [2..3] sum y~bar, [4..5] sum x~bar.(u-c),
+            // [6..7] sum (u-cx)/d, [8..9] sum (v-cy)/d   (even: image 1, odd: image 2)
+            float ns[10];
+#pragma unroll
+            for (int k = 0; k < 10; ++k) ns[k] = 0.f;
+            const float s1f = h.s1, s2f = h.s2;
+            for (int i = lane; i < N; i += 32) {
+                const float4 q = sp[i];
+                const float u1 = fmaf(ax, q.x, bx), v1 = fmaf(ay, q.y, by);
+                const float u2 = fmaf(ax, q.z, bx), v2 = fmaf(ay, q.w, by);
+                const float du1 = u1 - h.c1x, dv1 = v1 - h.c1y, du2 = u2 - h.c2x, dv2 = v2 - h.c2y;
+                const float gr = has_gr ? sgr[i] : 0.f;
+                float wb, xb[4];
+                row_adjoint<float>(s1f * du1, s1f * dv1, s2f * du2, s2f * dv2, sw[i], gr, ff, zf, wb, xb);
+                gw_out[i] = wb;
+                float cb[4] = {0.f, 0.f, 0.f, 0.f};
+                if (has_ge) {
+                    float ge_unused[9] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+                    epi_adjoint<float>(u1, v1, u2, v2, Fo, clamp_at, sge[i], ge_unused, cb);
+                }
+                ns[0] += xb[0]; ns[2] += xb[1]; ns[4] = fmaf(xb[0], du1, fmaf(xb[1], dv1, ns[4]));
+                ns[1] += xb[2]; ns[3] += xb[3]; ns[5] = fmaf(xb[2], du2, fmaf(xb[3], dv2, ns[5]));
+                const float q1 = fmaf(du1, du1, dv1 * dv1), q2 = fmaf(du2, du2, dv2 * dv2);
+                const float id1 = (q1 > 0.f) ? rsqrtf(q1) : 0.f, id2 = (q2 > 0.f) ? rsqrtf(q2) : 0.f;
+                ns[6] = fmaf(du1, id1, ns[6]); ns[8] = fmaf(dv1, id1, ns[8]);
+                ns[7] = fmaf(du2, id2, ns[7]); ns[9] = fmaf(dv2, id2, ns[9]);
+                // partial gradient w.r.t. the primed coordinates; same lane reads and writes index i
+                sw[i] = fmaf(s1f, xb[0], cb[0]);
+                sgr[i] = fmaf(s1f, xb[1], cb[1]);
+                sge[i] = fmaf(s2f, xb[2], cb[2]);
+                sx4[i] = fmaf(s2f, xb[3], cb[3]);
+            }
+#pragma unroll
+            for (int k = 0; k < 10; ++k) ns[k] = warp_sum(ns[k]);
+            NormAdjointSums S;
+#pragma unroll
+            for (int im = 0; im < 2; ++im) {
+                S.sx[im] = ns[im]; S.sy[im] = ns[2 + im]; S.sd[im] = ns[4 + im];
+                S.dx[im] = ns[6 + im]; S.dy[im] = ns[8 + im];
+            }
+            const double sc[2] = {static_cast<double>(h.s1), static_cast<double>(h.s2)};
+            const double ccx[2] = {static_cast<double>(h.c1x), static_cast<double>(h.c2x)};
+            const double ccy[2] = {static_cast<double>(h.c1y), static_cast<double>(h.c2y)};
+            NormAdjointCoef C;
+            norm_adjoint(ob, F2, sc, ccx, ccy, S, N, C);
+            const float A1 = static_cast<float>(C.A[0]), A2 = static_cast<float>(C.A[1]);
+            const float B1x = static_cast<float>(C.Bx[0]), B1y = static_cast<float>(C.By[0]);
+            const float B2x = static_cast<float>(C.Bx[1]), B2y = static_cast<float>(C.By[1]);
+            __syncwarp();
+            // ---- pass 3: add the mean / mean-distance terms, chain through the affine, write [N,4] ----
+            float4* __restrict__ gm_out = reinterpret_cast<float4*>(p.gmatches) + pair * static_cast<size_t>(N);
+#pragma unroll 2
+            for (int i = lane; i < N; i += 32) {
+                const float4 q = sp[i];
+                const float du1 = fmaf(ax, q.x, bx) - h.c1x, dv1 = fmaf(ay, q.y, by) - h.c1y;
+                const float du2 = fmaf(ax, q.z, bx) - h.c2x, dv2 = fmaf(ay, q.w, by) - h.c2y;
+                const float q1 = fmaf(du1, du1, dv1 * dv1), q2 = fmaf(du2, du2, dv2 * dv2);
+                const float id1 = (q1 > 0.f) ? A1 * rsqrtf(q1) : 0.f, id2 = (q2 > 0.f) ? A2 * rsqrtf(q2) : 0.f;
+                float4 g;
+                g.x = ax * (sw[i] + fmaf(du1, id1, B1x));
+                g.y = ay * (sgr[i] + fmaf(dv1, id1, B1y));
+                g.z = ax * (sge[i] + fmaf(du2, id2, B2x));
+                g.w = ay * (sx4[i] + fmaf(dv2, id2, B2y));
+                gm_out[i] = g;
+            }
         }
+        // the coordinate path wrote into the stage through the generic proxy; the refill is an async-proxy write
+        if constexpr (COORDS) fence_proxy_async();
         __syncwarp();
         if (lane == 0) mbar_arrive(&empty[stage]);
     }
@@ -198,25 +278,40 @@ __global__ void __launch_bounds__(kThreads, 1) fepe_fit_bwd_kernel(const FitPara
 extern "C" int fepe_fit_bwd(const float* matches, const float* weights, int B, int N, float ax, float bx, float ay,
                             float by, float clamp_at, const double* saved, const float* gF, const float* gresid,
                             const float* gepi, float* gweights, void* stream) {
+    return fepe_fit_bwd_coords(matches, weights, B, N, ax, bx, ay, by, clamp_at, saved, gF, gresid, gepi, gweights,
+                               nullptr, stream);
+}
+
+extern "C" int fepe_fit_bwd_coords(const float* matches, const float* weights, int B, int N, float ax, float bx,
+                                   float ay, float by, float clamp_at, const double* saved, const float* gF,
+                                   const float* gresid, const float* gepi, float* gweights, float* gmatches,
+                                   void* stream) {
     if (B == 0) return 0;
     if (!matches || !weights || !saved || !gF || !gweights || B < 0 || N <= 0) return FEPE_E_BADARG;
     if (reinterpret_cast<uintptr_t>(matches) & 15u) return FEPE_E_BADARG;
     fepe::DeviceInfo& d = fepe::device_info();
     if (d.ok != 1) return FEPE_E_NODEVICE;
     fepe::FitParams p{};
-    if (!fepe::make_ring(N, 28, d.smem_optin, p.ring)) return FEPE_E_TOOLARGE;
+    if (gmatches != nullptr && (reinterpret_cast<uintptr_t>(gmatches) & 15u)) return FEPE_E_BADARG;
+    if (!fepe::make_ring(N, gmatches != nullptr ? 32 : 28, d.smem_optin, p.ring)) return FEPE_E_TOOLARGE;
     p.matches = matches; p.weights = weights; p.B = B; p.N = N;
     p.ax = ax; p.bx = bx; p.ay = ay; p.by = by; p.clamp_at = clamp_at;
     p.saved = const_cast<double*>(saved);
-    p.gF = gF; p.gresid = gresid; p.gepi = gepi; p.gweights = gweights;
+    p.gF = gF; p.gresid = gresid; p.gepi = gepi; p.gweights = gweights; p.gmatches = gmatches;
     cudaError_t e = cudaSuccess;
     if (!d.bwd_configured) {
-        e = cudaFuncSetAttribute(fepe::fepe_fit_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        e = cudaFuncSetAttribute(fepe::fepe_fit_bwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 d.smem_optin);
+        if (e != cudaSuccess) return static_cast<int>(e);
+        e = cudaFuncSetAttribute(fepe::fepe_fit_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  d.smem_optin);
         if (e != cudaSuccess) return static_cast<int>(e);
         d.bwd_configured = 1;
     }
     const int grid = B < d.sms ? B : d.sms;
-    fepe::fepe_fit_bwd_kernel<<<grid, fepe::kThreads, p.ring.total_bytes, static_cast<cudaStream_t>(stream)>>>(p);
+    if (gmatches != nullptr)
+        fepe::fepe_fit_bwd_kernel<true><<<grid, fepe::kThreads, p.ring.total_bytes, static_cast<cudaStream_t>(stream)>>>(p);
+    else
+        fepe::fepe_fit_bwd_kernel<false><<<grid, fepe::kThreads, p.ring.total_bytes, static_cast<cudaStream_t>(stream)>>>(p);
     return static_cast<int>(cudaGetLastError());
 }

@@ -28,6 +28,8 @@ _SIGNATURES = {
                             _c_p, _c_p, _c_p, _c_p, _c_p]),
     "fepe_fit_bwd": (_c_i, [_c_p, _c_p, _c_i, _c_i, _c_f, _c_f, _c_f, _c_f, _c_f,
                             _c_p, _c_p, _c_p, _c_p, _c_p, _c_p]),
+    "fepe_fit_bwd_coords": (_c_i, [_c_p, _c_p, _c_i, _c_i, _c_f, _c_f, _c_f, _c_f, _c_f,
+                                   _c_p, _c_p, _c_p, _c_p, _c_p, _c_p, _c_p]),
     "fepe_pose_fwd": (_c_i, [_c_p, _c_p, _c_i, _c_i, _c_f, _c_f, _c_f, _c_f, _c_p, _c_p, _c_p, _c_p, _c_p,
                              _c_i, _c_f, _c_p, _c_p]),
     "fepe_fit_pose_fwd": (_c_i, [_c_p, _c_p, _c_i, _c_i, _c_f, _c_f, _c_f, _c_f, _c_f, _c_p, _c_p, _c_p, _c_p,

@@ -10,8 +10,9 @@ What differs from the reference, deliberately:
   * ``if_cpu_svd`` is accepted and ignored -- there is no host round trip at all;
   * the sign of the null vector f is canonical (largest entry positive) instead of LAPACK's arbitrary
     one; F and the signed ``residual`` follow it, everything else is sign invariant;
-  * gradients flow to the WEIGHTS (hence to both MLPs); the gradient w.r.t. the coordinates
-    (``if_learn_offsets`` / trainable SuperPoint) is not implemented yet and raises;
+  * gradients flow to the WEIGHTS (hence to both MLPs) and, when the coordinates require a gradient
+    (``if_learn_offsets``, a trainable keypoint front-end), to the COORDINATES as well
+    (``fepe_fit_bwd_coords``: Hartley transforms, row normalisation, eigenvector, epipolar distance);
   * the broken reference options ``if_des``, ``if_tri_depth`` are rejected.
 """
 import torch
@@ -55,8 +56,6 @@ class Fit(nn.Module):
             raise NotImplementedError("normalize_SVD=False is never used by the reference (DeepFNet.py:353)")
 
     def forward(self, pts1, pts2, weights, if_print=False, matches_good_unique_num=None):
-        if pts1.requires_grad or pts2.requires_grad:
-            raise NotImplementedError("fepe_b200.Fit: gradient w.r.t. the coordinates is not implemented")
         # the kernel takes (x1,y1,x2,y2) rows; homogeneous inputs are assumed to have z = 1 as in every
         # call site of the reference (NormalizeAndExpand_HW keeps the third row [0,0,1])
         matches = torch.cat((pts1[:, :, :2], pts2[:, :, :2]), 2).contiguous()
@@ -73,15 +72,12 @@ class DeepFNet(nn.Module):
         if if_des or if_tri_depth:
             raise NotImplementedError("if_des / if_tri_depth are broken in the reference itself "
                                       "(DeepFNet.py:484,508) and are not provided")
-        if if_learn_offsets:
-            raise NotImplementedError("if_learn_offsets needs the coordinate gradient of the fit, which this "
-                                      "build does not provide yet (DESIGN.md, 'next')")
         if not if_quality:
             quality_size = 0
         self.if_quality = if_quality
         self.if_img_w = if_img_w
         self.if_goodCorresArch = if_goodCorresArch
-        self.if_learn_offsets = False
+        self.if_learn_offsets = bool(if_learn_offsets)
         self.image_size = image_size
         self.depth = depth
         if if_goodCorresArch:
@@ -92,9 +88,13 @@ class DeepFNet(nn.Module):
         else:
             self.input_weights = ErrorEstimator(4 + quality_size)
             self.update_weights = ErrorEstimator(4 + quality_size + 3)   # + weights, epi_res, residual
+            if if_learn_offsets:      # DeepFNet.py:341-342
+                self.update_offsets = ErrorEstimator(4 + quality_size + 3, output_size=4, if_bn=False)
         if is_test:
             self.input_weights.eval()
             self.update_weights.eval()
+            if self.if_learn_offsets and hasattr(self, "update_offsets"):
+                self.update_offsets.eval()
         self.norm_HW = NormalizeAndExpand_HW(self.image_size, is_cuda, is_test)
         self.fit = Fit(is_cuda, is_test, if_cpu_svd)
 
@@ -109,6 +109,8 @@ class DeepFNet(nn.Module):
 
     def get_input(self, data_batch, offsets=None, iter=None):
         pts = data_batch['matches_xy_ori']
+        if offsets is not None:                       # DeepFNet.py:369-373
+            pts = pts + offsets.permute(0, 2, 1)
         pts1, pts2, T1, T2 = self.norm_HW(pts)
         pts1 = pts1.permute(0, 2, 1)
         pts2 = pts2.permute(0, 2, 1)
@@ -148,6 +150,11 @@ class DeepFNet(nn.Module):
             epi_res = epi.unsqueeze(1)
             epi_res_layers.append(epi_res)
             net_in = torch.cat((pts_normalized_in, weights_prod, epi_res, residual.unsqueeze(1)), 1)
+            if self.if_learn_offsets:                 # DeepFNet.py:489-505: offsets replace (not accumulate)
+                offsets_accu = self.update_offsets(net_in)
+                pts_normalized_in, pts1, pts2, T1, T2 = self.get_input(data_batch, offsets_accu, _it)
+                matches = (data_batch['matches_xy_ori'].float() + offsets_accu.permute(0, 2, 1)).contiguous()
+                net_in = torch.cat((pts_normalized_in, weights_prod, epi_res, residual.unsqueeze(1)), 1)
             logits = self.update_weights(net_in)
             weights_pts = self._softmax(self.update_weights, logits)
             weights_prod = weights_pts * data_batch['weights_im'] if self.if_img_w else weights_pts
@@ -157,9 +164,12 @@ class DeepFNet(nn.Module):
         out, residual, _ = ops.FitFunction.apply(matches, weights_prod.reshape(B, N), *aff, 0.5)
         residual_layers.append(residual)
         out_layers.append(out)
-        return {
+        preds = {
             "logits": logits.squeeze(1), 'logits_layers': logits_layers, 'F_est': out,
             'epi_res_layers': epi_res_layers, 'T1': T1, 'T2': T2, 'out_layers': out_layers,
             'pts1': pts1, 'pts2': pts2, 'weights': weights_prod, 'residual_layers': residual_layers,
             'weights_layers': weights_layers,
         }
+        if self.if_learn_offsets and self.depth > 1:
+            preds['offsets'] = offsets_accu           # DeepFNet.py:549-550
+        return preds

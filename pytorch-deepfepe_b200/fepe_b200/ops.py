@@ -140,9 +140,10 @@ def fit_pose_forward(matches: torch.Tensor, weights: torch.Tensor, affine, K: to
 
 def fit_backward(matches: torch.Tensor, weights: torch.Tensor, saved: torch.Tensor, gF: torch.Tensor,
                  gres: Optional[torch.Tensor], gepi: Optional[torch.Tensor], affine=IDENTITY_AFFINE,
-                 clamp_at: float = 0.5) -> torch.Tensor:
+                 clamp_at: float = 0.5, want_coords: bool = False):
     """d loss / d weights [B,N] from the upstream gradients of (F, residual, epi).  One launch of
-    fepe_fit_bwd (include/fepe_b200.h)."""
+    fepe_fit_bwd (include/fepe_b200.h).  `want_coords`: also d loss / d matches [B,N,4] (fepe_fit_bwd_coords);
+    returns (gweights, gmatches) then."""
     matches = _check_cuda_f32(matches, "matches")
     weights = _check_cuda_f32(weights, "weights")
     B, N, _ = matches.shape
@@ -154,27 +155,28 @@ def fit_backward(matches: torch.Tensor, weights: torch.Tensor, saved: torch.Tens
     gepi = _check_cuda_f32(gepi, "gepi").reshape(B, N) if gepi is not None else None
     with torch.cuda.device(matches.device):
         gw = torch.empty(B, N, dtype=torch.float32, device=matches.device)
-        st = _lib.lib().fepe_fit_bwd(matches.data_ptr(), weights.data_ptr(), B, N,
-                                     affine[0], affine[1], affine[2], affine[3], float(clamp_at),
-                                     saved.contiguous().data_ptr(), gF.data_ptr(),
-                                     gres.data_ptr() if gres is not None else None,
-                                     gepi.data_ptr() if gepi is not None else None,
-                                     gw.data_ptr(), _stream_ptr())
-    _lib.check(st, "fepe_fit_bwd")
-    return gw
+        gm = torch.empty(B, N, 4, dtype=torch.float32, device=matches.device) if want_coords else None
+        st = _lib.lib().fepe_fit_bwd_coords(matches.data_ptr(), weights.data_ptr(), B, N,
+                                            affine[0], affine[1], affine[2], affine[3], float(clamp_at),
+                                            saved.contiguous().data_ptr(), gF.data_ptr(),
+                                            gres.data_ptr() if gres is not None else None,
+                                            gepi.data_ptr() if gepi is not None else None,
+                                            gw.data_ptr(), gm.data_ptr() if gm is not None else None, _stream_ptr())
+    _lib.check(st, "fepe_fit_bwd_coords")
+    return (gw, gm) if want_coords else gw
 
 
 class FitFunction(torch.autograd.Function):
-    """Differentiable (w.r.t. the weights) fused weighted 8-point fit.
+    """Differentiable fused weighted 8-point fit.
 
     forward(matches [B,N,4], weights [B,N], ax, bx, ay, by, clamp_at) -> F [B,3,3], residual [B,N], epi [B,N]
-    The gradient w.r.t. the coordinates is not produced (the reference only needs it with
-    if_learn_offsets / a trainable SuperPoint front-end; DESIGN.md lists it under "next")."""
+    backward: d/d weights always; d/d matches (fepe_fit_bwd_coords) only when `matches` requires a gradient
+    (if_learn_offsets / a trainable keypoint front-end in the reference)."""
 
     @staticmethod
     def forward(ctx, matches, weights, ax, bx, ay, by, clamp_at):
         aff = (float(ax), float(bx), float(ay), float(by))
-        need = weights.requires_grad
+        need = weights.requires_grad or matches.requires_grad
         F, res, epi, saved = fit_forward(matches, weights, aff, clamp_at, want_epi=True, want_saved=need)
         ctx.aff, ctx.clamp_at = aff, float(clamp_at)
         if need:
@@ -187,9 +189,11 @@ class FitFunction(torch.autograd.Function):
         matches, weights, saved = ctx.saved_tensors
         B, N = matches.shape[0], matches.shape[1]
         gF = torch.zeros(B, 3, 3, device=matches.device) if gF is None else gF.contiguous()
-        gw = fit_backward(matches, weights, saved, gF, gres.contiguous() if gres is not None else None,
-                          gepi.contiguous() if gepi is not None else None, ctx.aff, ctx.clamp_at)
-        return None, gw.reshape(weights.shape), None, None, None, None, None
+        want_coords = ctx.needs_input_grad[0]
+        g = fit_backward(matches, weights, saved, gF, gres.contiguous() if gres is not None else None,
+                         gepi.contiguous() if gepi is not None else None, ctx.aff, ctx.clamp_at, want_coords)
+        gw, gm = g if want_coords else (g, None)
+        return gm, gw.reshape(weights.shape), None, None, None, None, None
 
 
 class PoseLossFunction(torch.autograd.Function):

@@ -2,6 +2,8 @@
 // eigen / SVD routines can be checked against LAPACK on a machine without a GPU.  Test
 // infrastructure: built on the fly by tests/test_math_host.py with g++.
 #include "fepe_math.cuh"
+#include "fepe_fit_adjoint.cuh"
+#include <vector>
 
 extern "C" {
 
@@ -128,5 +130,115 @@ void shim_quat(const double* R, double* q) {
     for (int i = 0; i < 9; ++i) r[i] = R[i];
     fepe::rot_to_quat(r, qq);
     for (int i = 0; i < 4; ++i) q[i] = qq[i];
+}
+
+// Whole weighted 8-point fit of ONE pair and its backward (weights AND coordinates) in fp64 on the host, built from the
+// product's own pieces: eig9_smallest, rank2_project(+adjoint), eig9_pinv_apply (fepe_math.cuh) and row_adjoint,
+// epi_adjoint, norm_adjoint (fepe_fit_adjoint.cuh).  The loops mirror the passes of fepe_fit_bwd_kernel.
+// m: [N,4] (u1,v1,u2,v2) already in the frame Fit.forward receives; outputs: F [9], res [N], epi [N], gw [N], gm [N,4].
+void shim_fit_pair_fwd_bwd(const double* m, const double* w, int N, double clamp_at, const double* gF,
+                           const double* gres, const double* gepi, double* F_out, double* res, double* epi,
+                           double* gw, double* gm) {
+    using namespace fepe;
+    double s[2], cx[2], cy[2];
+    for (int im = 0; im < 2; ++im) {
+        double sx = 0, sy = 0, sd = 0;
+        for (int i = 0; i < N; ++i) { sx += m[4 * i + 2 * im]; sy += m[4 * i + 2 * im + 1]; }
+        cx[im] = sx / N; cy[im] = sy / N;
+        for (int i = 0; i < N; ++i) {
+            const double du = m[4 * i + 2 * im] - cx[im], dv = m[4 * i + 2 * im + 1] - cy[im];
+            sd += sqrt(du * du + dv * dv);
+        }
+        s[im] = 1.4142 / (sd / N);
+    }
+    double g36[36];
+    for (int e = 0; e < 36; ++e) g36[e] = 0.0;
+    for (int i = 0; i < N; ++i) {
+        const double x1 = s[0] * (m[4 * i] - cx[0]), y1 = s[0] * (m[4 * i + 1] - cy[0]);
+        const double x2 = s[1] * (m[4 * i + 2] - cx[1]), y2 = s[1] * (m[4 * i + 3] - cy[1]);
+        const double sc = w[i] * w[i] / ((x1 * x1 + y1 * y1 + 1) * (x2 * x2 + y2 * y2 + 1));
+        const double a[6] = {x2 * x2, x2 * y2, x2, y2 * y2, y2, 1.0};
+        const double b[6] = {x1 * x1, x1 * y1, x1, y1 * y1, y1, 1.0};
+        for (int u = 0; u < 6; ++u)
+            for (int v = 0; v < 6; ++v) g36[u * 6 + v] += sc * a[u] * b[v];
+    }
+    double f[9], lambda, F2[9], v3[3], sigma3;
+    eig9_smallest(g36, f, lambda);
+    rank2_project(f, F2, v3, sigma3);
+    // out = T2^T F2 T1
+    const double T1[9] = {s[0], 0, -s[0] * cx[0], 0, s[0], -s[0] * cy[0], 0, 0, 1};
+    const double T2[9] = {s[1], 0, -s[1] * cx[1], 0, s[1], -s[1] * cy[1], 0, 0, 1};
+    double tmp[9], Fo[9];
+    mat3_mul(F2, T1, tmp);
+    mat3_mul_tn(T2, tmp, Fo);
+    for (int k = 0; k < 9; ++k) F_out[k] = Fo[k];
+    // pass 1 of the backward (+ forward outputs)
+    double hs[9], ge[9];
+    for (int k = 0; k < 9; ++k) { hs[k] = 0; ge[k] = 0; }
+    std::vector<double> cbe(4 * static_cast<size_t>(N));
+    for (int i = 0; i < N; ++i) {
+        const double x1 = s[0] * (m[4 * i] - cx[0]), y1 = s[0] * (m[4 * i + 1] - cy[0]);
+        const double x2 = s[1] * (m[4 * i + 2] - cx[1]), y2 = s[1] * (m[4 * i + 3] - cy[1]);
+        const double inv = 1.0 / sqrt((x1 * x1 + y1 * y1 + 1) * (x2 * x2 + y2 * y2 + 1));
+        const double a[3] = {x2, y2, 1.0}, b[3] = {x1, y1, 1.0};
+        double dot = 0;
+        for (int j = 0; j < 3; ++j)
+            for (int k = 0; k < 3; ++k) {
+                dot += f[3 * j + k] * a[j] * b[k];
+                hs[3 * j + k] += gres[i] * w[i] * inv * a[j] * b[k];
+            }
+        res[i] = w[i] * dot * inv;
+        double cb[4];
+        epi_adjoint<double>(m[4 * i], m[4 * i + 1], m[4 * i + 2], m[4 * i + 3], Fo, clamp_at, gepi[i], ge, cb);
+        for (int k = 0; k < 4; ++k) cbe[4 * i + k] = cb[k];
+        // forward value of the epipolar distance (same expressions as epi_adjoint)
+        {
+            const double u1 = m[4 * i], v1 = m[4 * i + 1], u2 = m[4 * i + 2], v2 = m[4 * i + 3];
+            const double l10 = u2 * Fo[0] + v2 * Fo[3] + Fo[6], l11 = u2 * Fo[1] + v2 * Fo[4] + Fo[7],
+                         l12 = u2 * Fo[2] + v2 * Fo[5] + Fo[8];
+            const double l20 = Fo[0] * u1 + Fo[1] * v1 + Fo[2], l21 = Fo[3] * u1 + Fo[4] * v1 + Fo[5];
+            const double dd = l10 * u1 + l11 * v1 + l12;
+            const double d = fabs(dd) * (1.0 / (sqrt(l10 * l10 + l11 * l11) + 1e-6) + 1.0 / (sqrt(l20 * l20 + l21 * l21) + 1e-6));
+            epi[i] = d < clamp_at ? d : clamp_at;
+        }
+    }
+    double ob[9], Ab[9], X[9];
+    for (int k = 0; k < 9; ++k) ob[k] = ge[k] + gF[k];
+    {   // F2bar = T2 ob T1^T
+        double t[9];
+        mat3_mul(T2, ob, t);
+        mat3_mul_nt(t, T1, Ab);
+        (void)X;
+    }
+    double fb[9], z[9];
+    rank2_project_adjoint(f, v3, Ab, fb);
+    for (int k = 0; k < 9; ++k) fb[k] += hs[k];
+    eig9_pinv_apply(g36, f, lambda, fb, z);
+    // pass 2
+    NormAdjointSums S{};
+    std::vector<double> xbs(4 * static_cast<size_t>(N));
+    for (int i = 0; i < N; ++i) {
+        const double du1 = m[4 * i] - cx[0], dv1 = m[4 * i + 1] - cy[0], du2 = m[4 * i + 2] - cx[1], dv2 = m[4 * i + 3] - cy[1];
+        double xb[4], wb;
+        row_adjoint<double>(s[0] * du1, s[0] * dv1, s[1] * du2, s[1] * dv2, w[i], gres[i], f, z, wb, xb);
+        gw[i] = wb;
+        for (int k = 0; k < 4; ++k) xbs[4 * i + k] = xb[k];
+        S.sx[0] += xb[0]; S.sy[0] += xb[1]; S.sd[0] += xb[0] * du1 + xb[1] * dv1;
+        S.sx[1] += xb[2]; S.sy[1] += xb[3]; S.sd[1] += xb[2] * du2 + xb[3] * dv2;
+        const double d1 = sqrt(du1 * du1 + dv1 * dv1), d2 = sqrt(du2 * du2 + dv2 * dv2);
+        if (d1 > 0) { S.dx[0] += du1 / d1; S.dy[0] += dv1 / d1; }
+        if (d2 > 0) { S.dx[1] += du2 / d2; S.dy[1] += dv2 / d2; }
+    }
+    NormAdjointCoef C;
+    norm_adjoint(ob, F2, s, cx, cy, S, N, C);
+    // pass 3
+    for (int i = 0; i < N; ++i) {
+        for (int im = 0; im < 2; ++im) {
+            const double du = m[4 * i + 2 * im] - cx[im], dv = m[4 * i + 2 * im + 1] - cy[im];
+            const double d = sqrt(du * du + dv * dv), id = d > 0 ? 1.0 / d : 0.0;
+            gm[4 * i + 2 * im] = s[im] * xbs[4 * i + 2 * im] + C.A[im] * du * id + C.Bx[im] + cbe[4 * i + 2 * im];
+            gm[4 * i + 2 * im + 1] = s[im] * xbs[4 * i + 2 * im + 1] + C.A[im] * dv * id + C.By[im] + cbe[4 * i + 2 * im + 1];
+        }
+    }
 }
 }

@@ -87,3 +87,64 @@ def test_against_oracle_autograd(mode, B, N, which):
     s32 = torch.sign((F32.detach().double() * Fo.detach()).sum((1, 2))).float()
     ((F32 * s32.view(-1, 1, 1) * gF).sum() + (r32 * s32.view(-1, 1) * gr).sum() + (e32 * ge).sum()).backward()
     _check(wv.grad.cpu().reshape(B, 1, N), wo.grad, gw_ref32=w32.grad)
+
+
+# ---------------------------------------------------------------------------------------------------
+# gradient w.r.t. the coordinates (fepe_fit_bwd_coords): if_learn_offsets / trainable keypoints in the reference
+@pytest.mark.parametrize("mode,B,N", [("softmax", 6, 1000), ("inlier", 4, 2000), ("uniform", 5, 333), ("softmax", 3, 37),
+                                      ("softmax", 300, 128)])
+@pytest.mark.parametrize("which", ["all", "F_only", "res_only", "epi_only"])
+def test_coordinate_gradient_against_oracle_autograd(mode, B, N, which):
+    """d loss / d matches_xy_ori [B,N,4] (pixels) against fp64 autograd through the oracle's NormalizeAndExpand_HW +
+    Fit.normalize + weighted_svd + compute_epi_residual.  Bar: 1e-3 relative L2 per pair, or 3x the reference's own
+    fp32-vs-fp64 error where that is larger (same rule as the weight gradient)."""
+    if B > 64 and which != "all":
+        pytest.skip("large batch once")
+    d = synth.make_batch(B, N, seed=300 + N, weight_mode=mode)
+    aff = ops.hw_affine(d["image_size"])
+    g = torch.Generator().manual_seed(N + 1)
+    gF = torch.randn(B, 3, 3, generator=g) if which in ("all", "F_only") else torch.zeros(B, 3, 3)
+    gr = torch.randn(B, N, generator=g) if which in ("all", "res_only") else torch.zeros(B, N)
+    ge = torch.randn(B, N, generator=g) if which in ("all", "epi_only") else torch.zeros(B, N)
+
+    def oracle(dtype):
+        m = T(d["matches_xy_ori"]).to(dtype).requires_grad_(True)
+        w = T(d["weights"]).to(dtype).requires_grad_(True)
+        p1, p2, _ = O.norm_hw(m, d["image_size"])
+        Fo, ro = O.fit_weighted_svd(p1, p2, w)
+        eo = O.epi_residual(p1, p2, Fo, 0.5)
+        return m, w, Fo, ro, eo
+
+    mo, wo, Fo, ro, eo = oracle(torch.float64)
+    mu = T(d["matches_xy_ori"]).cuda().requires_grad_(True)
+    wu = T(d["weights"]).cuda().requires_grad_(True)
+    F, res, epi = ops.FitFunction.apply(mu, wu, *aff, 0.5)
+    s = torch.sign((F.detach().cpu().double() * Fo.detach()).sum((1, 2)))
+    (((Fo * s.view(-1, 1, 1)) * gF.double()).sum() + ((ro * s.view(-1, 1)) * gr.double()).sum() + (eo * ge.double()).sum()).backward()
+    ((F * gF.cuda()).sum() + (res * gr.cuda()).sum() + (epi * ge.cuda()).sum()).backward()
+    m32, w32, F32, r32, e32 = oracle(torch.float32)
+    s32 = torch.sign((F32.detach().double() * Fo.detach()).sum((1, 2))).float()
+    ((F32 * s32.view(-1, 1, 1) * gF).sum() + (r32 * s32.view(-1, 1) * gr).sum() + (e32 * ge).sum()).backward()
+    assert mu.grad is not None and mu.grad.shape == (B, N, 4) and bool(torch.isfinite(mu.grad).all())
+    _check(mu.grad.cpu(), mo.grad, gw_ref32=m32.grad)
+    _check(wu.grad.cpu().reshape(B, 1, N), wo.grad, gw_ref32=w32.grad)      # weights unchanged by the coords path
+
+
+def test_fit_module_passes_coordinate_gradient():
+    """Fit.forward(pts1, pts2, weights) with pts requiring grad (the reference's module boundary)."""
+    from fepe_b200.models import Fit
+    d = synth.make_batch(4, 500, seed=11, weight_mode="softmax")
+    p1, p2, _ = O.norm_hw(T(d["matches_xy_ori"]), d["image_size"])
+    w = T(d["weights"])
+    a1, a2 = p1.clone().double().requires_grad_(True), p2.clone().double().requires_grad_(True)
+    Fo, ro = O.fit_weighted_svd(a1, a2, w.double())
+    b1, b2 = p1.clone().cuda().requires_grad_(True), p2.clone().cuda().requires_grad_(True)
+    F, res = Fit()(b1, b2, w.cuda())
+    g = torch.Generator().manual_seed(5)
+    gF, gr = torch.randn(4, 3, 3, generator=g), torch.randn(4, 500, generator=g)
+    s = torch.sign((F.detach().cpu().double() * Fo.detach()).sum((1, 2)))
+    ((Fo * s.view(-1, 1, 1) * gF.double()).sum() + (ro * s.view(-1, 1) * gr.double()).sum()).backward()
+    ((F * gF.cuda()).sum() + (res * gr.cuda()).sum()).backward()
+    _check(b1.grad.cpu()[:, :, :2], a1.grad[:, :, :2], tol=2e-3)
+    _check(b2.grad.cpu()[:, :, :2], a2.grad[:, :, :2], tol=2e-3)
+    assert float(b1.grad[:, :, 2].abs().max()) == 0.0      # z = 1 is a constant of the boundary

@@ -19,8 +19,8 @@ def shim():
     os.makedirs(BUILD, exist_ok=True)
     so = os.path.join(BUILD, "host_shim.so")
     src = os.path.join(ROOT, "tests", "host_shim.cpp")
-    hdr = os.path.join(CSRC, "fepe_math.cuh")
-    if not os.path.exists(so) or os.path.getmtime(so) < max(os.path.getmtime(src), os.path.getmtime(hdr)):
+    hdrs = [os.path.join(CSRC, h) for h in ("fepe_math.cuh", "fepe_fit_adjoint.cuh")]
+    if not os.path.exists(so) or os.path.getmtime(so) < max([os.path.getmtime(src)] + [os.path.getmtime(h) for h in hdrs]):
         subprocess.check_call(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-Wno-unknown-pragmas",
                                "-x", "c++", "-I", CSRC, src, "-o", so])
     lib = ctypes.CDLL(so)
@@ -41,6 +41,7 @@ def shim():
     lib.shim_quat.argtypes = [dp, dp]
     lib.shim_pose_adjoint.argtypes = [dp, dp, dp, ctypes.c_int, ctypes.c_int, ctypes.c_double, ctypes.c_double, dp]
     lib.shim_rank2_adjoint.argtypes = [dp, dp, dp]
+    lib.shim_fit_pair_fwd_bwd.argtypes = [dp, dp, ctypes.c_int, ctypes.c_double] + [dp] * 8
     return lib
 
 
@@ -294,3 +295,44 @@ def test_pose_head_adjoint_matches_autograd_through_the_oracle(shim):
         err = np.linalg.norm(got - ref) / np.linalg.norm(ref)
         worst = max(worst, err)
     assert worst < 1e-6, worst
+
+
+@pytest.mark.parametrize("mode", ["uniform", "softmax", "inlier"])
+def test_fit_backward_weights_and_coordinates_match_autograd_through_the_oracle(shim, mode):
+    """The adjoint pieces the backward kernel is built from (fepe_fit_adjoint.cuh: row_adjoint, epi_adjoint,
+    norm_adjoint; fepe_math.cuh: rank2_project_adjoint, eig9_pinv_apply), chained on the host in fp64 exactly like
+    the kernel's passes, against torch autograd (fp64) through the oracle's Fit.normalize / weighted_svd /
+    compute_epi_residual restatement: d loss / d weights AND d loss / d coordinates."""
+    import torch
+    from oracle import fepe_oracle as O
+    d = synth.make_batch(3, 300, seed=4, weight_mode=mode)
+    m = torch.from_numpy(d["matches_xy_ori"]).double()
+    w = torch.from_numpy(d["weights"]).double()
+    p1, p2, _ = O.norm_hw(m, d["image_size"])
+    rel = lambda a, b: np.linalg.norm(a - b) / np.linalg.norm(b)
+    for b in range(3):
+        u = torch.cat((p1[b, :, :2], p2[b, :, :2]), 1).clone().requires_grad_(True)
+        wb = w[b].reshape(1, 1, -1).clone().requires_grad_(True)
+        N = u.shape[0]
+        ones = torch.ones(1, N, 1, dtype=torch.float64)
+        q1, q2 = torch.cat((u[None, :, :2], ones), 2), torch.cat((u[None, :, 2:], ones), 2)
+        out, res = O.fit_weighted_svd(q1, q2, wb)
+        epi = O.epi_residual(q1, q2, out, 0.5)
+        g = torch.Generator().manual_seed(b)
+        gF = torch.randn(1, 3, 3, generator=g, dtype=torch.float64)
+        gr = torch.randn(1, N, generator=g, dtype=torch.float64)
+        ge = torch.randn(1, N, generator=g, dtype=torch.float64)
+        un = np.ascontiguousarray(u.detach().numpy())
+        wn = np.ascontiguousarray(wb.detach().numpy().reshape(-1))
+        Fo, r, e, gw, gm = np.zeros(9), np.zeros(N), np.zeros(N), np.zeros(N), np.zeros((N, 4))
+        gFn, grn, gen = (np.ascontiguousarray(t.numpy().reshape(-1)) for t in (gF, gr, ge))
+        shim.shim_fit_pair_fwd_bwd(_ptr(un), _ptr(wn), N, 0.5, _ptr(gFn), _ptr(grn), _ptr(gen), _ptr(Fo), _ptr(r),
+                                   _ptr(e), _ptr(gw), _ptr(gm))
+        on = out.detach().numpy().reshape(-1)
+        sgn = 1.0 if np.linalg.norm(Fo - on) < np.linalg.norm(Fo + on) else -1.0   # LAPACK's sign of f is arbitrary
+        ((sgn * out * gF).sum() + (sgn * res * gr).sum() + (epi * ge).sum()).backward()
+        assert rel(Fo, sgn * on) < 1e-9
+        assert np.abs(r - sgn * res.detach().numpy().reshape(-1)).max() < 1e-12
+        assert np.abs(e - epi.detach().numpy().reshape(-1)).max() < 1e-8
+        assert rel(gw, wb.grad.numpy().reshape(-1)) < 1e-8
+        assert rel(gm, u.grad.numpy()) < 1e-8

@@ -89,3 +89,44 @@ def test_error_estimator_matches_reference_output(golden):
     with torch.no_grad():
         y = ee(T(golden["ee_x"]).cuda())
     np.testing.assert_allclose(y.cpu().numpy(), golden["ee_y"], rtol=1e-3, atol=1e-4)
+
+
+def test_learn_offsets_matches_reference_forward_and_backward():
+    """DeepFNet(if_learn_offsets=True) against the UNMODIFIED reference module run in fp64 on the CPU
+    (tests/golden/make_golden_offsets.py -> reference_offsets.npz): same seed => same initial parameters; offsets,
+    per-layer F and the parameter gradients of all three networks (the offsets net only gets a gradient through the
+    coordinate gradient of the fit, fepe_fit_bwd_coords).  Tolerances: the networks run in fp32 here vs fp64 there."""
+    import os
+    g = dict(np.load(os.path.join(os.path.dirname(__file__), "golden", "reference_offsets.npz"), allow_pickle=False))
+    torch.manual_seed(78)
+    net = DeepFNet(depth=3, image_size=[376, 1241, 3], if_quality=False, is_cuda=True, if_cpu_svd=False,
+                   if_learn_offsets=True).cuda()
+    assert sorted(net.state_dict().keys()) == sorted(g["state_keys"].tolist())
+    m = T(g["matches"]).cuda()
+    outs = net({"matches_xy_ori": m, "matches_good_unique_nums": torch.tensor([200, 200]),
+                "t_scene_scale": torch.ones(2, 1, 1).cuda()})
+    assert outs["offsets"].shape == (2, 4, 200)
+    np.testing.assert_allclose(outs["offsets"].detach().cpu().numpy(), g["offsets"], atol=5e-3)
+    np.testing.assert_allclose(outs["pts1"].detach().cpu().numpy(), g["pts1"], atol=1e-5)
+    for l in range(3):
+        err = O.sign_aligned_rel_err(outs["out_layers"][l].detach().cpu(), T(g["F_layers"][l]))
+        print("layer", l, "F rel err", err.tolist())
+        assert float(err.max()) < 5e-3
+    loss = 0.0
+    for Fl in outs["out_layers"]:
+        loss = loss + O.epi_residual(outs["pts1"], outs["pts2"], Fl, 0.1).mean()
+    for r in outs["residual_layers"]:
+        loss = loss + 1e3 * (r ** 2).sum(1).mean()
+    loss.backward()
+    assert abs(float(loss) - float(g["loss"])) < 2e-3 * abs(float(g["loss"]))
+    params = dict(net.named_parameters())
+    worst = 0.0
+    for key, ref in g.items():
+        if not key.startswith("grad/") or np.linalg.norm(ref) < 1e-8:      # conv biases in front of an InstanceNorm: 0
+            continue
+        got = params[key[5:]].grad.detach().cpu().numpy().astype(np.float64)
+        rel = np.linalg.norm(got - ref) / np.linalg.norm(ref)
+        print(key, "rel grad err %.2e" % rel)
+        worst = max(worst, rel)
+    assert float(params["update_offsets.fw.15.weight"].grad.abs().sum()) > 0
+    assert worst < 5e-2, worst
