@@ -165,6 +165,27 @@ int fepe_mlp_last_bwd(const float* dlogits, const void* X, const float* W, void*
 int fepe_mlp_first_bwd(const void* dY, const float* X0, const float* W, float* dX0, float* dW, int B, int N, int Npad,
                        int Ci, int Co, void* stream);
 
+/* ---- validation pose recovery ----------------------------------------------------
+ * Replaces, per (layer, pair), the host work of deepFEPE/dsac_tools/utils_F.py:909-954 goodCorr_eval_nondecompose
+ * (called per sample from train_good_utils.py:553-646 val_rt through a process pool):
+ *   cv2.recoverPose(E_hat, p1s, p2s, focal=K[0,0], pp=(K[0,2],K[1,2]))  -- decomposeEssentialMat, DLT triangulation of
+ *   every correspondence for the four (R,t) candidates, cheirality + 50-unit distance test, most-points-in-front wins --
+ *   then utils_geo.invert_Rt / rot12_to_angle_error / vector_angle against the ground-truth motion.
+ *   E        [L,B,9]  essential matrices (row-major), any scale
+ *   K        [B,9]    intrinsics; like the reference call, focal = K[0,0] serves both axes
+ *   matches  [B,N,4]  (x1,y1,x2,y2) pixels, 16-byte aligned
+ *   n_valid  [B] or NULL: only the first n_valid[b] correspondences of pair b take part
+ *   Rt_scene [B,16] or NULL: delta_Rtijs_4_4 (scene motion); errors are 180 / 90 without it or with < 5 points
+ *   out      [L,B,FEPE_RECOVER_OUT_FLOATS]: [0..8] R  [9..11] t  [12] points in front of the winner (cv2's return value)
+ *            [13] winning candidate 0..3 = (R1,t),(R2,t),(R1,-t),(R2,-t)  [14..17] the four counts
+ *            [18] err_q  [19] err_t (degrees)  [20] correspondences used
+ *   mask     [L,B,N] or NULL: 255 where the winner's point passed (cv2's mask), else 0
+ */
+#define FEPE_RECOVER_OUT_FLOATS 24
+int fepe_recover_pose(const float* E, const float* K, const float* matches, const int* n_valid,
+                      int L, int B, int N, float distance_thresh, const float* Rt_scene,
+                      float* out, unsigned char* mask, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

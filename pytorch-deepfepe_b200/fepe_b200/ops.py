@@ -166,6 +166,40 @@ def fit_backward(matches: torch.Tensor, weights: torch.Tensor, saved: torch.Tens
     return (gw, gm) if want_coords else gw
 
 
+def recover_pose(E: torch.Tensor, K: torch.Tensor, matches: torch.Tensor, Rt_scene: Optional[torch.Tensor] = None,
+                 n_valid: Optional[torch.Tensor] = None, distance_thresh: float = 50.0, want_mask: bool = False):
+    """Validation pose recovery on the device (include/fepe_b200.h: fepe_recover_pose) -- what
+    cv2.recoverPose(E, p1, p2, focal=K[0,0], pp=(K[0,2],K[1,2])) + the angular errors against the ground truth do per
+    sample in deepFEPE/dsac_tools/utils_F.py:909-954.
+
+    E [L,B,3,3] or [B,3,3]; K [B,3,3]; matches [B,N,4] pixels; Rt_scene [B,4,4] (delta_Rtijs_4_4); n_valid [B] int32.
+    Returns (out [L,B,24], mask [L,B,N] uint8 | None); out[..., :9] = R, [9:12] = t, [12] = points in front,
+    [18] / [19] = err_q / err_t in degrees."""
+    E = _check_cuda_f32(E, "E")
+    if E.dim() == 3:
+        E = E.unsqueeze(0)
+    L, B = E.shape[0], E.shape[1]
+    K = _check_cuda_f32(K, "K").reshape(B, 9)
+    matches = _check_cuda_f32(matches, "matches")
+    if matches.dim() != 3 or matches.shape[0] != B or matches.shape[2] != 4:
+        raise RuntimeError("fepe_b200: matches must be [B,N,4] (x1,y1,x2,y2)")
+    N = matches.shape[1]
+    rt = _check_cuda_f32(Rt_scene, "Rt_scene").reshape(B, 16) if Rt_scene is not None else None
+    if n_valid is not None:
+        if not n_valid.is_cuda or n_valid.dtype != torch.int32 or n_valid.numel() != B:
+            raise RuntimeError("fepe_b200: n_valid must be a CUDA int32 tensor of B elements")
+        n_valid = n_valid.contiguous()
+    with torch.cuda.device(E.device):
+        out = torch.empty(L, B, _lib.RECOVER_OUT_FLOATS, dtype=torch.float32, device=E.device)
+        mask = torch.empty(L, B, N, dtype=torch.uint8, device=E.device) if want_mask else None
+        st = _lib.lib().fepe_recover_pose(E.data_ptr(), K.data_ptr(), matches.data_ptr(),
+                                          n_valid.data_ptr() if n_valid is not None else None, L, B, N,
+                                          float(distance_thresh), rt.data_ptr() if rt is not None else None,
+                                          out.data_ptr(), mask.data_ptr() if mask is not None else None, _stream_ptr())
+    _lib.check(st, "fepe_recover_pose")
+    return out, mask
+
+
 class FitFunction(torch.autograd.Function):
     """Differentiable fused weighted 8-point fit.
 

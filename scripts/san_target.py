@@ -15,6 +15,9 @@ for kern in ("ring", "small"):
         w = torch.from_numpy(d["weights"]).cuda().requires_grad_(True)
         F, r, e = ops.FitFunction.apply(m, w.reshape(B, N), *aff, 0.5)
         (F.sum() + r.sum() + e.sum()).backward()
+        mc = m.clone().requires_grad_(True)              # coordinate-gradient path (fepe_fit_bwd_coords)
+        F2, r2, e2 = ops.FitFunction.apply(mc, w.reshape(B, N), *aff, 0.5)
+        (F2.sum() + r2.sum() + e2.sum()).backward()
         t = lambda k: torch.from_numpy(d[k]).cuda()
         ops.pose_forward(F.detach(), t("Ks"), aff, t("q_cam"), t("t_cam"), t("delta_Rtijs_4_4"), t("pts1_virt"), t("pts2_virt"))
 ee = ErrorEstimator(4).cuda()
@@ -23,3 +26,8 @@ with torch.no_grad():
     ee(torch.rand(2, 4, 333, device="cuda"))
 torch.cuda.synchronize()
 print("sanitizer target done")
+d = synth.make_batch(3, 333, seed=2)
+t = lambda k: torch.from_numpy(d[k]).cuda()
+ops.recover_pose(t("E_gt"), t("Ks"), t("matches_xy_ori"), t("delta_Rtijs_4_4"), want_mask=True)
+torch.cuda.synchronize()
+print("recover_pose done")

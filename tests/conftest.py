@@ -1,5 +1,7 @@
 """pytest configuration: path setup, the `gpu` marker, shared fixtures."""
+import ctypes
 import os
+import subprocess
 import sys
 
 import numpy as np
@@ -20,3 +22,40 @@ def golden():
     """Outputs of the unmodified reference on seeded inputs (tests/golden/make_golden.py)."""
     path = os.path.join(ROOT, "tests", "golden", "reference_outputs.npz")
     return dict(np.load(path, allow_pickle=False))
+
+
+CSRC = os.path.join(ROOT, "pytorch-deepfepe_b200", "csrc")
+BUILD = os.path.join(ROOT, "tests", "_build")
+
+
+@pytest.fixture(scope="session")
+def shim():
+    os.makedirs(BUILD, exist_ok=True)
+    so = os.path.join(BUILD, "host_shim.so")
+    src = os.path.join(ROOT, "tests", "host_shim.cpp")
+    hdrs = [os.path.join(CSRC, h) for h in ("fepe_math.cuh", "fepe_fit_adjoint.cuh", "fepe_recover.cuh")]
+    if not os.path.exists(so) or os.path.getmtime(so) < max([os.path.getmtime(src)] + [os.path.getmtime(h) for h in hdrs]):
+        subprocess.check_call(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-Wno-unknown-pragmas",
+                               "-x", "c++", "-I", CSRC, src, "-o", so])
+    lib = ctypes.CDLL(so)
+    dp = ctypes.POINTER(ctypes.c_double)
+    lib.shim_eig9.argtypes = [dp, dp, dp]
+    lib.shim_eig9.restype = ctypes.c_int
+    lib.shim_eig9_multishift.argtypes = [dp, dp, dp]
+    lib.shim_eig9_multishift.restype = ctypes.c_int
+    lib.shim_eig9_multishift128.argtypes = [dp, dp, dp]
+    lib.shim_eig9_multishift128.restype = ctypes.c_int
+    lib.shim_pinv.argtypes = [dp, dp, ctypes.c_double, dp, dp]
+    lib.shim_svd3.argtypes = [dp, dp, dp, dp]
+    lib.shim_svd3_direct.argtypes = [dp, dp, dp, dp]
+    lib.shim_rank2.argtypes = [dp, dp]
+    lib.shim_g36_index.argtypes = [ctypes.c_int, ctypes.c_int]
+    lib.shim_g36_index.restype = ctypes.c_int
+    lib.shim_essential.argtypes = [dp] * 6
+    lib.shim_quat.argtypes = [dp, dp]
+    lib.shim_pose_adjoint.argtypes = [dp, dp, dp, ctypes.c_int, ctypes.c_int, ctypes.c_double, ctypes.c_double, dp]
+    lib.shim_rank2_adjoint.argtypes = [dp, dp, dp]
+    lib.shim_fit_pair_fwd_bwd.argtypes = [dp, dp, ctypes.c_int, ctypes.c_double] + [dp] * 8
+    ip, fp, bp = ctypes.POINTER(ctypes.c_int), ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_ubyte)
+    lib.shim_recover_pose.argtypes = [dp, dp, fp, ctypes.c_int, ctypes.c_double, dp, dp, dp, ip, ip, dp, bp]
+    return lib

@@ -2,6 +2,12 @@
 (deepFEPE/models/DeepFNet.py:341-342, 369-373, 489-505) run in fp64 on the CPU of the build container, forward
 and backward, on a seeded synthetic batch.  Pins the coordinate-gradient path (fepe_fit_bwd_coords) end to end
 through the reference's own module.  Run once:  python tests/golden/make_golden_offsets.py
+
+Sign of the null vector: the reference feeds the SIGNED residual X f of one layer to the networks of the next
+(DeepFNet.py:487), and the sign of f = V[:, -1] is whatever LAPACK returns.  To make the multi-layer run comparable,
+`torch.svd` (third-party, not reference code) is wrapped here so that the last right singular vector of an [N,9]
+matrix has its largest-magnitude entry positive -- the convention of fepe_fit_fwd.  Any sign is a valid SVD; the
+reference's own source is untouched.
 """
 import contextlib
 import io
@@ -17,6 +23,18 @@ import make_golden as MG  # noqa: E402  (path setup + import stubs)
 
 SEED, DEPTH, B, N = 78, 3, 2, 200
 
+_svd = torch.svd
+
+
+def svd_canonical_null_vector(A, *args, **kwargs):
+    U, S, V = _svd(A, *args, **kwargs)
+    if A.dim() == 2 and A.shape[1] == 9:
+        v = V[:, -1].detach()
+        flip = torch.ones(9, dtype=V.dtype)
+        flip[-1] = torch.sign(v[v.abs().argmax()])
+        U, V = U * flip, V * flip          # still A = U diag(S) V^T
+    return U, S, V
+
 
 def main():
     MG.install_stubs()
@@ -28,6 +46,7 @@ def main():
     out = {}
     cuda_backup = torch.Tensor.cuda
     torch.Tensor.cuda = lambda self, *a, **k: self      # DeepFNet.__init__ calls .cuda() (:356)
+    torch.svd = svd_canonical_null_vector
     try:
         torch.manual_seed(SEED)
         with contextlib.redirect_stdout(io.StringIO()):
@@ -65,6 +84,7 @@ def main():
                 out["grad/" + name] = p.grad.numpy()
     finally:
         torch.Tensor.cuda = cuda_backup
+        torch.svd = _svd
     path = os.path.join(HERE, "reference_offsets.npz")
     np.savez_compressed(path, **out)
     print(f"wrote {path}: {len(out)} arrays, {os.path.getsize(path) / 1024:.0f} KiB, loss {float(loss):.6f}")

@@ -3,6 +3,7 @@
 // infrastructure: built on the fly by tests/test_math_host.py with g++.
 #include "fepe_math.cuh"
 #include "fepe_fit_adjoint.cuh"
+#include "fepe_recover.cuh"
 #include <vector>
 
 extern "C" {
@@ -240,5 +241,47 @@ void shim_fit_pair_fwd_bwd(const double* m, const double* w, int N, double clamp
             gm[4 * i + 2 * im + 1] = s[im] * xbs[4 * i + 2 * im + 1] + C.A[im] * dv * id + C.By[im] + cbe[4 * i + 2 * im + 1];
         }
     }
+}
+
+// Host run of the pieces of fepe_recover_pose_kernel in its own order (fepe_recover.cuh + essential_decompose):
+// E [9], K [9], m [N,4] pixels (as floats converted to double, like the kernel), Rt_scene [16] ->
+// out: R [9], t [3], counts [4], best, err_q, err_t; mask [N] of the winner.
+void shim_recover_pose(const double* E, const double* K, const float* m, int N, double thresh, const double* Rt,
+                       double* R_out, double* t_out, int* counts, int* best_out, double* errs, unsigned char* mask) {
+    using namespace fepe;
+    double e[9], R1[9], R2[9], t[3], U[9], S[3], V[9];
+    for (int i = 0; i < 9; ++i) e[i] = E[i];
+    essential_decompose(e, R1, R2, t, U, S, V);
+    const double inv_f = 1.0 / K[0], ppx = K[2], ppy = K[5];
+    std::vector<unsigned char> bits(static_cast<size_t>(N), 0);
+    for (int c = 0; c < 4; ++c) {
+        double P[12];
+        recover_candidate(c, R1, R2, t, P);
+        counts[c] = 0;
+        for (int i = 0; i < N; ++i) {
+            const double x1 = (static_cast<double>(m[4 * i]) - ppx) * inv_f, y1 = (static_cast<double>(m[4 * i + 1]) - ppy) * inv_f;
+            const double x2 = (static_cast<double>(m[4 * i + 2]) - ppx) * inv_f, y2 = (static_cast<double>(m[4 * i + 3]) - ppy) * inv_f;
+            double X[4];
+            triangulate_dlt(x1, y1, x2, y2, P, X);
+            if (cheirality_ok(X, P, thresh)) { bits[i] |= static_cast<unsigned char>(1u << c); counts[c] += 1; }
+        }
+    }
+    const int best = recover_select(counts[0], counts[1], counts[2], counts[3]);
+    *best_out = best;
+    double Pb[12], R[9], tt[3];
+    recover_candidate(best, R1, R2, t, Pb);
+    for (int r = 0; r < 3; ++r) {
+        for (int c = 0; c < 3; ++c) R[3 * r + c] = Pb[4 * r + c];
+        tt[r] = Pb[4 * r + 3];
+    }
+    for (int i = 0; i < 9; ++i) R_out[i] = R[i];
+    for (int i = 0; i < 3; ++i) t_out[i] = tt[i];
+    for (int i = 0; i < N; ++i) mask[i] = ((bits[i] >> best) & 1u) ? 255 : 0;
+    double Rs[9], ts[3];
+    for (int r = 0; r < 3; ++r) {
+        for (int c = 0; c < 3; ++c) Rs[3 * r + c] = Rt[4 * r + c];
+        ts[r] = Rt[4 * r + 3];
+    }
+    recover_errors(R, tt, Rs, ts, errs[0], errs[1]);
 }
 }

@@ -41,7 +41,7 @@ def _check(gw_ours, gw_ref, tol=1e-3, gw_ref32=None):
         c = gw_ref32.double().flatten(1)
         rel32 = (c - b).norm(dim=1) / b.norm(dim=1).clamp_min(1e-300)
         print("reference fp32 autograd vs fp64:", ["%.1e" % v for v in rel32.tolist()])
-        assert bool((rel <= torch.maximum(torch.full_like(rel, tol), 3.0 * rel32)).all()), (rel, rel32)
+        assert bool((rel <= torch.maximum(torch.full_like(rel, tol), 3.0 * rel32.clamp(max=1e-2))).all()), (rel, rel32)
     else:
         assert float(rel.max()) < tol, rel
 
@@ -84,7 +84,7 @@ def test_against_oracle_autograd(mode, B, N, which):
     w32 = T(d["weights"]).clone().requires_grad_(True)
     F32, r32 = O.fit_weighted_svd(p1, p2, w32)
     e32 = O.epi_residual(p1, p2, F32, 0.5)
-    s32 = torch.sign((F32.detach().double() * Fo.detach()).sum((1, 2))).float()
+    s32 = torch.sign((F32.detach().double() * F.detach().cpu().double()).sum((1, 2))).float()
     ((F32 * s32.view(-1, 1, 1) * gF).sum() + (r32 * s32.view(-1, 1) * gr).sum() + (e32 * ge).sum()).backward()
     _check(wv.grad.cpu().reshape(B, 1, N), wo.grad, gw_ref32=w32.grad)
 
@@ -123,7 +123,7 @@ def test_coordinate_gradient_against_oracle_autograd(mode, B, N, which):
     (((Fo * s.view(-1, 1, 1)) * gF.double()).sum() + ((ro * s.view(-1, 1)) * gr.double()).sum() + (eo * ge.double()).sum()).backward()
     ((F * gF.cuda()).sum() + (res * gr.cuda()).sum() + (epi * ge.cuda()).sum()).backward()
     m32, w32, F32, r32, e32 = oracle(torch.float32)
-    s32 = torch.sign((F32.detach().double() * Fo.detach()).sum((1, 2))).float()
+    s32 = torch.sign((F32.detach().double() * F.detach().cpu().double()).sum((1, 2))).float()
     ((F32 * s32.view(-1, 1, 1) * gF).sum() + (r32 * s32.view(-1, 1) * gr).sum() + (e32 * ge).sum()).backward()
     assert mu.grad is not None and mu.grad.shape == (B, N, 4) and bool(torch.isfinite(mu.grad).all())
     _check(mu.grad.cpu(), mo.grad, gw_ref32=m32.grad)

@@ -30,3 +30,27 @@ def test_staged_step_equals_direct_calls():
     assert torch.equal(pose_h, pose[0].cpu())
     assert torch.equal(st.d_res.cpu(), res.cpu()) and torch.equal(st.d_epi.cpu(), epi.cpu())
     assert st.in_bytes == 4 * (B * N * 5 + B * (9 + 4 + 3 + 16) + 2 * B * 100 * 3 + 0) or st.in_bytes >= 4 * B * N * 5
+
+
+def test_captured_step_replays_with_new_host_data():
+    """StagedStep.capture / replay: the graph re-reads the pinned buffer on every replay, so new host data gives new
+    results, equal to the eager path."""
+    B, N = 16, 400
+    dev = torch.device("cuda")
+    d0 = synth.make_batch(B, N, seed=21, weight_mode="softmax")
+    d1 = synth.make_batch(B, N, seed=22, weight_mode="inlier")
+    aff = ops.hw_affine(d0["image_size"])
+    st = StagedStep(B, N, d0["pts1_virt"].shape[1], dev)
+    stream = torch.cuda.Stream()
+    st.pack(d0, out=st.h_in)
+    st.capture(stream, aff)
+    ref = StagedStep(B, N, d0["pts1_virt"].shape[1], dev)
+    for d in (d1, d0, d1):
+        st.pack(d, out=st.h_in)
+        st.replay()
+        stream.synchronize()
+        F_g, pose_g = (t.clone() for t in st.results())
+        ref.run(stream, aff, host=ref.pack(d))
+        stream.synchronize()
+        F_e, pose_e = ref.results()
+        assert torch.equal(F_g, F_e) and torch.equal(pose_g, pose_e)
