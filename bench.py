@@ -56,7 +56,7 @@ def parse_args():
     ap.add_argument("--ncorr", type=int, default=1000, help="correspondences per pair (C2: 1000)")
     ap.add_argument("--sat-batch", type=int, default=32768, help="batch of the saturating roofline run")
     ap.add_argument("--no-graph", action="store_true", help="launch eagerly instead of replaying CUDA graphs")
-    ap.add_argument("--streams", type=int, default=2,
+    ap.add_argument("--streams", type=int, default=4,
                     help="parallel branches the K independent steps are issued on (1 = strictly back to back)")
     ap.add_argument("--no-extras", action="store_true", help="skip e2e / cpu_baseline / saturating legs")
     ap.add_argument("--phases", action="store_true", help="print per-phase SM cycles of the fused kernel")
@@ -384,7 +384,8 @@ def run_ours(args):
     fit_us = fit_secs / max(args.steps, 200) * 1e6
     peak, peak_src = measured_peak_gbs()
     achieved = fit_bytes(B, N) / (fit_us * 1e-6) / 1e9
-    small = B <= 2 * torch.cuda.get_device_properties(dev).multi_processor_count and N * 20 <= 56 * 1024
+    sms = torch.cuda.get_device_properties(dev).multi_processor_count
+    small = B <= (6 if N * 20 <= 28 * 1024 else 2) * sms and N * 20 <= 56 * 1024      # fepe_fit.cu: fit_fwd_impl
     fit_kernel = "fepe_fit_fwd_small_kernel" if small else "fepe_fit_fwd_kernel"
     roofline = {"bound": "hbm", "kernel": fit_kernel, "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": ncu_traffic(B, N), "launch_us": fit_us,
@@ -403,7 +404,7 @@ def run_ours(args):
                    "l2_policy": f"ring of {ring_n} distinct batches ({ring_n * per_batch_bytes / 2**20:.0f} MiB) > 126 MiB L2",
                    "launch": "eager" if args.no_graph else
                    f"one CUDA graph of the K step launches on {n_branch} parallel branch(es) (independent batches)"},
-        "gpu_launches": args.steps * (1 if B <= 2 * torch.cuda.get_device_properties(0).multi_processor_count else 2),
+        "gpu_launches": args.steps * (1 if small else 2),
         "roofline": roofline,
     }
 

@@ -19,6 +19,8 @@
 #ifndef FEPE_B200_H
 #define FEPE_B200_H
 
+#include <stddef.h>
+
 #ifdef __cplusplus
 extern "C" {
 #endif
@@ -185,6 +187,22 @@ int fepe_mlp_first_bwd(const void* dY, const float* X0, const float* W, float* d
 int fepe_recover_pose(const float* E, const float* K, const float* matches, const int* n_valid,
                       int L, int B, int N, float distance_thresh, const float* Rt_scene,
                       float* out, unsigned char* mask, void* stream);
+
+/* ---- mutual nearest-neighbour descriptor matching ---------------------------------
+ * Replaces, per sample, SP_tracker.nn_match_two_way(desc1.T, desc2.T, nn_thresh) at
+ * deepFEPE/train_good_utils.py:683-691 (numpy on the host after a D2H copy of both descriptor sets; PointTracker of the
+ * un-vendored `superpoint` package): distances sqrt(2 - 2 clip(<d1_i, d2_j>, -1, 1)), row-wise nearest neighbour below
+ * nn_thresh whose column-wise nearest neighbour points back; matches ordered by the first index.
+ *   desc1    [B,N1,D], desc2 [B,N2,D]  fp32, L2-normalised rows, 16-byte aligned, D a multiple of 16
+ *   n1, n2   [B] valid keypoints per image, or NULL (= N1 / N2)
+ *   workspace  fepe_nn_match_workspace_bytes(B,N1,N2) bytes of device memory, 8-byte aligned (caller-owned)
+ *   idx1, idx2 [B,N1] int32, score [B,N1] fp32: the first count[b] entries of row b are the matches
+ *              (matching_mask[0], [1], [2] of the reference); count [B] int32
+ */
+size_t fepe_nn_match_workspace_bytes(int B, int N1, int N2);
+int fepe_nn_match(const float* desc1, const float* desc2, const int* n1, const int* n2,
+                  int B, int N1, int N2, int D, float nn_thresh, void* workspace,
+                  int* idx1, int* idx2, float* score, int* count, void* stream);
 
 #ifdef __cplusplus
 }

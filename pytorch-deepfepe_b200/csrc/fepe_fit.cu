@@ -271,11 +271,15 @@ __device__ __forceinline__ int eig9_smallest_cta(const double* __restrict__ g36,
     return rounds;
 }
 
+// 2 warps x 6 CTAs per SM (168 registers, ~200 B of spills in the solver) instead of 4 x 2 (226 registers): a single
+// launch is ~9 % slower (21.9 vs 20.1 us at 256 pairs), but independent launches that overlap -- the steady state of a
+// pipelined caller and of bench.py -- gain 35 % (25.8 M vs 19.1 M pairs/s): half as many lanes repeat the eigen-solve
+// and three times as many CTAs hide each other's latency (profiles/r1_small_kernel_variants.txt).
 #ifndef FEPE_SMALL_WARPS
-#define FEPE_SMALL_WARPS 4
+#define FEPE_SMALL_WARPS 2
 #endif
 #ifndef FEPE_SMALL_MINBLOCKS
-#define FEPE_SMALL_MINBLOCKS 2
+#define FEPE_SMALL_MINBLOCKS 6
 #endif
 constexpr int kSmallWarps = FEPE_SMALL_WARPS;
 constexpr int kSmallThreads = kSmallWarps * 32;
@@ -537,7 +541,10 @@ static int fit_fwd_impl(const float* matches, const float* weights, int B, int N
     // Small batches are bound by the latency of one pair: spread each pair over a CTA of 4 warps.
     const int small_bytes = ((N * 20 + 127) / 128) * 128;
     const char* force = getenv("FEPE_FIT_KERNEL");     // "ring" | "small": development override
-    bool use_small = (B <= 2 * d.sms) && (small_bytes <= 56 * 1024);
+    // one wave of the latency kernel: 6 CTAs per SM while a pair's stage is <= 28 KB (N <= 1400), else 2 (measured
+    // crossovers against the ring kernel, profiles/r1_kernel_crossover.txt)
+    const int small_ctas_per_sm = (small_bytes <= 28 * 1024) ? 6 : 2;
+    bool use_small = (B <= small_ctas_per_sm * d.sms) && (small_bytes <= 56 * 1024);
     if (force != nullptr) use_small = (force[0] == 's') && (force[1] == 'm') && (small_bytes <= 56 * 1024);
     // Batches that fill the machine several times over go through the split pipeline (fepe_fit_split.cu).
     bool use_split = !use_small && (B >= fepe::kSplitMinPairsPerSM * d.sms) && fepe::split_path_supported(p, d);

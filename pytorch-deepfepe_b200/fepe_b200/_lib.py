@@ -38,6 +38,8 @@ _SIGNATURES = {
     "fepe_pose_bwd": (_c_i, [_c_p, _c_p, _c_i, _c_i, _c_f, _c_f, _c_f, _c_f, _c_p, _c_p, _c_p, _c_p, _c_i, _c_f,
                              _c_p, _c_p, _c_p, _c_p, _c_p, _c_p]),
     "fepe_recover_pose": (_c_i, [_c_p, _c_p, _c_p, _c_p, _c_i, _c_i, _c_i, _c_f, _c_p, _c_p, _c_p, _c_p]),
+    "fepe_nn_match_workspace_bytes": (ctypes.c_size_t, [_c_i, _c_i, _c_i]),
+    "fepe_nn_match": (_c_i, [_c_p, _c_p, _c_p, _c_p, _c_i, _c_i, _c_i, _c_i, _c_f, _c_p, _c_p, _c_p, _c_p, _c_p, _c_p]),
     "fepe_mlp_first": (_c_i, [_c_p, _c_p, _c_p, _c_p, _c_p, _c_i, _c_i, _c_i, _c_i, _c_i, _c_p]),
     "fepe_mlp_gemm": (_c_i, [_c_p, _c_p, _c_p, _c_p, _c_p, _c_i, _c_i, _c_i, _c_i, _c_i, _c_p]),
     "fepe_mlp_norm": (_c_i, [_c_p, _c_p, _c_p, _c_p, _c_p, _c_i, _c_i, _c_i, _c_i, _c_f, _c_f, _c_p]),

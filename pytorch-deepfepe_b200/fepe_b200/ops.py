@@ -200,6 +200,39 @@ def recover_pose(E: torch.Tensor, K: torch.Tensor, matches: torch.Tensor, Rt_sce
     return out, mask
 
 
+def nn_match_two_way(desc1: torch.Tensor, desc2: torch.Tensor, nn_thresh: float,
+                     n1: Optional[torch.Tensor] = None, n2: Optional[torch.Tensor] = None):
+    """Mutual nearest-neighbour matching of L2-normalised descriptors for a whole batch (include/fepe_b200.h:
+    fepe_nn_match) -- PointTracker.nn_match_two_way of the reference's call site train_good_utils.py:685-689.
+
+    desc1 [B,N1,D], desc2 [B,N2,D] fp32 CUDA (one ROW per keypoint); n1, n2 [B] int32 valid counts or None.
+    Returns idx1 [B,N1] int32, idx2 [B,N1] int32, score [B,N1] fp32, count [B] int32: the first count[b] columns of
+    row b are the reference's matching_mask[0], [1], [2]."""
+    desc1 = _check_cuda_f32(desc1, "desc1")
+    desc2 = _check_cuda_f32(desc2, "desc2")
+    if desc1.dim() != 3 or desc2.dim() != 3 or desc1.shape[0] != desc2.shape[0] or desc1.shape[2] != desc2.shape[2]:
+        raise RuntimeError("fepe_b200: descriptors must be [B,N1,D] and [B,N2,D]")
+    B, N1, D = desc1.shape
+    N2 = desc2.shape[1]
+    for name, t in (("n1", n1), ("n2", n2)):
+        if t is not None and (not t.is_cuda or t.dtype != torch.int32 or t.numel() != B):
+            raise RuntimeError(f"fepe_b200: {name} must be a CUDA int32 tensor of B elements")
+    dev = desc1.device
+    with torch.cuda.device(dev):
+        ws = torch.empty(_lib.lib().fepe_nn_match_workspace_bytes(B, N1, N2) // 8, dtype=torch.int64, device=dev)
+        idx1 = torch.empty(B, N1, dtype=torch.int32, device=dev)
+        idx2 = torch.empty(B, N1, dtype=torch.int32, device=dev)
+        score = torch.empty(B, N1, dtype=torch.float32, device=dev)
+        count = torch.empty(B, dtype=torch.int32, device=dev)
+        st = _lib.lib().fepe_nn_match(desc1.data_ptr(), desc2.data_ptr(),
+                                      n1.contiguous().data_ptr() if n1 is not None else None,
+                                      n2.contiguous().data_ptr() if n2 is not None else None,
+                                      B, N1, N2, D, float(nn_thresh), ws.data_ptr(), idx1.data_ptr(), idx2.data_ptr(),
+                                      score.data_ptr(), count.data_ptr(), _stream_ptr())
+    _lib.check(st, "fepe_nn_match")
+    return idx1, idx2, score, count
+
+
 class FitFunction(torch.autograd.Function):
     """Differentiable fused weighted 8-point fit.
 

@@ -31,3 +31,9 @@ t = lambda k: torch.from_numpy(d[k]).cuda()
 ops.recover_pose(t("E_gt"), t("Ks"), t("matches_xy_ori"), t("delta_Rtijs_4_4"), want_mask=True)
 torch.cuda.synchronize()
 print("recover_pose done")
+rng = torch.Generator(device="cuda").manual_seed(0)
+d1 = torch.nn.functional.normalize(torch.randn(2, 333, 256, device="cuda", generator=rng), dim=2)
+d2 = torch.nn.functional.normalize(torch.randn(2, 200, 256, device="cuda", generator=rng), dim=2)
+ops.nn_match_two_way(d1, d2, 1.0, torch.tensor([333, 100], dtype=torch.int32, device="cuda"), None)
+torch.cuda.synchronize()
+print("nn_match done")

@@ -128,3 +128,41 @@ def test_fused_fit_pose_equals_two_calls(B, N, with_virt, with_rt):
     assert torch.equal(F0, F1) and torch.equal(r0, r1) and torch.equal(e0, e1)
     assert torch.equal(s0[:, :56], s1[:, :56])
     np.testing.assert_allclose(p1.cpu().numpy(), p0.cpu().numpy(), rtol=1e-6, atol=1e-6)
+
+
+def test_get_Rt_loss_mirror_matches_oracle_values_and_gradient(golden):
+    """fepe_b200.losses.get_Rt_loss (the reference's name / arguments / dict, train_good_utils.py:64-295) against the
+    oracle's restatement of the same loop in fp64, values and d loss / d E, and against the reference's own numbers."""
+    from fepe_b200.losses import get_Rt_loss, pose_loss_from_Rt_loss
+    # (1) the reference's own outputs for its own E (golden fixture)
+    E = T(golden["pose_E"]).cuda()
+    B = E.shape[0]
+    r = get_Rt_loss([E], None, None, None, T(golden["pose_Rt"]), T(golden["pose_qcam"]), T(golden["pose_tcam"]), device="cuda")
+    np.testing.assert_allclose(r["q_l2_error_layers_list"][0].cpu().numpy(), golden["pose_q_l2"][0], atol=2e-5)
+    np.testing.assert_allclose(r["t_l2_error_layers_list"][0].cpu().numpy(), golden["pose_t_l2"][0], atol=2e-5)
+    np.testing.assert_allclose(r["R_angle_error_layers_list"][0], golden["pose_R_ang"][0], atol=2e-3)
+    np.testing.assert_allclose(r["t_angle_error_layers_list"][0], golden["pose_t_ang"][0], atol=2e-3)
+    assert set(r) == {"t_l2_error_mean", "q_l2_error_mean", "t_l2_error_list", "q_l2_error_list", "R_angle_error_mean",
+                      "R_angle_error_list", "t_angle_error_mean", "t_angle_error_list", "R_angle_error_layers_list",
+                      "t_angle_error_layers_list", "t_l2_error_layers_list", "q_l2_error_layers_list"}
+    # (2) three layers of perturbed essential matrices: loss value and gradient vs fp64 autograd through the oracle
+    d = synth.make_batch(12, 64, seed=21, outlier_frac=0.0)
+    gen = torch.Generator().manual_seed(3)
+    E0 = T(d["E_gt"])
+    layers = [(E0 + s * torch.randn(E0.shape, generator=gen)) for s in (0.08, 0.04, 0.02)]
+    ours = [e.clone().cuda().requires_grad_(True) for e in layers]
+    r = get_Rt_loss(ours, T(d["Ks"]), None, None, T(d["delta_Rtijs_4_4"]), T(d["q_cam"]).cuda(), T(d["t_cam"]).cuda())
+    loss = pose_loss_from_Rt_loss(r, clamp_q=0.1, clamp_t=0.5, balance_q=1.0, balance_t=0.1)
+    loss.backward()
+    ref_in = [e.clone().double().requires_grad_(True) for e in layers]
+    lo, q_all, t_all, ra, ta = O.pose_loss(ref_in, T(d["q_cam"]).double(), T(d["t_cam"]).double(),
+                                           T(d["delta_Rtijs_4_4"]).double(), 0.1, 0.5, 1.0, 0.1)
+    lo.backward()
+    assert abs(float(loss) - float(lo)) < 1e-5
+    np.testing.assert_allclose(torch.stack(r["q_l2_error_layers_list"]).detach().cpu().numpy(), q_all.detach().numpy(), atol=2e-5)
+    np.testing.assert_allclose(np.stack(r["R_angle_error_layers_list"]), ra.numpy(), atol=1e-3)
+    np.testing.assert_allclose(np.stack(r["t_angle_error_layers_list"]), ta.numpy(), atol=1e-3)
+    assert abs(r["R_angle_error_mean"] - float(ra.mean(1).mean())) < 1e-3
+    for a, b in zip(ours, ref_in):
+        rel = float((a.grad.cpu().double() - b.grad).norm() / b.grad.norm().clamp_min(1e-30))
+        assert rel < 2e-3, rel
