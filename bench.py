@@ -580,14 +580,28 @@ def run_c5(args):
     entry.build()
     from fepe_b200 import synth, dist as fdist
     from fepe_b200.models import DeepFNet
+    from fepe_b200.matching import get_matches_from_descriptors
+    from fepe_b200.losses import get_Rt_loss, pose_loss_from_Rt_loss
     B, N = 16, args.ncorr
+    NKP, DESC = 1200, 256                    # keypoints per image and descriptor size (SuperPoint: 256)
     torch.manual_seed(0)
-    net = DeepFNet(depth=5, image_size=list(synth.KITTI_IMAGE_SIZE), if_quality=False).cuda()
+    # with_quality (configs/kitti_corr_baseline.yaml): the match score is the one quality channel
+    net = DeepFNet(depth=5, image_size=list(synth.KITTI_IMAGE_SIZE), if_quality=True, quality_size=1).cuda()
     opt = torch.optim.Adam(net.parameters(), lr=1e-4)          # configs/kitti_corr_baseline.yaml:62
-    d = synth.make_batch(B, N, seed=500 + rank)
+    # "SuperPoint frozen / random desc": a synthetic two-view scene gives NKP corresponding keypoints; image 2's are
+    # shuffled and carry noisy copies of image 1's random unit descriptors.  The step starts from keypoints + descriptors.
+    d = synth.make_batch(B, NKP, seed=500 + rank)
     T = lambda k: torch.from_numpy(d[k]).to(dev)
-    batch = {"matches_xy_ori": T("matches_xy_ori")}
+    gen = torch.Generator(device=dev).manual_seed(1234 + rank)
+    m_all = T("matches_xy_ori")
+    perm = torch.stack([torch.randperm(NKP, device=dev, generator=gen) for _ in range(B)])
+    kp1 = m_all[:, :, :2].contiguous()
+    kp2 = torch.gather(m_all[:, :, 2:], 1, perm.unsqueeze(-1).expand(-1, -1, 2)).contiguous()
+    desc1 = torch.nn.functional.normalize(torch.randn(B, NKP, DESC, device=dev, generator=gen), dim=2)
+    desc2 = torch.gather(desc1, 1, perm.unsqueeze(-1).expand(-1, -1, DESC))
+    desc2 = torch.nn.functional.normalize(desc2 + 0.03 * torch.randn(B, NKP, DESC, device=dev, generator=gen), dim=2).contiguous()
     v1, v2 = T("pts1_virt"), T("pts2_virt")
+    Ks, Rt, q_cam, t_cam = T("Ks"), T("delta_Rtijs_4_4"), T("q_cam"), T("t_cam")
 
     def epi(p1, p2, Fm, clamp):            # utils_F.compute_epi_residual with torch ops (loss glue stays the reference's)
         l1, l2 = p2 @ Fm, p1 @ Fm.transpose(1, 2)
@@ -595,22 +609,33 @@ def run_c5(args):
         dist_ = dd.abs() * (1 / (l1[:, :, :2].norm(2, 2) + 1e-6) + 1 / (l2[:, :, :2].norm(2, 2) + 1e-6))
         return torch.clamp(dist_, max=clamp)
 
-    times = {"fwd": 0.0, "bwd": 0.0, "allreduce": 0.0}
+    times = {"match": 0.0, "fwd": 0.0, "bwd": 0.0, "allreduce": 0.0}
+    n_matches = []
 
     def step():
-        ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(5)]
         opt.zero_grad(set_to_none=True)
         ev[0].record()
+        # train_good_utils.py:649-724: mutual-NN matches -> [B,N,4] + quality (fepe_nn_match, on the device)
+        mt = get_matches_from_descriptors(kp1, kp2, desc1, desc2, 1.0, out_num_points=N, generator=gen)
+        batch = {"matches_xy_ori": mt["xs"], "quality": mt["quality"]}
+        n_matches.append(mt["num_matches"])
+        ev[1].record()
         outs = net(batch)
         T1 = outs["T1"]
         p1 = (T1 @ v1.transpose(1, 2)).transpose(1, 2)
         p2 = (T1 @ v2.transpose(1, 2)).transpose(1, 2)
-        loss = sum(epi(p1, p2, Fo, CLAMP_LOSS).mean() for Fo in outs["out_layers"]) / len(outs["out_layers"])
-        ev[1].record()
-        loss.backward()
+        loss_F = sum(epi(p1, p2, Fo, CLAMP_LOSS).mean() for Fo in outs["out_layers"]) / len(outs["out_layers"])
+        # get_all_loss_DeepF: E_i = K^T T2^T F_i T1 K (train_good_utils.py:356-358); get_Rt_loss (:64-295) on the device
+        TK = T1 @ Ks
+        E_layers = [TK.transpose(1, 2) @ Fo @ TK for Fo in outs["out_layers"]]
+        rt = get_Rt_loss(E_layers, None, None, None, Rt, q_cam, t_cam)
+        loss = loss_F + pose_loss_from_Rt_loss(rt)            # Train_model_pipeline.py:580-592 (if_qt_loss)
         ev[2].record()
-        fdist.allreduce_mean_grads_(list(net.parameters()))
+        loss.backward()
         ev[3].record()
+        fdist.allreduce_mean_grads_(list(net.parameters()))
+        ev[4].record()
         opt.step()
         return ev
 
@@ -632,7 +657,8 @@ def run_c5(args):
         torch.cuda.synchronize()
         secs_ = fdist.max_over_ranks(e0.elapsed_time(e1) * 1e-3, dev)
         for ev in evs:
-            times["fwd"] += ev[0].elapsed_time(ev[1]); times["bwd"] += ev[1].elapsed_time(ev[2]); times["allreduce"] += ev[2].elapsed_time(ev[3])
+            times["match"] += ev[0].elapsed_time(ev[1]); times["fwd"] += ev[1].elapsed_time(ev[2])
+            times["bwd"] += ev[2].elapsed_time(ev[3]); times["allreduce"] += ev[3].elapsed_time(ev[4])
         return secs_, {k: v / steps for k, v in times.items()}
 
     secs32, br32 = run(False)
@@ -641,8 +667,11 @@ def run_c5(args):
             "steps": steps, "warmup": warm, "ms_per_step": secs / steps * 1e3, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "bf16 MLP forward+backward on tcgen05 (fp32 accumulate) + f32/f64 solver kernels",
             "data": "synthetic",
-            "config": {"workload": f"C5: DeepFNet training step, depth 5, {B} pairs/GPU x N={N}, F-loss, Adam, "
-                                   "one flattened gradient all-reduce (NCCL)", "global_batch": world * B},
+            "config": {"workload": f"C5: training step from keypoints + random descriptors ({NKP} per image, {DESC}-d): mutual-NN "
+                                   f"matching -> {N} matches + quality, DeepFNet depth 5, {B} pairs/GPU, F-loss + q/t pose "
+                                   "loss (device get_Rt_loss), Adam, one flattened gradient all-reduce (NCCL)",
+                       "global_batch": world * B,
+                       "mean_matches_per_pair": float(torch.stack(n_matches[-steps:]).float().mean())},
             "ms_breakdown": br,
             "fp32_autograd_mlp": {"value": world * B * steps / secs32, "ms_per_step": secs32 / steps * 1e3,
                                   "ms_breakdown": br32},
