@@ -204,6 +204,25 @@ int fepe_nn_match(const float* desc1, const float* desc2, const int* n1, const i
                   int B, int N1, int N2, int D, float nn_thresh, void* workspace,
                   int* idx1, int* idx2, float* score, int* count, void* stream);
 
+/* ---- ground truth + virtual correspondences of a batch ----------------------------
+ * Replaces, per sample, the host work of the reference's dataset (deepFEPE/datasets/kitti_odo_corr.py:290-302, :526-566):
+ *   E, F = utils_F.E_F_from_Rt_np(R, t, K)  (dsac_tools/utils_F.py:835-846);
+ *   utils_misc.get_virt_x1x2_np(image_size, F, K, pts1_virt_b, pts2_virt_b)  (dsac_tools/utils_misc.py:173-199) =
+ *   cv2.correctMatches(F, pts2_virt_b, pts1_virt_b) with OpenCV's NaNs replaced by 0, homogeneous, and K^-1 applied;
+ *   q_cam, t_cam of the inverse motion and q_scene, t_scene  (dsac_tools/utils_geo.py:88-117 R_to_q_np).
+ *   K        [B,9]    intrinsics
+ *   Rt_scene [B,16]   scene motion x2 = R x1 + t (relative_scene_poses[1] / delta_Rtijs_4_4), or NULL with F_in
+ *   F_in     [B,9]    or NULL: fundamental matrix to correct the grid onto instead of the one built from Rt_scene
+ *   grid1, grid2 [P,2] pixel grids pts1_virt_b, pts2_virt_b (utils_misc.py:163-171: 10x10 points, P = 100)
+ *   gt       [B,FEPE_GT_FLOATS] or NULL: [0..8] E  [9..17] F  [18..21] q_cam (w,x,y,z; w >= 0)  [22..24] t_cam
+ *            [25..28] q_scene  [29..31] t_scene      (needs Rt_scene)
+ *   pts1_virt, pts2_virt [B,P,3] homogeneous pixels with pts2^T F pts1 = 0
+ *   pts_virt_normalized  [B,P,3] or NULL: K^-1 pts1_virt -- the reference returns this for BOTH normalised keys
+ */
+#define FEPE_GT_FLOATS 32
+int fepe_gt_virt(const float* K, const float* Rt_scene, const float* F_in, const float* grid1, const float* grid2,
+                 int B, int P, float* gt, float* pts1_virt, float* pts2_virt, float* pts_virt_normalized, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

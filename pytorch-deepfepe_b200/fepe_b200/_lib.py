@@ -15,6 +15,7 @@ LIB_PATH = os.environ.get("FEPE_B200_LIB") or os.path.join(os.path.dirname(_HERE
 SAVED_DOUBLES = 64          # FEPE_SAVED_DOUBLES
 POSE_OUT_FLOATS = 32        # FEPE_POSE_OUT_FLOATS
 RECOVER_OUT_FLOATS = 24     # FEPE_RECOVER_OUT_FLOATS
+GT_FLOATS = 32              # FEPE_GT_FLOATS
 
 _lib = None
 
@@ -38,6 +39,7 @@ _SIGNATURES = {
     "fepe_pose_bwd": (_c_i, [_c_p, _c_p, _c_i, _c_i, _c_f, _c_f, _c_f, _c_f, _c_p, _c_p, _c_p, _c_p, _c_i, _c_f,
                              _c_p, _c_p, _c_p, _c_p, _c_p, _c_p]),
     "fepe_recover_pose": (_c_i, [_c_p, _c_p, _c_p, _c_p, _c_i, _c_i, _c_i, _c_f, _c_p, _c_p, _c_p, _c_p]),
+    "fepe_gt_virt": (_c_i, [_c_p, _c_p, _c_p, _c_p, _c_p, _c_i, _c_i, _c_p, _c_p, _c_p, _c_p, _c_p]),
     "fepe_nn_match_workspace_bytes": (ctypes.c_size_t, [_c_i, _c_i, _c_i]),
     "fepe_nn_match": (_c_i, [_c_p, _c_p, _c_p, _c_p, _c_i, _c_i, _c_i, _c_i, _c_f, _c_p, _c_p, _c_p, _c_p, _c_p, _c_p]),
     "fepe_mlp_first": (_c_i, [_c_p, _c_p, _c_p, _c_p, _c_p, _c_i, _c_i, _c_i, _c_i, _c_i, _c_p]),

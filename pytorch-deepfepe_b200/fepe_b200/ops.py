@@ -200,6 +200,39 @@ def recover_pose(E: torch.Tensor, K: torch.Tensor, matches: torch.Tensor, Rt_sce
     return out, mask
 
 
+def gt_virt(K: torch.Tensor, Rt_scene: Optional[torch.Tensor], grid1: torch.Tensor, grid2: torch.Tensor,
+            F_in: Optional[torch.Tensor] = None, want_normalized: bool = True):
+    """Ground truth + virtual correspondences of a batch on the device (include/fepe_b200.h: fepe_gt_virt) -- per sample
+    utils_F.E_F_from_Rt_np, utils_misc.get_virt_x1x2_np (cv2.correctMatches) and R_to_q_np in the reference's dataset
+    (deepFEPE/datasets/kitti_odo_corr.py:290-302, :526-566).
+
+    K [B,3,3]; Rt_scene [B,4,4] or None (then F_in [B,3,3] is required); grid1, grid2 [P,2] pixel grids.
+    Returns (gt [B,32] | None, pts1_virt [B,P,3], pts2_virt [B,P,3], pts_virt_normalized [B,P,3] | None)."""
+    K = _check_cuda_f32(K, "K")
+    B = K.shape[0]
+    K = K.reshape(B, 9)
+    rt = _check_cuda_f32(Rt_scene, "Rt_scene").reshape(B, 16) if Rt_scene is not None else None
+    fin = _check_cuda_f32(F_in, "F_in").reshape(B, 9) if F_in is not None else None
+    if rt is None and fin is None:
+        raise RuntimeError("fepe_b200: gt_virt needs Rt_scene or F_in")
+    grid1 = _check_cuda_f32(grid1, "grid1")
+    grid2 = _check_cuda_f32(grid2, "grid2")
+    if grid1.dim() != 2 or grid1.shape[1] != 2 or grid1.shape != grid2.shape:
+        raise RuntimeError("fepe_b200: grids must both be [P,2]")
+    P = grid1.shape[0]
+    dev = K.device
+    with torch.cuda.device(dev):
+        gt = torch.empty(B, _lib.GT_FLOATS, dtype=torch.float32, device=dev) if rt is not None else None
+        p1 = torch.empty(B, P, 3, dtype=torch.float32, device=dev)
+        p2 = torch.empty(B, P, 3, dtype=torch.float32, device=dev)
+        pn = torch.empty(B, P, 3, dtype=torch.float32, device=dev) if want_normalized else None
+        ptr = lambda t: t.data_ptr() if t is not None else None
+        st = _lib.lib().fepe_gt_virt(K.data_ptr(), ptr(rt), ptr(fin), grid1.data_ptr(), grid2.data_ptr(), B, P,
+                                     ptr(gt), p1.data_ptr(), p2.data_ptr(), ptr(pn), _stream_ptr())
+    _lib.check(st, "fepe_gt_virt")
+    return gt, p1, p2, pn
+
+
 def nn_match_two_way(desc1: torch.Tensor, desc2: torch.Tensor, nn_thresh: float,
                      n1: Optional[torch.Tensor] = None, n2: Optional[torch.Tensor] = None):
     """Mutual nearest-neighbour matching of L2-normalised descriptors for a whole batch (include/fepe_b200.h:

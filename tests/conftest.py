@@ -33,7 +33,7 @@ def shim():
     os.makedirs(BUILD, exist_ok=True)
     so = os.path.join(BUILD, "host_shim.so")
     src = os.path.join(ROOT, "tests", "host_shim.cpp")
-    hdrs = [os.path.join(CSRC, h) for h in ("fepe_math.cuh", "fepe_fit_adjoint.cuh", "fepe_recover.cuh")]
+    hdrs = [os.path.join(CSRC, h) for h in ("fepe_math.cuh", "fepe_fit_adjoint.cuh", "fepe_recover.cuh", "fepe_virt.cuh")]
     if not os.path.exists(so) or os.path.getmtime(so) < max([os.path.getmtime(src)] + [os.path.getmtime(h) for h in hdrs]):
         subprocess.check_call(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-Wno-unknown-pragmas",
                                "-x", "c++", "-I", CSRC, src, "-o", so])
@@ -58,4 +58,9 @@ def shim():
     lib.shim_fit_pair_fwd_bwd.argtypes = [dp, dp, ctypes.c_int, ctypes.c_double] + [dp] * 8
     ip, fp, bp = ctypes.POINTER(ctypes.c_int), ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_ubyte)
     lib.shim_recover_pose.argtypes = [dp, dp, fp, ctypes.c_int, ctypes.c_double, dp, dp, dp, ip, ip, dp, bp]
+    lib.shim_correct_matches.argtypes = [dp, fp, fp, ctypes.c_int, fp, fp]
+    lib.shim_correct_matches.restype = ctypes.c_int
+    lib.shim_solve_poly6.argtypes = [dp, dp]
+    lib.shim_solve_poly6.restype = ctypes.c_int
+    lib.shim_gt_from_motion.argtypes = [fp, fp, dp]
     return lib

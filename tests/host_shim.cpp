@@ -4,6 +4,7 @@
 #include "fepe_math.cuh"
 #include "fepe_fit_adjoint.cuh"
 #include "fepe_recover.cuh"
+#include "fepe_virt.cuh"
 #include <vector>
 
 extern "C" {
@@ -284,4 +285,35 @@ void shim_recover_pose(const double* E, const double* K, const float* m, int N, 
     }
     recover_errors(R, tt, Rs, ts, errs[0], errs[1]);
 }
+// Host run of fepe_gt_virt_kernel's per-thread work (fepe_virt.cuh), fp32 rounding of the outputs included.
+int shim_correct_matches(const double* F, const float* pts1, const float* pts2, int P, float* out1, float* out2) {
+    double f[9];
+    for (int i = 0; i < 9; ++i) f[i] = F[i];
+    int nan_count = 0;
+    for (int i = 0; i < P; ++i) {
+        double o[4];
+        const bool ok = fepe::correct_match_pair(f, pts1[2 * i], pts1[2 * i + 1], pts2[2 * i], pts2[2 * i + 1], o);
+        if (!ok) { ++nan_count; for (int k = 0; k < 4; ++k) o[k] = 0.0; }
+        out1[2 * i] = static_cast<float>(o[0]); out1[2 * i + 1] = static_cast<float>(o[1]);
+        out2[2 * i] = static_cast<float>(o[2]); out2[2 * i + 1] = static_cast<float>(o[3]);
+    }
+    return nan_count;
+}
+
+int shim_solve_poly6(const double* k, double* t_re) {
+    double kk[7], tt[6];
+    for (int i = 0; i < 7; ++i) kk[i] = k[i];
+    const int n = fepe::solve_poly6_cv(kk, tt);
+    for (int i = 0; i < 6; ++i) t_re[i] = tt[i];
+    return n;
+}
+
+void shim_gt_from_motion(const float* K, const float* Rt, double* gt) {
+    double k[9], rt[16], g[32], kinv[9];
+    for (int i = 0; i < 9; ++i) k[i] = K[i];
+    for (int i = 0; i < 16; ++i) rt[i] = Rt[i];
+    fepe::gt_from_motion(k, rt, g, kinv);
+    for (int i = 0; i < 32; ++i) gt[i] = g[i];
+}
+
 }
