@@ -432,15 +432,21 @@ def run_ours(args):
                 stages[j].replay()
 
         e2e_steps = max(50, min(args.steps, 400))
-        # the PCIe ceiling of THIS box at this moment: the same pinned buffers copied with nothing else in the step
-        for rep in range(2):
-            torch.cuda.synchronize()
-            tp0 = time.perf_counter()
-            for i in range(100):
-                with torch.cuda.stream(streams[i % nbuf]):
-                    stages[i % nbuf].d_in.copy_(stages[i % nbuf].h_in, non_blocking=True)
-            torch.cuda.synchronize()
-            h2d_only_us = (time.perf_counter() - tp0) / 100 * 1e6
+        # the PCIe ceiling of THIS box at this moment: the same pinned buffers copied back to back with nothing else,
+        # as ONE captured graph of 16 copies (eager copies would time the host's launch path, not the link)
+        gcopy = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(gcopy, stream=streams[0]):
+            for i in range(16):
+                stages[i % nbuf].d_in.copy_(stages[i % nbuf].h_in, non_blocking=True)
+        gcopy.replay()
+        torch.cuda.synchronize()
+        c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        c0.record()
+        for _ in range(5):
+            gcopy.replay()
+        c1.record()
+        torch.cuda.synchronize()
+        h2d_only_us = c0.elapsed_time(c1) / (5 * 16) * 1e3
         for i in range(6):
             e2e_step(i)
         torch.cuda.synchronize()
