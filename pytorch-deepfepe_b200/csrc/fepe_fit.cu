@@ -42,7 +42,7 @@ __device__ __noinline__ void solve_pair(double* __restrict__ scratch, int lane) 
     }
     double f[9], lambda;
     const long long t0 = clock64();
-    const int rounds = eig9_smallest_warp(scratch, f, lambda, lane);
+    const int rounds = eig9_smallest_warp(scratch, f, lambda, lane, scratch + kSolF);   // slots 36..63 are free until the results land
     const long long t1 = clock64();
     double F2[9], v3[3], sigma3;
     rank2_project(f, F2, v3, sigma3);
@@ -210,11 +210,35 @@ __global__ void __launch_bounds__(kThreads, 1) fepe_fit_fwd_kernel(const FitPara
 // so lambda_min is bracketed NW*32-fold per round and fewer rounds are needed (host emulation:
 // tests/host_shim.cpp shim_eig9_multishift_n).  Every thread calls it with the same g36 (shared memory) and gets the
 // same f / lambda back; `okm` (NW words) and `xch` (16 doubles) are shared-memory exchange buffers.
+// Tridiagonal form (fepe_math.cuh tridiag9): warp 0 reduces G = Q T Q^T once and parks T and the reflectors in `tri`
+// (52 doubles of shared memory); a lane's shift then costs a tridiagonal LDL^T (8 multipliers, 9 pivots) instead of a
+// dense 9x9 one, and the eigenvector of T is carried back with the reflectors at the end.
+constexpr int kTriDoubles = 52;      // ta[9] tb[8] hv[28] htau[7]
 template <int NW>
 __device__ __forceinline__ int eig9_smallest_cta(const double* __restrict__ g36, double (&f)[9], double& lambda,
-                                                 int warp, int lane, unsigned* okm, double* xch) {
+                                                 int warp, int lane, unsigned* okm, double* xch, double* tri) {
+    if (warp == 0) {
+        double ta[9], tb[8], hv[28], htau[7];
+        tridiag9(g36, ta, tb, hv, htau);
+        if (lane == 0) {
+#pragma unroll
+            for (int i = 0; i < 9; ++i) tri[i] = ta[i];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) tri[9 + i] = tb[i];
+#pragma unroll
+            for (int i = 0; i < 28; ++i) tri[17 + i] = hv[i];
+#pragma unroll
+            for (int i = 0; i < 7; ++i) tri[45 + i] = htau[i];
+        }
+    }
+    __syncthreads();
+    double ta[9], tb[8];
+#pragma unroll
+    for (int i = 0; i < 9; ++i) ta[i] = tri[i];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) tb[i] = tri[9 + i];
     Eig9Bracket b;
-    if (!eig9_bracket_init(g36, b)) {
+    if (!tri9_bracket_init(ta, b)) {
 #pragma unroll
         for (int i = 0; i < 9; ++i) f[i] = (i == 8) ? 1.0 : 0.0;
         lambda = 0.0;
@@ -233,7 +257,7 @@ __device__ __forceinline__ int eig9_smallest_cta(const double* __restrict__ g36,
         for (int i = 0; i < 9; ++i) xl[i] = x[i];
         int nneg;
         double rho_l, r_l, c_l;
-        eig9_lane_round(g36, mu, tiny, 2, xl, nneg, rho_l, r_l, c_l);
+        tri9_lane_round(ta, tb, mu, tiny, 2, xl, nneg, rho_l, r_l, c_l);
         ++rounds;
         const unsigned ok = __ballot_sync(0xffffffffu, nneg == 0);
         if (lane == 0) okm[warp] = ok;
@@ -266,6 +290,7 @@ __device__ __forceinline__ int eig9_smallest_cta(const double* __restrict__ g36,
         for (int i = 0; i < 9; ++i) x[i] = xch[4 + i];
         if (eig9_bracket_update(b, mu_best, mu_fail, rho, r, c)) break;
     }
+    tridiag9_back(tri + 17, tri + 45, x);
     canonical_sign9(x, f);
     lambda = rho;
     return rounds;
@@ -296,6 +321,7 @@ __global__ void __launch_bounds__(kSmallThreads, FEPE_SMALL_MINBLOCKS) fepe_fit_
     __shared__ double gram[kScratchDoubles];
     __shared__ unsigned eig_ok[kSmallWarps];
     __shared__ double eig_xch[16];
+    __shared__ double eig_tri[kTriDoubles];
     __shared__ float pose_in[POSE ? 32 : 1];                                // K(9) q(4) t(3) R_scene(9)
     __shared__ float pose_virt[POSE ? 2 * kVirtPerLane * 3 * 32 : 1];      // [img][u][c][lane]
 
@@ -420,7 +446,7 @@ __global__ void __launch_bounds__(kSmallThreads, FEPE_SMALL_MINBLOCKS) fepe_fit_
     {
         double f[9], lambda;
         const long long te0 = clock64();
-        const int rounds = eig9_smallest_cta<kSmallWarps>(gram, f, lambda, warp, lane, eig_ok, eig_xch);
+        const int rounds = eig9_smallest_cta<kSmallWarps>(gram, f, lambda, warp, lane, eig_ok, eig_xch, eig_tri);
         const long long te1 = clock64();
         double F2[9], v3[3], sigma3;
         rank2_project(f, F2, v3, sigma3);

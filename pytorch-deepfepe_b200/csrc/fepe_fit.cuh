@@ -57,12 +57,25 @@ struct PairNorm {
 };
 
 
-// Warp driver of the multi-shift eigen-solver (scalar pieces and rationale in fepe_math.cuh).
+// Warp driver of the multi-shift eigen-solver (scalar pieces and rationale in fepe_math.cuh), on the tridiagonal form:
+// every lane reduces G = Q T Q^T (uniform work), a lane's shift is then a tridiagonal LDL^T.  The 28 reflector entries
+// wait in `hv_s` (shared memory the caller does not need during the solve) instead of 56 registers.
 // All 32 lanes call it with the same g36; returns the number of rounds.
 __device__ __forceinline__ int eig9_smallest_warp(const double* __restrict__ g36, double (&f)[9], double& lambda,
-                                                  int lane) {
+                                                  int lane, double* hv_s) {
+    double ta[9], tb[8], htau[7];
+    {
+        double hv[28];
+        tridiag9(g36, ta, tb, hv, htau);
+        __syncwarp();          // whatever the caller kept in hv_s has been read by every lane
+        if (lane == 0) {
+#pragma unroll
+            for (int i = 0; i < 28; ++i) hv_s[i] = hv[i];
+        }
+        __syncwarp();
+    }
     Eig9Bracket b;
-    if (!eig9_bracket_init(g36, b)) {
+    if (!tri9_bracket_init(ta, b)) {
 #pragma unroll
         for (int i = 0; i < 9; ++i) f[i] = (i == 8) ? 1.0 : 0.0;
         lambda = 0.0;
@@ -80,7 +93,7 @@ __device__ __forceinline__ int eig9_smallest_warp(const double* __restrict__ g36
         for (int i = 0; i < 9; ++i) xl[i] = x[i];
         int nneg;
         double rho_l, r_l, c_l;
-        eig9_lane_round(g36, mu, tiny, 2, xl, nneg, rho_l, r_l, c_l);
+        tri9_lane_round(ta, tb, mu, tiny, 2, xl, nneg, rho_l, r_l, c_l);
         ++rounds;
         const unsigned ok = __ballot_sync(0xffffffffu, nneg == 0);
         const unsigned bad = ~ok;
@@ -100,6 +113,8 @@ __device__ __forceinline__ int eig9_smallest_warp(const double* __restrict__ g36
         for (int i = 0; i < 9; ++i) x[i] = __shfl_sync(0xffffffffu, xl[i], best);
         if (eig9_bracket_update(b, mu_best, mu_fail, rho, r, c)) break;
     }
+    tridiag9_back(hv_s, htau, x);
+    __syncwarp();              // every lane has read the reflectors: the caller may reuse hv_s
     canonical_sign9(x, f);
     lambda = rho;
     return rounds;

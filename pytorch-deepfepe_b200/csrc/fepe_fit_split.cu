@@ -272,7 +272,7 @@ __global__ void __launch_bounds__(32) fepe_solve_kernel(const FitParams p) {
 
     double f[9], lambda;
     const StridedG36<kSolveStride> view{g + lane};
-    const int its = eig9_smallest(view, f, lambda);
+    const int its = eig9_smallest_tri(view, f, lambda);
     double F2[9], v3[3], sigma3;
     rank2_project(f, F2, v3, sigma3);
     float Fo[9];

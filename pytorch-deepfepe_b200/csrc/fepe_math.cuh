@@ -348,6 +348,150 @@ FEPE_HD bool eig9_bracket_update(Eig9Bracket& b, double mu_best, double mu_fail,
     return done;
 }
 
+// ---------------------------------------------------------------------------------------------
+// Tridiagonal form of the eigenproblem.  Every shift of the (multi-shift) inverse iteration above costs a
+// 9x9 LDL^T factorisation -- 165 dependent-ish FMAs and 9 reciprocals -- and the drivers need 3..6 of them per
+// pair.  One Householder reduction G = Q T Q^T (450 FMAs, once per pair) makes every later shift a
+// TRIDIAGONAL factorisation: 8 multipliers, 9 pivots, ~30 operations; the inertia count, the two solves per
+// shift and the stop rule are unchanged, and the eigenvector of T is carried back with the seven reflectors.
+// Backward stable like the shifted LDL^T it replaces: eigenvector error ~ eps |G| / (lambda_8 - lambda_9).
+//   ta[9], tb[8]    diagonal / sub-diagonal of T
+//   hv[28], htau[7] reflector k acts on indices k+1..8: H_k = I - tau_k v_k v_k^T, v_k = (1, hv[off_k..]),
+//                   off_k = k(15-k)/2, 7-k stored entries (LAPACK dsytd2 convention, lower triangle)
+// ---------------------------------------------------------------------------------------------
+FEPE_HD constexpr int tri9_off(int k) { return k * (15 - k) / 2; }
+
+template <class G36>
+FEPE_HD void tridiag9(const G36& g36, double (&ta)[9], double (&tb)[8], double (&hv)[28], double (&htau)[7]) {
+    double A[45];      // lower triangle, (i,j), i >= j at i(i+1)/2 + j
+#pragma unroll
+    for (int i = 0; i < 9; ++i) {
+#pragma unroll
+        for (int j = 0; j <= i; ++j) A[i * (i + 1) / 2 + j] = g36[g36_index(i, j)];
+    }
+#pragma unroll
+    for (int k = 0; k < 7; ++k) {
+        const double alpha = A[(k + 1) * (k + 2) / 2 + k];
+        double xn2 = 0.0;
+#pragma unroll
+        for (int i = k + 2; i < 9; ++i) xn2 = fma(A[i * (i + 1) / 2 + k], A[i * (i + 1) / 2 + k], xn2);
+        const bool live = xn2 > 0.0;
+        const double nrm = fast_sqrt(fma(alpha, alpha, xn2));
+        const double beta = live ? ((alpha >= 0.0) ? -nrm : nrm) : alpha;
+        const double tau = live ? (beta - alpha) * fast_rcp(beta) : 0.0;
+        const double sc = live ? fast_rcp(alpha - beta) : 0.0;
+        double v[9], w[9];
+        v[k + 1] = 1.0;
+#pragma unroll
+        for (int i = k + 2; i < 9; ++i) v[i] = A[i * (i + 1) / 2 + k] * sc;
+        ta[k] = A[k * (k + 1) / 2 + k];
+        tb[k] = beta;
+        htau[k] = tau;
+#pragma unroll
+        for (int i = k + 2; i < 9; ++i) hv[tri9_off(k) + i - (k + 2)] = v[i];
+        // w = tau A22 v - (tau/2)(tau v^T A22 v) v;  A22 -= v w^T + w v^T
+        double pv = 0.0;
+#pragma unroll
+        for (int i = k + 1; i < 9; ++i) {
+            double acc = 0.0;
+#pragma unroll
+            for (int j = k + 1; j < 9; ++j)
+                acc = fma((i >= j) ? A[i * (i + 1) / 2 + j] : A[j * (j + 1) / 2 + i], v[j], acc);
+            w[i] = tau * acc;
+            pv = fma(w[i], v[i], pv);
+        }
+        const double h = 0.5 * tau * pv;
+#pragma unroll
+        for (int i = k + 1; i < 9; ++i) w[i] = fma(-h, v[i], w[i]);
+#pragma unroll
+        for (int i = k + 1; i < 9; ++i) {
+#pragma unroll
+            for (int j = k + 1; j <= i; ++j)
+                A[i * (i + 1) / 2 + j] -= fma(v[i], w[j], w[i] * v[j]);
+        }
+    }
+    ta[7] = A[7 * 8 / 2 + 7];
+    tb[7] = A[8 * 9 / 2 + 7];
+    ta[8] = A[8 * 9 / 2 + 8];
+}
+
+// x <- Q x = H_0 H_1 ... H_6 x: an eigenvector of T becomes the eigenvector of G.
+FEPE_HD void tridiag9_back(const double* __restrict__ hv, const double* __restrict__ htau, double (&x)[9]) {
+#pragma unroll
+    for (int k = 6; k >= 0; --k) {
+        double s = x[k + 1];
+#pragma unroll
+        for (int i = k + 2; i < 9; ++i) s = fma(hv[tri9_off(k) + i - (k + 2)], x[i], s);
+        s *= htau[k];
+        x[k + 1] -= s;
+#pragma unroll
+        for (int i = k + 2; i < 9; ++i) x[i] = fma(-s, hv[tri9_off(k) + i - (k + 2)], x[i]);
+    }
+}
+
+// eig9_bracket_init for the tridiagonal form (trace and smallest diagonal entry of T bound lambda_min as G's do).
+FEPE_HD bool tri9_bracket_init(const double (&ta)[9], Eig9Bracket& b) {
+    double tr = 0.0, dmin = 1e300;
+#pragma unroll
+    for (int r = 0; r < 9; ++r) {
+        tr += ta[r];
+        dmin = ta[r] < dmin ? ta[r] : dmin;
+    }
+    b.tr = tr;
+    b.lo = -1e-14 * tr;
+    b.hi = dmin;
+    b.r_prev = -1.0;
+    b.lo_heur = b.lo;
+    b.round = 0;
+    return (tr > 0.0) && (tr < 1e300);
+}
+
+// One lane's work for a round on T: LDL^T of T - mu I (inertia count), `nsolve` inverse-iteration solves from x.
+// Same outputs as eig9_lane_round.
+FEPE_HD void tri9_lane_round(const double (&ta)[9], const double (&tb)[8], double mu, double tiny, int nsolve,
+                             double (&x)[9], int& nneg, double& rho, double& r, double& contraction) {
+    double rd[9], l[8];
+    nneg = 0;
+    double d = ta[0] - mu;
+#pragma unroll
+    for (int k = 0; k < 9; ++k) {
+        if (d < 0.0) ++nneg;
+        if (fabs(d) < tiny) d = (d < 0.0) ? -tiny : tiny;
+        rd[k] = fast_rcp(d);
+        if (k < 8) {
+            l[k] = tb[k] * rd[k];
+            d = fma(-l[k], tb[k], ta[k + 1] - mu);
+        }
+    }
+    rho = 0.0;
+    r = 0.0;
+    contraction = 1.0;
+    for (int rep = 0; rep < nsolve; ++rep) {
+        double y[9];
+        y[0] = x[0];
+#pragma unroll
+        for (int k = 1; k < 9; ++k) y[k] = fma(-l[k - 1], y[k - 1], x[k]);
+#pragma unroll
+        for (int k = 0; k < 9; ++k) y[k] *= rd[k];
+#pragma unroll
+        for (int k = 7; k >= 0; --k) y[k] = fma(-l[k], y[k + 1], y[k]);
+        double nrm2 = 0.0;
+#pragma unroll
+        for (int i = 0; i < 9; ++i) nrm2 += y[i] * y[i];
+        const double inv = fast_rsqrt(nrm2);
+        double c = 0.0;
+#pragma unroll
+        for (int i = 0; i < 9; ++i) { y[i] *= inv; c += y[i] * x[i]; }
+        double e2 = 0.0;
+#pragma unroll
+        for (int i = 0; i < 9; ++i) { const double e = x[i] - c * y[i]; e2 += e * e; x[i] = y[i]; }
+        rho = mu + c * inv;
+        const double r_new = fast_sqrt(e2) * inv;
+        if (rep > 0) contraction = r_new * fast_rcp(r + 1e-300);
+        r = r_new;
+    }
+}
+
 // Canonical sign: the entry of largest magnitude is made positive (LAPACK's sign is arbitrary).
 FEPE_HD void canonical_sign9(const double (&x)[9], double (&f)[9]) {
     int imax = 0;
@@ -371,6 +515,62 @@ FEPE_HD void eig9_start_vector(double (&x)[9]) {
                           0.3565350492999395};
 #pragma unroll
     for (int i = 0; i < 9; ++i) x[i] = x0[i];
+}
+
+// Serial driver on the tridiagonal form: the shift sequence, inertia safeguard and stop rule of eig9_smallest, with
+// one Householder reduction in front and a tridiagonal factorisation per shift (one lane per pair: fepe_solve_kernel).
+template <class G36>
+FEPE_HD int eig9_smallest_tri(const G36& g36, double (&f)[9], double& lambda) {
+    double ta[9], tb[8], hv[28], htau[7];
+    tridiag9(g36, ta, tb, hv, htau);
+    double tr = 0.0;
+#pragma unroll
+    for (int r = 0; r < 9; ++r) tr += ta[r];
+    if (!(tr > 0.0) || !(tr < 1e300)) {   // empty / all-zero-weight / non-finite input
+#pragma unroll
+        for (int i = 0; i < 9; ++i) f[i] = (i == 8) ? 1.0 : 0.0;
+        lambda = 0.0;
+        return 0;
+    }
+    const double tiny = 1e-18 * tr;
+    double x[9];
+    eig9_start_vector(x);
+    double mu = -1e-14 * tr;
+    double lo = mu;
+    double rho = 0.0;
+    double r_prev = -1.0;
+    int it = 0;
+    for (; it < 24; ++it) {
+        double xl[9];
+#pragma unroll
+        for (int i = 0; i < 9; ++i) xl[i] = x[i];
+        int nneg;
+        double rho_l, r, c_l;
+        tri9_lane_round(ta, tb, mu, tiny, (it == 0) ? 2 : 1, xl, nneg, rho_l, r, c_l);
+        if (nneg > 0) {         // overshot lambda_min: go back half way to the last safe shift
+            mu = 0.5 * (mu + lo);
+            continue;
+        }
+        lo = mu;
+        rho = rho_l;
+#pragma unroll
+        for (int i = 0; i < 9; ++i) x[i] = xl[i];
+        if (r <= 1e-17 * tr) { ++it; break; }
+        if (r_prev >= 0.0) {
+            const double q = (r_prev > 0.0) ? r * fast_rcp(r_prev) : 2.0;
+            if (q < 1.0) {
+                if (r * q <= 1e-8 * (rho - mu) * (1.0 - q)) { ++it; break; }
+            }
+            if (q >= 0.5 && r_prev <= 1e-9 * tr) { ++it; break; }   // stagnated at the rounding floor
+        }
+        r_prev = r;
+        const double cand = rho - r * 1.0000001 - 4e-16 * tr;
+        if (cand > mu) mu = cand;
+    }
+    tridiag9_back(hv, htau, x);
+    canonical_sign9(x, f);
+    lambda = rho;
+    return it;
 }
 
 // z = (G - lambda I)^+ rhs restricted to the complement of f (used by the backward pass):

@@ -58,6 +58,10 @@ def shim():
     lib.shim_fit_pair_fwd_bwd.argtypes = [dp, dp, ctypes.c_int, ctypes.c_double] + [dp] * 8
     ip, fp, bp = ctypes.POINTER(ctypes.c_int), ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_ubyte)
     lib.shim_recover_pose.argtypes = [dp, dp, fp, ctypes.c_int, ctypes.c_double, dp, dp, dp, ip, ip, dp, bp]
+    lib.shim_tridiag9.argtypes = [dp, dp, dp, dp]
+    for name in ("shim_eig9_tri32", "shim_eig9_tri64", "shim_eig9_tri_serial"):
+        getattr(lib, name).argtypes = [dp, dp, dp]
+        getattr(lib, name).restype = ctypes.c_int
     lib.shim_correct_matches.argtypes = [dp, fp, fp, ctypes.c_int, fp, fp]
     lib.shim_correct_matches.restype = ctypes.c_int
     lib.shim_solve_poly6.argtypes = [dp, dp]

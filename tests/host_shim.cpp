@@ -316,4 +316,71 @@ void shim_gt_from_motion(const float* K, const float* Rt, double* gt) {
     for (int i = 0; i < 32; ++i) gt[i] = g[i];
 }
 
+// Householder tridiagonalisation of the Gram matrix + the reflectors applied to the columns of the identity (Q).
+void shim_tridiag9(const double* g36, double* ta, double* tb, double* Q) {
+    double a[9], b[8], hv[28], ht[7];
+    fepe::tridiag9(g36, a, b, hv, ht);
+    for (int i = 0; i < 9; ++i) ta[i] = a[i];
+    for (int i = 0; i < 8; ++i) tb[i] = b[i];
+    for (int c = 0; c < 9; ++c) {
+        double x[9];
+        for (int i = 0; i < 9; ++i) x[i] = (i == c) ? 1.0 : 0.0;
+        fepe::tridiag9_back(hv, ht, x);
+        for (int i = 0; i < 9; ++i) Q[i * 9 + c] = x[i];
+    }
+}
+
+// Host emulation of the multi-shift drivers on the TRIDIAGONAL form (eig9_smallest_cta / _warp with tri9_lane_round).
+int shim_eig9_tri_n(const double* g36, double* f, double* lambda, int nlanes) {
+    double ta[9], tb[8], hv[28], ht[7];
+    fepe::tridiag9(g36, ta, tb, hv, ht);
+    fepe::Eig9Bracket b;
+    if (nlanes < 3 || nlanes > 128 || !fepe::tri9_bracket_init(ta, b)) {
+        for (int i = 0; i < 9; ++i) f[i] = (i == 8) ? 1.0 : 0.0;
+        *lambda = 0.0;
+        return 0;
+    }
+    const double tiny = 1e-18 * b.tr;
+    double x[9];
+    fepe::eig9_start_vector(x);
+    double rho = 0.0;
+    int rounds = 0;
+    while (rounds < 10) {
+        double mu[128], rho_l[128], r_l[128], c_l[128], xl[128][9];
+        int nneg[128];
+        for (int lane = 0; lane < nlanes; ++lane) {
+            mu[lane] = fepe::eig9_lane_shift(b, lane, nlanes);
+            double xx[9];
+            for (int i = 0; i < 9; ++i) xx[i] = x[i];
+            fepe::tri9_lane_round(ta, tb, mu[lane], tiny, 2, xx, nneg[lane], rho_l[lane], r_l[lane], c_l[lane]);
+            for (int i = 0; i < 9; ++i) xl[lane][i] = xx[i];
+        }
+        ++rounds;
+        int first_fail = nlanes;
+        for (int lane = nlanes - 1; lane >= 0; --lane) if (nneg[lane] != 0) first_fail = lane;
+        const int best = first_fail - 1;
+        if (best < 0) { b.lo = b.lo * 64.0 - 1e-13 * b.tr; b.lo_heur = b.lo; continue; }
+        const double mu_fail = (first_fail < nlanes) ? mu[first_fail] : -1.0;
+        rho = rho_l[best];
+        for (int i = 0; i < 9; ++i) x[i] = xl[best][i];
+        if (fepe::eig9_bracket_update(b, mu[best], mu_fail, rho, r_l[best], c_l[best])) break;
+    }
+    fepe::tridiag9_back(hv, ht, x);
+    double ff[9];
+    fepe::canonical_sign9(x, ff);
+    for (int i = 0; i < 9; ++i) f[i] = ff[i];
+    *lambda = rho;
+    return rounds;
+}
+int shim_eig9_tri_serial(const double* g36, double* f, double* lambda) {
+    double ff[9];
+    double lam;
+    int it = fepe::eig9_smallest_tri(g36, ff, lam);
+    for (int i = 0; i < 9; ++i) f[i] = ff[i];
+    *lambda = lam;
+    return it;
+}
+int shim_eig9_tri32(const double* g36, double* f, double* lambda) { return shim_eig9_tri_n(g36, f, lambda, 32); }
+int shim_eig9_tri64(const double* g36, double* f, double* lambda) { return shim_eig9_tri_n(g36, f, lambda, 64); }
+
 }

@@ -60,7 +60,7 @@ def test_g36_layout_matches_kron(shim):
     np.testing.assert_allclose(full_gram(shim, g36), G, rtol=1e-12, atol=1e-12)
 
 
-@pytest.mark.parametrize("solver", ["shim_eig9", "shim_eig9_multishift", "shim_eig9_multishift128"])
+@pytest.mark.parametrize("solver", ["shim_eig9", "shim_eig9_multishift", "shim_eig9_multishift128", "shim_eig9_tri32", "shim_eig9_tri64", "shim_eig9_tri_serial"])
 @pytest.mark.parametrize("mode", ["uniform", "softmax", "peaked", "inlier"])
 def test_eig9_on_scene_grams(shim, mode, solver):
     worst, its = 0.0, []
@@ -83,7 +83,7 @@ def test_eig9_on_scene_grams(shim, mode, solver):
     print(solver, mode, 'mean rounds / factorisations', np.mean(its), 'max', max(its))
 
 
-@pytest.mark.parametrize("solver", ["shim_eig9", "shim_eig9_multishift", "shim_eig9_multishift128"])
+@pytest.mark.parametrize("solver", ["shim_eig9", "shim_eig9_multishift", "shim_eig9_multishift128", "shim_eig9_tri32", "shim_eig9_tri64", "shim_eig9_tri_serial"])
 def test_eig9_random_spd_and_degenerate(shim, solver):
     solve = getattr(shim, solver)
     rng = np.random.default_rng(1)
@@ -114,6 +114,31 @@ def test_eig9_random_spd_and_degenerate(shim, solver):
     G = full_gram(shim, g36)
     assert np.isfinite(f).all() and abs(np.linalg.norm(f) - 1) < 1e-12
     assert np.linalg.norm(G @ f - lam[0] * f) <= 1e-10 * np.trace(G)
+
+
+def test_tridiag9_is_an_orthogonal_similarity(shim):
+    """G = Q T Q^T with Q orthogonal and T tridiagonal (fepe_math.cuh tridiag9 / tridiag9_back)."""
+    rng = np.random.default_rng(4)
+    for trial in range(60):
+        if trial % 2:
+            g36, _ = scene_gram(trial, ["uniform", "softmax", "peaked", "inlier"][trial % 4])
+        else:
+            a, b = rng.normal(size=(30, 3)), rng.normal(size=(30, 3))
+            g36 = gram36(a, b, rng.uniform(size=30)) * 10.0 ** rng.integers(-12, 6)
+        G = full_gram(shim, g36)
+        ta, tb, Q = np.zeros(9), np.zeros(8), np.zeros(81)
+        shim.shim_tridiag9(_ptr(g36), _ptr(ta), _ptr(tb), _ptr(Q))
+        Q = Q.reshape(9, 9)
+        T = np.diag(ta) + np.diag(tb, 1) + np.diag(tb, -1)
+        nG = np.abs(G).max()
+        np.testing.assert_allclose(Q.T @ Q, np.eye(9), atol=1e-14)
+        np.testing.assert_allclose(Q @ T @ Q.T, G, atol=3e-15 * nG)
+        np.testing.assert_allclose(np.linalg.eigvalsh(T), np.linalg.eigvalsh(G), atol=1e-14 * nG)
+    # already tridiagonal / diagonal input: reflectors degenerate to the identity, no NaN
+    g36 = gram36(np.eye(3)[[0, 1, 2]], np.eye(3)[[0, 1, 2]], np.ones(3))
+    ta, tb, Q = np.zeros(9), np.zeros(8), np.zeros(81)
+    shim.shim_tridiag9(_ptr(g36), _ptr(ta), _ptr(tb), _ptr(Q))
+    assert np.isfinite(ta).all() and np.isfinite(tb).all() and np.isfinite(Q).all()
 
 
 def test_pinv_apply(shim):
