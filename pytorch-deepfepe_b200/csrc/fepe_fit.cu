@@ -238,7 +238,8 @@ __device__ __forceinline__ int eig9_smallest_cta(const double* __restrict__ g36,
 #pragma unroll
     for (int i = 0; i < 8; ++i) tb[i] = tri[9 + i];
     Eig9Bracket b;
-    if (!tri9_bracket_init(ta, b)) {
+    const double tr_g = tri9_normalise(ta, tb);
+    if (!(tr_g > 0.0) || !tri9_bracket_init(ta, b)) {
 #pragma unroll
         for (int i = 0; i < 9; ++i) f[i] = (i == 8) ? 1.0 : 0.0;
         lambda = 0.0;
@@ -246,6 +247,33 @@ __device__ __forceinline__ int eig9_smallest_cta(const double* __restrict__ g36,
     }
     const double tiny = 1e-18 * b.tr;
     const int L = warp * 32 + lane;
+    // Sturm probes: NW*32 shifts per probe, nothing exchanged but the ballots (double-buffered: one barrier per probe).
+    // One geometric + kProbes-1 linear probes leave lambda_min bracketed to ~1e-6 relative, so the first full round
+    // below -- factorisation + two solves per lane -- already converges for any ordinary eigen-gap.
+    {
+        double tb2[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) tb2[i] = tb[i] * tb[i];
+        constexpr int kProbes = (NW >= 2) ? 4 : 5;
+        tri9_probe_begin(b, NW * 32);
+#pragma unroll 1
+        for (int sub = 0; sub < kProbes; ++sub) {
+            const int cnt = tri9_sturm_count(ta, tb2, tri9_probe_shift(b, L, NW * 32, sub));
+            const unsigned ok = __ballot_sync(0xffffffffu, cnt == 0);
+            unsigned* okb = okm + (sub & 1) * NW;
+            if (lane == 0) okb[warp] = ok;
+            __syncthreads();
+            int first_fail = NW * 32;
+#pragma unroll
+            for (int w = NW - 1; w >= 0; --w) {
+                const unsigned bad = ~okb[w];
+                if (bad) first_fail = w * 32 + __ffs(bad) - 1;
+            }
+            tri9_probe_update(b, first_fail, NW * 32, sub);
+        }
+        tri9_probe_finish(b);
+        __syncthreads();       // the full rounds reuse okm[0..NW)
+    }
     double x[9];
     eig9_start_vector(x);
     double rho = 0.0;
@@ -292,7 +320,7 @@ __device__ __forceinline__ int eig9_smallest_cta(const double* __restrict__ g36,
     }
     tridiag9_back(tri + 17, tri + 45, x);
     canonical_sign9(x, f);
-    lambda = rho;
+    lambda = rho * tr_g;
     return rounds;
 }
 
@@ -319,7 +347,7 @@ __global__ void __launch_bounds__(kSmallThreads, FEPE_SMALL_MINBLOCKS) fepe_fit_
     __shared__ float red[kSmallWarps][4];
     __shared__ double gram_w[kSmallWarps][36];
     __shared__ double gram[kScratchDoubles];
-    __shared__ unsigned eig_ok[kSmallWarps];
+    __shared__ unsigned eig_ok[2 * kSmallWarps];
     __shared__ double eig_xch[16];
     __shared__ double eig_tri[kTriDoubles];
     __shared__ float pose_in[POSE ? 32 : 1];                                // K(9) q(4) t(3) R_scene(9)

@@ -75,13 +75,27 @@ __device__ __forceinline__ int eig9_smallest_warp(const double* __restrict__ g36
         __syncwarp();
     }
     Eig9Bracket b;
-    if (!tri9_bracket_init(ta, b)) {
+    const double tr_g = tri9_normalise(ta, tb);
+    if (!(tr_g > 0.0) || !tri9_bracket_init(ta, b)) {
 #pragma unroll
         for (int i = 0; i < 9; ++i) f[i] = (i == 8) ? 1.0 : 0.0;
         lambda = 0.0;
         return 0;
     }
     const double tiny = 1e-18 * b.tr;
+    {   // Sturm probes (fepe_math.cuh): 32 shifts each, one ballot, no exchange
+        double tb2[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) tb2[i] = tb[i] * tb[i];
+        tri9_probe_begin(b, 32);
+#pragma unroll 1
+        for (int sub = 0; sub < 5; ++sub) {
+            const int cnt = tri9_sturm_count(ta, tb2, tri9_probe_shift(b, lane, 32, sub));
+            const unsigned bad = ~__ballot_sync(0xffffffffu, cnt == 0);
+            tri9_probe_update(b, bad ? (__ffs(bad) - 1) : 32, 32, sub);
+        }
+        tri9_probe_finish(b);
+    }
     double x[9];
     eig9_start_vector(x);
     double rho = 0.0;
@@ -116,7 +130,7 @@ __device__ __forceinline__ int eig9_smallest_warp(const double* __restrict__ g36
     tridiag9_back(hv_s, htau, x);
     __syncwarp();              // every lane has read the reflectors: the caller may reuse hv_s
     canonical_sign9(x, f);
-    lambda = rho;
+    lambda = rho * tr_g;
     return rounds;
 }
 

@@ -252,6 +252,7 @@ struct Eig9Bracket {
     double hi;        // upper limit for lambda_min (first failing shift, Rayleigh quotient, min diagonal)
     double r_prev;    // residual of the previous round's best lane (<0: none)
     double lo_heur;   // heuristic (unverified) lower end for lanes 1..31: max(lo, rho - r)
+    float geo_step;   // log2 step of the geometric Sturm probe (tri9_probe_begin)
     int round;
 };
 
@@ -288,7 +289,7 @@ FEPE_HD double eig9_lane_shift(const Eig9Bracket& b, int lane, int nlanes = 32) 
 #endif
     }
     const double lo = (b.lo_heur > 0.0) ? b.lo_heur : 0.0;
-    return lo + (b.hi - lo) * (static_cast<double>(lane - 1) / static_cast<double>(nlanes - 1)) * 0.999;
+    return lo + (b.hi - lo) * (static_cast<double>(lane - 1) * (1.0 / static_cast<double>(nlanes - 1))) * 0.999;
 }
 
 // One lane's work for a round: factor at `mu`, `nsolve` inverse-iteration solves starting from x.
@@ -371,10 +372,16 @@ FEPE_HD void tridiag9(const G36& g36, double (&ta)[9], double (&tb)[8], double (
     }
 #pragma unroll
     for (int k = 0; k < 7; ++k) {
+        // every sum below is split over two accumulators: the reduction is one dependent chain per reflector, and a
+        // chain of m FMAs costs m x 8 cycles on a warp that has nothing else to issue
         const double alpha = A[(k + 1) * (k + 2) / 2 + k];
-        double xn2 = 0.0;
+        double xa = 0.0, xb = 0.0;
 #pragma unroll
-        for (int i = k + 2; i < 9; ++i) xn2 = fma(A[i * (i + 1) / 2 + k], A[i * (i + 1) / 2 + k], xn2);
+        for (int i = k + 2; i < 9; ++i) {
+            const double e = A[i * (i + 1) / 2 + k];
+            if ((i - k) & 1) xa = fma(e, e, xa); else xb = fma(e, e, xb);
+        }
+        const double xn2 = xa + xb;
         const bool live = xn2 > 0.0;
         const double nrm = fast_sqrt(fma(alpha, alpha, xn2));
         const double beta = live ? ((alpha >= 0.0) ? -nrm : nrm) : alpha;
@@ -390,17 +397,19 @@ FEPE_HD void tridiag9(const G36& g36, double (&ta)[9], double (&tb)[8], double (
 #pragma unroll
         for (int i = k + 2; i < 9; ++i) hv[tri9_off(k) + i - (k + 2)] = v[i];
         // w = tau A22 v - (tau/2)(tau v^T A22 v) v;  A22 -= v w^T + w v^T
-        double pv = 0.0;
+        double pa = 0.0, pb = 0.0;
 #pragma unroll
         for (int i = k + 1; i < 9; ++i) {
-            double acc = 0.0;
+            double acc0 = 0.0, acc1 = 0.0;
 #pragma unroll
-            for (int j = k + 1; j < 9; ++j)
-                acc = fma((i >= j) ? A[i * (i + 1) / 2 + j] : A[j * (j + 1) / 2 + i], v[j], acc);
-            w[i] = tau * acc;
-            pv = fma(w[i], v[i], pv);
+            for (int j = k + 1; j < 9; ++j) {
+                const double e = (i >= j) ? A[i * (i + 1) / 2 + j] : A[j * (j + 1) / 2 + i];
+                if ((j - k) & 1) acc0 = fma(e, v[j], acc0); else acc1 = fma(e, v[j], acc1);
+            }
+            w[i] = tau * (acc0 + acc1);
+            if ((i - k) & 1) pa = fma(w[i], v[i], pa); else pb = fma(w[i], v[i], pb);
         }
-        const double h = 0.5 * tau * pv;
+        const double h = 0.5 * tau * (pa + pb);
 #pragma unroll
         for (int i = k + 1; i < 9; ++i) w[i] = fma(-h, v[i], w[i]);
 #pragma unroll
@@ -419,14 +428,39 @@ FEPE_HD void tridiag9(const G36& g36, double (&ta)[9], double (&tb)[8], double (
 FEPE_HD void tridiag9_back(const double* __restrict__ hv, const double* __restrict__ htau, double (&x)[9]) {
 #pragma unroll
     for (int k = 6; k >= 0; --k) {
-        double s = x[k + 1];
+        double s0 = x[k + 1], s1 = 0.0;
 #pragma unroll
-        for (int i = k + 2; i < 9; ++i) s = fma(hv[tri9_off(k) + i - (k + 2)], x[i], s);
-        s *= htau[k];
+        for (int i = k + 2; i < 9; ++i) {
+            if ((i - k) & 1) s1 = fma(hv[tri9_off(k) + i - (k + 2)], x[i], s1);
+            else s0 = fma(hv[tri9_off(k) + i - (k + 2)], x[i], s0);
+        }
+        const double s = (s0 + s1) * htau[k];
         x[k + 1] -= s;
 #pragma unroll
         for (int i = k + 2; i < 9; ++i) x[i] = fma(-s, hv[tri9_off(k) + i - (k + 2)], x[i]);
     }
+}
+
+// sum_i a_i b_i over 9 entries as three chains of three (24 + 16 cycles instead of 72)
+FEPE_HD double dot9(const double (&a)[9], const double (&b)[9]) {
+    const double s0 = fma(a[2], b[2], fma(a[1], b[1], a[0] * b[0]));
+    const double s1 = fma(a[5], b[5], fma(a[4], b[4], a[3] * b[3]));
+    const double s2 = fma(a[8], b[8], fma(a[7], b[7], a[6] * b[6]));
+    return (s0 + s1) + s2;
+}
+
+// Scale T to unit trace (the minors' recurrence then stays near 1); returns trace(G), or 0 for an empty / non-finite G.
+FEPE_HD double tri9_normalise(double (&ta)[9], double (&tb)[8]) {
+    double tr = 0.0;
+#pragma unroll
+    for (int r = 0; r < 9; ++r) tr += ta[r];
+    if (!(tr > 0.0) || !(tr < 1e300)) return 0.0;
+    const double inv = fast_rcp(tr);
+#pragma unroll
+    for (int r = 0; r < 9; ++r) ta[r] *= inv;
+#pragma unroll
+    for (int r = 0; r < 8; ++r) tb[r] *= inv;
+    return tr;
 }
 
 // eig9_bracket_init for the tridiagonal form (trace and smallest diagonal entry of T bound lambda_min as G's do).
@@ -446,23 +480,86 @@ FEPE_HD bool tri9_bracket_init(const double (&ta)[9], Eig9Bracket& b) {
     return (tr > 0.0) && (tr < 1e300);
 }
 
+// Number of eigenvalues of T below mu from the three-term recurrence of the leading principal minors
+// p_k = (a_k - mu) p_{k-1} - b_{k-1}^2 p_{k-2}: nine dependent FMAs, no division.  tb2 = tb^2.  T is expected scaled to
+// unit trace (|p_k| stays within a few binades of 1 unless eigenvalues cluster at mu; nowhere near the fp64 range).
+FEPE_HD int tri9_sturm_count(const double (&ta)[9], const double (&tb2)[8], double mu) {
+    // branch free: the count is the number of sign-bit changes along 1, p_1 .. p_9 (an exact zero reads as positive and
+    // hands its sign change to the successor); the integer work is off the FMA chain
+    double p_prev = 1.0, p_cur = ta[0] - mu;
+#if defined(__CUDA_ARCH__)
+    unsigned sgn = static_cast<unsigned>(__double2hiint(p_cur)) >> 31, last = sgn;
+    int cnt = static_cast<int>(sgn);
+#else
+    unsigned last = (p_cur < 0.0) ? 1u : 0u;
+    int cnt = static_cast<int>(last);
+#endif
+#pragma unroll
+    for (int k = 1; k < 9; ++k) {
+        const double p_next = fma(ta[k] - mu, p_cur, -tb2[k - 1] * p_prev);
+        p_prev = p_cur;
+        p_cur = p_next;
+#if defined(__CUDA_ARCH__)
+        const unsigned sg = static_cast<unsigned>(__double2hiint(p_cur)) >> 31;
+#else
+        const unsigned sg = (p_cur < 0.0) ? 1u : 0u;
+#endif
+        cnt += static_cast<int>(sg ^ last);
+        last = sg;
+    }
+    return cnt;
+}
+
+// Shift of lane `lane` in Sturm probe `sub` (pure function of the bracket: any lane can recompute any other lane's
+// shift, so a probe exchanges nothing but its ballot).  sub 0: geometric ladder over [1e-13 tr, hi] (b.geo_step =
+// log2(hi / 1e-13 tr) / (nlanes - 1), set by tri9_probe_begin); later probes: the interior points of
+// [max(lo_heur, 0), hi].  No fp64 division or transcendental on this path (~200 cycles each, three shifts per probe).
+FEPE_HD double tri9_probe_shift(const Eig9Bracket& b, int lane, int nlanes, int sub) {
+    if (sub == 0)
+        return (1e-13 * b.tr) * static_cast<double>(exp2f(static_cast<float>(lane) * b.geo_step));
+    const double lo = (b.lo_heur > 0.0) ? b.lo_heur : 0.0;
+    return fma(b.hi - lo, static_cast<double>(static_cast<float>(lane + 1) * (1.0f / static_cast<float>(nlanes + 1))), lo);
+}
+FEPE_HD void tri9_probe_begin(Eig9Bracket& b, int nlanes) {
+    const double a = 1e-13 * b.tr;
+    const double top = (b.hi > 2.0 * a) ? b.hi : 2.0 * a;
+    b.geo_step = log2f(static_cast<float>(top * fast_rcp(a))) * (1.0f / static_cast<float>(nlanes - 1));
+}
+
+// Fold a probe's outcome into the bracket: lanes below `first_fail` counted no eigenvalue under their shift.
+// Only the heuristic end moves -- b.lo stays the last shift whose FACTORISATION had inertia 0.
+FEPE_HD void tri9_probe_update(Eig9Bracket& b, int first_fail, int nlanes, int sub) {
+    const double new_lo = (first_fail > 0) ? tri9_probe_shift(b, first_fail - 1, nlanes, sub) : b.lo_heur;
+    const double new_hi = (first_fail < nlanes) ? tri9_probe_shift(b, first_fail, nlanes, sub) : b.hi;
+    b.lo_heur = new_lo;
+    b.hi = new_hi;
+}
+// After the last probe: leave a rounding margin under the bracket and switch eig9_lane_shift to its linear ladder.
+FEPE_HD void tri9_probe_finish(Eig9Bracket& b) {
+    if (b.lo_heur > 0.0) b.lo_heur = b.lo_heur - 4e-16 * b.tr;
+    if (b.round == 0) b.round = 1;
+}
+
 // One lane's work for a round on T: LDL^T of T - mu I (inertia count), `nsolve` inverse-iteration solves from x.
-// Same outputs as eig9_lane_round.
+// Same outputs as eig9_lane_round.  The pivots come from the minors' recurrence (d_k = p_k / p_{k-1}, nine independent
+// reciprocals) instead of the pivot recurrence (nine dependent ones); a lane whose shift is not below lambda_min may
+// produce inf / NaN iterates -- its nneg is non-zero and the drivers never read the rest.
 FEPE_HD void tri9_lane_round(const double (&ta)[9], const double (&tb)[8], double mu, double tiny, int nsolve,
                              double (&x)[9], int& nneg, double& rho, double& r, double& contraction) {
-    double rd[9], l[8];
-    nneg = 0;
-    double d = ta[0] - mu;
+    (void)tiny;
+    double p[10];
+    p[0] = 1.0;
+    p[1] = ta[0] - mu;
 #pragma unroll
-    for (int k = 0; k < 9; ++k) {
-        if (d < 0.0) ++nneg;
-        if (fabs(d) < tiny) d = (d < 0.0) ? -tiny : tiny;
-        rd[k] = fast_rcp(d);
-        if (k < 8) {
-            l[k] = tb[k] * rd[k];
-            d = fma(-l[k], tb[k], ta[k + 1] - mu);
-        }
-    }
+    for (int k = 1; k < 9; ++k) p[k + 1] = fma(ta[k] - mu, p[k], -(tb[k - 1] * tb[k - 1]) * p[k - 1]);
+    nneg = 0;
+#pragma unroll
+    for (int k = 0; k < 9; ++k) nneg += (p[k + 1] * p[k] > 0.0) ? 0 : 1;      // zero or NaN counts as a failure
+    double rd[9], l[8];
+#pragma unroll
+    for (int k = 0; k < 9; ++k) rd[k] = p[k] * fast_rcp(p[k + 1]);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) l[k] = tb[k] * rd[k];
     rho = 0.0;
     r = 0.0;
     contraction = 1.0;
@@ -475,18 +572,13 @@ FEPE_HD void tri9_lane_round(const double (&ta)[9], const double (&tb)[8], doubl
         for (int k = 0; k < 9; ++k) y[k] *= rd[k];
 #pragma unroll
         for (int k = 7; k >= 0; --k) y[k] = fma(-l[k], y[k + 1], y[k]);
-        double nrm2 = 0.0;
+        const double inv = fast_rsqrt(dot9(y, y));
+        const double c = dot9(y, x) * inv;              // x'.x with x' = y / |y|
+        double e[9];
 #pragma unroll
-        for (int i = 0; i < 9; ++i) nrm2 += y[i] * y[i];
-        const double inv = fast_rsqrt(nrm2);
-        double c = 0.0;
-#pragma unroll
-        for (int i = 0; i < 9; ++i) { y[i] *= inv; c += y[i] * x[i]; }
-        double e2 = 0.0;
-#pragma unroll
-        for (int i = 0; i < 9; ++i) { const double e = x[i] - c * y[i]; e2 += e * e; x[i] = y[i]; }
+        for (int i = 0; i < 9; ++i) { y[i] *= inv; e[i] = fma(-c, y[i], x[i]); x[i] = y[i]; }
         rho = mu + c * inv;
-        const double r_new = fast_sqrt(e2) * inv;
+        const double r_new = fast_sqrt(dot9(e, e)) * inv;
         if (rep > 0) contraction = r_new * fast_rcp(r + 1e-300);
         r = r_new;
     }

@@ -335,12 +335,26 @@ int shim_eig9_tri_n(const double* g36, double* f, double* lambda, int nlanes) {
     double ta[9], tb[8], hv[28], ht[7];
     fepe::tridiag9(g36, ta, tb, hv, ht);
     fepe::Eig9Bracket b;
-    if (nlanes < 3 || nlanes > 128 || !fepe::tri9_bracket_init(ta, b)) {
+    const double tr_g = fepe::tri9_normalise(ta, tb);
+    if (nlanes < 3 || nlanes > 128 || !(tr_g > 0.0) || !fepe::tri9_bracket_init(ta, b)) {
         for (int i = 0; i < 9; ++i) f[i] = (i == 8) ? 1.0 : 0.0;
         *lambda = 0.0;
         return 0;
     }
     const double tiny = 1e-18 * b.tr;
+    {
+        double tb2[8];
+        for (int i = 0; i < 8; ++i) tb2[i] = tb[i] * tb[i];
+        const int probes = (nlanes >= 64) ? 4 : 5;
+        fepe::tri9_probe_begin(b, nlanes);
+        for (int sub = 0; sub < probes; ++sub) {
+            int first_fail = nlanes;
+            for (int lane = nlanes - 1; lane >= 0; --lane)
+                if (fepe::tri9_sturm_count(ta, tb2, fepe::tri9_probe_shift(b, lane, nlanes, sub)) != 0) first_fail = lane;
+            fepe::tri9_probe_update(b, first_fail, nlanes, sub);
+        }
+        fepe::tri9_probe_finish(b);
+    }
     double x[9];
     fepe::eig9_start_vector(x);
     double rho = 0.0;
@@ -369,7 +383,7 @@ int shim_eig9_tri_n(const double* g36, double* f, double* lambda, int nlanes) {
     double ff[9];
     fepe::canonical_sign9(x, ff);
     for (int i = 0; i < 9; ++i) f[i] = ff[i];
-    *lambda = rho;
+    *lambda = rho * tr_g;
     return rounds;
 }
 int shim_eig9_tri_serial(const double* g36, double* f, double* lambda) {
