@@ -259,7 +259,7 @@ inline bool make_ring(int N, int bytes_per_corr, int smem_limit, RingLayout& r) 
 }
 
 // Split throughput pipeline (fepe_fit_split.cu); taken from kSplitMinPairsPerSM pairs per SM upwards (measured crossover)
-constexpr int kSplitMinPairsPerSM = 24;
+constexpr int kSplitMinPairsPerSM = 16;
 bool split_path_supported(const FitParams& p, const DeviceInfo& d);
 int launch_split(FitParams p, const DeviceInfo& d, cudaStream_t stream);
 

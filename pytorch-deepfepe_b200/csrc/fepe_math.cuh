@@ -609,26 +609,42 @@ FEPE_HD void eig9_start_vector(double (&x)[9]) {
     for (int i = 0; i < 9; ++i) x[i] = x0[i];
 }
 
-// Serial driver on the tridiagonal form: the shift sequence, inertia safeguard and stop rule of eig9_smallest, with
-// one Householder reduction in front and a tridiagonal factorisation per shift (one lane per pair: fepe_solve_kernel).
+// Serial driver on the tridiagonal form (one lane per pair: fepe_solve_kernel).  One Householder reduction, then
+// lambda_min is bracketed by BISECTION on Sturm counts -- a count is nine dependent FMAs, and every lane of a warp runs
+// the same fixed number of them, so 32 different pairs do not diverge -- and a factorisation just under the bracket
+// makes inverse iteration converge in its first round (two solves); the loop below only continues for tiny eigen-gaps.
 template <class G36>
 FEPE_HD int eig9_smallest_tri(const G36& g36, double (&f)[9], double& lambda) {
     double ta[9], tb[8], hv[28], htau[7];
     tridiag9(g36, ta, tb, hv, htau);
-    double tr = 0.0;
-#pragma unroll
-    for (int r = 0; r < 9; ++r) tr += ta[r];
-    if (!(tr > 0.0) || !(tr < 1e300)) {   // empty / all-zero-weight / non-finite input
+    const double tr_g = tri9_normalise(ta, tb);
+    if (!(tr_g > 0.0)) {                  // empty / all-zero-weight / non-finite input
 #pragma unroll
         for (int i = 0; i < 9; ++i) f[i] = (i == 8) ? 1.0 : 0.0;
         lambda = 0.0;
         return 0;
     }
-    const double tiny = 1e-18 * tr;
+    // from here on T has unit trace
+    double tb2[8], dmin = 1e300;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) tb2[i] = tb[i] * tb[i];
+#pragma unroll
+    for (int i = 0; i < 9; ++i) dmin = ta[i] < dmin ? ta[i] : dmin;
+    double mu = -1e-14;                   // G + 1e-14 tr I is numerically positive definite
+    {
+        double lo = 1e-13, hi = (dmin > 2e-13) ? dmin : 2e-13;     // e_i^T T e_i >= lambda_min
+        const bool below = tri9_sturm_count(ta, tb2, lo) > 0;      // lambda_min < 1e-13 tr: keep the safe shift
+        // 6 geometric steps (13 decades -> a factor < 2), then 18 arithmetic ones (-> ~4e-6 relative)
+#pragma unroll 1
+        for (int step = 0; step < 24; ++step) {
+            const double mid = (step < 6) ? fast_sqrt(lo * hi) : 0.5 * (lo + hi);
+            if (tri9_sturm_count(ta, tb2, mid) > 0) hi = mid; else lo = mid;
+        }
+        if (!below) mu = lo - 4e-16;
+    }
     double x[9];
     eig9_start_vector(x);
-    double mu = -1e-14 * tr;
-    double lo = mu;
+    double lo = -1e-14;
     double rho = 0.0;
     double r_prev = -1.0;
     int it = 0;
@@ -638,7 +654,7 @@ FEPE_HD int eig9_smallest_tri(const G36& g36, double (&f)[9], double& lambda) {
         for (int i = 0; i < 9; ++i) xl[i] = x[i];
         int nneg;
         double rho_l, r, c_l;
-        tri9_lane_round(ta, tb, mu, tiny, (it == 0) ? 2 : 1, xl, nneg, rho_l, r, c_l);
+        tri9_lane_round(ta, tb, mu, 1e-18, (it == 0) ? 2 : 1, xl, nneg, rho_l, r, c_l);
         if (nneg > 0) {         // overshot lambda_min: go back half way to the last safe shift
             mu = 0.5 * (mu + lo);
             continue;
@@ -647,21 +663,21 @@ FEPE_HD int eig9_smallest_tri(const G36& g36, double (&f)[9], double& lambda) {
         rho = rho_l;
 #pragma unroll
         for (int i = 0; i < 9; ++i) x[i] = xl[i];
-        if (r <= 1e-17 * tr) { ++it; break; }
-        if (r_prev >= 0.0) {
-            const double q = (r_prev > 0.0) ? r * fast_rcp(r_prev) : 2.0;
-            if (q < 1.0) {
-                if (r * q <= 1e-8 * (rho - mu) * (1.0 - q)) { ++it; break; }
-            }
-            if (q >= 0.5 && r_prev <= 1e-9 * tr) { ++it; break; }   // stagnated at the rounding floor
+        if (r <= 1e-17) { ++it; break; }
+        // eigenVECTOR error ~ r / (lambda_8 - lambda_9); the gap follows from the contraction q between two solves:
+        // gap = (rho - mu)(1/q - 1).  The first round measures q itself (two solves at one shift).
+        const double q = (it == 0) ? c_l : ((r_prev > 0.0) ? r * fast_rcp(r_prev) : 2.0);
+        if (it == 0 || r_prev >= 0.0) {
+            if (q < 1.0 && r * q <= 1e-8 * (rho - mu) * (1.0 - q)) { ++it; break; }
+            if (q >= 0.5 && ((it == 0) ? r : r_prev) <= 1e-9) { ++it; break; }   // stagnated at the rounding floor
         }
         r_prev = r;
-        const double cand = rho - r * 1.0000001 - 4e-16 * tr;
+        const double cand = rho - r * 1.0000001 - 4e-16;
         if (cand > mu) mu = cand;
     }
     tridiag9_back(hv, htau, x);
     canonical_sign9(x, f);
-    lambda = rho;
+    lambda = rho * tr_g;
     return it;
 }
 
