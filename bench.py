@@ -56,7 +56,7 @@ def parse_args():
     ap.add_argument("--ncorr", type=int, default=1000, help="correspondences per pair (C2: 1000)")
     ap.add_argument("--sat-batch", type=int, default=32768, help="batch of the saturating roofline run")
     ap.add_argument("--no-graph", action="store_true", help="launch eagerly instead of replaying CUDA graphs")
-    ap.add_argument("--streams", type=int, default=4,
+    ap.add_argument("--streams", type=int, default=8,
                     help="parallel branches the K independent steps are issued on (1 = strictly back to back)")
     ap.add_argument("--no-extras", action="store_true", help="skip e2e / cpu_baseline / saturating legs")
     ap.add_argument("--phases", action="store_true", help="print per-phase SM cycles of the fused kernel")
@@ -432,21 +432,32 @@ def run_ours(args):
                 stages[j].replay()
 
         e2e_steps = max(50, min(args.steps, 400))
-        # the PCIe ceiling of THIS box at this moment: the same pinned buffers copied back to back with nothing else,
-        # as ONE captured graph of 16 copies (eager copies would time the host's launch path, not the link)
-        gcopy = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(gcopy, stream=streams[0]):
-            for i in range(16):
-                stages[i % nbuf].d_in.copy_(stages[i % nbuf].h_in, non_blocking=True)
-        gcopy.replay()
+        # the PCIe ceiling of THIS box at this moment: the same pinned buffers copied with nothing else, issued exactly like
+        # the e2e steps (one captured graph per slot, round-robin over the slots' streams)
+        copy_graphs = []
+        for j in range(nbuf):
+            gc = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(gc, stream=streams[j]):
+                stages[j].d_in.copy_(stages[j].h_in, non_blocking=True)
+            copy_graphs.append(gc)
+        def copy_step(i):
+            with torch.cuda.stream(streams[i % nbuf]):
+                copy_graphs[i % nbuf].replay()
+
+        for i in range(2 * nbuf):
+            copy_step(i)
         torch.cuda.synchronize()
         c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        n_copy = 64
+        tc0 = time.perf_counter()
         c0.record()
-        for _ in range(5):
-            gcopy.replay()
+        for i in range(n_copy):
+            copy_step(i)
+        for st in streams:
+            torch.cuda.current_stream().wait_stream(st)
         c1.record()
         torch.cuda.synchronize()
-        h2d_only_us = c0.elapsed_time(c1) / (5 * 16) * 1e3
+        h2d_only_us = max(c0.elapsed_time(c1) * 1e-3, time.perf_counter() - tc0) / n_copy * 1e6
         for i in range(6):
             e2e_step(i)
         torch.cuda.synchronize()
