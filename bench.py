@@ -448,7 +448,7 @@ def run_ours(args):
             copy_step(i)
         torch.cuda.synchronize()
         c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        n_copy = 64
+        n_copy = max(50, min(args.steps, 400))
         tc0 = time.perf_counter()
         c0.record()
         for i in range(n_copy):
