@@ -69,6 +69,10 @@ def parse_args():
 
 
 # ------------------------------------------------------------------------------------------------
+# stdout carries exactly one JSON line: NCCL's version banner / debug log (stdout by default) goes to stderr instead
+os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+
+
 def dist_env():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
