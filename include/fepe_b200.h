@@ -140,7 +140,7 @@ int fepe_pose_bwd(const float* F, const float* K, int L, int B, float ax, float 
  * with Npad = N rounded up to 128 (padded rows are zero and excluded from the statistics); weights are
  * bf16 [Co, Ci] (Conv1d weight squeezed); accumulation is fp32 in tensor memory (tcgen05.mma).
  *   fepe_mlp_first  layer 1 from fp32 features X0 [B,N,Ci<=8]                -> Y [B*Npad,Co] + stats
- *   fepe_mlp_gemm   Y = X W^T + b (K % 64 == 0, Co % 64 == 0)                 -> Y + stats [B,Co,2] (stats may be NULL)
+ *   fepe_mlp_gemm   Y = X W^T + b (K % 64 == 0, Co % 64 == 0; b may be NULL)   -> Y + stats [B,Co,2] (stats may be NULL)
  *   fepe_mlp_norm   X' = LeakyReLU(gamma (Y - mean) rstd + beta) from stats (biased variance, eps)
  *   fepe_mlp_last   logits = X w + b (Co = 1), weights = softmax over the N rows of each pair
  * `stats` must be zeroed by the caller before fepe_mlp_first / fepe_mlp_gemm (they accumulate with atomics).

@@ -85,7 +85,7 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
 struct GemmParams {
     int M, K, Co;          // M = B * Npad
     int Npad, Nvalid;      // rows per pair (padded / real)
-    const float* bias;     // [Co]
+    const float* bias;     // [Co], or null (a bias in front of an InstanceNorm cancels in the normalisation)
     __nv_bfloat16* Y;      // [M, Co]
     float* stats;          // [B, Co, 2] (sum, sum of squares), zeroed by the caller
 };
@@ -108,12 +108,16 @@ fepe_mlp_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
     uint64_t* empty = full + STAGES;
     uint64_t* tmem_full = empty + STAGES;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
+    constexpr int kChunks = BN / 8;          // 16-byte chunks per tile row
+    __shared__ __align__(16) float sbias[BN];
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
     const int m0 = blockIdx.y * kGemmBM;     // n-tiles vary fastest: the CTAs sharing an A tile are co-scheduled
     const int n0 = blockIdx.x * BN;
     const int num_kb = p.K / kGemmBK;
+    const bool has_bias = p.bias != nullptr;
+    if (has_bias && threadIdx.x >= 128 && threadIdx.x < 128 + BN) sbias[threadIdx.x - 128] = __ldg(p.bias + n0 + threadIdx.x - 128);
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
@@ -170,24 +174,35 @@ fepe_mlp_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
         }
     } else if (warp >= 4) {
         // ---------------- epilogue: TMEM -> registers -> bf16 tile in smem ----------------
+        // The tile is kept as 16-byte chunks of 8 columns, chunk k of row r at slot (k + r) mod kChunks: a quarter warp
+        // (8 consecutive rows, or 8 consecutive chunks of one row) always touches 8 different slots = all 32 banks once,
+        // for the 16-byte stores here, the 4-byte statistics loads and the 16-byte loads of the final copy alike.
         const int q = warp & 3;                               // TMEM lane quarter this warp may read
         const int row = q * 32 + lane;                        // row inside the tile
         const int pair_row = (m0 % p.Npad) + row;             // row inside its pair
         const bool valid = pair_row < p.Nvalid;
         mbar_wait(tmem_full, 0);
         tcgen05_fence_after();
-        __nv_bfloat16* ty = reinterpret_cast<__nv_bfloat16*>(tile_y);
 #pragma unroll 1
         for (int c = 0; c < BN; c += 32) {
             uint32_t v[32];
             tmem_ld32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(c), v);
 #pragma unroll
-            for (int j = 0; j < 32; j += 2) {
-                const float y0 = valid ? __uint_as_float(v[j]) + __ldg(p.bias + n0 + c + j) : 0.f;
-                const float y1 = valid ? __uint_as_float(v[j + 1]) + __ldg(p.bias + n0 + c + j + 1) : 0.f;
-                // column-rotated placement keeps the 32 rows of a warp off the same bank
-                *reinterpret_cast<__nv_bfloat162*>(ty + row * BN + ((c + j + 2 * row) % BN)) =
-                    __floats2bfloat162_rn(y0, y1);
+            for (int g = 0; g < 4; ++g) {
+                uint32_t pk[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    float y0 = __uint_as_float(v[g * 8 + 2 * j]), y1 = __uint_as_float(v[g * 8 + 2 * j + 1]);
+                    if (has_bias) {
+                        const float2 bb = *reinterpret_cast<const float2*>(sbias + c + g * 8 + 2 * j);
+                        y0 += bb.x; y1 += bb.y;
+                    }
+                    const __nv_bfloat162 h = __floats2bfloat162_rn(valid ? y0 : 0.f, valid ? y1 : 0.f);
+                    pk[j] = *reinterpret_cast<const uint32_t*>(&h);
+                }
+                const int chunk = (c >> 3) + g;
+                *reinterpret_cast<uint4*>(tile_y + (row * kChunks + ((chunk + row) & (kChunks - 1))) * 16) =
+                    make_uint4(pk[0], pk[1], pk[2], pk[3]);
             }
         }
         tcgen05_fence_before();
@@ -196,28 +211,41 @@ fepe_mlp_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
 
     // ---- all 256 threads: column statistics from the bf16 tile, then coalesced store ----
     {
-        const __nv_bfloat16* ty = reinterpret_cast<const __nv_bfloat16*>(tile_y);
         const int pair = m0 / p.Npad;
         if (p.stats != nullptr) {        // (the data-gradient GEMM of the backward pass needs no statistics)
-        // every thread sums half a column (BN <= 128 columns x 2 halves = 256 threads)
-        for (int item = threadIdx.x; item < 2 * BN; item += kGemmThreads) {
-            const int col = item % BN, half = item / BN;
-            float s1 = 0.f, s2 = 0.f;
-#pragma unroll 8
-            for (int r = half * (kGemmBM / 2); r < (half + 1) * (kGemmBM / 2); ++r) {
-                const float y = __bfloat162float(ty[r * BN + ((col + 2 * r) % BN)]);
-                s1 += y;
-                s2 = fmaf(y, y, s2);
+            // a warp owns one chunk of 8 columns at a time: lane = (row residue rs = lane / 4, column pair cq = lane % 4)
+            // sums rows rs, rs + 8, ... of its two columns; the 8 residues are folded by 3 shuffle levels and the 4
+            // lanes with rs = 0 issue the 16 atomics of the chunk (BN x 2 atomics per tile)
+            const int rs = lane >> 2, cq = lane & 3;
+            for (int chunk = warp; chunk < kChunks; chunk += kGemmThreads / 32) {
+                float s1a = 0.f, s1b = 0.f, s2a = 0.f, s2b = 0.f;
+#pragma unroll 4
+                for (int r = rs; r < kGemmBM; r += 8) {
+                    const __nv_bfloat162 h = *reinterpret_cast<const __nv_bfloat162*>(
+                        tile_y + (r * kChunks + ((chunk + r) & (kChunks - 1))) * 16 + cq * 4);
+                    const float2 y = __bfloat1622float2(h);
+                    s1a += y.x; s2a = fmaf(y.x, y.x, s2a);
+                    s1b += y.y; s2b = fmaf(y.y, y.y, s2b);
+                }
+#pragma unroll
+                for (int off = 4; off < 32; off <<= 1) {
+                    s1a += __shfl_xor_sync(0xffffffffu, s1a, off);
+                    s2a += __shfl_xor_sync(0xffffffffu, s2a, off);
+                    s1b += __shfl_xor_sync(0xffffffffu, s1b, off);
+                    s2b += __shfl_xor_sync(0xffffffffu, s2b, off);
+                }
+                if (rs == 0) {
+                    float* st = p.stats + (static_cast<size_t>(pair) * p.Co + n0 + chunk * 8 + cq * 2) * 2;
+                    atomicAdd(st, s1a); atomicAdd(st + 1, s2a);
+                    atomicAdd(st + 2, s1b); atomicAdd(st + 3, s2b);
+                }
             }
-            atomicAdd(p.stats + (static_cast<size_t>(pair) * p.Co + n0 + col) * 2, s1);
-            atomicAdd(p.stats + (static_cast<size_t>(pair) * p.Co + n0 + col) * 2 + 1, s2);
         }
-        }
-        // store: each row of the tile is BN*2 bytes contiguous in Y
-        for (int idx = threadIdx.x; idx < kGemmBM * (BN / 2); idx += kGemmThreads) {
-            const int r = idx / (BN / 2), c2 = (idx % (BN / 2)) * 2;
-            const __nv_bfloat162 v = *reinterpret_cast<const __nv_bfloat162*>(ty + r * BN + ((c2 + 2 * r) % BN));
-            *reinterpret_cast<__nv_bfloat162*>(p.Y + static_cast<size_t>(m0 + r) * p.Co + n0 + c2) = v;
+        // store: each row of the tile is BN*2 bytes contiguous in Y, moved as 16-byte vectors
+        for (int idx = threadIdx.x; idx < kGemmBM * kChunks; idx += kGemmThreads) {
+            const int r = idx / kChunks, k = idx % kChunks;
+            const uint4 v = *reinterpret_cast<const uint4*>(tile_y + (r * kChunks + ((k + r) & (kChunks - 1))) * 16);
+            *reinterpret_cast<uint4*>(p.Y + static_cast<size_t>(m0 + r) * p.Co + n0 + k * 8) = v;
         }
     }
     __syncthreads();
@@ -251,28 +279,48 @@ __global__ void __launch_bounds__(256) fepe_mlp_norm_kernel(const __nv_bfloat16*
         sh[c] = beta[c] - mean * a;
     }
     __syncthreads();
+    // A thread keeps ONE group of 8 channels (its scale / shift live in registers) and walks down the rows: per 16-byte
+    // vector that is one load, 8 FMA, the LeakyReLU selects, 4 conversions and one store -- no shared-memory traffic in
+    // the loop -- with four rows in flight.  A warp covers 512 contiguous bytes of a row (or whole rows when Co < 256).
     const int vec_per_row = Co / 8;
     const size_t base = (static_cast<size_t>(b) * Npad + r0) * Co;
-    for (int idx = threadIdx.x; idx < 128 * vec_per_row; idx += blockDim.x) {
-        const int r = idx / vec_per_row, c = (idx % vec_per_row) * 8;
-        uint4 out = make_uint4(0u, 0u, 0u, 0u);
-        if (r0 + r < Nvalid) {
-            const uint4 in = *reinterpret_cast<const uint4*>(Y + base + static_cast<size_t>(r) * Co + c);
-            const uint32_t w[4] = {in.x, in.y, in.z, in.w};
-            uint32_t o[4];
+    const int nthr = static_cast<int>(blockDim.x);
+    const int rstep = (nthr >= vec_per_row) ? nthr / vec_per_row : 1;          // rows a pass of the CTA covers
+    const int rfirst = static_cast<int>(threadIdx.x) / vec_per_row;
+    const int rows_valid = (Nvalid - r0 < 128) ? ((Nvalid - r0 > 0) ? Nvalid - r0 : 0) : 128;
+    for (int cg = static_cast<int>(threadIdx.x) % vec_per_row; cg < vec_per_row && rfirst < rstep; cg += nthr) {
+        const int c = cg * 8;
+        float a[8], d[8];
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                const __nv_bfloat162 y = *reinterpret_cast<const __nv_bfloat162*>(&w[k]);
-                float t0 = fmaf(__low2float(y), sc[c + 2 * k], sh[c + 2 * k]);
-                float t1 = fmaf(__high2float(y), sc[c + 2 * k + 1], sh[c + 2 * k + 1]);
-                t0 = t0 > 0.f ? t0 : slope * t0;
-                t1 = t1 > 0.f ? t1 : slope * t1;
-                const __nv_bfloat162 v = __floats2bfloat162_rn(t0, t1);
-                o[k] = *reinterpret_cast<const uint32_t*>(&v);
+        for (int k = 0; k < 8; ++k) { a[k] = sc[c + k]; d[k] = sh[c + k]; }
+        for (int r = rfirst; r < 128; r += 4 * rstep) {
+            uint4 in[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int rr = r + u * rstep;
+                in[u] = make_uint4(0u, 0u, 0u, 0u);
+                if (rr < rows_valid) in[u] = __ldcs(reinterpret_cast<const uint4*>(Y + base + static_cast<size_t>(rr) * Co + c));
             }
-            out = make_uint4(o[0], o[1], o[2], o[3]);
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int rr = r + u * rstep;
+                if (rr >= 128) continue;
+                uint4 out = make_uint4(0u, 0u, 0u, 0u);                       // padded rows stay zero
+                if (rr < rows_valid) {
+                    const uint32_t w[4] = {in[u].x, in[u].y, in[u].z, in[u].w};
+                    uint32_t o[4];
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        const float2 y = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w[k]));
+                        const float t0 = fmaf(y.x, a[2 * k], d[2 * k]), t1 = fmaf(y.y, a[2 * k + 1], d[2 * k + 1]);
+                        const __nv_bfloat162 v = __floats2bfloat162_rn(t0 > 0.f ? t0 : slope * t0, t1 > 0.f ? t1 : slope * t1);
+                        o[k] = *reinterpret_cast<const uint32_t*>(&v);
+                    }
+                    out = make_uint4(o[0], o[1], o[2], o[3]);
+                }
+                *reinterpret_cast<uint4*>(X + base + static_cast<size_t>(rr) * Co + c) = out;
+            }
         }
-        *reinterpret_cast<uint4*>(X + base + static_cast<size_t>(r) * Co + c) = out;
     }
 }
 
@@ -327,16 +375,44 @@ __global__ void fepe_mlp_last_kernel(const __nv_bfloat16* __restrict__ X, const 
     extern __shared__ float sh[];            // [Npad] logits
     __shared__ float red[8];
     const int b = blockIdx.x;
-    for (int r = threadIdx.x; r < N; r += blockDim.x) {
-        const __nv_bfloat16* x = X + (static_cast<size_t>(b) * Npad + r) * Ci;
-        float acc = bias;
-        for (int k = 0; k < Ci; k += 2) {
-            const __nv_bfloat162 v = *reinterpret_cast<const __nv_bfloat162*>(x + k);
-            acc = fmaf(__low2float(v), W[k], acc);
-            acc = fmaf(__high2float(v), W[k + 1], acc);
+    {
+        // a warp per row, 16-byte vectors (a 256-channel row is exactly one vector per lane), four rows in flight
+        const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarp = blockDim.x >> 5;
+        const __nv_bfloat16* xb = X + static_cast<size_t>(b) * Npad * Ci;
+        for (int r = warp * 4; r < N; r += nwarp * 4) {
+            float acc[4] = {0.f, 0.f, 0.f, 0.f};
+            for (int k = lane * 8; k < Ci; k += 256) {
+                float w[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) w[j] = __ldg(W + k + j);
+                uint4 v[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    v[u] = make_uint4(0u, 0u, 0u, 0u);
+                    if (r + u < N) v[u] = __ldcs(reinterpret_cast<const uint4*>(xb + static_cast<size_t>(r + u) * Ci + k));
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const uint32_t q[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const float2 y = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&q[j]));
+                        acc[u] = fmaf(y.x, w[2 * j], acc[u]);
+                        acc[u] = fmaf(y.y, w[2 * j + 1], acc[u]);
+                    }
+                }
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+                for (int u = 0; u < 4; ++u) acc[u] += __shfl_xor_sync(0xffffffffu, acc[u], o);
+            }
+            if (lane < 4 && r + lane < N) {
+                const float v = ((lane == 0) ? acc[0] : (lane == 1) ? acc[1] : (lane == 2) ? acc[2] : acc[3]) + bias;
+                sh[r + lane] = v;
+                logits[static_cast<size_t>(b) * N + r + lane] = v;
+            }
         }
-        sh[r] = acc;
-        logits[static_cast<size_t>(b) * N + r] = acc;
     }
     __syncthreads();
     float mx = -3.4e38f;
@@ -777,7 +853,7 @@ int fepe_mlp_wgrad(const void* dY, const void* X, float* dW, int M, int Co, int 
 // Y = X W^T + b (bf16 in / out, fp32 accumulate on tcgen05) with per-(pair, channel) statistics.
 int fepe_mlp_gemm(const void* X, const void* W, const float* bias, void* Y, float* stats, int B, int Npad,
                   int Nvalid, int K, int Co, void* stream) {
-    if (!X || !W || !bias || !Y || B <= 0 || Npad <= 0 || (Npad % fepe::kGemmBM) != 0 || Nvalid > Npad ||
+    if (!X || !W || !Y || B <= 0 || Npad <= 0 || (Npad % fepe::kGemmBM) != 0 || Nvalid > Npad ||
         (K % fepe::kGemmBK) != 0 || (Co % 64) != 0)
         return FEPE_E_BADARG;
     fepe::GemmParams p{B * Npad, K, Co, Npad, Nvalid, bias, static_cast<__nv_bfloat16*>(Y), stats};
@@ -812,7 +888,7 @@ int fepe_mlp_first(const float* X0, const float* W, const float* bias, void* Y, 
 
 int fepe_mlp_last(const void* X, const float* W, float bias, float* logits, float* weights, int B, int N, int Npad,
                   int Ci, void* stream) {
-    if (!X || !W || !logits || !weights || B <= 0 || (Ci & 1)) return FEPE_E_BADARG;
+    if (!X || !W || !logits || !weights || B <= 0 || (Ci & 7)) return FEPE_E_BADARG;
     fepe::fepe_mlp_last_kernel<<<B, 256, Npad * sizeof(float), static_cast<cudaStream_t>(stream)>>>(
         static_cast<const __nv_bfloat16*>(X), W, bias, logits, weights, N, Npad, Ci);
     return static_cast<int>(cudaGetLastError());

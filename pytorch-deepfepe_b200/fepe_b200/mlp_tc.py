@@ -177,7 +177,7 @@ class TensorCoreMLPFunction(torch.autograd.Function):
                     grads[4 * i] = dW.reshape(c, ci, 1)
                     wt = wb[i].t().contiguous()                # [ci, c]: the data-gradient GEMM's "weight"
                     dXn = torch.empty(M, ci, dtype=torch.bfloat16, device=dev)
-                    _lib.check(lib.fepe_mlp_gemm(dY.data_ptr(), wt.data_ptr(), zeros_b(ci).data_ptr(), dXn.data_ptr(),
+                    _lib.check(lib.fepe_mlp_gemm(dY.data_ptr(), wt.data_ptr(), None, dXn.data_ptr(),
                                                  None, B, Npad, Npad, c, ci, st), "fepe_mlp_gemm(dgrad)")
                     dX = dXn
                 else:
