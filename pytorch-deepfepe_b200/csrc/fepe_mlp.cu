@@ -20,6 +20,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdlib.h>
+#include <string.h>
 
 #include "../../include/fepe_b200.h"
 #include "fepe_common.cuh"
@@ -252,6 +253,218 @@ fepe_mlp_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
     if (warp == 2) {
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
                      "r"(static_cast<uint32_t>(BN < 32 ? 32 : BN)));
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Persistent variant of the same GEMM: one CTA per SM walks over the output tiles (n fastest), the
+// accumulator is DOUBLE-BUFFERED in TMEM (2 x BN columns) so that the epilogue of tile j overlaps the
+// main loop of tile j+1, and the operand ring keeps running across tile boundaries.  Why: the
+// one-tile-per-CTA kernel above pays TMEM allocation, barrier set-up and a serial load -> MMA ->
+// epilogue chain per tile, which is most of the time of the thin layers (K = 128: two k-blocks), and
+// with 128 x 128 tiles the fat layer (K = 1024) saturates the L2 (64 flop per operand byte against the
+// ~12 TB/s the L2 slices deliver); BN = 256 raises that to 85 flop/B.
+//
+// 12 warps: warp 0 = TMA producer (one lane), warp 1 = MMA issuer (one lane), warp 2 = TMEM allocator,
+// warps 4-11 = two epilogue groups of four warps (TMEM lane quarter = warp % 4); group g drains the
+// columns [g BN/2, (g+1) BN/2) of the accumulator in chunks of 64 columns through its own 16 KB tile
+// (same swizzled 16-byte-chunk layout, statistics and 16-byte stores as above).
+// ------------------------------------------------------------------------------------------------
+constexpr int kPersistThreads = 384;
+constexpr int kEpiCols = 64;                         // columns per epilogue pass of a group
+constexpr int kEpiTileBytes = kGemmBM * kEpiCols * 2;
+
+__device__ __forceinline__ void epi_group_sync(int g) {
+    asm volatile("bar.sync %0, %1;" ::"r"(g + 1), "r"(128) : "memory");
+}
+
+template <int BN, int STAGES>
+__global__ void __launch_bounds__(kPersistThreads, 1)
+fepe_mlp_gemm_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w,
+                             const GemmParams p) {
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    constexpr int kABytes = kGemmBM * kGemmBK * 2;       // 16 KB
+    constexpr int kBBytes = BN * kGemmBK * 2;
+    constexpr int kStageBytes = kABytes + kBBytes;
+    constexpr int kChunks = kEpiCols / 8;                // 16-byte chunks per row of an epilogue tile
+    constexpr uint32_t kTmemCols = 2 * BN;               // 256 or 512: a power of two
+    unsigned char* epi_tiles = smem + STAGES * kStageBytes;                  // [2 groups][128][64] bf16
+    uint64_t* full = reinterpret_cast<uint64_t*>(epi_tiles + 2 * kEpiTileBytes);
+    uint64_t* empty = full + STAGES;
+    uint64_t* tmem_full = empty + STAGES;                // [2]
+    uint64_t* tmem_empty = tmem_full + 2;                // [2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int num_kb = p.K / kGemmBK;
+    const int n_tiles = p.Co / BN;
+    const int tiles = (p.M / kGemmBM) * n_tiles;
+    const int n_local = (tiles - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) /
+                        static_cast<int>(gridDim.x);
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+        for (int b = 0; b < 2; ++b) { mbar_init(&tmem_full[b], 1); mbar_init(&tmem_empty[b], 8); }
+        fence_barrier_init();
+    }
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                     "r"(kTmemCols));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    tcgen05_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ---------------- TMA producer: the ring runs across tile boundaries ----------------
+        if (lane == 0) {
+            uint32_t it = 0;
+            for (int j = 0; j < n_local; ++j) {
+                const int t = static_cast<int>(blockIdx.x) + j * static_cast<int>(gridDim.x);
+                const int m0 = (t / n_tiles) * kGemmBM, n0 = (t % n_tiles) * BN;
+                for (int kb = 0; kb < num_kb; ++kb, ++it) {
+                    const uint32_t s = it % STAGES;
+                    const uint32_t ph = (it / STAGES) & 1u;
+                    mbar_wait(&empty[s], ph ^ 1u);
+                    unsigned char* sa = smem + s * kStageBytes;
+                    mbar_arrive_expect_tx(&full[s], kStageBytes);
+                    tma_load_2d(sa, &map_a, kb * kGemmBK, m0, &full[s]);
+                    tma_load_2d(sa + kABytes, &map_w, kb * kGemmBK, n0, &full[s]);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ---------------- MMA issuer ----------------
+        constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(BN >> 3) << 17) |
+                                   (static_cast<uint32_t>(kGemmBM >> 4) << 24);
+        uint32_t it = 0;
+        for (int j = 0; j < n_local; ++j) {
+            const uint32_t b = static_cast<uint32_t>(j) & 1u;
+            const uint32_t use = static_cast<uint32_t>(j) >> 1;                // how often buffer b was used before
+            mbar_wait(&tmem_empty[b], (use & 1u) ^ 1u);                        // drained by the epilogue (free at first use)
+            tcgen05_fence_after();
+            const uint32_t tmem_d = tmem_base + b * static_cast<uint32_t>(BN);
+            for (int kb = 0; kb < num_kb; ++kb, ++it) {
+                const uint32_t s = it % STAGES;
+                const uint32_t ph = (it / STAGES) & 1u;
+                mbar_wait(&full[s], ph);
+                tcgen05_fence_after();
+                if (lane == 0) {
+                    const unsigned char* sa = smem + s * kStageBytes;
+                    const uint64_t da = umma_desc_k_sw128(sa);
+                    const uint64_t db = umma_desc_k_sw128(sa + kABytes);
+#pragma unroll
+                    for (int k = 0; k < kGemmBK / 16; ++k) {
+                        umma_bf16(tmem_d, da + static_cast<uint64_t>(k * 2), db + static_cast<uint64_t>(k * 2), idesc,
+                                  (kb | k) != 0 ? 1u : 0u);
+                    }
+                    tcgen05_commit(&empty[s]);
+                    if (kb == num_kb - 1) tcgen05_commit(&tmem_full[b]);
+                }
+                __syncwarp();
+            }
+        }
+    } else if (warp >= 4) {
+        // ---------------- epilogue groups ----------------
+        const int ew = warp - 4;
+        const int g = ew >> 2;                                // column half of the accumulator
+        const int wq = ew & 3;                                // warp inside the group
+        const int q = warp & 3;                               // TMEM lane quarter this warp may read (== wq)
+        const int row = q * 32 + lane;
+        const int et = wq * 32 + lane;                        // thread inside the group
+        unsigned char* tile_y = epi_tiles + g * kEpiTileBytes;
+        const bool has_bias = p.bias != nullptr;
+        const int rs = lane >> 2, cq = lane & 3;
+        for (int j = 0; j < n_local; ++j) {
+            const int t = static_cast<int>(blockIdx.x) + j * static_cast<int>(gridDim.x);
+            const int m0 = (t / n_tiles) * kGemmBM, n0 = (t % n_tiles) * BN;
+            const uint32_t b = static_cast<uint32_t>(j) & 1u;
+            const uint32_t use = static_cast<uint32_t>(j) >> 1;
+            const int pair = m0 / p.Npad;
+            const bool valid = (m0 - pair * p.Npad) + row < p.Nvalid;
+            mbar_wait(&tmem_full[b], use & 1u);
+            tcgen05_fence_after();
+#pragma unroll 1
+            for (int cc = 0; cc < BN / 2; cc += kEpiCols) {
+                const int col0 = g * (BN / 2) + cc;           // first accumulator column of this pass
+#pragma unroll
+                for (int c = 0; c < kEpiCols; c += 32) {
+                    uint32_t v[32];
+                    tmem_ld32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + b * static_cast<uint32_t>(BN) +
+                                  static_cast<uint32_t>(col0 + c), v);
+                    if (has_bias) {
+#pragma unroll
+                        for (int i = 0; i < 32; ++i)
+                            v[i] = __float_as_uint(__uint_as_float(v[i]) + __ldg(p.bias + n0 + col0 + c + i));
+                    }
+                    if (!valid) {
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) v[i] = 0u;
+                    }
+#pragma unroll
+                    for (int gg = 0; gg < 4; ++gg) {
+                        uint32_t pk[4];
+#pragma unroll
+                        for (int jj = 0; jj < 4; ++jj) {
+                            const __nv_bfloat162 h = __floats2bfloat162_rn(__uint_as_float(v[gg * 8 + 2 * jj]),
+                                                                           __uint_as_float(v[gg * 8 + 2 * jj + 1]));
+                            pk[jj] = *reinterpret_cast<const uint32_t*>(&h);
+                        }
+                        const int chunk = (c >> 3) + gg;
+                        *reinterpret_cast<uint4*>(tile_y + (row * kChunks + ((chunk + row) & (kChunks - 1))) * 16) =
+                            make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                    }
+                }
+                if (cc + kEpiCols >= BN / 2) {                // last read of this accumulator buffer: hand it back
+                    tcgen05_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&tmem_empty[b]);
+                }
+                epi_group_sync(g);
+                if (p.stats != nullptr) {
+                    for (int chunk = wq; chunk < kChunks; chunk += 4) {
+                        float s1a = 0.f, s1b = 0.f, s2a = 0.f, s2b = 0.f;
+#pragma unroll 4
+                        for (int r = rs; r < kGemmBM; r += 8) {
+                            const __nv_bfloat162 h = *reinterpret_cast<const __nv_bfloat162*>(
+                                tile_y + (r * kChunks + ((chunk + r) & (kChunks - 1))) * 16 + cq * 4);
+                            const float2 y = __bfloat1622float2(h);
+                            s1a += y.x; s2a = fmaf(y.x, y.x, s2a);
+                            s1b += y.y; s2b = fmaf(y.y, y.y, s2b);
+                        }
+#pragma unroll
+                        for (int off = 4; off < 32; off <<= 1) {
+                            s1a += __shfl_xor_sync(0xffffffffu, s1a, off);
+                            s2a += __shfl_xor_sync(0xffffffffu, s2a, off);
+                            s1b += __shfl_xor_sync(0xffffffffu, s1b, off);
+                            s2b += __shfl_xor_sync(0xffffffffu, s2b, off);
+                        }
+                        if (rs == 0) {
+                            float* st = p.stats + (static_cast<size_t>(pair) * p.Co + n0 + col0 + chunk * 8 + cq * 2) * 2;
+                            atomicAdd(st, s1a); atomicAdd(st + 1, s2a);
+                            atomicAdd(st + 2, s1b); atomicAdd(st + 3, s2b);
+                        }
+                    }
+                }
+#pragma unroll
+                for (int idx = et; idx < kGemmBM * kChunks; idx += 128) {
+                    const int r = idx / kChunks, k = idx % kChunks;
+                    const uint4 v = *reinterpret_cast<const uint4*>(tile_y + (r * kChunks + ((k + r) & (kChunks - 1))) * 16);
+                    *reinterpret_cast<uint4*>(p.Y + static_cast<size_t>(m0 + r) * p.Co + n0 + col0 + k * 8) = v;
+                }
+                epi_group_sync(g);                            // the tile is rewritten by the next pass
+            }
+        }
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tcgen05_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols));
     }
 }
 
@@ -781,6 +994,29 @@ static int launch_gemm(const void* X, const void* W, const GemmParams& p, cudaSt
     return static_cast<int>(cudaGetLastError());
 }
 
+template <int BN, int STAGES>
+static int launch_gemm_persist(const void* X, const void* W, const GemmParams& p, cudaStream_t stream) {
+    CUtensorMap ma, mw;
+    if (!make_map(&ma, X, p.M, p.K, kGemmBM) || !make_map(&mw, W, p.Co, p.K, BN)) return FEPE_E_NODEVICE;
+    constexpr int smem = STAGES * (kGemmBM * kGemmBK * 2 + BN * kGemmBK * 2) + 2 * kEpiTileBytes + 256 + 1024;
+    static int sms[64] = {0};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (sms[dev & 63] == 0) {
+        cudaError_t e = cudaFuncSetAttribute(fepe_mlp_gemm_persist_kernel<BN, STAGES>,
+                                             cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e != cudaSuccess) return static_cast<int>(e);
+        int n = 0;
+        e = cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+        if (e != cudaSuccess || n <= 0) return FEPE_E_NODEVICE;
+        sms[dev & 63] = n;
+    }
+    const int tiles = (p.M / kGemmBM) * (p.Co / BN);
+    const int grid = tiles < sms[dev & 63] ? tiles : sms[dev & 63];
+    fepe_mlp_gemm_persist_kernel<BN, STAGES><<<grid, kPersistThreads, smem, stream>>>(ma, mw, p);
+    return static_cast<int>(cudaGetLastError());
+}
+
 template <int BN>
 static int launch_wgrad(const void* dY, const void* X, const WgradParams& p, int slabs, cudaStream_t stream) {
     CUtensorMap my, mx;
@@ -860,6 +1096,15 @@ int fepe_mlp_gemm(const void* X, const void* W, const float* bias, void* Y, floa
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     // 2 stages / 2 CTAs per SM: the epilogue of one CTA overlaps the main loop of the other.  Measured faster
     // than 4 stages / 1 CTA per SM on every layer (profiles/r1_mlp_timing.txt).  FEPE_MLP_STAGES=2|4 overrides.
+    // Default for Co % 128 == 0: the persistent kernel (double-buffered TMEM accumulator, 128 x 256 tiles when Co
+    // allows).  FEPE_MLP_GEMM=tile selects the one-tile-per-CTA kernel, FEPE_MLP_GEMM=persist128 forces BN = 128.
+    const char* mode = getenv("FEPE_MLP_GEMM");
+    const bool tile_mode = mode != nullptr && strcmp(mode, "tile") == 0;
+    if (!tile_mode && Co % 128 == 0) {
+        const bool force128 = mode != nullptr && strcmp(mode, "persist128") == 0;
+        if (Co % 256 == 0 && !force128) return fepe::launch_gemm_persist<256, 4>(X, W, p, st);
+        return fepe::launch_gemm_persist<128, 6>(X, W, p, st);
+    }
     int stages = 2;
     if (const char* ev = getenv("FEPE_MLP_STAGES")) stages = (ev[0] == '2') ? 2 : 4;
     if (Co % 128 == 0)

@@ -1,0 +1,52 @@
+"""A/B timing of the MLP GEMM variants (FEPE_MLP_GEMM = tile | persist128 | persist) on the ErrorEstimator's
+layer shapes, of the whole ErrorEstimator and of a DeepFNet forward.  Development aid."""
+import sys, os
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path[:0] = [ROOT, os.path.join(ROOT, "pytorch-deepfepe_b200")]
+import torch
+from fepe_b200 import synth, _lib
+from fepe_b200.models import DeepFNet, ErrorEstimator
+
+def ev(fn, iters=10, warm=3):
+    for _ in range(warm): fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters): fn()
+    e1.record(); torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / iters
+
+lib = _lib.lib()
+FLOP_PER_PT = 2 * (4 * 64 + 64 * 128 + 128 * 1024 + 1024 * 512 + 512 * 256 + 256)
+N = 1000; Npad = 1024
+for B in (64, 512):
+    for K, Co in [(64, 128), (128, 1024), (1024, 512), (512, 256)]:
+        X = torch.randn(B * Npad, K, device="cuda").bfloat16(); W = (torch.randn(Co, K, device="cuda") / K ** 0.5).bfloat16()
+        Y = torch.empty(B * Npad, Co, device="cuda", dtype=torch.bfloat16)
+        stats = torch.zeros(B, Co, 2, device="cuda")
+        ref = None
+        for mode in ("tile", "persist128", "persist"):
+            os.environ["FEPE_MLP_GEMM"] = mode
+            call = lambda: lib.fepe_mlp_gemm(X.data_ptr(), W.data_ptr(), 0, Y.data_ptr(), stats.data_ptr(), B, Npad, N, K, Co, torch.cuda.current_stream().cuda_stream)
+            stats.zero_(); Y.fill_(7.0)
+            assert call() == 0
+            torch.cuda.synchronize()
+            if ref is None: ref = (Y.clone(), stats.clone())
+            dy = float((Y.float() - ref[0].float()).abs().max()); ds = float(((stats - ref[1]).abs() / (ref[1].abs() + 1.0)).max())
+            t = ev(call)
+            print(f"B={B} gemm K={K} Co={Co} {mode:10s}: {t*1e3:7.1f} us  {2*B*Npad*K*Co/t/1e9:7.1f} TFLOP/s  {(B*Npad*(K+Co)*2)/t/1e6:6.0f} GB/s  |dY| vs tile {dy:.3g}  rel dstats {ds:.2g}", flush=True)
+for mode in ("tile", "persist128", "persist"):
+    os.environ["FEPE_MLP_GEMM"] = mode
+    for B in (64, 512):
+        ee = ErrorEstimator(4).cuda(); ee.tensor_cores = True
+        x = torch.rand(B, 4, N, device="cuda")
+        with torch.no_grad():
+            t = ev(lambda: ee(x))
+        print(f"{mode:10s} ErrorEstimator B={B}: {t:.3f} ms  {B*N*FLOP_PER_PT/t/1e9:.1f} TFLOP/s", flush=True)
+    net = DeepFNet(depth=5, image_size=[376, 1241, 3], if_quality=False).cuda()
+    net.enable_tensor_core_mlp()
+    d = synth.make_batch(64, N, seed=1)
+    m = torch.from_numpy(d["matches_xy_ori"]).cuda().repeat(8, 1, 1).contiguous()
+    with torch.no_grad():
+        t = ev(lambda: net({"matches_xy_ori": m}), iters=5, warm=2)
+    print(f"{mode:10s} DeepFNet forward depth 5 B=512: {t:.2f} ms  {512/t*1e3:.0f} pairs/s", flush=True)

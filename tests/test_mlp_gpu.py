@@ -11,9 +11,14 @@ from fepe_b200.models import DeepFNet, ErrorEstimator
 pytestmark = pytest.mark.gpu
 
 
+@pytest.mark.parametrize("mode", ["persist", "persist128", "tile"])
 @pytest.mark.parametrize("B,N,K,Co", [(1, 128, 64, 64), (2, 100, 64, 128), (3, 1000, 128, 1024), (2, 1000, 1024, 512),
-                                      (2, 333, 512, 256)])
-def test_gemm_against_torch_fp32(B, N, K, Co):
+                                      (2, 333, 512, 256), (40, 1000, 128, 256), (37, 900, 192, 384)])
+def test_gemm_against_torch_fp32(B, N, K, Co, mode, monkeypatch):
+    # mode: the persistent kernel (default; 128 x 256 tiles when Co allows), the same with 128 x 128 tiles, and the
+    # one-tile-per-CTA kernel (FEPE_MLP_GEMM is read by the library on every call).  The two larger cases give every
+    # persistent CTA several tiles (both TMEM accumulator buffers and the operand ring wrap around).
+    monkeypatch.setenv("FEPE_MLP_GEMM", mode)
     lib = _lib.lib()
     torch.manual_seed(0)
     Npad = (N + 127) // 128 * 128
