@@ -140,7 +140,7 @@ int fepe_pose_bwd(const float* F, const float* K, int L, int B, float ax, float 
  * with Npad = N rounded up to 128 (padded rows are zero and excluded from the statistics); weights are
  * bf16 [Co, Ci] (Conv1d weight squeezed); accumulation is fp32 in tensor memory (tcgen05.mma).
  *   fepe_mlp_first  layer 1 from fp32 features X0 [B,N,Ci<=8]                -> Y [B*Npad,Co] + stats
- *   fepe_mlp_gemm   Y = X W^T + b (K % 64 == 0, Co % 64 == 0; b may be NULL)   -> Y + stats [B,Co,2] (stats may be NULL)
+ *   fepe_mlp_gemm   Y = X W^T + b (K % 64 == 0, Co % 64 == 0; b may be NULL, else 16-byte aligned) -> Y + stats [B,Co,2] (stats may be NULL)
  *   fepe_mlp_norm   X' = LeakyReLU(gamma (Y - mean) rstd + beta) from stats (biased variance, eps)
  *   fepe_mlp_last   logits = X w + b (Co = 1), weights = softmax over the N rows of each pair
  * `stats` must be zeroed by the caller before fepe_mlp_first / fepe_mlp_gemm (they accumulate with atomics).
@@ -151,6 +151,16 @@ int fepe_mlp_gemm(const void* X, const void* W, const float* bias, void* Y, floa
                   int Nvalid, int K, int Co, void* stream);
 int fepe_mlp_norm(const void* Y, const float* stats, const float* gamma, const float* beta, void* X, int B, int Npad,
                   int Nvalid, int Co, float eps, float slope, void* stream);
+/* Inference with the InstanceNorm + LeakyReLU of layer l fused into the GEMM of layer l+1 (the normalised activations
+ * X' are never written to memory): fepe_mlp_scale_shift turns the statistics of layer l into per-(pair, channel)
+ * (a, d) with x' = LeakyReLU(a y + d) -- ss [B, Co/2, 4] fp32 = (a_c, a_c+1, d_c, d_c+1), 16-byte aligned; with
+ * clear_stats != 0 it also zeroes `stats` for the next accumulation -- and fepe_mlp_gemm_norm computes
+ * Y = LeakyReLU(a Yprev + d) W^T + b from the PRE-norm output Yprev [B*Npad, K] of layer l (Co % 128 == 0,
+ * 0 < slope < 1).  Same arithmetic as fepe_mlp_norm followed by fepe_mlp_gemm (identical bf16 results). */
+int fepe_mlp_scale_shift(float* stats, const float* gamma, const float* beta, float* ss, int B, int Co, int Nvalid,
+                         float eps, int clear_stats, void* stream);
+int fepe_mlp_gemm_norm(const void* Yprev, const float* ss, float slope, const void* W, const float* bias, void* Y,
+                       float* stats, int B, int Npad, int Nvalid, int K, int Co, void* stream);
 int fepe_mlp_last(const void* X, const float* W, float bias, float* logits, float* weights, int B, int N, int Npad,
                   int Ci, void* stream);
 /* training path: weight gradient of one Conv1d(k=1): dW[Co,Ci] += dY[M,Co]^T X[M,Ci] on tcgen05 (bf16 operands read

@@ -89,6 +89,8 @@ struct GemmParams {
     const float* bias;     // [Co], or null (a bias in front of an InstanceNorm cancels in the normalisation)
     __nv_bfloat16* Y;      // [M, Co]
     float* stats;          // [B, Co, 2] (sum, sum of squares), zeroed by the caller
+    const float* ss;       // fused-norm variant only: [B, K/2, 4] = (a_2q, a_2q+1, d_2q, d_2q+1), x' = LeakyReLU(a y + d)
+    float slope;
 };
 
 // STAGES = 4 with one CTA per SM, or STAGES = 2 with two CTAs per SM: in the second configuration the
@@ -271,6 +273,7 @@ fepe_mlp_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
 // (same swizzled 16-byte-chunk layout, statistics and 16-byte stores as above).
 // ------------------------------------------------------------------------------------------------
 constexpr int kPersistThreads = 384;
+constexpr int kPersistFuseThreads = 512;             // + warps 12-15: operand transform of the fused-norm variant
 constexpr int kEpiCols = 64;                         // columns per epilogue pass of a group
 constexpr int kEpiTileBytes = kGemmBM * kEpiCols * 2;
 
@@ -278,8 +281,8 @@ __device__ __forceinline__ void epi_group_sync(int g) {
     asm volatile("bar.sync %0, %1;" ::"r"(g + 1), "r"(128) : "memory");
 }
 
-template <int BN, int STAGES>
-__global__ void __launch_bounds__(kPersistThreads, 1)
+template <int BN, int STAGES, bool FUSE>
+__global__ void __launch_bounds__(FUSE ? kPersistFuseThreads : kPersistThreads, 1)
 fepe_mlp_gemm_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w,
                              const GemmParams p) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
@@ -292,7 +295,8 @@ fepe_mlp_gemm_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __
     unsigned char* epi_tiles = smem + STAGES * kStageBytes;                  // [2 groups][128][64] bf16
     uint64_t* full = reinterpret_cast<uint64_t*>(epi_tiles + 2 * kEpiTileBytes);
     uint64_t* empty = full + STAGES;
-    uint64_t* tmem_full = empty + STAGES;                // [2]
+    uint64_t* ready = empty + STAGES;                    // FUSE: the A tile of the stage has been transformed
+    uint64_t* tmem_full = ready + STAGES;                // [2]
     uint64_t* tmem_empty = tmem_full + 2;                // [2]
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
 
@@ -305,7 +309,7 @@ fepe_mlp_gemm_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __
                         static_cast<int>(gridDim.x);
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+        for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); mbar_init(&ready[s], 4); }
         for (int b = 0; b < 2; ++b) { mbar_init(&tmem_full[b], 1); mbar_init(&tmem_empty[b], 8); }
         fence_barrier_init();
     }
@@ -351,7 +355,7 @@ fepe_mlp_gemm_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __
             for (int kb = 0; kb < num_kb; ++kb, ++it) {
                 const uint32_t s = it % STAGES;
                 const uint32_t ph = (it / STAGES) & 1u;
-                mbar_wait(&full[s], ph);
+                mbar_wait(FUSE ? &ready[s] : &full[s], ph);
                 tcgen05_fence_after();
                 if (lane == 0) {
                     const unsigned char* sa = smem + s * kStageBytes;
@@ -368,7 +372,53 @@ fepe_mlp_gemm_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __
                 __syncwarp();
             }
         }
-    } else if (warp >= 4) {
+    } else if (FUSE && warp >= 12) {
+        // ---------------- operand transform (fused InstanceNorm + LeakyReLU of the previous layer) ----------------
+        // The A tile holds the previous layer's PRE-norm output; x' = LeakyReLU(a y + d) with the per-(pair, channel)
+        // (a, d) of fepe_mlp_scale_shift is applied in place before the MMA reads the stage.  Thread tt owns the
+        // physical 16-byte chunk `pos` of rows r0, r0 + 16, ...; under the 128-byte swizzle that is the logical chunk
+        // pos ^ (r0 & 7) for all of them (16 i leaves r & 7 unchanged), so its eight channels -- and their (a, d),
+        // requested before the stage's data are waited for -- are the same for every row of a k-block.
+        const int tt = static_cast<int>(threadIdx.x) - 384;
+        const int pos = tt & 7;
+        const int r0 = tt >> 3;
+        const int cl = pos ^ (r0 & 7);
+        const float2 slope2 = make_float2(p.slope, p.slope);
+        uint32_t it = 0;
+        for (int j = 0; j < n_local; ++j) {
+            const int t = static_cast<int>(blockIdx.x) + j * static_cast<int>(gridDim.x);
+            const int pair = ((t / n_tiles) * kGemmBM) / p.Npad;
+            const float4* ssp = reinterpret_cast<const float4*>(p.ss) + (static_cast<size_t>(pair) * p.K) / 2;
+            for (int kb = 0; kb < num_kb; ++kb, ++it) {
+                const uint32_t s = it % STAGES;
+                const uint32_t ph = (it / STAGES) & 1u;
+                float4 c[4];                                    // (a, a, d, d) of channel pairs 0..3 of the chunk
+#pragma unroll
+                for (int q = 0; q < 4; ++q) c[q] = __ldg(ssp + (kb * kGemmBK + cl * 8) / 2 + q);
+                mbar_wait(&full[s], ph);
+                unsigned char* sa = smem + s * kStageBytes + r0 * 128 + pos * 16;
+#pragma unroll
+                for (int i = 0; i < kGemmBM / 16; ++i) {
+                    uint4* ptr = reinterpret_cast<uint4*>(sa + i * 2048);
+                    const uint4 u = *ptr;
+                    const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+                    uint32_t o[4];
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        const float2 y = make_float2(__uint_as_float(w[q] << 16), __uint_as_float(w[q] & 0xffff0000u));
+                        const float2 tv = __ffma2_rn(y, make_float2(c[q].x, c[q].y), make_float2(c[q].z, c[q].w));
+                        const float2 sv = __fmul2_rn(tv, slope2);
+                        const __nv_bfloat162 h = __floats2bfloat162_rn(fmaxf(tv.x, sv.x), fmaxf(tv.y, sv.y));
+                        o[q] = *reinterpret_cast<const uint32_t*>(&h);
+                    }
+                    *ptr = make_uint4(o[0], o[1], o[2], o[3]);
+                }
+                fence_proxy_async();                            // generic-proxy writes -> visible to the MMA's async proxy
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&ready[s]);
+            }
+        }
+    } else if (warp >= 4 && warp < 12) {
         // ---------------- epilogue groups ----------------
         const int ew = warp - 4;
         const int g = ew >> 2;                                // column half of the accumulator
@@ -378,7 +428,6 @@ fepe_mlp_gemm_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __
         const int et = wq * 32 + lane;                        // thread inside the group
         unsigned char* tile_y = epi_tiles + g * kEpiTileBytes;
         const bool has_bias = p.bias != nullptr;
-        const int rs = lane >> 2, cq = lane & 3;
         for (int j = 0; j < n_local; ++j) {
             const int t = static_cast<int>(blockIdx.x) + j * static_cast<int>(gridDim.x);
             const int m0 = (t / n_tiles) * kGemmBM, n0 = (t % n_tiles) * BN;
@@ -397,9 +446,15 @@ fepe_mlp_gemm_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __
                     tmem_ld32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + b * static_cast<uint32_t>(BN) +
                                   static_cast<uint32_t>(col0 + c), v);
                     if (has_bias) {
+                        const float4* bp = reinterpret_cast<const float4*>(p.bias + n0 + col0 + c);   // 16-byte aligned
 #pragma unroll
-                        for (int i = 0; i < 32; ++i)
-                            v[i] = __float_as_uint(__uint_as_float(v[i]) + __ldg(p.bias + n0 + col0 + c + i));
+                        for (int i = 0; i < 8; ++i) {
+                            const float4 bb = __ldg(bp + i);
+                            v[4 * i + 0] = __float_as_uint(__uint_as_float(v[4 * i + 0]) + bb.x);
+                            v[4 * i + 1] = __float_as_uint(__uint_as_float(v[4 * i + 1]) + bb.y);
+                            v[4 * i + 2] = __float_as_uint(__uint_as_float(v[4 * i + 2]) + bb.z);
+                            v[4 * i + 3] = __float_as_uint(__uint_as_float(v[4 * i + 3]) + bb.w);
+                        }
                     }
                     if (!valid) {
 #pragma unroll
@@ -426,29 +481,40 @@ fepe_mlp_gemm_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __
                 }
                 epi_group_sync(g);
                 if (p.stats != nullptr) {
-                    for (int chunk = wq; chunk < kChunks; chunk += 4) {
-                        float s1a = 0.f, s1b = 0.f, s2a = 0.f, s2b = 0.f;
-#pragma unroll 4
-                        for (int r = rs; r < kGemmBM; r += 8) {
-                            const __nv_bfloat162 h = *reinterpret_cast<const __nv_bfloat162*>(
-                                tile_y + (r * kChunks + ((chunk + r) & (kChunks - 1))) * 16 + cq * 4);
-                            const float2 y = __bfloat1622float2(h);
-                            s1a += y.x; s2a = fmaf(y.x, y.x, s2a);
-                            s1b += y.y; s2b = fmaf(y.y, y.y, s2b);
-                        }
+                    // Column statistics of the 128 x 64 tile.  Warp wq owns the 16-byte chunks 2 wq and 2 wq + 1; lane =
+                    // (chunk half, row residue rg = lane % 16) reads rows rg, rg + 16, ... of its chunk as 16-byte vectors
+                    // (a quarter warp = 8 consecutive rows of one chunk = 8 different slots) into 16 independent
+                    // accumulators a[2c] = sum, a[2c+1] = sum of squares of column c.  A reduce-scatter over the 16 row
+                    // residues (15 exchanges) leaves entry rg in lane rg, i.e. the chunk's 16 consecutive floats of
+                    // `stats`: ONE fully populated atomic instruction per warp and pass.
+                    const int kc = 2 * wq + (lane >> 4);
+                    const int rg = lane & 15;
+                    float a[16];
 #pragma unroll
-                        for (int off = 4; off < 32; off <<= 1) {
-                            s1a += __shfl_xor_sync(0xffffffffu, s1a, off);
-                            s2a += __shfl_xor_sync(0xffffffffu, s2a, off);
-                            s1b += __shfl_xor_sync(0xffffffffu, s1b, off);
-                            s2b += __shfl_xor_sync(0xffffffffu, s2b, off);
-                        }
-                        if (rs == 0) {
-                            float* st = p.stats + (static_cast<size_t>(pair) * p.Co + n0 + col0 + chunk * 8 + cq * 2) * 2;
-                            atomicAdd(st, s1a); atomicAdd(st + 1, s2a);
-                            atomicAdd(st + 2, s1b); atomicAdd(st + 3, s2b);
+                    for (int i = 0; i < 16; ++i) a[i] = 0.f;
+#pragma unroll
+                    for (int i = 0; i < kGemmBM / 16; ++i) {
+                        const int r = rg + 16 * i;
+                        const uint4 u = *reinterpret_cast<const uint4*>(tile_y + (r * kChunks + ((kc + r) & (kChunks - 1))) * 16);
+                        const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            const float y0 = __uint_as_float(w[k] << 16), y1 = __uint_as_float(w[k] & 0xffff0000u);
+                            a[4 * k + 0] += y0; a[4 * k + 1] = fmaf(y0, y0, a[4 * k + 1]);
+                            a[4 * k + 2] += y1; a[4 * k + 3] = fmaf(y1, y1, a[4 * k + 3]);
                         }
                     }
+#pragma unroll
+                    for (int h = 8; h >= 1; h >>= 1) {
+                        const bool up = (lane & h) != 0;
+#pragma unroll
+                        for (int i = 0; i < h; ++i) {
+                            const float send = up ? a[i] : a[i + h];
+                            const float keep = up ? a[i + h] : a[i];
+                            a[i] = keep + __shfl_xor_sync(0xffffffffu, send, h);
+                        }
+                    }
+                    atomicAdd(p.stats + (static_cast<size_t>(pair) * p.Co + n0 + col0 + kc * 8) * 2 + rg, a[0]);
                 }
 #pragma unroll
                 for (int idx = et; idx < kGemmBM * kChunks; idx += 128) {
@@ -466,6 +532,25 @@ fepe_mlp_gemm_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __
         tcgen05_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols));
     }
+}
+
+// (a, d) of the fused-norm GEMM: x' = LeakyReLU(a y + d), a = gamma rstd, d = beta - mean a (the same fp32 expressions
+// as fepe_mlp_norm_kernel, so both paths produce the same bf16 activations).  One thread per channel pair; layout
+// ss[b][c/2] = (a_c, a_c+1, d_c, d_c+1).  With `clear` the statistics are zeroed for the next layer's accumulation.
+__global__ void __launch_bounds__(256) fepe_mlp_scale_shift_kernel(float* __restrict__ stats, const float* __restrict__ gamma,
+                                                                   const float* __restrict__ beta, float4* __restrict__ ss,
+                                                                   int total_pairs, int Co, int Nvalid, float eps, int clear) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;       // channel pair of (b, c)
+    if (i >= total_pairs) return;
+    const int c = (i % (Co / 2)) * 2;
+    float4* sp = reinterpret_cast<float4*>(stats) + i;         // (s1_c, s2_c, s1_c+1, s2_c+1)
+    const float4 v = *sp;
+    const float invN = 1.0f / static_cast<float>(Nvalid);
+    const float m0 = v.x * invN, m1 = v.z * invN;
+    const float var0 = fmaxf(v.y * invN - m0 * m0, 0.f), var1 = fmaxf(v.w * invN - m1 * m1, 0.f);
+    const float a0 = rsqrtf(var0 + eps) * gamma[c], a1 = rsqrtf(var1 + eps) * gamma[c + 1];
+    ss[i] = make_float4(a0, a1, beta[c] - m0 * a0, beta[c + 1] - m1 * a1);
+    if (clear) *sp = make_float4(0.f, 0.f, 0.f, 0.f);
 }
 
 // X'[m][c] = LeakyReLU(gamma[c] (Y[m][c] - mean[b][c]) rstd[b][c] + beta[c]); padded rows -> 0.
@@ -994,7 +1079,7 @@ static int launch_gemm(const void* X, const void* W, const GemmParams& p, cudaSt
     return static_cast<int>(cudaGetLastError());
 }
 
-template <int BN, int STAGES>
+template <int BN, int STAGES, bool FUSE>
 static int launch_gemm_persist(const void* X, const void* W, const GemmParams& p, cudaStream_t stream) {
     CUtensorMap ma, mw;
     if (!make_map(&ma, X, p.M, p.K, kGemmBM) || !make_map(&mw, W, p.Co, p.K, BN)) return FEPE_E_NODEVICE;
@@ -1003,7 +1088,7 @@ static int launch_gemm_persist(const void* X, const void* W, const GemmParams& p
     int dev = 0;
     cudaGetDevice(&dev);
     if (sms[dev & 63] == 0) {
-        cudaError_t e = cudaFuncSetAttribute(fepe_mlp_gemm_persist_kernel<BN, STAGES>,
+        cudaError_t e = cudaFuncSetAttribute(fepe_mlp_gemm_persist_kernel<BN, STAGES, FUSE>,
                                              cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         if (e != cudaSuccess) return static_cast<int>(e);
         int n = 0;
@@ -1013,7 +1098,7 @@ static int launch_gemm_persist(const void* X, const void* W, const GemmParams& p
     }
     const int tiles = (p.M / kGemmBM) * (p.Co / BN);
     const int grid = tiles < sms[dev & 63] ? tiles : sms[dev & 63];
-    fepe_mlp_gemm_persist_kernel<BN, STAGES><<<grid, kPersistThreads, smem, stream>>>(ma, mw, p);
+    fepe_mlp_gemm_persist_kernel<BN, STAGES, FUSE><<<grid, FUSE ? kPersistFuseThreads : kPersistThreads, smem, stream>>>(ma, mw, p);
     return static_cast<int>(cudaGetLastError());
 }
 
@@ -1092,7 +1177,8 @@ int fepe_mlp_gemm(const void* X, const void* W, const float* bias, void* Y, floa
     if (!X || !W || !Y || B <= 0 || Npad <= 0 || (Npad % fepe::kGemmBM) != 0 || Nvalid > Npad ||
         (K % fepe::kGemmBK) != 0 || (Co % 64) != 0)
         return FEPE_E_BADARG;
-    fepe::GemmParams p{B * Npad, K, Co, Npad, Nvalid, bias, static_cast<__nv_bfloat16*>(Y), stats};
+    if (reinterpret_cast<uintptr_t>(bias) & 15u) return FEPE_E_BADARG;   // read as 16-byte vectors
+    fepe::GemmParams p{B * Npad, K, Co, Npad, Nvalid, bias, static_cast<__nv_bfloat16*>(Y), stats, nullptr, 0.f};
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     // 2 stages / 2 CTAs per SM: the epilogue of one CTA overlaps the main loop of the other.  Measured faster
     // than 4 stages / 1 CTA per SM on every layer (profiles/r1_mlp_timing.txt).  FEPE_MLP_STAGES=2|4 overrides.
@@ -1102,14 +1188,39 @@ int fepe_mlp_gemm(const void* X, const void* W, const float* bias, void* Y, floa
     const bool tile_mode = mode != nullptr && strcmp(mode, "tile") == 0;
     if (!tile_mode && Co % 128 == 0) {
         const bool force128 = mode != nullptr && strcmp(mode, "persist128") == 0;
-        if (Co % 256 == 0 && !force128) return fepe::launch_gemm_persist<256, 4>(X, W, p, st);
-        return fepe::launch_gemm_persist<128, 6>(X, W, p, st);
+        if (Co % 256 == 0 && !force128) return fepe::launch_gemm_persist<256, 4, false>(X, W, p, st);
+        return fepe::launch_gemm_persist<128, 6, false>(X, W, p, st);
     }
     int stages = 2;
     if (const char* ev = getenv("FEPE_MLP_STAGES")) stages = (ev[0] == '2') ? 2 : 4;
     if (Co % 128 == 0)
         return stages == 2 ? fepe::launch_gemm<128, 2>(X, W, p, st) : fepe::launch_gemm<128, 4>(X, W, p, st);
     return stages == 2 ? fepe::launch_gemm<64, 2>(X, W, p, st) : fepe::launch_gemm<64, 4>(X, W, p, st);
+}
+
+// Fused variant for inference: the A operand is the previous layer's PRE-norm output Yprev [B*Npad, K] and the
+// InstanceNorm + LeakyReLU of that layer is applied to the operand tiles in shared memory (ss from fepe_mlp_scale_shift).
+int fepe_mlp_gemm_norm(const void* Yprev, const float* ss, float slope, const void* W, const float* bias, void* Y,
+                       float* stats, int B, int Npad, int Nvalid, int K, int Co, void* stream) {
+    if (!Yprev || !ss || !W || !Y || B <= 0 || Npad <= 0 || (Npad % fepe::kGemmBM) != 0 || Nvalid > Npad ||
+        (K % fepe::kGemmBK) != 0 || (Co % 128) != 0 || (reinterpret_cast<uintptr_t>(ss) & 15u) ||
+        (reinterpret_cast<uintptr_t>(bias) & 15u) || !(slope > 0.f && slope < 1.f))
+        return FEPE_E_BADARG;
+    fepe::GemmParams p{B * Npad, K, Co, Npad, Nvalid, bias, static_cast<__nv_bfloat16*>(Y), stats, ss, slope};
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (Co % 256 == 0) return fepe::launch_gemm_persist<256, 4, true>(Yprev, W, p, st);
+    return fepe::launch_gemm_persist<128, 6, true>(Yprev, W, p, st);
+}
+
+int fepe_mlp_scale_shift(float* stats, const float* gamma, const float* beta, float* ss, int B, int Co, int Nvalid,
+                         float eps, int clear_stats, void* stream) {
+    if (!stats || !gamma || !beta || !ss || B <= 0 || Co <= 0 || (Co & 1) || Nvalid <= 0 ||
+        (reinterpret_cast<uintptr_t>(stats) & 15u) || (reinterpret_cast<uintptr_t>(ss) & 15u))
+        return FEPE_E_BADARG;
+    const int total = B * (Co / 2);
+    fepe::fepe_mlp_scale_shift_kernel<<<(total + 255) / 256, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        stats, gamma, beta, reinterpret_cast<float4*>(ss), total, Co, Nvalid, eps, clear_stats);
+    return static_cast<int>(cudaGetLastError());
 }
 
 int fepe_mlp_norm(const void* Y, const float* stats, const float* gamma, const float* beta, void* X, int B, int Npad,

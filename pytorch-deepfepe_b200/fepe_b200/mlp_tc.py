@@ -31,6 +31,12 @@ class TensorCoreMLP:
             raise RuntimeError("TensorCoreMLP: the first layer supports at most 8 input channels")
         self._versions = None
         self._buf_key = None
+        # fuse_norm: InstanceNorm + LeakyReLU of layers 1-4 applied to the next GEMM's operand tiles in shared memory
+        # (fepe_mlp_gemm_norm) instead of a separate pass over memory; same bf16 results as the unfused kernels.
+        self.fuse_norm = True
+        # A Conv1d bias in front of an InstanceNorm cancels in the mean subtraction; the inference GEMMs skip it (the
+        # rounding of Y to bf16 is then relative to the centred scale of the channel, never to its offset).
+        self.drop_bias = True
 
     # -- parameters in the layouts the kernels want (refreshed when the module's parameters change) --
     def _refresh(self):
@@ -54,6 +60,7 @@ class TensorCoreMLP:
         if key != self._buf_key:
             self.act = [torch.empty(B * Npad, 1024, dtype=torch.bfloat16, device=dev) for _ in range(2)]
             self.stats = torch.empty(B, 1024, 2, dtype=torch.float32, device=dev)
+            self.ss = torch.empty(B, 512, 4, dtype=torch.float32, device=dev)
             self._buf_key = key
         return self.act, self.stats
 
@@ -74,14 +81,17 @@ class TensorCoreMLP:
             stats.zero_()
             _lib.check(lib.fepe_mlp_first(x0.data_ptr(), self.w0.data_ptr(), self.b[0].data_ptr(), ya.data_ptr(),
                                           stats.data_ptr(), B, N, Npad, Cin, 64, st), "fepe_mlp_first")
+            k = 64
+            bias = [0 if self.drop_bias else b.data_ptr() for b in self.b]
+            if self.fuse_norm:
+                return self._fused_tail(lib, st, ya, xa, stats, bias, B, N, Npad, dev, slope)
             _lib.check(lib.fepe_mlp_norm(ya.data_ptr(), stats.data_ptr(), self.gamma[0].data_ptr(),
                                          self.beta[0].data_ptr(), xa.data_ptr(), B, Npad, N, 64, self.eps[0], slope, st),
                        "fepe_mlp_norm")
-            k = 64
             for i in range(1, 5):
                 co = _CH[i]
                 stats.zero_()
-                _lib.check(lib.fepe_mlp_gemm(xa.data_ptr(), self.w[i].data_ptr(), self.b[i].data_ptr(), ya.data_ptr(),
+                _lib.check(lib.fepe_mlp_gemm(xa.data_ptr(), self.w[i].data_ptr(), bias[i], ya.data_ptr(),
                                              stats.data_ptr(), B, Npad, N, k, co, st), "fepe_mlp_gemm")
                 _lib.check(lib.fepe_mlp_norm(ya.data_ptr(), stats.data_ptr(), self.gamma[i].data_ptr(),
                                              self.beta[i].data_ptr(), xa.data_ptr(), B, Npad, N, co, self.eps[i], slope,
@@ -91,6 +101,29 @@ class TensorCoreMLP:
             weights = torch.empty(B, 1, N, dtype=torch.float32, device=dev)
             _lib.check(lib.fepe_mlp_last(xa.data_ptr(), self.w_last.data_ptr(), self.b_last, logits.data_ptr(),
                                          weights.data_ptr(), B, N, Npad, 256, st), "fepe_mlp_last")
+        return logits, weights
+
+
+    def _fused_tail(self, lib, st, src, dst, stats, bias, B, N, Npad, dev, slope):
+        """Layers 2-5 with the previous layer's norm fused into the GEMM operand path; `src` holds layer 1's pre-norm
+        output and `stats` its statistics."""
+        ss = self.ss
+        k = 64
+        for i in range(1, 5):
+            co = _CH[i]
+            _lib.check(lib.fepe_mlp_scale_shift(stats.data_ptr(), self.gamma[i - 1].data_ptr(), self.beta[i - 1].data_ptr(),
+                                                ss.data_ptr(), B, k, N, self.eps[i - 1], 1, st), "fepe_mlp_scale_shift")
+            _lib.check(lib.fepe_mlp_gemm_norm(src.data_ptr(), ss.data_ptr(), slope, self.w[i].data_ptr(), bias[i],
+                                              dst.data_ptr(), stats.data_ptr(), B, Npad, N, k, co, st),
+                       "fepe_mlp_gemm_norm")
+            src, dst = dst, src
+            k = co
+        _lib.check(lib.fepe_mlp_norm(src.data_ptr(), stats.data_ptr(), self.gamma[4].data_ptr(), self.beta[4].data_ptr(),
+                                     dst.data_ptr(), B, Npad, N, 256, self.eps[4], slope, st), "fepe_mlp_norm")
+        logits = torch.empty(B, 1, N, dtype=torch.float32, device=dev)
+        weights = torch.empty(B, 1, N, dtype=torch.float32, device=dev)
+        _lib.check(lib.fepe_mlp_last(dst.data_ptr(), self.w_last.data_ptr(), self.b_last, logits.data_ptr(),
+                                     weights.data_ptr(), B, N, Npad, 256, st), "fepe_mlp_last")
         return logits, weights
 
 

@@ -35,8 +35,31 @@ for B in (64, 512):
             dy = float((Y.float() - ref[0].float()).abs().max()); ds = float(((stats - ref[1]).abs() / (ref[1].abs() + 1.0)).max())
             t = ev(call)
             print(f"B={B} gemm K={K} Co={Co} {mode:10s}: {t*1e3:7.1f} us  {2*B*Npad*K*Co/t/1e9:7.1f} TFLOP/s  {(B*Npad*(K+Co)*2)/t/1e6:6.0f} GB/s  |dY| vs tile {dy:.3g}  rel dstats {ds:.2g}", flush=True)
-for mode in ("tile", "persist128", "persist"):
+# fused norm -> GEMM against norm kernel + GEMM, per layer
+os.environ["FEPE_MLP_GEMM"] = "persist"
+for B in (64, 512):
+    for K, Co in [(64, 128), (128, 1024), (1024, 512), (512, 256)]:
+        Yp = torch.randn(B * Npad, K, device="cuda").bfloat16(); W = (torch.randn(Co, K, device="cuda") / K ** 0.5).bfloat16()
+        X = torch.empty_like(Yp); Y = torch.empty(B * Npad, Co, device="cuda", dtype=torch.bfloat16)
+        ps = torch.rand(B, K, 2, device="cuda") * 1000 + 1000; g = torch.ones(K, device="cuda"); be = torch.zeros(K, device="cuda")
+        ss = torch.empty(B, K // 2, 4, device="cuda"); stats = torch.zeros(B, Co, 2, device="cuda")
+        s_ = torch.cuda.current_stream().cuda_stream
+        def unf():
+            lib.fepe_mlp_norm(Yp.data_ptr(), ps.data_ptr(), g.data_ptr(), be.data_ptr(), X.data_ptr(), B, Npad, N, K, 1e-5, 0.01, s_)
+            lib.fepe_mlp_gemm(X.data_ptr(), W.data_ptr(), 0, Y.data_ptr(), stats.data_ptr(), B, Npad, N, K, Co, s_)
+        def fus():
+            lib.fepe_mlp_scale_shift(ps.data_ptr(), g.data_ptr(), be.data_ptr(), ss.data_ptr(), B, K, N, 1e-5, 0, s_)
+            assert lib.fepe_mlp_gemm_norm(Yp.data_ptr(), ss.data_ptr(), 0.01, W.data_ptr(), 0, Y.data_ptr(), stats.data_ptr(), B, Npad, N, K, Co, s_) == 0
+        tu, tf = ev(unf), ev(fus)
+        print(f"B={B} K={K} Co={Co}: norm + gemm {tu*1e3:7.1f} us | fused {tf*1e3:7.1f} us ({2*B*Npad*K*Co/tf/1e9:7.1f} TFLOP/s)", flush=True)
+import fepe_b200.mlp_tc as _mt
+for mode, fuse in (("tile", False), ("persist128", False), ("persist", False), ("persist", True)):
     os.environ["FEPE_MLP_GEMM"] = mode
+    _orig = _mt.TensorCoreMLP.__init__
+    def _init(self, fw, _o=_orig, _f=fuse):
+        _o(self, fw); self.fuse_norm = _f
+    _mt.TensorCoreMLP.__init__ = _init
+    mode = mode + ("+fuse" if fuse else "")
     for B in (64, 512):
         ee = ErrorEstimator(4).cuda(); ee.tensor_cores = True
         x = torch.rand(B, 4, N, device="cuda")
@@ -50,3 +73,4 @@ for mode in ("tile", "persist128", "persist"):
     with torch.no_grad():
         t = ev(lambda: net({"matches_xy_ori": m}), iters=5, warm=2)
     print(f"{mode:10s} DeepFNet forward depth 5 B=512: {t:.2f} ms  {512/t*1e3:.0f} pairs/s", flush=True)
+    _mt.TensorCoreMLP.__init__ = _orig

@@ -64,6 +64,69 @@ def test_error_estimator_tensor_core_path(cin, B, N):
     assert float(((sm - ref_sm).abs() / ref_sm)[big].max()) < 0.15
 
 
+@pytest.mark.parametrize("B,N,K,Co", [(2, 100, 64, 128), (3, 1000, 128, 1024), (40, 1000, 1024, 512), (37, 900, 192, 384)])
+def test_gemm_norm_fused_equals_norm_then_gemm(B, N, K, Co):
+    """fepe_mlp_gemm_norm (InstanceNorm + LeakyReLU applied to the operand tiles in shared memory) against
+    fepe_mlp_norm followed by fepe_mlp_gemm: the same arithmetic, so Y is bit-identical and the statistics agree to
+    fp32 summation order."""
+    lib = _lib.lib()
+    torch.manual_seed(2)
+    st = torch.cuda.current_stream().cuda_stream
+    Npad = (N + 127) // 128 * 128
+    Yprev = (torch.randn(B, Npad, K, device="cuda") * 2 + 0.5).bfloat16()
+    Yprev[:, N:] = 0
+    pstats = torch.stack([Yprev[:, :N].float().sum(1), (Yprev[:, :N].float() ** 2).sum(1)], dim=2).contiguous()
+    gamma = torch.empty(K, device="cuda").uniform_(0.5, 1.5)
+    beta = torch.empty(K, device="cuda").uniform_(-0.3, 0.3)
+    W = (torch.randn(Co, K, device="cuda") / K ** 0.5).bfloat16()
+    X = torch.empty(B * Npad, K, device="cuda", dtype=torch.bfloat16)
+    Y0 = torch.empty(B * Npad, Co, device="cuda", dtype=torch.bfloat16)
+    Y1 = torch.full((B * Npad, Co), 3.0, device="cuda", dtype=torch.bfloat16)
+    s0 = torch.zeros(B, Co, 2, device="cuda")
+    s1 = torch.zeros(B, Co, 2, device="cuda")
+    ss = torch.empty(B, K // 2, 4, device="cuda")
+    assert lib.fepe_mlp_norm(Yprev.data_ptr(), pstats.data_ptr(), gamma.data_ptr(), beta.data_ptr(), X.data_ptr(), B, Npad,
+                             N, K, 1e-5, 0.01, st) == 0
+    assert lib.fepe_mlp_gemm(X.data_ptr(), W.data_ptr(), 0, Y0.data_ptr(), s0.data_ptr(), B, Npad, N, K, Co, st) == 0
+    keep = pstats.clone()
+    assert lib.fepe_mlp_scale_shift(pstats.data_ptr(), gamma.data_ptr(), beta.data_ptr(), ss.data_ptr(), B, K, N, 1e-5, 1,
+                                    st) == 0
+    assert lib.fepe_mlp_gemm_norm(Yprev.data_ptr(), ss.data_ptr(), 0.01, W.data_ptr(), 0, Y1.data_ptr(), s1.data_ptr(), B,
+                                  Npad, N, K, Co, st) == 0
+    torch.cuda.synchronize()
+    assert float(pstats.abs().max()) == 0.0                      # clear_stats
+    mean = keep[..., 0] / N
+    a = torch.rsqrt((keep[..., 1] / N - mean * mean).clamp_min(0) + 1e-5) * gamma
+    np.testing.assert_allclose(ss.reshape(B, K // 2, 2, 2)[:, :, 0].reshape(B, K).cpu(), a.cpu(), rtol=2e-6)
+    np.testing.assert_allclose(ss.reshape(B, K // 2, 2, 2)[:, :, 1].reshape(B, K).cpu(), (beta - mean * a).cpu(), rtol=1e-5,
+                               atol=1e-6)
+    assert torch.equal(Y0, Y1)
+    np.testing.assert_allclose(s1.cpu(), s0.cpu(), rtol=1e-4, atol=1e-3)
+
+
+@pytest.mark.parametrize("cin,B,N", [(4, 3, 1000), (7, 2, 333), (4, 40, 1000)])
+def test_error_estimator_fused_norm_equals_unfused(cin, B, N):
+    from fepe_b200.mlp_tc import TensorCoreMLP
+    torch.manual_seed(5)
+    ee = ErrorEstimator(cin).cuda()
+    with torch.no_grad():
+        for m in ee.fw:
+            if isinstance(m, torch.nn.InstanceNorm1d):
+                m.weight.uniform_(0.5, 1.5)
+                m.bias.uniform_(-0.3, 0.3)
+    x = torch.rand(B, cin, N, device="cuda")
+    tc = TensorCoreMLP(ee.fw)
+    with torch.no_grad():
+        tc.fuse_norm = False
+        l0, w0 = tc(x)
+        tc.fuse_norm = True
+        l1, w1 = tc(x)
+    torch.cuda.synchronize()
+    # identical bf16 activations layer by layer; only the fp32 statistics are summed in a different order
+    assert float((l0 - l1).abs().max()) < 2e-2 * max(1.0, float(l0.std()))
+    np.testing.assert_allclose(w1.cpu().numpy(), w0.cpu().numpy(), rtol=5e-2, atol=1e-7)
+
+
 def test_deepfnet_inference_with_tensor_core_mlp():
     torch.manual_seed(3)
     kw = dict(depth=5, image_size=[376, 1241, 3], if_quality=False)
