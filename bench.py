@@ -578,12 +578,14 @@ def run_c4(args):
             "vs_baseline": None, "dtype": "bf16 MLP (fp32 accumulate) + f32/f64 solver", "data": "synthetic",
             "config": {"workload": f"C4: DeepFNet forward depth 5 (5 ErrorEstimator evaluations on tcgen05 + 5 fused fits), "
                                    f"batch={B} x N={N}, inference", "batch_per_gpu": B, "ncorr": N},
-            "roofline": {"bound": "tensor", "kernel": "fepe_mlp_gemm_kernel (whole step counted)",
+            "roofline": {"bound": "tensor", "kernel": "fepe_mlp_gemm_persist_kernel (whole step counted)",
                          "achieved": flops / (secs / steps) / 1e12, "peak": peak_tf, "unit": "TFLOP/s",
                          "frac": flops / (secs / steps) / 1e12 / peak_tf, "traffic": None,
                          "note": "MLP flops of the step / step time: includes the memory-bound norm kernels and the fits"},
             "fp32_cudnn_mlp_pairs_per_sec": world * B * max(3, steps // 10) / secs32,
-            "gpu_launches": steps * (5 * 16 + 5)}
+            # per ErrorEstimator evaluation: first, 4 x scale_shift, 3 x gemm_norm, norm + gemm (the 128 -> 1024 layer
+            # keeps its norm kernel), last_norm = 11 launches; one fit launch per DeepFNet iteration
+            "gpu_launches": steps * (5 * 11 + 5)}
     if rank == 0:
         print(json.dumps(line), flush=True)
 

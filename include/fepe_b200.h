@@ -161,6 +161,9 @@ int fepe_mlp_scale_shift(float* stats, const float* gamma, const float* beta, fl
                          float eps, int clear_stats, void* stream);
 int fepe_mlp_gemm_norm(const void* Yprev, const float* ss, float slope, const void* W, const float* bias, void* Y,
                        float* stats, int B, int Npad, int Nvalid, int K, int Co, void* stream);
+/* fepe_mlp_last on the PRE-norm output Y [B*Npad, Ci] of the last block (its InstanceNorm + LeakyReLU fused in). */
+int fepe_mlp_last_norm(const void* Y, const float* ss, float slope, const float* W, float bias, float* logits,
+                       float* weights, int B, int N, int Npad, int Ci, void* stream);
 int fepe_mlp_last(const void* X, const float* W, float bias, float* logits, float* weights, int B, int N, int Npad,
                   int Ci, void* stream);
 /* training path: weight gradient of one Conv1d(k=1): dW[Co,Ci] += dY[M,Co]^T X[M,Ci] on tcgen05 (bf16 operands read

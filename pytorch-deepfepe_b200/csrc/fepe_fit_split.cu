@@ -295,7 +295,8 @@ constexpr int kResidPrefetch = 4;
 
 __global__ void __launch_bounds__(kResidThreads) fepe_resid_kernel(const FitParams p) {
     pdl_launch_dependents();
-    const size_t pair = blockIdx.x;
+    // Highest pair first: K1 walks the batch upwards, so the pairs it read last are the ones still in the 126 MB L2.
+    const size_t pair = gridDim.x - 1 - blockIdx.x;
     const int N = p.N;
     const int tid = threadIdx.x;
     const float4* gp = reinterpret_cast<const float4*>(p.matches) + pair * static_cast<size_t>(N);

@@ -385,16 +385,37 @@ fepe_mlp_gemm_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __
         const int cl = pos ^ (r0 & 7);
         const float2 slope2 = make_float2(p.slope, p.slope);
         uint32_t it = 0;
-        for (int j = 0; j < n_local; ++j) {
+        // (a, a, d, d) of channel pairs 0..3 of the chunk, requested one k-block ahead and before the wait for the
+        // stage: this role is the slowest stage of the pipeline, so its data are usually waiting and a load issued next
+        // to its use would be fully exposed (under the epilogue's store traffic an L1/L2 hit takes > 1000 cycles here).
+        // Measured alternatives (profiles/r1_mlp_fused_norm.md): no prefetch 860 us, this 772 us, two k-blocks ahead
+        // issued after the hand-over 950 us on the K = 1024 layer.
+        auto ss_ptr = [&](int j, int kb) {
             const int t = static_cast<int>(blockIdx.x) + j * static_cast<int>(gridDim.x);
             const int pair = ((t / n_tiles) * kGemmBM) / p.Npad;
-            const float4* ssp = reinterpret_cast<const float4*>(p.ss) + (static_cast<size_t>(pair) * p.K) / 2;
+            return reinterpret_cast<const float4*>(p.ss) + (static_cast<size_t>(pair) * p.K + kb * kGemmBK + cl * 8) / 2;
+        };
+        float4 cn[4];
+        if (n_local > 0) {
+            const float4* sp0 = ss_ptr(0, 0);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) cn[q] = __ldg(sp0 + q);
+        }
+        for (int j = 0; j < n_local; ++j) {
             for (int kb = 0; kb < num_kb; ++kb, ++it) {
                 const uint32_t s = it % STAGES;
                 const uint32_t ph = (it / STAGES) & 1u;
-                float4 c[4];                                    // (a, a, d, d) of channel pairs 0..3 of the chunk
+                float4 c[4];
 #pragma unroll
-                for (int q = 0; q < 4; ++q) c[q] = __ldg(ssp + (kb * kGemmBK + cl * 8) / 2 + q);
+                for (int q = 0; q < 4; ++q) c[q] = cn[q];
+                {
+                    const bool last_kb = kb + 1 == num_kb;
+                    if (!last_kb || j + 1 < n_local) {
+                        const float4* spn = last_kb ? ss_ptr(j + 1, 0) : ss_ptr(j, kb + 1);
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) cn[q] = __ldg(spn + q);
+                    }
+                }
                 mbar_wait(&full[s], ph);
                 unsigned char* sa = smem + s * kStageBytes + r0 * 128 + pos * 16;
 #pragma unroll
@@ -489,9 +510,9 @@ fepe_mlp_gemm_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __
                     // `stats`: ONE fully populated atomic instruction per warp and pass.
                     const int kc = 2 * wq + (lane >> 4);
                     const int rg = lane & 15;
-                    float a[16];
+                    float2 s1p[4], s2p[4];                     // packed fp32 pairs: FADD2 / FFMA2, two columns per instruction
 #pragma unroll
-                    for (int i = 0; i < 16; ++i) a[i] = 0.f;
+                    for (int k = 0; k < 4; ++k) { s1p[k] = make_float2(0.f, 0.f); s2p[k] = make_float2(0.f, 0.f); }
 #pragma unroll
                     for (int i = 0; i < kGemmBM / 16; ++i) {
                         const int r = rg + 16 * i;
@@ -499,10 +520,15 @@ fepe_mlp_gemm_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __
                         const uint32_t w[4] = {u.x, u.y, u.z, u.w};
 #pragma unroll
                         for (int k = 0; k < 4; ++k) {
-                            const float y0 = __uint_as_float(w[k] << 16), y1 = __uint_as_float(w[k] & 0xffff0000u);
-                            a[4 * k + 0] += y0; a[4 * k + 1] = fmaf(y0, y0, a[4 * k + 1]);
-                            a[4 * k + 2] += y1; a[4 * k + 3] = fmaf(y1, y1, a[4 * k + 3]);
+                            const float2 y = make_float2(__uint_as_float(w[k] << 16), __uint_as_float(w[k] & 0xffff0000u));
+                            s1p[k] = __fadd2_rn(s1p[k], y);
+                            s2p[k] = __ffma2_rn(y, y, s2p[k]);
                         }
+                    }
+                    float a[16];
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        a[4 * k + 0] = s1p[k].x; a[4 * k + 1] = s2p[k].x; a[4 * k + 2] = s1p[k].y; a[4 * k + 3] = s2p[k].y;
                     }
 #pragma unroll
                     for (int h = 8; h >= 1; h >>= 1) {
@@ -668,8 +694,12 @@ __global__ void __launch_bounds__(128) fepe_mlp_first_kernel(const float* __rest
 }
 
 // last layer (Ci -> 1) + softmax over the N rows of a pair.  One CTA per pair, 256 threads.
+// FUSE: X is the PRE-norm output of layer 5 and x' = LeakyReLU(a y + d), rounded to bf16 like the stored activation of
+// the unfused path, is formed on the fly from ss (fepe_mlp_scale_shift layout).
+template <bool FUSE>
 __global__ void fepe_mlp_last_kernel(const __nv_bfloat16* __restrict__ X, const float* __restrict__ W, float bias,
-                                     float* __restrict__ logits, float* __restrict__ weights, int N, int Npad, int Ci) {
+                                     float* __restrict__ logits, float* __restrict__ weights, int N, int Npad, int Ci,
+                                     const float4* __restrict__ ss, float slope) {
     extern __shared__ float sh[];            // [Npad] logits
     __shared__ float red[8];
     const int b = blockIdx.x;
@@ -683,6 +713,11 @@ __global__ void fepe_mlp_last_kernel(const __nv_bfloat16* __restrict__ X, const 
                 float w[8];
 #pragma unroll
                 for (int j = 0; j < 8; ++j) w[j] = __ldg(W + k + j);
+                float4 cf[4];
+                if constexpr (FUSE) {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) cf[j] = __ldg(ss + (static_cast<size_t>(b) * Ci + k) / 2 + j);
+                }
                 uint4 v[4];
 #pragma unroll
                 for (int u = 0; u < 4; ++u) {
@@ -694,7 +729,12 @@ __global__ void fepe_mlp_last_kernel(const __nv_bfloat16* __restrict__ X, const 
                     const uint32_t q[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {
-                        const float2 y = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&q[j]));
+                        float2 y = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&q[j]));
+                        if constexpr (FUSE) {
+                            const float2 tv = __ffma2_rn(y, make_float2(cf[j].x, cf[j].y), make_float2(cf[j].z, cf[j].w));
+                            const float2 sv = __fmul2_rn(tv, make_float2(slope, slope));
+                            y = __bfloat1622float2(__floats2bfloat162_rn(fmaxf(tv.x, sv.x), fmaxf(tv.y, sv.y)));
+                        }
                         acc[u] = fmaf(y.x, w[2 * j], acc[u]);
                         acc[u] = fmaf(y.y, w[2 * j + 1], acc[u]);
                     }
@@ -1245,8 +1285,20 @@ int fepe_mlp_first(const float* X0, const float* W, const float* bias, void* Y, 
 int fepe_mlp_last(const void* X, const float* W, float bias, float* logits, float* weights, int B, int N, int Npad,
                   int Ci, void* stream) {
     if (!X || !W || !logits || !weights || B <= 0 || (Ci & 7)) return FEPE_E_BADARG;
-    fepe::fepe_mlp_last_kernel<<<B, 256, Npad * sizeof(float), static_cast<cudaStream_t>(stream)>>>(
-        static_cast<const __nv_bfloat16*>(X), W, bias, logits, weights, N, Npad, Ci);
+    fepe::fepe_mlp_last_kernel<false><<<B, 256, Npad * sizeof(float), static_cast<cudaStream_t>(stream)>>>(
+        static_cast<const __nv_bfloat16*>(X), W, bias, logits, weights, N, Npad, Ci, nullptr, 0.f);
+    return static_cast<int>(cudaGetLastError());
+}
+
+// fepe_mlp_last on the PRE-norm output Y of the last block, with that block's InstanceNorm + LeakyReLU fused in.
+int fepe_mlp_last_norm(const void* Y, const float* ss, float slope, const float* W, float bias, float* logits,
+                       float* weights, int B, int N, int Npad, int Ci, void* stream) {
+    if (!Y || !ss || !W || !logits || !weights || B <= 0 || (Ci & 7) || (reinterpret_cast<uintptr_t>(ss) & 15u) ||
+        !(slope > 0.f && slope < 1.f))
+        return FEPE_E_BADARG;
+    fepe::fepe_mlp_last_kernel<true><<<B, 256, Npad * sizeof(float), static_cast<cudaStream_t>(stream)>>>(
+        static_cast<const __nv_bfloat16*>(Y), W, bias, logits, weights, N, Npad, Ci, reinterpret_cast<const float4*>(ss),
+        slope);
     return static_cast<int>(cudaGetLastError());
 }
 

@@ -47,6 +47,7 @@ _SIGNATURES = {
     "fepe_mlp_norm": (_c_i, [_c_p, _c_p, _c_p, _c_p, _c_p, _c_i, _c_i, _c_i, _c_i, _c_f, _c_f, _c_p]),
     "fepe_mlp_last": (_c_i, [_c_p, _c_p, _c_f, _c_p, _c_p, _c_i, _c_i, _c_i, _c_i, _c_p]),
     "fepe_mlp_scale_shift": (_c_i, [_c_p, _c_p, _c_p, _c_p, _c_i, _c_i, _c_i, _c_f, _c_i, _c_p]),
+    "fepe_mlp_last_norm": (_c_i, [_c_p, _c_p, _c_f, _c_p, _c_f, _c_p, _c_p, _c_i, _c_i, _c_i, _c_i, _c_p]),
     "fepe_mlp_gemm_norm": (_c_i, [_c_p, _c_p, _c_f, _c_p, _c_p, _c_p, _c_p, _c_i, _c_i, _c_i, _c_i, _c_i, _c_p]),
     "fepe_mlp_wgrad": (_c_i, [_c_p, _c_p, _c_p, _c_i, _c_i, _c_i, _c_p]),
     "fepe_mlp_normbwd": (_c_i, [_c_p, _c_p, _c_p, _c_p, _c_p, _c_p, _c_p, _c_i, _c_i, _c_i, _c_i, _c_f, _c_f, _c_p]),

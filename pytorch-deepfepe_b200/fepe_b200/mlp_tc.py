@@ -37,6 +37,7 @@ class TensorCoreMLP:
         # A Conv1d bias in front of an InstanceNorm cancels in the mean subtraction; the inference GEMMs skip it (the
         # rounding of Y to bf16 is then relative to the centred scale of the channel, never to its offset).
         self.drop_bias = True
+        self.unfused_k = (128,)         # operand widths whose layer keeps the separate norm kernel (see _fused_tail)
 
     # -- parameters in the layouts the kernels want (refreshed when the module's parameters change) --
     def _refresh(self):
@@ -61,6 +62,7 @@ class TensorCoreMLP:
             self.act = [torch.empty(B * Npad, 1024, dtype=torch.bfloat16, device=dev) for _ in range(2)]
             self.stats = torch.empty(B, 1024, 2, dtype=torch.float32, device=dev)
             self.ss = torch.empty(B, 512, 4, dtype=torch.float32, device=dev)
+            self.xn = torch.empty(B * Npad, 128, dtype=torch.bfloat16, device=dev)   # normalised operand of an unfused layer
             self._buf_key = key
         return self.act, self.stats
 
@@ -111,19 +113,30 @@ class TensorCoreMLP:
         k = 64
         for i in range(1, 5):
             co = _CH[i]
-            _lib.check(lib.fepe_mlp_scale_shift(stats.data_ptr(), self.gamma[i - 1].data_ptr(), self.beta[i - 1].data_ptr(),
-                                                ss.data_ptr(), B, k, N, self.eps[i - 1], 1, st), "fepe_mlp_scale_shift")
-            _lib.check(lib.fepe_mlp_gemm_norm(src.data_ptr(), ss.data_ptr(), slope, self.w[i].data_ptr(), bias[i],
-                                              dst.data_ptr(), stats.data_ptr(), B, Npad, N, k, co, st),
-                       "fepe_mlp_gemm_norm")
+            if k in self.unfused_k:
+                # thin operand, wide output (128 -> 1024): the GEMM is bound by its epilogue, the operand would be
+                # transformed once per n-tile, and the norm pass over 128 channels is cheap -- measured faster unfused
+                _lib.check(lib.fepe_mlp_norm(src.data_ptr(), stats.data_ptr(), self.gamma[i - 1].data_ptr(),
+                                             self.beta[i - 1].data_ptr(), self.xn.data_ptr(), B, Npad, N, k,
+                                             self.eps[i - 1], slope, st), "fepe_mlp_norm")
+                stats.zero_()
+                _lib.check(lib.fepe_mlp_gemm(self.xn.data_ptr(), self.w[i].data_ptr(), bias[i], dst.data_ptr(),
+                                             stats.data_ptr(), B, Npad, N, k, co, st), "fepe_mlp_gemm")
+            else:
+                _lib.check(lib.fepe_mlp_scale_shift(stats.data_ptr(), self.gamma[i - 1].data_ptr(),
+                                                    self.beta[i - 1].data_ptr(), ss.data_ptr(), B, k, N, self.eps[i - 1],
+                                                    1, st), "fepe_mlp_scale_shift")
+                _lib.check(lib.fepe_mlp_gemm_norm(src.data_ptr(), ss.data_ptr(), slope, self.w[i].data_ptr(), bias[i],
+                                                  dst.data_ptr(), stats.data_ptr(), B, Npad, N, k, co, st),
+                           "fepe_mlp_gemm_norm")
             src, dst = dst, src
             k = co
-        _lib.check(lib.fepe_mlp_norm(src.data_ptr(), stats.data_ptr(), self.gamma[4].data_ptr(), self.beta[4].data_ptr(),
-                                     dst.data_ptr(), B, Npad, N, 256, self.eps[4], slope, st), "fepe_mlp_norm")
+        _lib.check(lib.fepe_mlp_scale_shift(stats.data_ptr(), self.gamma[4].data_ptr(), self.beta[4].data_ptr(),
+                                            ss.data_ptr(), B, 256, N, self.eps[4], 0, st), "fepe_mlp_scale_shift")
         logits = torch.empty(B, 1, N, dtype=torch.float32, device=dev)
         weights = torch.empty(B, 1, N, dtype=torch.float32, device=dev)
-        _lib.check(lib.fepe_mlp_last(dst.data_ptr(), self.w_last.data_ptr(), self.b_last, logits.data_ptr(),
-                                     weights.data_ptr(), B, N, Npad, 256, st), "fepe_mlp_last")
+        _lib.check(lib.fepe_mlp_last_norm(src.data_ptr(), ss.data_ptr(), slope, self.w_last.data_ptr(), self.b_last,
+                                          logits.data_ptr(), weights.data_ptr(), B, N, Npad, 256, st), "fepe_mlp_last_norm")
         return logits, weights
 
 
