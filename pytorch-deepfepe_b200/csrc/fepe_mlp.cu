@@ -281,7 +281,11 @@ __device__ __forceinline__ void epi_group_sync(int g) {
     asm volatile("bar.sync %0, %1;" ::"r"(g + 1), "r"(128) : "memory");
 }
 
-template <int BN, int STAGES, bool FUSE>
+// FUSE: 0 = plain GEMM (8 epilogue warps); 1 = fused norm with 8 epilogue + 4 transform warps, (a, d) read from global
+// memory; 2 = fused norm with 4 epilogue warps (one group, four passes per 256-column tile: the fused layers are bound by
+// the operand path, not by the epilogue) + 8 transform warps, (a, d) of the k-block delivered by the TMA producer into a
+// 512-byte slot next to the stage (no global load, hence nothing for fence.proxy.async to wait for, in the transform).
+template <int BN, int STAGES, int FUSE>
 __global__ void __launch_bounds__(FUSE ? kPersistFuseThreads : kPersistThreads, 1)
 fepe_mlp_gemm_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w,
                              const GemmParams p) {
@@ -292,7 +296,11 @@ fepe_mlp_gemm_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __
     constexpr int kStageBytes = kABytes + kBBytes;
     constexpr int kChunks = kEpiCols / 8;                // 16-byte chunks per row of an epilogue tile
     constexpr uint32_t kTmemCols = 2 * BN;               // 256 or 512: a power of two
+    constexpr int kNG = (FUSE == 2) ? 1 : 2;             // epilogue groups of four warps
+    constexpr int kTW = (FUSE == 2) ? 8 : 4;             // transform warps (FUSE only): the last kTW warps of the CTA
+    constexpr int kSsBytes = kGemmBK * 8;                // (a, d) fp32 of the 64 channels of a k-block
     unsigned char* epi_tiles = smem + STAGES * kStageBytes;                  // [2 groups][128][64] bf16
+    unsigned char* ss_ring = epi_tiles + kEpiTileBytes;                      // FUSE == 2: [STAGES][512 B] in group 1's tile
     uint64_t* full = reinterpret_cast<uint64_t*>(epi_tiles + 2 * kEpiTileBytes);
     uint64_t* empty = full + STAGES;
     uint64_t* ready = empty + STAGES;                    // FUSE: the A tile of the stage has been transformed
@@ -309,8 +317,8 @@ fepe_mlp_gemm_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __
                         static_cast<int>(gridDim.x);
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); mbar_init(&ready[s], 4); }
-        for (int b = 0; b < 2; ++b) { mbar_init(&tmem_full[b], 1); mbar_init(&tmem_empty[b], 8); }
+        for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); mbar_init(&ready[s], kTW); }
+        for (int b = 0; b < 2; ++b) { mbar_init(&tmem_full[b], 1); mbar_init(&tmem_empty[b], 4 * kNG); }
         fence_barrier_init();
     }
     if (warp == 2) {
@@ -335,9 +343,14 @@ fepe_mlp_gemm_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __
                     const uint32_t ph = (it / STAGES) & 1u;
                     mbar_wait(&empty[s], ph ^ 1u);
                     unsigned char* sa = smem + s * kStageBytes;
-                    mbar_arrive_expect_tx(&full[s], kStageBytes);
+                    mbar_arrive_expect_tx(&full[s], kStageBytes + (FUSE == 2 ? kSsBytes : 0));
                     tma_load_2d(sa, &map_a, kb * kGemmBK, m0, &full[s]);
                     tma_load_2d(sa + kABytes, &map_w, kb * kGemmBK, n0, &full[s]);
+                    if constexpr (FUSE == 2) {
+                        const int pair = m0 / p.Npad;
+                        bulk_g2s(ss_ring + s * kSsBytes, p.ss + (static_cast<size_t>(pair) * p.K + kb * kGemmBK) * 2, kSsBytes,
+                                 &full[s]);
+                    }
                 }
             }
         }
@@ -372,14 +385,15 @@ fepe_mlp_gemm_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __
                 __syncwarp();
             }
         }
-    } else if (FUSE && warp >= 12) {
+    } else if (FUSE && warp >= 16 - kTW) {
         // ---------------- operand transform (fused InstanceNorm + LeakyReLU of the previous layer) ----------------
         // The A tile holds the previous layer's PRE-norm output; x' = LeakyReLU(a y + d) with the per-(pair, channel)
         // (a, d) of fepe_mlp_scale_shift is applied in place before the MMA reads the stage.  Thread tt owns the
         // physical 16-byte chunk `pos` of rows r0, r0 + 16, ...; under the 128-byte swizzle that is the logical chunk
         // pos ^ (r0 & 7) for all of them (16 i leaves r & 7 unchanged), so its eight channels -- and their (a, d),
         // requested before the stage's data are waited for -- are the same for every row of a k-block.
-        const int tt = static_cast<int>(threadIdx.x) - 384;
+        constexpr int kRowStep = kTW * 4;                       // rows between two chunks of a thread (16 or 32)
+        const int tt = static_cast<int>(threadIdx.x) - (kPersistFuseThreads - kTW * 32);
         const int pos = tt & 7;
         const int r0 = tt >> 3;
         const int cl = pos ^ (r0 & 7);
@@ -396,7 +410,7 @@ fepe_mlp_gemm_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __
             return reinterpret_cast<const float4*>(p.ss) + (static_cast<size_t>(pair) * p.K + kb * kGemmBK + cl * 8) / 2;
         };
         float4 cn[4];
-        if (n_local > 0) {
+        if (FUSE == 1 && n_local > 0) {
             const float4* sp0 = ss_ptr(0, 0);
 #pragma unroll
             for (int q = 0; q < 4; ++q) cn[q] = __ldg(sp0 + q);
@@ -406,9 +420,9 @@ fepe_mlp_gemm_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __
                 const uint32_t s = it % STAGES;
                 const uint32_t ph = (it / STAGES) & 1u;
                 float4 c[4];
+                if constexpr (FUSE == 1) {
 #pragma unroll
-                for (int q = 0; q < 4; ++q) c[q] = cn[q];
-                {
+                    for (int q = 0; q < 4; ++q) c[q] = cn[q];
                     const bool last_kb = kb + 1 == num_kb;
                     if (!last_kb || j + 1 < n_local) {
                         const float4* spn = last_kb ? ss_ptr(j + 1, 0) : ss_ptr(j, kb + 1);
@@ -417,10 +431,15 @@ fepe_mlp_gemm_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __
                     }
                 }
                 mbar_wait(&full[s], ph);
+                if constexpr (FUSE == 2) {
+                    const float4* sl = reinterpret_cast<const float4*>(ss_ring + s * kSsBytes) + cl * 4;
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) c[q] = sl[q];
+                }
                 unsigned char* sa = smem + s * kStageBytes + r0 * 128 + pos * 16;
 #pragma unroll
-                for (int i = 0; i < kGemmBM / 16; ++i) {
-                    uint4* ptr = reinterpret_cast<uint4*>(sa + i * 2048);
+                for (int i = 0; i < kGemmBM / kRowStep; ++i) {
+                    uint4* ptr = reinterpret_cast<uint4*>(sa + i * (kRowStep * 128));
                     const uint4 u = *ptr;
                     const uint32_t w[4] = {u.x, u.y, u.z, u.w};
                     uint32_t o[4];
@@ -439,7 +458,7 @@ fepe_mlp_gemm_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __
                 if (lane == 0) mbar_arrive(&ready[s]);
             }
         }
-    } else if (warp >= 4 && warp < 12) {
+    } else if (warp >= 4 && warp < 4 + 4 * kNG) {
         // ---------------- epilogue groups ----------------
         const int ew = warp - 4;
         const int g = ew >> 2;                                // column half of the accumulator
@@ -459,8 +478,8 @@ fepe_mlp_gemm_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __
             mbar_wait(&tmem_full[b], use & 1u);
             tcgen05_fence_after();
 #pragma unroll 1
-            for (int cc = 0; cc < BN / 2; cc += kEpiCols) {
-                const int col0 = g * (BN / 2) + cc;           // first accumulator column of this pass
+            for (int cc = 0; cc < BN / kNG; cc += kEpiCols) {
+                const int col0 = g * (BN / kNG) + cc;         // first accumulator column of this pass
 #pragma unroll
                 for (int c = 0; c < kEpiCols; c += 32) {
                     uint32_t v[32];
@@ -495,7 +514,7 @@ fepe_mlp_gemm_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __
                             make_uint4(pk[0], pk[1], pk[2], pk[3]);
                     }
                 }
-                if (cc + kEpiCols >= BN / 2) {                // last read of this accumulator buffer: hand it back
+                if (cc + kEpiCols >= BN / kNG) {              // last read of this accumulator buffer: hand it back
                     tcgen05_fence_before();
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&tmem_empty[b]);
@@ -1119,7 +1138,7 @@ static int launch_gemm(const void* X, const void* W, const GemmParams& p, cudaSt
     return static_cast<int>(cudaGetLastError());
 }
 
-template <int BN, int STAGES, bool FUSE>
+template <int BN, int STAGES, int FUSE>
 static int launch_gemm_persist(const void* X, const void* W, const GemmParams& p, cudaStream_t stream) {
     CUtensorMap ma, mw;
     if (!make_map(&ma, X, p.M, p.K, kGemmBM) || !make_map(&mw, W, p.Co, p.K, BN)) return FEPE_E_NODEVICE;
@@ -1228,8 +1247,8 @@ int fepe_mlp_gemm(const void* X, const void* W, const float* bias, void* Y, floa
     const bool tile_mode = mode != nullptr && strcmp(mode, "tile") == 0;
     if (!tile_mode && Co % 128 == 0) {
         const bool force128 = mode != nullptr && strcmp(mode, "persist128") == 0;
-        if (Co % 256 == 0 && !force128) return fepe::launch_gemm_persist<256, 4, false>(X, W, p, st);
-        return fepe::launch_gemm_persist<128, 6, false>(X, W, p, st);
+        if (Co % 256 == 0 && !force128) return fepe::launch_gemm_persist<256, 4, 0>(X, W, p, st);
+        return fepe::launch_gemm_persist<128, 6, 0>(X, W, p, st);
     }
     int stages = 2;
     if (const char* ev = getenv("FEPE_MLP_STAGES")) stages = (ev[0] == '2') ? 2 : 4;
@@ -1248,8 +1267,14 @@ int fepe_mlp_gemm_norm(const void* Yprev, const float* ss, float slope, const vo
         return FEPE_E_BADARG;
     fepe::GemmParams p{B * Npad, K, Co, Npad, Nvalid, bias, static_cast<__nv_bfloat16*>(Y), stats, ss, slope};
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    if (Co % 256 == 0) return fepe::launch_gemm_persist<256, 4, true>(Yprev, W, p, st);
-    return fepe::launch_gemm_persist<128, 6, true>(Yprev, W, p, st);
+    // FEPE_MLP_FUSE=1 selects the first fused variant (8 epilogue + 4 transform warps, (a, d) from global memory)
+    const char* fv = getenv("FEPE_MLP_FUSE");
+    if (fv != nullptr && fv[0] == '1') {
+        if (Co % 256 == 0) return fepe::launch_gemm_persist<256, 4, 1>(Yprev, W, p, st);
+        return fepe::launch_gemm_persist<128, 6, 1>(Yprev, W, p, st);
+    }
+    if (Co % 256 == 0) return fepe::launch_gemm_persist<256, 4, 2>(Yprev, W, p, st);
+    return fepe::launch_gemm_persist<128, 6, 2>(Yprev, W, p, st);
 }
 
 int fepe_mlp_scale_shift(float* stats, const float* gamma, const float* beta, float* ss, int B, int Co, int Nvalid,

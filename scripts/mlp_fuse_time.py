@@ -36,9 +36,13 @@ for B in ((512,) if "--ncu" in sys.argv else (64, 512)):
             assert lib.fepe_mlp_gemm_norm(Yp.data_ptr(), ss.data_ptr(), 0.01, W.data_ptr(), 0, Y.data_ptr(), stats.data_ptr(), B, Npad, N, K, Co, s_) == 0
         if "--ncu" in sys.argv:
             fus(); fus(); torch.cuda.synchronize(); sys.exit(0)
-        tu, tf = ev(unf), ev(fus)
-        print(f"B={B} K={K} Co={Co}: norm + gemm {tu*1e3:7.1f} us | fused {tf*1e3:7.1f} us ({2*B*Npad*K*Co/tf/1e9:7.1f} TFLOP/s)", flush=True)
-for fuse in (False, True):
+        tu = ev(unf)
+        os.environ["FEPE_MLP_FUSE"] = "1"; tf1 = ev(fus)
+        os.environ["FEPE_MLP_FUSE"] = "2"; tf = ev(fus)
+        print(f"B={B} K={K} Co={Co}: norm + gemm {tu*1e3:7.1f} us | fused v1 {tf1*1e3:7.1f} us | fused v2 {tf*1e3:7.1f} us ({2*B*Npad*K*Co/tf/1e9:7.1f} TFLOP/s)", flush=True)
+for fuse, fv in ((False, "2"), (True, "1"), (True, "2")):
+    os.environ["FEPE_MLP_FUSE"] = fv
+    print(f"-- FEPE_MLP_FUSE={fv}")
     for B in (64, 512):
         ee = ErrorEstimator(4).cuda(); ee.tensor_cores = True
         x = torch.rand(B, 4, N, device="cuda")
