@@ -1267,14 +1267,17 @@ int fepe_mlp_gemm_norm(const void* Yprev, const float* ss, float slope, const vo
         return FEPE_E_BADARG;
     fepe::GemmParams p{B * Npad, K, Co, Npad, Nvalid, bias, static_cast<__nv_bfloat16*>(Y), stats, ss, slope};
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    // FEPE_MLP_FUSE=1 selects the first fused variant (8 epilogue + 4 transform warps, (a, d) from global memory)
+    // Default: variant 1 (8 epilogue + 4 transform warps, (a, d) prefetched from global memory).  FEPE_MLP_FUSE=2
+    // selects variant 2 (4 epilogue + 8 transform warps, (a, d) through a shared-memory slot of the stage): measured
+    // equal or slower on every layer (profiles/r1_mlp_fused_norm.md) -- the fused layers are bound by the bytes in flight
+    // through the L2 and by shared-memory bandwidth, not by the transform's latency -- kept as the tested alternative.
     const char* fv = getenv("FEPE_MLP_FUSE");
-    if (fv != nullptr && fv[0] == '1') {
-        if (Co % 256 == 0) return fepe::launch_gemm_persist<256, 4, 1>(Yprev, W, p, st);
-        return fepe::launch_gemm_persist<128, 6, 1>(Yprev, W, p, st);
+    if (fv != nullptr && fv[0] == '2') {
+        if (Co % 256 == 0) return fepe::launch_gemm_persist<256, 4, 2>(Yprev, W, p, st);
+        return fepe::launch_gemm_persist<128, 6, 2>(Yprev, W, p, st);
     }
-    if (Co % 256 == 0) return fepe::launch_gemm_persist<256, 4, 2>(Yprev, W, p, st);
-    return fepe::launch_gemm_persist<128, 6, 2>(Yprev, W, p, st);
+    if (Co % 256 == 0) return fepe::launch_gemm_persist<256, 4, 1>(Yprev, W, p, st);
+    return fepe::launch_gemm_persist<128, 6, 1>(Yprev, W, p, st);
 }
 
 int fepe_mlp_scale_shift(float* stats, const float* gamma, const float* beta, float* ss, int B, int Co, int Nvalid,
