@@ -65,13 +65,16 @@ __device__ __forceinline__ void pass_dist(const float4* __restrict__ sp, int N, 
 // Register-tile variants of passes 1+2 for threads that own at most TILE correspondences: one round of
 // shared-memory loads serves both passes, and every chain (sum, sqrt) has TILE-way instruction-level
 // parallelism -- these passes are latency-bound, not throughput-bound.
-template <int TILE>
+// LAST_ONLY: the caller guarantees (TILE - 1) * stride <= N, i.e. only the last element of a thread can lie beyond N
+// (N = 1000 with 64 threads x 16: elements 0..14 reach 959) -- no bounds test, select or predicate for the others.
+template <int TILE, bool LAST_ONLY = false>
 __device__ __forceinline__ void tile_load(const float4* __restrict__ sp, int N, int start, int stride,
                                           float4 (&q)[TILE]) {
 #pragma unroll
     for (int u = 0; u < TILE; ++u) {
         const int i = start + u * stride;
-        q[u] = (i < N) ? sp[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+        if (LAST_ONLY && u < TILE - 1) q[u] = sp[i];
+        else q[u] = (i < N) ? sp[i] : make_float4(0.f, 0.f, 0.f, 0.f);
     }
 }
 template <int TILE>
@@ -85,7 +88,7 @@ __device__ __forceinline__ void tile_sums(const float4 (&q)[TILE], float (&out)[
     out[2] = (c[0] + c[1]) + (c[2] + c[3]);
     out[3] = (d[0] + d[1]) + (d[2] + d[3]);
 }
-template <int TILE>
+template <int TILE, bool LAST_ONLY = false>
 __device__ __forceinline__ void tile_dist(const float4 (&q)[TILE], int N, int start, int stride, float ax, float ay,
                                           const PairNorm& h, float (&out)[2]) {
     float d1[4] = {0.f, 0.f, 0.f, 0.f}, d2[4] = {0.f, 0.f, 0.f, 0.f};
@@ -94,7 +97,7 @@ __device__ __forceinline__ void tile_dist(const float4 (&q)[TILE], int N, int st
     for (int u = 0; u < TILE; ++u) {
         const float u1 = fmaf(ax, q[u].x, o1x), v1 = fmaf(ay, q[u].y, o1y);
         const float u2 = fmaf(ax, q[u].z, o2x), v2 = fmaf(ay, q[u].w, o2y);
-        const bool live = start + u * stride < N;
+        const bool live = (LAST_ONLY && u < TILE - 1) ? true : (start + u * stride < N);
         d1[u & 3] += live ? approx_sqrt(fmaf(u1, u1, v1 * v1)) : 0.f;
         d2[u & 3] += live ? approx_sqrt(fmaf(u2, u2, v2 * v2)) : 0.f;
     }

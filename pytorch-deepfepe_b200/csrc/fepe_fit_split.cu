@@ -94,7 +94,8 @@ __global__ void __launch_bounds__(kGramThreads, 1) fepe_gram_kernel(const FitPar
     const float ax = p.ax, bx = p.bx, ay = p.ay, by = p.by;
     float* red_t = red + team * T * 8;                      // [T][8]: 0..3 sums, 4..5 distances
     double* gram_t = gram_w + team * T * 36;                // [T][36]
-    const bool reduce_in_stage = p.ring.stage_bytes >= T * 36 * 32 * 8;
+    constexpr int kRedStride = 33;                          // doubles per (warp, entry) row: 32 lanes + 1 of padding
+    const bool reduce_in_stage = p.ring.stage_bytes >= T * 36 * kRedStride * 8;
 
     for (int j = team; j < n_local; j += G) {
         const int stage = j % S;
@@ -115,7 +116,12 @@ __global__ void __launch_bounds__(kGramThreads, 1) fepe_gram_kernel(const FitPar
         PairNorm h;
         float sums[4], dist[2] = {0.f, 0.f};
         const bool tiled = N <= kHartleyTile * TS;           // every thread owns <= kHartleyTile correspondences
-        if (tiled) {
+        const bool last_only = tiled && N >= (kHartleyTile - 1) * TS;   // only a thread's last element can be beyond N
+        if (last_only) {
+            float4 q[kHartleyTile];
+            tile_load<kHartleyTile, true>(sp, N, tt, TS, q);
+            tile_sums(q, sums);
+        } else if (tiled) {
             float4 q[kHartleyTile];
             tile_load(sp, N, tt, TS, q);
             tile_sums(q, sums);
@@ -136,8 +142,12 @@ __global__ void __launch_bounds__(kGramThreads, 1) fepe_gram_kernel(const FitPar
             }
         }
         finish_norm(h, sums, dist, N, ax, bx, ay, by, false);
-        if (tiled) {
+        if (last_only) {
             float4 q[kHartleyTile];                          // second round of loads: cheaper than 64 live registers
+            tile_load<kHartleyTile, true>(sp, N, tt, TS, q);
+            tile_dist<kHartleyTile, true>(q, N, tt, TS, ax, ay, h, dist);
+        } else if (tiled) {
+            float4 q[kHartleyTile];
             tile_load(sp, N, tt, TS, q);
             tile_dist(q, N, tt, TS, ax, ay, h, dist);
         } else {
@@ -163,23 +173,25 @@ __global__ void __launch_bounds__(kGramThreads, 1) fepe_gram_kernel(const FitPar
         if (reduce_in_stage) {
             // Cross-lane reduction through the pair's own stage (its correspondences are dead now): every lane
             // stores its 36 partial sums, thread e of the team adds up the T*32 partials of entry e.  A third of
-            // the instructions of the shuffle reduce-scatter (no selects), and no per-warp second level.
+            // the instructions of the shuffle reduce-scatter (no selects), and no per-warp second level.  Rows are
+            // padded to 33 doubles: the 16 lanes of a half warp (consecutive entries, same column) then read 16
+            // different 8-byte banks with plain immediate offsets -- no rotation arithmetic in front of the loads.
             team_sync<T>(team);                              // all reads of the stage are done
-            double* tb = reinterpret_cast<double*>(sb);      // [T*36][32]
+            double* tb = reinterpret_cast<double*>(sb);      // [T*36][33]
 #pragma unroll
-            for (int e = 0; e < 36; ++e) tb[(wt * 36 + e) * 32 + lane] = acc[e];
+            for (int e = 0; e < 36; ++e) tb[(wt * 36 + e) * kRedStride + lane] = acc[e];
             team_sync<T>(team);
             const int e = (T == 1) ? lane : tt;              // T == 1: entries 32..35 in a second trip below
             if (e < 36) {
                 double tot = 0.0;
 #pragma unroll
                 for (int w = 0; w < T; ++w) {
-                    const double* row = tb + (w * 36 + e) * 32;
+                    const double* row = tb + (w * 36 + e) * kRedStride;
 #pragma unroll
                     for (int k = 0; k < 32; k += 16) {       // 16 loads in flight, pairwise tree: depth 4 instead of 16
                         double v[16];
 #pragma unroll
-                        for (int u = 0; u < 16; ++u) v[u] = row[(k + u + e) & 31];   // rotated: conflict-free across entries
+                        for (int u = 0; u < 16; ++u) v[u] = row[k + u];
 #pragma unroll
                         for (int u = 0; u < 8; ++u) v[u] += v[u + 8];
 #pragma unroll
@@ -191,10 +203,10 @@ __global__ void __launch_bounds__(kGramThreads, 1) fepe_gram_kernel(const FitPar
             }
             if constexpr (T == 1) {
                 if (lane < 4) {
-                    const double* row = tb + (32 + lane) * 32;
+                    const double* row = tb + (32 + lane) * kRedStride;
                     double t0 = 0.0, t1 = 0.0;
 #pragma unroll
-                    for (int k = 0; k < 32; k += 2) { t0 += row[(k + lane) & 31]; t1 += row[(k + 1 + lane) & 31]; }
+                    for (int k = 0; k < 32; k += 2) { t0 += row[k]; t1 += row[k + 1]; }
                     st[16 + 32 + lane] = t0 + t1;
                 }
             }

@@ -3,9 +3,12 @@
 // followed by InstanceNorm1d(affine) (statistics over the N correspondences of ONE pair) and
 // LeakyReLU(0.01).
 //
-//   fepe_mlp_gemm_kernel   Y[M,Co] = X[M,Ci] . W[Co,Ci]^T + b   bf16 in, fp32 accumulate in TMEM
-//                          (tcgen05.mma, operands staged by TMA with 128-byte swizzle), bf16 out,
-//                          plus per-(pair, channel) sum / sum of squares for the InstanceNorm that follows.
+//   fepe_mlp_gemm_persist_kernel   Y[M,Co] = X[M,Ci] . W[Co,Ci]^T + b   bf16 in, fp32 accumulate in TMEM
+//                          (tcgen05.mma, operands staged by TMA with 128-byte swizzle), bf16 out, plus per-(pair,
+//                          channel) sum / sum of squares for the InstanceNorm that follows.  Persistent CTAs, accumulator
+//                          double-buffered in TMEM, 128 x 256 tiles; optionally with the PREVIOUS block's InstanceNorm +
+//                          LeakyReLU applied to the operand tiles in shared memory (fepe_mlp_gemm_norm).
+//   fepe_mlp_gemm_kernel   the same GEMM, one tile per CTA (Co % 128 != 0, and the A/B reference of the persistent one).
 //   fepe_mlp_norm_kernel   X'[M,Co] = LeakyReLU(gamma (Y - mean) rstd + beta), bf16 (memory bound).
 //   fepe_mlp_first_kernel  layer 1 (Ci = 4..8: too thin for a GEMM tile) on CUDA cores.
 //   fepe_mlp_last_kernel   layer 6 (Co = 1) + softmax over the N correspondences of a pair.
@@ -13,8 +16,9 @@
 // Rows: M = B * Npad, Npad = N rounded up to 128 so that a 128-row tile never straddles two pairs;
 // padded rows are excluded from the statistics and written as zeros.
 //
-// Warp roles in the GEMM CTA (256 threads): warp 0 = TMA producer, warp 1 = MMA issuer (one elected
-// lane), warp 2 = TMEM allocator, warps 4-7 = epilogue (TMEM lane quarter = warp % 4).
+// Warp roles in the one-tile GEMM CTA (256 threads): warp 0 = TMA producer, warp 1 = MMA issuer (one elected
+// lane), warp 2 = TMEM allocator, warps 4-7 = epilogue (TMEM lane quarter = warp % 4); the persistent kernel's roles
+// are described in front of it.
 #include <cuda.h>
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
