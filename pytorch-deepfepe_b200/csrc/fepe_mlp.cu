@@ -285,6 +285,61 @@ __device__ __forceinline__ void epi_group_sync(int g) {
     asm volatile("bar.sync %0, %1;" ::"r"(g + 1), "r"(128) : "memory");
 }
 
+// A 128 x 64 bf16 tile in shared memory as 16-byte chunks of 8 columns, chunk k of row r at slot (k + r) mod 8: a quarter
+// warp (8 consecutive rows of one chunk, or the 8 chunks of one row) always touches 8 different slots = all 32 banks once.
+__device__ __forceinline__ unsigned char* tile64_chunk(unsigned char* tile, int r, int k) {
+    return tile + (r * (kEpiCols / 8) + ((k + r) & (kEpiCols / 8 - 1))) * 16;
+}
+// Column statistics of such a tile, called by the four warps (wq = 0..3) of a 128-thread group.  Warp wq owns the chunks
+// 2 wq and 2 wq + 1; lane = (chunk half, row residue rg = lane % 16) reads rows rg, rg + 16, ... of its chunk as 16-byte
+// vectors into 16 independent accumulators (packed FADD2 / FFMA2: a[4k] / a[4k+2] = sums, a[4k+1] / a[4k+3] = sums of
+// squares of columns 2k / 2k+1).  A reduce-scatter over the 16 row residues (15 exchanges) leaves entry rg in lane rg,
+// i.e. the chunk's 16 consecutive floats of `stats` ([column][sum, sum of squares]): ONE fully populated atomic
+// instruction per warp.  `stats64` points at the statistics of the tile's first column.
+__device__ __forceinline__ void tile64_stats(unsigned char* tile, int wq, int lane, float* stats64) {
+    const int kc = 2 * wq + (lane >> 4);
+    const int rg = lane & 15;
+    float2 s1p[4], s2p[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { s1p[k] = make_float2(0.f, 0.f); s2p[k] = make_float2(0.f, 0.f); }
+#pragma unroll
+    for (int i = 0; i < kGemmBM / 16; ++i) {
+        const uint4 u = *reinterpret_cast<const uint4*>(tile64_chunk(tile, rg + 16 * i, kc));
+        const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const float2 y = make_float2(__uint_as_float(w[k] << 16), __uint_as_float(w[k] & 0xffff0000u));
+            s1p[k] = __fadd2_rn(s1p[k], y);
+            s2p[k] = __ffma2_rn(y, y, s2p[k]);
+        }
+    }
+    float a[16];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        a[4 * k + 0] = s1p[k].x; a[4 * k + 1] = s2p[k].x; a[4 * k + 2] = s1p[k].y; a[4 * k + 3] = s2p[k].y;
+    }
+#pragma unroll
+    for (int h = 8; h >= 1; h >>= 1) {
+        const bool up = (lane & h) != 0;
+#pragma unroll
+        for (int i = 0; i < h; ++i) {
+            const float send = up ? a[i] : a[i + h];
+            const float keep = up ? a[i + h] : a[i];
+            a[i] = keep + __shfl_xor_sync(0xffffffffu, send, h);
+        }
+    }
+    atomicAdd(stats64 + kc * 16 + rg, a[0]);
+}
+// Coalesced copy of the tile to Y (row pitch ld elements): thread et of the group moves 8 chunks, 8 consecutive threads
+// one 128-byte row segment.  `y64` points at the tile's first element.
+__device__ __forceinline__ void tile64_store(unsigned char* tile, int et, __nv_bfloat16* y64, int ld) {
+#pragma unroll
+    for (int idx = et; idx < kGemmBM * (kEpiCols / 8); idx += 128) {
+        const int r = idx / (kEpiCols / 8), k = idx % (kEpiCols / 8);
+        *reinterpret_cast<uint4*>(y64 + static_cast<size_t>(r) * ld + k * 8) = *reinterpret_cast<const uint4*>(tile64_chunk(tile, r, k));
+    }
+}
+
 // FUSE: 0 = plain GEMM (8 epilogue warps); 1 = fused norm with 8 epilogue + 4 transform warps, (a, d) read from global
 // memory; 2 = fused norm with 4 epilogue warps (one group, four passes per 256-column tile: the fused layers are bound by
 // the operand path, not by the epilogue) + 8 transform warps, (a, d) of the k-block delivered by the TMA producer into a
@@ -298,7 +353,6 @@ fepe_mlp_gemm_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __
     constexpr int kABytes = kGemmBM * kGemmBK * 2;       // 16 KB
     constexpr int kBBytes = BN * kGemmBK * 2;
     constexpr int kStageBytes = kABytes + kBBytes;
-    constexpr int kChunks = kEpiCols / 8;                // 16-byte chunks per row of an epilogue tile
     constexpr uint32_t kTmemCols = 2 * BN;               // 256 or 512: a power of two
     constexpr int kNG = (FUSE == 2) ? 1 : 2;             // epilogue groups of four warps
     constexpr int kTW = (FUSE == 2) ? 8 : 4;             // transform warps (FUSE only): the last kTW warps of the CTA
@@ -514,8 +568,7 @@ fepe_mlp_gemm_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __
                             pk[jj] = *reinterpret_cast<const uint32_t*>(&h);
                         }
                         const int chunk = (c >> 3) + gg;
-                        *reinterpret_cast<uint4*>(tile_y + (row * kChunks + ((chunk + row) & (kChunks - 1))) * 16) =
-                            make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                        *reinterpret_cast<uint4*>(tile64_chunk(tile_y, row, chunk)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
                     }
                 }
                 if (cc + kEpiCols >= BN / kNG) {              // last read of this accumulator buffer: hand it back
@@ -524,53 +577,9 @@ fepe_mlp_gemm_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __
                     if (lane == 0) mbar_arrive(&tmem_empty[b]);
                 }
                 epi_group_sync(g);
-                if (p.stats != nullptr) {
-                    // Column statistics of the 128 x 64 tile.  Warp wq owns the 16-byte chunks 2 wq and 2 wq + 1; lane =
-                    // (chunk half, row residue rg = lane % 16) reads rows rg, rg + 16, ... of its chunk as 16-byte vectors
-                    // (a quarter warp = 8 consecutive rows of one chunk = 8 different slots) into 16 independent
-                    // accumulators a[2c] = sum, a[2c+1] = sum of squares of column c.  A reduce-scatter over the 16 row
-                    // residues (15 exchanges) leaves entry rg in lane rg, i.e. the chunk's 16 consecutive floats of
-                    // `stats`: ONE fully populated atomic instruction per warp and pass.
-                    const int kc = 2 * wq + (lane >> 4);
-                    const int rg = lane & 15;
-                    float2 s1p[4], s2p[4];                     // packed fp32 pairs: FADD2 / FFMA2, two columns per instruction
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) { s1p[k] = make_float2(0.f, 0.f); s2p[k] = make_float2(0.f, 0.f); }
-#pragma unroll
-                    for (int i = 0; i < kGemmBM / 16; ++i) {
-                        const int r = rg + 16 * i;
-                        const uint4 u = *reinterpret_cast<const uint4*>(tile_y + (r * kChunks + ((kc + r) & (kChunks - 1))) * 16);
-                        const uint32_t w[4] = {u.x, u.y, u.z, u.w};
-#pragma unroll
-                        for (int k = 0; k < 4; ++k) {
-                            const float2 y = make_float2(__uint_as_float(w[k] << 16), __uint_as_float(w[k] & 0xffff0000u));
-                            s1p[k] = __fadd2_rn(s1p[k], y);
-                            s2p[k] = __ffma2_rn(y, y, s2p[k]);
-                        }
-                    }
-                    float a[16];
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) {
-                        a[4 * k + 0] = s1p[k].x; a[4 * k + 1] = s2p[k].x; a[4 * k + 2] = s1p[k].y; a[4 * k + 3] = s2p[k].y;
-                    }
-#pragma unroll
-                    for (int h = 8; h >= 1; h >>= 1) {
-                        const bool up = (lane & h) != 0;
-#pragma unroll
-                        for (int i = 0; i < h; ++i) {
-                            const float send = up ? a[i] : a[i + h];
-                            const float keep = up ? a[i + h] : a[i];
-                            a[i] = keep + __shfl_xor_sync(0xffffffffu, send, h);
-                        }
-                    }
-                    atomicAdd(p.stats + (static_cast<size_t>(pair) * p.Co + n0 + col0 + kc * 8) * 2 + rg, a[0]);
-                }
-#pragma unroll
-                for (int idx = et; idx < kGemmBM * kChunks; idx += 128) {
-                    const int r = idx / kChunks, k = idx % kChunks;
-                    const uint4 v = *reinterpret_cast<const uint4*>(tile_y + (r * kChunks + ((k + r) & (kChunks - 1))) * 16);
-                    *reinterpret_cast<uint4*>(p.Y + static_cast<size_t>(m0 + r) * p.Co + n0 + col0 + k * 8) = v;
-                }
+                if (p.stats != nullptr)
+                    tile64_stats(tile_y, wq, lane, p.stats + (static_cast<size_t>(pair) * p.Co + n0 + col0) * 2);
+                tile64_store(tile_y, et, p.Y + static_cast<size_t>(m0) * p.Co + n0 + col0, p.Co);
                 epi_group_sync(g);                            // the tile is rewritten by the next pass
             }
         }
@@ -671,49 +680,60 @@ __global__ void __launch_bounds__(256) fepe_mlp_norm_kernel(const __nv_bfloat16*
     }
 }
 
-// layer 1: X0 [B,N,Ci] fp32 (Ci <= 8) -> Y [B*Npad, Co=64] bf16 + stats.  One CTA per (pair, 128-row slab):
-// thread = row computes its 64 outputs into a shared tile, then thread = channel sums the slab's column.
+// layer 1: X0 [B,N,Ci] fp32 (Ci <= 8) -> Y [B*Npad, Co=64] bf16 + stats.  One CTA of 128 threads per (pair, 128-row
+// slab): thread = row computes its 64 outputs four channels at a time (weights transposed in shared memory and read as
+// broadcast 16-byte vectors, packed FFMA2), rounds them to bf16 into the same rotated-chunk tile as the GEMM epilogue, and
+// the tile's column statistics and coalesced 16-byte stores are the GEMM epilogue's own (tile64_stats / tile64_store).
+// CI > 0: compile-time channel count (4 and 7 are the reference's configurations); CI = 0: run-time Ci with guards.
+template <int CI>
 __global__ void __launch_bounds__(128) fepe_mlp_first_kernel(const float* __restrict__ X0, const float* __restrict__ W,
                                                              const float* __restrict__ bias,
                                                              __nv_bfloat16* __restrict__ Y, float* __restrict__ stats,
-                                                             int B, int N, int Npad, int Ci, int Co) {
-    __shared__ __nv_bfloat16 tile[128][64 + 2];
-    __shared__ float w_s[64 * 8], b_s[64];
+                                                             int B, int N, int Npad, int Ci_rt, int Co) {
+    __shared__ __align__(16) unsigned char tile[kEpiTileBytes];   // [128][64] bf16, rotated 16-byte chunks
+    __shared__ __align__(16) float w_t[8 * 64];                   // [k][c]: W^T, zero beyond Ci
+    __shared__ __align__(16) float b_s[64];
+    const int Ci = (CI > 0) ? CI : Ci_rt;
     const int b = blockIdx.y;
-    const int r = blockIdx.x * 128 + threadIdx.x;
-    for (int i = threadIdx.x; i < Co * Ci; i += 128) w_s[i] = W[i];
-    for (int i = threadIdx.x; i < Co; i += 128) b_s[i] = bias[i];
-    __syncthreads();
+    const int row = threadIdx.x;
+    const int r = blockIdx.x * 128 + row;
+    for (int i = threadIdx.x; i < 8 * 64; i += 128) {
+        const int k = i >> 6, c = i & 63;
+        w_t[i] = (k < Ci) ? W[c * Ci + k] : 0.f;
+    }
+    if (threadIdx.x < 64) b_s[threadIdx.x] = bias[threadIdx.x];
     float x[8];
     const bool valid = r < N;
 #pragma unroll
     for (int k = 0; k < 8; ++k) x[k] = (valid && k < Ci) ? X0[(static_cast<size_t>(b) * N + r) * Ci + k] : 0.f;
-    for (int c = 0; c < Co; ++c) {
-        float y = 0.f;
-        if (valid) {
-            y = b_s[c];
+    __syncthreads();
+    constexpr int KMAX = (CI > 0) ? CI : 8;
 #pragma unroll
-            for (int k = 0; k < 8; ++k)
-                if (k < Ci) y = fmaf(w_s[c * Ci + k], x[k], y);
+    for (int chunk = 0; chunk < 8; ++chunk) {                     // 8 channels = one 16-byte chunk of the tile
+        uint32_t pk[4];
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+            const int c = chunk * 8 + half * 4;
+            const float4 bb = *reinterpret_cast<const float4*>(b_s + c);
+            float2 y01 = make_float2(bb.x, bb.y), y23 = make_float2(bb.z, bb.w);
+#pragma unroll
+            for (int k = 0; k < KMAX; ++k) {                      // same order of accumulation as the scalar loop: b, k = 0, 1, ...
+                const float4 w4 = *reinterpret_cast<const float4*>(w_t + k * 64 + c);
+                const float2 xx = make_float2(x[k], x[k]);
+                y01 = __ffma2_rn(make_float2(w4.x, w4.y), xx, y01);
+                y23 = __ffma2_rn(make_float2(w4.z, w4.w), xx, y23);
+            }
+            if (!valid) { y01 = make_float2(0.f, 0.f); y23 = make_float2(0.f, 0.f); }
+            const __nv_bfloat162 h0 = __floats2bfloat162_rn(y01.x, y01.y), h1 = __floats2bfloat162_rn(y23.x, y23.y);
+            pk[half * 2 + 0] = *reinterpret_cast<const uint32_t*>(&h0);
+            pk[half * 2 + 1] = *reinterpret_cast<const uint32_t*>(&h1);
         }
-        tile[threadIdx.x][c] = __float2bfloat16(y);
+        *reinterpret_cast<uint4*>(tile64_chunk(tile, row, chunk)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
     }
     __syncthreads();
-    if (threadIdx.x < Co) {
-        float s1 = 0.f, s2 = 0.f;
-        for (int rr = 0; rr < 128; ++rr) {
-            const float y = __bfloat162float(tile[rr][threadIdx.x]);
-            s1 += y;
-            s2 = fmaf(y, y, s2);
-        }
-        atomicAdd(stats + (static_cast<size_t>(b) * Co + threadIdx.x) * 2, s1);
-        atomicAdd(stats + (static_cast<size_t>(b) * Co + threadIdx.x) * 2 + 1, s2);
-    }
-    for (int idx = threadIdx.x; idx < 128 * (Co / 2); idx += 128) {
-        const int rr = idx / (Co / 2), c2 = (idx % (Co / 2)) * 2;
-        *reinterpret_cast<__nv_bfloat162*>(Y + (static_cast<size_t>(b) * Npad + blockIdx.x * 128 + rr) * Co + c2) =
-            *reinterpret_cast<const __nv_bfloat162*>(&tile[rr][c2]);
-    }
+    tile64_stats(tile, static_cast<int>(threadIdx.x) >> 5, static_cast<int>(threadIdx.x) & 31,
+                 stats + static_cast<size_t>(b) * Co * 2);
+    tile64_store(tile, static_cast<int>(threadIdx.x), Y + (static_cast<size_t>(b) * Npad + blockIdx.x * 128) * Co, Co);
 }
 
 // last layer (Ci -> 1) + softmax over the N rows of a pair.  One CTA per pair, 256 threads.
@@ -1309,8 +1329,11 @@ int fepe_mlp_first(const float* X0, const float* W, const float* bias, void* Y, 
                    int Ci, int Co, void* stream) {
     if (!X0 || !W || !bias || !Y || !stats || B <= 0 || Ci <= 0 || Ci > 8 || Co != 64 || (Npad % 128) != 0) return FEPE_E_BADARG;
     dim3 grid(Npad / 128, B);
-    fepe::fepe_mlp_first_kernel<<<grid, 128, 0, static_cast<cudaStream_t>(stream)>>>(
-        X0, W, bias, static_cast<__nv_bfloat16*>(Y), stats, B, N, Npad, Ci, Co);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    __nv_bfloat16* y = static_cast<__nv_bfloat16*>(Y);
+    if (Ci == 4) fepe::fepe_mlp_first_kernel<4><<<grid, 128, 0, st>>>(X0, W, bias, y, stats, B, N, Npad, Ci, Co);
+    else if (Ci == 7) fepe::fepe_mlp_first_kernel<7><<<grid, 128, 0, st>>>(X0, W, bias, y, stats, B, N, Npad, Ci, Co);
+    else fepe::fepe_mlp_first_kernel<0><<<grid, 128, 0, st>>>(X0, W, bias, y, stats, B, N, Npad, Ci, Co);
     return static_cast<int>(cudaGetLastError());
 }
 
