@@ -1150,12 +1150,14 @@ static int launch_gemm(const void* X, const void* W, const GemmParams& p, cudaSt
     CUtensorMap ma, mw;
     if (!make_map(&ma, X, p.M, p.K, kGemmBM) || !make_map(&mw, W, p.Co, p.K, BN)) return FEPE_E_NODEVICE;
     constexpr int smem = STAGES * (kGemmBM * kGemmBK * 2 + BN * kGemmBK * 2) + kGemmBM * BN * 2 + 256 + 1024;
-    static bool configured = false;
-    if (!configured) {
+    static bool configured[64] = {false};                 // the attribute is per device
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (!configured[dev & 63]) {
         cudaError_t e =
             cudaFuncSetAttribute(fepe_mlp_gemm_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         if (e != cudaSuccess) return static_cast<int>(e);
-        configured = true;
+        configured[dev & 63] = true;
     }
     dim3 grid(p.Co / BN, p.M / kGemmBM);
     fepe_mlp_gemm_kernel<BN, STAGES><<<grid, kGemmThreads, smem, stream>>>(ma, mw, p);
@@ -1190,11 +1192,13 @@ static int launch_wgrad(const void* dY, const void* X, const WgradParams& p, int
     CUtensorMap my, mx;
     if (!make_map(&my, dY, p.M, p.Co, 64) || !make_map(&mx, X, p.M, p.Ci, 64)) return FEPE_E_NODEVICE;
     constexpr int smem = 3 * (64 * 128 * 2 + 64 * BN * 2) + 256 + 1024;
-    static bool configured = false;
-    if (!configured) {
+    static bool configured[64] = {false};                 // the attribute is per device
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (!configured[dev & 63]) {
         cudaError_t e = cudaFuncSetAttribute(fepe_mlp_wgrad_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         if (e != cudaSuccess) return static_cast<int>(e);
-        configured = true;
+        configured[dev & 63] = true;
     }
     dim3 grid(p.Ci / BN, p.Co / 128, slabs);
     fepe_mlp_wgrad_kernel<BN><<<grid, kGemmThreads, smem, stream>>>(my, mx, p);
