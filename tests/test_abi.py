@@ -64,6 +64,46 @@ def test_ctypes_signatures_match_the_header(built):
         assert got == want_args, f"{name}: ctypes {''.join(got)} vs header {''.join(want_args)}"
 
 
+_INFO_ONLY = ("fepe_version", "fepe_max_correspondences", "fepe_nn_match_workspace_bytes")
+
+
+def test_entry_points_reject_null_pointers_before_touching_cuda(built):
+    """Error behaviour of the boundary, checked without a GPU: every compute entry point validates its arguments before
+    its first CUDA call -- null buffers with positive sizes return FEPE_E_BADARG (-1) instead of a CUDA error or a fault
+    -- and the solver / pose / matcher entry points treat an empty batch as a successful no-op."""
+    import ctypes
+    lib = built.lib()
+    for name, (res, args) in built._SIGNATURES.items():
+        if name in _INFO_ONLY:
+            continue
+        fn = getattr(lib, name)
+        nulls = [0.0 if a is ctypes.c_float else (0 if a is ctypes.c_void_p else 128) for a in args]
+        assert fn(*nulls) == -1, f"{name}: null pointers must give FEPE_E_BADARG"
+        zeros = [0.0 if a is ctypes.c_float else 0 for a in args]
+        want = -1 if name.startswith("fepe_mlp_") else 0          # the MLP entry points require B > 0
+        assert fn(*zeros) == want, f"{name}: empty batch"
+    assert lib.fepe_nn_match_workspace_bytes(10, 10, 10) > 0
+    assert lib.fepe_max_correspondences() in (-3,) or lib.fepe_max_correspondences() > 1000   # -3: no sm_100 device here
+
+
+def test_mlp_entry_points_reject_bad_shapes(built):
+    """Shape / alignment contract of the tensor-core MLP entry points (include/fepe_b200.h), again without a GPU."""
+    lib = built.lib()
+    p = 0x1000                                   # a non-null, 16-byte aligned dummy: validation fails before any access
+    assert lib.fepe_mlp_gemm(p, p, 0, p, p, 2, 250, 200, 128, 256, 0) == -1        # Npad not a multiple of 128
+    assert lib.fepe_mlp_gemm(p, p, 0, p, p, 2, 256, 300, 128, 256, 0) == -1        # more valid rows than padded rows
+    assert lib.fepe_mlp_gemm(p, p, 0, p, p, 2, 256, 200, 100, 256, 0) == -1        # K not a multiple of 64
+    assert lib.fepe_mlp_gemm(p, p, 0, p, p, 2, 256, 200, 128, 100, 0) == -1        # Co not a multiple of 64
+    assert lib.fepe_mlp_gemm(p, p, p + 4, p, p, 2, 256, 200, 128, 256, 0) == -1    # bias not 16-byte aligned
+    assert lib.fepe_mlp_gemm_norm(p, p, 0.01, p, 0, p, p, 2, 256, 200, 128, 192, 0) == -1    # fused variant: Co % 128
+    assert lib.fepe_mlp_gemm_norm(p, p + 4, 0.01, p, 0, p, p, 2, 256, 200, 128, 256, 0) == -1  # ss not 16-byte aligned
+    assert lib.fepe_mlp_gemm_norm(p, p, 1.5, p, 0, p, p, 2, 256, 200, 128, 256, 0) == -1     # slope outside (0, 1)
+    assert lib.fepe_mlp_scale_shift(p, p, p, p, 2, 63, 200, 1e-5, 0, 0) == -1      # odd channel count
+    assert lib.fepe_mlp_last_norm(p, p, 0.0, p, 0.0, p, p, 2, 200, 256, 256, 0) == -1        # slope outside (0, 1)
+    assert lib.fepe_mlp_first(p, p, p, p, p, 2, 200, 256, 9, 64, 0) == -1          # more than 8 input channels
+    assert lib.fepe_mlp_wgrad(p, p, p, 100, 128, 64, 0) == -1                      # M not a multiple of 64
+
+
 def test_no_cpu_fallback(built):
     from fepe_b200 import ops
     with pytest.raises(RuntimeError, match="CUDA"):
