@@ -1,0 +1,101 @@
+"""Numerical experiment (CPU, numpy): can the 36-entry fp64 Gram of the fit be replaced by an fp32 Gram plus an
+iterative refinement whose residual is formed from the constraint ROWS (g = X^T (X f), 9 accumulators), at the
+reference's own accuracy class?
+
+For every synthetic scene (the oracle's generator, all weight modes) it reports the sign-aligned relative error of f
+against the fp64 truth for: the reference's arithmetic (fp32 SVD of X), an fp32 Gram alone, and the fp32 Gram followed
+by k refinement steps  f <- normalise(f - (G32 - mu I)^+ (g - rho f)),  g = X^T (X f) with fp32 rows / products and
+either fp32 or fp64 accumulation of the 9 sums.  This is test-side research code: nothing here is on the product path."""
+import os, sys
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path[:0] = [ROOT, os.path.join(ROOT, "pytorch-deepfepe_b200")]
+import numpy as np
+import torch
+from fepe_b200 import synth
+from oracle import fepe_oracle as O
+
+
+def rows_fp32(d):
+    """X [B,N,9] in fp32 exactly as the reference builds it (Hartley in fp32, normalised rows times w)."""
+    m = torch.from_numpy(d["matches_xy_ori"])
+    p1, p2, _ = O.norm_hw(m, d["image_size"])
+    w = torch.from_numpy(d["weights"]).squeeze(1).unsqueeze(2)
+    p1n, _ = O.hartley(p1)
+    p2n, _ = O.hartley(p2)
+    return (O.constraint_rows(p1n, p2n) * w).numpy().astype(np.float32)
+
+
+def null_vec(G):
+    lam, V = np.linalg.eigh(G)
+    return V[:, 0], lam
+
+
+def err(f, ft):
+    f = f / np.linalg.norm(f)
+    return min(np.linalg.norm(f - ft), np.linalg.norm(f + ft))
+
+
+def gram32(X, chunks=64):
+    """fp32 products and fp32 accumulation, `chunks` partial sums (lanes) combined at the end like the kernel would."""
+    N = X.shape[0]
+    acc = np.zeros((chunks, 9, 9), np.float32)
+    for c in range(chunks):
+        Xc = X[c::chunks]
+        for i in range(Xc.shape[0]):
+            acc[c] += np.outer(Xc[i], Xc[i]).astype(np.float32)
+    return acc.astype(np.float64).sum(0)       # cross-lane combine in fp64 (36 values, once per pair)
+
+
+def refine(X32, G32, f, steps, acc64):
+    lam, V = np.linalg.eigh(G32)
+    out = []
+    for _ in range(steps):
+        f32 = f.astype(np.float32)
+        r = (X32 * f32).sum(1, dtype=np.float32)                       # r_i = x_i . f, fp32
+        if acc64:
+            g = (X32.astype(np.float64) * r.astype(np.float64)[:, None]).sum(0)
+        else:
+            g = (X32 * r[:, None]).astype(np.float32).sum(0, dtype=np.float32).astype(np.float64)
+        rho = float(f @ g)
+        res = g - rho * f
+        # correction in the eigenbasis of the fp32 Gram, excluding its own smallest direction
+        coef = V.T @ res
+        shift = lam[0]
+        delta = V[:, 1:] @ (coef[1:] / (lam[1:] - shift))
+        f = f - delta
+        f = f / np.linalg.norm(f)
+        out.append(f.copy())
+    return out
+
+
+def main():
+    rng_cases = [("uniform", 1000), ("softmax", 1000), ("inlier", 1000), ("peaked", 1000), ("inlier", 2000), ("inlier", 200)]
+    print(f"{'mode':8s} {'N':>5s} | {'ref fp32 SVD':>12s} {'fp32 Gram':>10s} | {'+1 (fp32 g)':>11s} {'+2 (fp32 g)':>11s} | {'+1 (fp64 g)':>11s} {'+2 (fp64 g)':>11s} | gap_rel")
+    worst = {}
+    for mode, N in rng_cases:
+        d = synth.make_batch(12, N, seed=11 + N, weight_mode=mode)
+        X = rows_fp32(d)
+        for b in range(X.shape[0]):
+            Xb = X[b]
+            G64 = Xb.astype(np.float64).T @ Xb.astype(np.float64)
+            ft, lam = null_vec(G64)
+            gap = (lam[1] - lam[0]) / lam[-1]
+            _, _, Vt = np.linalg.svd(Xb)                                # LAPACK sgesdd on fp32 rows = the reference's arithmetic
+            e_ref = err(Vt[-1].astype(np.float64), ft)
+            G32 = gram32(Xb)
+            f0, _ = null_vec(G32)
+            e0 = err(f0, ft)
+            a = refine(Xb, G32, f0, 2, acc64=False)
+            c = refine(Xb, G32, f0, 2, acc64=True)
+            row = (e_ref, e0, err(a[0], ft), err(a[1], ft), err(c[0], ft), err(c[1], ft))
+            key = (mode, N)
+            worst[key] = tuple(max(x, y) for x, y in zip(worst.get(key, (0,) * 6), row))
+            if b < 3:
+                print(f"{mode:8s} {N:5d} | {row[0]:12.2e} {row[1]:10.2e} | {row[2]:11.2e} {row[3]:11.2e} | {row[4]:11.2e} {row[5]:11.2e} | {gap:.1e}")
+    print("\nworst over 12 scenes per case:")
+    for (mode, N), row in worst.items():
+        print(f"{mode:8s} {N:5d} | {row[0]:12.2e} {row[1]:10.2e} | {row[2]:11.2e} {row[3]:11.2e} | {row[4]:11.2e} {row[5]:11.2e}")
+
+
+if __name__ == "__main__":
+    main()
