@@ -68,6 +68,41 @@ def refine(X32, G32, f, steps, acc64):
     return out
 
 
+def f_to_F(f, T1, T2):
+    """rank-2 projection + de-normalisation in fp64 (what the kernel does after the eigen-solve)."""
+    U, S, Vt = np.linalg.svd(f.reshape(3, 3))
+    S[2] = 0.0
+    return T2.T @ (U @ np.diag(S) @ Vt) @ T1
+
+
+def parity_against_reference():
+    """The number the GPU tests assert: relative Frobenius distance (sign aligned) between OUR F and the reference's
+    F (oracle = fp32 torch.svd path) -- for the fp64 Gram (today's kernel), the fp32 Gram alone and fp32 Gram + 1 step."""
+    print("\nparity of F against the reference path (bar 1e-4): max over 12 scenes per case")
+    print(f"{'mode':8s} {'N':>5s} | {'fp64 Gram':>10s} {'fp32 Gram':>10s} {'fp32 + 1 step':>13s}")
+    for mode, N in [("uniform", 1000), ("softmax", 1000), ("inlier", 1000), ("peaked", 1000), ("inlier", 2000), ("inlier", 200)]:
+        d = synth.make_batch(12, N, seed=11 + N, weight_mode=mode)
+        m = torch.from_numpy(d["matches_xy_ori"])
+        p1, p2, _ = O.norm_hw(m, d["image_size"])
+        Fref, _ = O.fit_weighted_svd(p1, p2, torch.from_numpy(d["weights"]))
+        _, T1 = O.hartley(p1)
+        _, T2 = O.hartley(p2)
+        X = rows_fp32(d)
+        worst = [0.0, 0.0, 0.0]
+        for b in range(12):
+            Xb = X[b]
+            t1, t2 = T1[b].numpy().astype(np.float64), T2[b].numpy().astype(np.float64)
+            G64 = Xb.astype(np.float64).T @ Xb.astype(np.float64)
+            G32 = gram32(Xb)
+            f64, _ = null_vec(G64)
+            f32, _ = null_vec(G32)
+            f1 = refine(Xb, G32, f32, 1, acc64=False)[0]
+            for k, f in enumerate((f64, f32, f1)):
+                Fo = torch.from_numpy(f_to_F(f, t1, t2)).float().unsqueeze(0)
+                worst[k] = max(worst[k], float(O.sign_aligned_rel_err(Fo, Fref[b:b + 1]).max()))
+        print(f"{mode:8s} {N:5d} | {worst[0]:10.2e} {worst[1]:10.2e} {worst[2]:13.2e}")
+
+
 def main():
     rng_cases = [("uniform", 1000), ("softmax", 1000), ("inlier", 1000), ("peaked", 1000), ("inlier", 2000), ("inlier", 200)]
     print(f"{'mode':8s} {'N':>5s} | {'ref fp32 SVD':>12s} {'fp32 Gram':>10s} | {'+1 (fp32 g)':>11s} {'+2 (fp32 g)':>11s} | {'+1 (fp64 g)':>11s} {'+2 (fp64 g)':>11s} | gap_rel")
@@ -99,3 +134,4 @@ def main():
 
 if __name__ == "__main__":
     main()
+    parity_against_reference()
