@@ -103,6 +103,39 @@ def parity_against_reference():
         print(f"{mode:8s} {N:5d} | {worst[0]:10.2e} {worst[1]:10.2e} {worst[2]:13.2e}")
 
 
+def floors():
+    """Which precision does g = X^T (X f0) need?  Scenes of tests/test_math_host.py (30 % outliers that the weights do
+    NOT suppress in the softmax / uniform modes, so the residuals are large): worst error of f after one step with
+    (fp32 r, fp32 products and sums), (fp32 r, exact products summed in fp64) and (everything fp64)."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from test_math_host import scene_gram
+    print("\nprecision of g (scenes of tests/test_math_host.py): worst of 12 scenes")
+    print(f"{'mode':8s} | {'fp32 Gram':>10s} {'r32,g32':>10s} {'r32,g64':>10s} {'r64,g64':>10s}")
+    for mode in ("softmax", "peaked", "inlier", "uniform"):
+        worst = [0.0] * 4
+        for seed in range(12):
+            _, X = scene_gram(seed, mode, N=1000, noise=0.5 if seed % 2 else 0.1)
+            X32 = X.astype(np.float32)
+            X64 = X32.astype(np.float64)
+            ft = np.linalg.eigh(X64.T @ X64)[1][:, 0]
+            G32 = gram32(X32)
+            l32, V32 = np.linalg.eigh(G32)
+            f0 = V32[:, 0]
+
+            def step(g):
+                res = g - float(f0 @ g) * f0
+                coef = V32.T @ res
+                f = f0 - V32[:, 1:] @ (coef[1:] / (l32[1:] - l32[0]))
+                return f / np.linalg.norm(f)
+            r32 = (X32 * f0.astype(np.float32)).sum(1, dtype=np.float32)
+            g_a = (X32 * r32[:, None]).astype(np.float32).sum(0, dtype=np.float32).astype(np.float64)
+            g_b = (X64 * r32.astype(np.float64)[:, None]).sum(0)
+            g_c = (X64 * (X64 @ f0)[:, None]).sum(0)
+            es = [err(f0, ft), err(step(g_a), ft), err(step(g_b), ft), err(step(g_c), ft)]
+            worst = [max(a, b) for a, b in zip(worst, es)]
+        print(f"{mode:8s} | " + " ".join(f"{w:10.2e}" for w in worst))
+
+
 def main():
     rng_cases = [("uniform", 1000), ("softmax", 1000), ("inlier", 1000), ("peaked", 1000), ("inlier", 2000), ("inlier", 200)]
     print(f"{'mode':8s} {'N':>5s} | {'ref fp32 SVD':>12s} {'fp32 Gram':>10s} | {'+1 (fp32 g)':>11s} {'+2 (fp32 g)':>11s} | {'+1 (fp64 g)':>11s} {'+2 (fp64 g)':>11s} | gap_rel")
@@ -135,3 +168,4 @@ def main():
 if __name__ == "__main__":
     main()
     parity_against_reference()
+    floors()

@@ -330,3 +330,44 @@ def test_fit_backward_weights_and_coordinates_match_autograd_through_the_oracle(
         assert np.abs(e - epi.detach().numpy().reshape(-1)).max() < 1e-8
         assert rel(gw, wb.grad.numpy().reshape(-1)) < 1e-8
         assert rel(gm, u.grad.numpy()) < 1e-8
+
+
+@pytest.mark.parametrize("mode", ["softmax", "peaked", "inlier"])
+def test_fp32_gram_plus_one_row_space_refinement_step(shim, mode):
+    """Groundwork for DESIGN 7.1, run through the PRODUCT's own solver and pseudo-inverse (fepe_math.cuh on the host):
+    an fp32 Gram (fp32 products and sums, as 36 FFMA per correspondence would give) loses 1e-5..1e-4 of the null
+    vector on inlier-favouring weights, and ONE refinement step whose residual is formed from the fp32 constraint rows,
+    g = X^T (X f0), f1 = normalise(f0 - (G32 - lambda)^+ (g - rho f0)), brings it back to the accuracy class of an SVD of
+    X (< 1e-6 against the fp64 answer), because X^T scales the rounding of the row products by sigma_8 only.  r = X f0 may
+    be fp32; the nine sums of g need exact products and fp64 accumulation (with fp32 sums the step is as inaccurate as the
+    fp32 Gram whenever the residuals are large -- scripts/research/refine_numerics.py, profiles/r1_refine_numerics.txt)."""
+    worst0, worst1 = 0.0, 0.0
+    for seed in range(12):
+        g36_64, X = scene_gram(seed, mode, N=1000, noise=0.5 if seed % 2 else 0.1)
+        X32 = X.astype(np.float32)
+        ft = np.linalg.eigh(X32.astype(np.float64).T @ X32.astype(np.float64))[1][:, 0]
+        # fp32 Gram: 64 lanes' partial sums in fp32, combined in fp64 once per pair
+        G32 = np.zeros((9, 9))
+        for lane in range(64):
+            acc = np.zeros((9, 9), np.float32)
+            for row in X32[lane::64]:
+                acc += np.outer(row, row).astype(np.float32)
+            G32 += acc
+        g36 = np.zeros(36)
+        for r in range(9):
+            for c in range(9):
+                g36[shim.shim_g36_index(r, c)] = 0.5 * (G32[r, c] + G32[c, r])
+        f0, lam = np.zeros(9), np.zeros(1)
+        shim.shim_eig9_tri_serial(_ptr(g36), _ptr(f0), _ptr(lam))
+        err = lambda f: min(np.linalg.norm(f - ft), np.linalg.norm(f + ft))
+        r = (X32 * f0.astype(np.float32)).sum(1, dtype=np.float32)
+        g = (X32.astype(np.float64) * r.astype(np.float64)[:, None]).sum(0)
+        res = np.ascontiguousarray(g - float(f0 @ g) * f0)
+        z = np.zeros(9)
+        shim.shim_pinv(_ptr(g36), _ptr(f0), float(lam[0]), _ptr(res), _ptr(z))
+        f1 = f0 - z
+        f1 /= np.linalg.norm(f1)
+        worst0, worst1 = max(worst0, err(f0)), max(worst1, err(f1))
+    print(f"{mode}: fp32 Gram alone {worst0:.2e}, after one refinement step {worst1:.2e}")
+    assert worst1 < 1e-6
+    assert worst1 < 0.05 * worst0 or worst0 < 2e-6
