@@ -744,6 +744,30 @@ FEPE_HD void eig9_pinv_apply(const double* __restrict__ g36, const double (&f)[9
     for (int i = 0; i < 9; ++i) z[i] = y[i] - f[i] * fy;
 }
 
+// One refinement step of the smallest eigenvector against an INEXACT Gram matrix: g36 is the Gram as
+// accumulated (e.g. in fp32), (f0, lambda0) its smallest eigenpair, g = X^T (X f0) formed from the constraint rows with
+// exact products and fp64 sums.  f1 = normalise(f0 - (G - lambda0)^+ (g - (f0.g) f0)), sign convention of
+// canonical_sign9.  X^T scales the rounding of the row products by sigma_8 only, so f1 has the accuracy class of an SVD
+// of X while G only needs to be good enough for the correction to contract (its relative error against the eigen-gap).
+// Not yet called by a kernel; tested on the host (tests/test_math_host.py).
+FEPE_HD void eig9_refine_step(const double* __restrict__ g36, const double (&f0)[9], double lambda0,
+                              const double (&g)[9], double (&f1)[9]) {
+    double rho = 0.0;
+#pragma unroll
+    for (int i = 0; i < 9; ++i) rho += f0[i] * g[i];
+    double res[9], z[9];
+#pragma unroll
+    for (int i = 0; i < 9; ++i) res[i] = g[i] - rho * f0[i];
+    eig9_pinv_apply(g36, f0, lambda0, res, z);
+    double x[9], n2 = 0.0;
+#pragma unroll
+    for (int i = 0; i < 9; ++i) { x[i] = f0[i] - z[i]; n2 += x[i] * x[i]; }
+    const double inv = 1.0 / sqrt(n2);
+#pragma unroll
+    for (int i = 0; i < 9; ++i) x[i] *= inv;
+    canonical_sign9(x, f1);
+}
+
 // ---------------------------------------------------------------------------------------------
 // 3x3 SVD, A = U diag(S) V^T, one-sided (Hestenes) Jacobi in fp64, singular values sorted
 // descending, det(U) = det(V) = +1 is NOT enforced (signs follow the rotations); u3 is rebuilt as

@@ -46,6 +46,8 @@ def shim():
     lib.shim_eig9_multishift128.argtypes = [dp, dp, dp]
     lib.shim_eig9_multishift128.restype = ctypes.c_int
     lib.shim_pinv.argtypes = [dp, dp, ctypes.c_double, dp, dp]
+    lib.shim_refine_step.argtypes = [dp, dp, ctypes.c_double, dp, dp]
+    lib.shim_refine_step.restype = None
     lib.shim_svd3.argtypes = [dp, dp, dp, dp]
     lib.shim_svd3_direct.argtypes = [dp, dp, dp, dp]
     lib.shim_rank2.argtypes = [dp, dp]

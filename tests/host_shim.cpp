@@ -25,6 +25,13 @@ void shim_pinv(const double* g36, const double* f, double lambda, const double* 
     for (int i = 0; i < 9; ++i) z[i] = zz[i];
 }
 
+void shim_refine_step(const double* g36, const double* f0, double lambda0, const double* g, double* f1) {
+    double ff[9], gg[9], out[9];
+    for (int i = 0; i < 9; ++i) { ff[i] = f0[i]; gg[i] = g[i]; }
+    fepe::eig9_refine_step(g36, ff, lambda0, gg, out);
+    for (int i = 0; i < 9; ++i) f1[i] = out[i];
+}
+
 void shim_svd3(const double* A, double* U, double* S, double* V) {
     double a[9], u[9], s[3], v[9];
     for (int i = 0; i < 9; ++i) a[i] = A[i];

@@ -362,11 +362,9 @@ def test_fp32_gram_plus_one_row_space_refinement_step(shim, mode):
         err = lambda f: min(np.linalg.norm(f - ft), np.linalg.norm(f + ft))
         r = (X32 * f0.astype(np.float32)).sum(1, dtype=np.float32)
         g = (X32.astype(np.float64) * r.astype(np.float64)[:, None]).sum(0)
-        res = np.ascontiguousarray(g - float(f0 @ g) * f0)
-        z = np.zeros(9)
-        shim.shim_pinv(_ptr(g36), _ptr(f0), float(lam[0]), _ptr(res), _ptr(z))
-        f1 = f0 - z
-        f1 /= np.linalg.norm(f1)
+        f1 = np.zeros(9)
+        shim.shim_refine_step(_ptr(g36), _ptr(f0), float(lam[0]), _ptr(np.ascontiguousarray(g)), _ptr(f1))   # fepe_math.cuh
+        assert abs(np.linalg.norm(f1) - 1) < 1e-12 and f1[np.argmax(np.abs(f1))] > 0
         worst0, worst1 = max(worst0, err(f0)), max(worst1, err(f1))
     print(f"{mode}: fp32 Gram alone {worst0:.2e}, after one refinement step {worst1:.2e}")
     assert worst1 < 1e-6
