@@ -3,8 +3,16 @@
 
 Contract (one JSON line on rank 0):
   python bench.py [--gpus N] [--steps K] [--warmup W]            ours (CUDA kernels via the C ABI)
-  python bench.py --impl reference [...]                         the reference's CPU algorithm (oracle port)
+  python bench.py --impl reference [...]                         the UNMODIFIED reference's CPU path (oracle/_ref; the
+                                                                 oracle port only if that copy is absent)
   torchrun --nproc-per-node N bench.py --gpus N ...              one rank per GPU, weak scaling
+  --workload C2 (default, the contract line) | C3 (64 x 2000, same step) | C4 (DeepFNet forward) | C5 (training step)
+
+Timing: the K steps are recorded as ONE CUDA graph; that graph is replayed R times back to back so that the timed
+region lasts >= 20 ms (`replays` in the line; `value` = pairs of K*R steps / time).  `value` issues the steps of a graph
+on 8 parallel branches (independent batches); `value_serial` is the same measurement with ONE branch, i.e. launches
+strictly back to back.  `bwd` is the forward + backward step (fit with saved state, loss head, head backward, fit
+backward).  With more than one rank the line also carries `training_step`: the C5 step with its gradient all-reduce.
 
 Workload (BASELINE.json configs[1]): one STEP = one batch of 256 image pairs x 1000 synthetic
 correspondences (KITTI-shaped intrinsics, 0.5 px noise, 30 % outliers) through
@@ -60,11 +68,15 @@ def parse_args():
                     help="parallel branches the K independent steps are issued on (1 = strictly back to back)")
     ap.add_argument("--no-extras", action="store_true", help="skip e2e / cpu_baseline / saturating legs")
     ap.add_argument("--phases", action="store_true", help="print per-phase SM cycles of the fused kernel")
-    ap.add_argument("--workload", choices=["C2", "C4", "C5"], default="C2",
-                    help="C2 (default, the contract line): solver only.  C4: whole DeepFNet forward (depth 5, "
+    ap.add_argument("--workload", choices=["C2", "C3", "C4", "C5"], default="C2",
+                    help="C2 (default, the contract line): solver only, 256 x 1000.  C3: the same step at 64 pairs x 2000 "
+                         "correspondences (pose loss).  C4: whole DeepFNet forward (depth 5, "
                          "ErrorEstimator on tcgen05 + 5 fits), batch 512 x N=1000.  C5: training step (forward, F-loss, backward "
                          "through the analytic fit backward, one flattened NCCL all-reduce, Adam), 16 pairs per GPU.  "
-                         "C4 / C5 are extra lines, not the contract")
+                         "C3 / C4 / C5 are extra lines, not the contract")
+    ap.add_argument("--min-ms", type=float, default=20.0, help="minimum duration of the timed region (graph replays)")
+    ap.add_argument("--mlp", choices=["tc32", "bf16", "torch"], default="tc32",
+                    help="C4 / C5: weight-MLP path (tc32 = split-fp16 tcgen05 at fp32 parity, the default of the model)")
     return ap.parse_args()
 
 
@@ -178,6 +190,23 @@ class DeviceBatch:
         self.res = torch.empty(B, N, device=dev)
         self.epi = torch.empty(B, N, device=dev)
         self.pose = torch.empty(1, B, _lib.POSE_OUT_FLOATS, device=dev)
+        self.saved = None               # backward state, allocated by enable_backward()
+
+    def enable_backward(self, seed: int):
+        """Buffers of the forward + backward step: the fit's saved state and fixed upstream gradients of the residual /
+        epipolar-residual rows (in the model they come from the next layer's network)."""
+        from fepe_b200 import _lib
+        B, N = self.m.shape[0], self.m.shape[1]
+        dev = self.m.device
+        g = torch.Generator(device=dev).manual_seed(seed)
+        self.saved = torch.empty(B, _lib.SAVED_DOUBLES, dtype=torch.float64, device=dev)
+        self.gres = torch.randn(B, N, device=dev, generator=g) * 1e-3
+        self.gepi = torch.randn(B, N, device=dev, generator=g) * 1e-3
+        self.gq = torch.full((1, B), 1.0 / B, device=dev)
+        self.gt = torch.full((1, B), 0.1 / B, device=dev)
+        self.gl = torch.full((1, B), 1.0 / B, device=dev)
+        self.dF = torch.empty(1, B, 3, 3, device=dev)
+        self.gw = torch.empty(B, N, device=dev)
 
 
 def step_fit(db: DeviceBatch, aff):
@@ -190,6 +219,23 @@ def step_full(db: DeviceBatch, aff):
     # one call of the C ABI (fepe_fit_pose_fwd); at the config batch it is ONE kernel (pose head fused into the fit)
     ops.fit_pose_forward(db.m, db.w, aff, db.K, db.q, db.tt, db.Rt, db.v1, db.v2, clamp_at=CLAMP_EPI,
                          virt_clamp_at=CLAMP_LOSS, out=(db.F, db.res, db.epi, None, db.pose[0]))
+
+
+def step_fwd_bwd(db: DeviceBatch, aff):
+    """Forward + backward of the solver step through the public ops: fit (saving its per-pair state) + loss head, then
+    the head's backward (dL/dF of the q / t L2 errors and the F-loss) and the fit's backward (dL/dweights)."""
+    from fepe_b200 import ops
+    ops.fit_pose_forward(db.m, db.w, aff, db.K, db.q, db.tt, db.Rt, db.v1, db.v2, clamp_at=CLAMP_EPI,
+                         virt_clamp_at=CLAMP_LOSS, out=(db.F, db.res, db.epi, db.saved, db.pose[0]))
+    ops.pose_backward(db.F.unsqueeze(0), db.K, aff, db.q, db.tt, db.v1, db.v2, CLAMP_LOSS, db.pose, db.gq, db.gt, db.gl,
+                      out=db.dF)
+    ops.fit_backward(db.m, db.w, db.saved, db.dF[0], db.gres, db.gepi, aff, CLAMP_EPI, out=(db.gw, None))
+
+
+def bwd_bytes(B: int, N: int) -> int:
+    # forward 28 N + 36 (+ 512 B saved state written) and backward 32 N (20 B inputs + the two upstream rows read, 4 B
+    # weight gradient written) + 512 B state read + 36 B dF per pair (DESIGN.md 3.2)
+    return B * (28 * N + 36 + 512) + B * (32 * N + 512 + 36)
 
 
 def capture(fn):
@@ -241,17 +287,100 @@ def timed_loop(callables, steps: int, warmup: int, barrier=None):
 
 
 # ------------------------------------------------------------------------------------------------
+def measure_steps(step_fns, K: int, W: int, n_branch: int, min_ms: float, barrier, reduce_max, no_graph: bool):
+    """Time the step: W warm-up steps, then the K-step unit replayed R times back to back so that the timed region
+    lasts >= min_ms (R is agreed over the ranks).  With graphs, len(step_fns) // K graphs tile the ring of batches, so
+    consecutive replays keep walking through DISTINCT batches (> L2) instead of re-running the same K.
+    Returns (seconds, steps timed = K * R, R, t0_wall, t1_wall)."""
+    n = len(step_fns)
+    if no_graph:
+        one, _, _ = timed_loop(step_fns, K, W)
+        R = int(reduce_max(max(1, int(np.ceil(min_ms * 1e-3 / max(one, 1e-9))))))
+        secs, t0, t1 = timed_loop(step_fns, K * R, 0, barrier)
+        return secs, K * R, R, t0, t1
+    G = 1 if K >= n else max(1, n // K)
+    g_warm = capture_pipelined(step_fns, W, 0, n_branch)
+    graphs = [capture_pipelined(step_fns, K, W + j * K, n_branch) for j in range(G)]
+    torch.cuda.synchronize()
+    g_warm.replay()
+    one, _, _ = timed_loop([graphs[-1].replay], 1, 0)
+    R = int(reduce_max(max(1, int(np.ceil(min_ms * 1e-3 / max(one, 1e-9))))))
+    secs, t0, t1 = timed_loop([g.replay for g in graphs], R, 0, barrier)
+    return secs, K * R, R, t0, t1
+
+
+def workload_shape(args):
+    """(B, N, label) of the solver workloads: C2 = BASELINE.json configs[1], C3 = configs[2]."""
+    if args.workload == "C3":
+        B = 64 if args.batch == 256 else args.batch
+        N = 2000 if args.ncorr == 1000 else args.ncorr
+        return B, N, f"C3: batch={B} pairs x N={N} corr, 30% outliers, Fit + epi residual + F-loss + E->R,t (pose loss)"
+    return args.batch, args.ncorr, (f"C2: batch={args.batch} pairs x N={args.ncorr} corr, 30% outliers, "
+                                    "Fit + epi residual + F-loss + E->R,t")
+
+
+def bench_config(label: str, B: int, N: int) -> dict:
+    """The keys both arms share (the driver compares the two `config` dicts)."""
+    return {"workload": label, "batch_per_gpu": B, "ncorr": N}
+
+
+# ------------------------------------------------------------------------------------------------
+_REF = {"tried": False, "ns": None, "fit": None, "nhw": None}
+
+
+def reference_modules():
+    """The UNMODIFIED reference (oracle/_ref, made by oracle/make_ref.py) or None."""
+    if not _REF["tried"]:
+        _REF["tried"] = True
+        try:
+            from oracle import ref_env
+            with ref_env.quiet():
+                ns = ref_env.import_reference()
+                _REF["fit"] = ns.Fit(is_cuda=False, if_cpu_svd=False)
+            _REF["ns"] = ns
+        except Exception as e:                                     # noqa: BLE001
+            print(f"bench.py: unmodified reference unavailable ({e}); using the oracle port", file=sys.stderr)
+    return _REF["ns"]
+
+
 def reference_step(d: dict):
-    """The reference's CPU algorithm for one batch (oracle port): Fit + epipolar residual + F-loss +
-    E + pose decomposition / errors.  Returns nothing; timed by the caller."""
-    from oracle import fepe_oracle as O
+    """The reference's own CPU path for one batch: NormalizeAndExpand_HW + Fit(is_cuda=False) (DeepFNet.py:93-257) +
+    compute_epi_residual (utils_F.py:400-413) + get_all_loss_DeepF (F-loss, E; train_good_utils.py:298) +
+    get_Rt_loss(device='cpu') (:64), all UNMODIFIED from oracle/_ref.  Falls back to the oracle port only when that
+    copy is absent.  Returns nothing; timed by the caller."""
     T = torch.from_numpy
-    with torch.no_grad():
-        p1, p2, Tn = O.norm_hw(T(d["matches_xy_ori"]), d["image_size"])
-        Fo, res = O.fit_weighted_svd(p1, p2, T(d["weights"]))
-        O.epi_residual(p1, p2, Fo, CLAMP_EPI)
-        _, _, E_layers = O.f_loss_layers([Fo], Tn, Tn, T(d["pts1_virt"]), T(d["pts2_virt"]), T(d["Ks"]), CLAMP_LOSS)
-        O.pose_errors(E_layers[0], T(d["q_cam"]), T(d["t_cam"]), T(d["delta_Rtijs_4_4"]))
+    ns = reference_modules()
+    if ns is None:
+        from oracle import fepe_oracle as O
+        with torch.no_grad():
+            p1, p2, Tn = O.norm_hw(T(d["matches_xy_ori"]), d["image_size"])
+            Fo, res = O.fit_weighted_svd(p1, p2, T(d["weights"]))
+            O.epi_residual(p1, p2, Fo, CLAMP_EPI)
+            _, _, E_layers = O.f_loss_layers([Fo], Tn, Tn, T(d["pts1_virt"]), T(d["pts2_virt"]), T(d["Ks"]), CLAMP_LOSS)
+            O.pose_errors(E_layers[0], T(d["q_cam"]), T(d["t_cam"]), T(d["delta_Rtijs_4_4"]))
+        return
+    from oracle import ref_env
+    with torch.no_grad(), ref_env.quiet():
+        m = T(d["matches_xy_ori"])
+        nhw = ns.NormalizeAndExpand_HW(d["image_size"], is_cuda=False)
+        p1, p2, T1, T2 = nhw(m)
+        p1, p2 = p1.permute(0, 2, 1).contiguous(), p2.permute(0, 2, 1).contiguous()
+        w = T(d["weights"])
+        Fo, res = _REF["fit"](p1, p2, w)
+        epi = ns.utils_F.compute_epi_residual(p1, p2, Fo)
+        outs = {"weights": w, "F_est": Fo, "T1": T1, "T2": T2, "out_layers": [Fo], "residual_layers": [res],
+                "weights_layers": [w], "epi_res_layers": [epi.unsqueeze(1)]}
+        lp = {"depth": 1, "clamp_at": CLAMP_LOSS, "if_tri_depth": False, "if_sample_loss": False}
+        _, _, _, _, _, _, E_layers = ns.tgu.get_all_loss_DeepF(outs, T(d["pts1_virt"]), T(d["pts2_virt"]), T(d["Ks"]), lp,
+                                                               get_residual_summaries=False)
+        ns.tgu.get_Rt_loss(E_layers, T(d["Ks"]), m[:, :, :2], m[:, :, 2:], T(d["delta_Rtijs_4_4"]), T(d["q_cam"]),
+                           T(d["t_cam"]), device="cpu")
+
+
+def reference_kind():
+    return ("reference", "the unmodified reference from oracle/_ref: NormalizeAndExpand_HW + Fit(is_cuda=False) + "
+            "compute_epi_residual + get_all_loss_DeepF + get_Rt_loss(device='cpu')") if reference_modules() is not None \
+        else ("port", "oracle/fepe_oracle.py (per-pair torch.svd loop, deepFEPE/models/DeepFNet.py:232-240)")
 
 
 def pick_cpu_threads(d: dict) -> int:
@@ -285,9 +414,10 @@ def run_reference(args):
     rank, world, _ = dist_env()
     if rank != 0:
         return
-    B, N = args.batch, args.ncorr
+    B, N, label = workload_shape(args)
     base = make_host_batches(2, B, N, seed0=1000)
     pick_cpu_threads(base[0])
+    kind, how = reference_kind()
     # calibrate the per-step sample so that the whole run stays within ~2 minutes
     t = time.perf_counter()
     reference_step(slice_batch(base[0], min(B, 32)))
@@ -306,12 +436,10 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"C2: batch={B} pairs x N={N} corr, 30% outliers, Fit + epi residual + F-loss + E->R,t",
-                   "pairs_per_step_sample": n_s, "ncorr": N},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+        "config": bench_config(label, B, N),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": torch.get_num_threads(), "kind": kind,
                          "host_cores": os.cpu_count(),
-                         "sample": f"{n_s} of the {B} pairs of a step, {args.steps} steps; oracle/fepe_oracle.py "
-                                   "(per-pair torch.svd loop like deepFEPE/models/DeepFNet.py:232-240) on host cores"},
+                         "sample": f"{n_s} of the {B} pairs of a step, {args.steps} steps; {how} on host cores"},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -338,15 +466,26 @@ def run_ours(args):
     entry.build()
     from fepe_b200 import ops, synth, _lib
 
-    B, N = args.batch, args.ncorr
+    B, N, label = workload_shape(args)
+    K = args.steps
     aff = ops.hw_affine(synth.KITTI_IMAGE_SIZE)
     per_batch_bytes = B * N * 20
     ring_n = max(2, int(np.ceil(1.6 * L2_BYTES / per_batch_bytes)))
     ring_n = min(ring_n, 96)
     n_branch = 1 if args.no_graph else max(1, args.streams)
-    ring_n = (ring_n + n_branch - 1) // n_branch * n_branch      # a batch's output buffers stay on one branch
+    if K < ring_n:
+        ring_n = (ring_n + K - 1) // K * K                        # ring_n // K graphs tile the ring exactly
+    else:
+        ring_n = (ring_n + n_branch - 1) // n_branch * n_branch   # a batch's output buffers stay on one branch
     sampler = ClockSampler(local)
     sampler.start()
+
+    def reduce_max(v: float) -> float:
+        if not use_dist:
+            return v
+        tt = torch.tensor([v], device=dev, dtype=torch.float64)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        return float(tt.item())
 
     host = make_host_batches(ring_n, B, N, seed0=10_000 * (rank + 1))
     ring = [DeviceBatch(d, dev) for d in host]
@@ -354,63 +493,96 @@ def run_ours(args):
         step_full(db, aff)          # first-use configuration happens outside any graph capture
     torch.cuda.synchronize()
 
+    step_fns = [(lambda db=db: step_full(db, aff)) for db in ring]
     if args.no_graph:
-        full_calls = [(lambda db=db: step_full(db, aff)) for db in ring]
-        fit_calls = [(lambda db=db: step_full(db, aff)) for db in ring]
+        fit_calls = step_fns
     else:
         s = torch.cuda.Stream()
         with torch.cuda.stream(s):
-            fit_graphs = [capture(lambda db=db: step_full(db, aff)) for db in ring]     # the timed step's own launch
+            fit_graphs = [capture(fn) for fn in step_fns]     # the timed step's own launch
         torch.cuda.synchronize()
-        full_calls = None                      # the contract loop is recorded below as one pipelined graph
         fit_calls = [g.replay for g in fit_graphs]
 
-    # ---- the contract number: K steps, device timed, max over ranks -----------------------------
+    # ---- the contract number: K-step unit, device timed, >= min_ms, max over ranks ---------------
     W = max(args.warmup, 3)
-    if args.no_graph:
-        secs, t0, t1 = timed_loop(full_calls, args.steps, W, barrier)
+    secs, n_timed, replays, t0, t1 = measure_steps(step_fns, K, W, n_branch, args.min_ms, barrier, reduce_max,
+                                                   args.no_graph)
+    secs = reduce_max(secs)
+    value = world * B * n_timed / secs
+    # the same with ONE branch: launches strictly back to back (what a caller without parallel streams gets)
+    if n_branch > 1:
+        secs1, n1, _, _, _ = measure_steps(step_fns, K, W, 1, args.min_ms, barrier, reduce_max, args.no_graph)
+        value_serial = world * B * n1 / reduce_max(secs1)
     else:
-        # W warm-up steps and EXACTLY K timed steps, each set recorded as one graph over n_branch branches
-        step_fns = [(lambda db=db: step_full(db, aff)) for db in ring]
-        g_warm = capture_pipelined(step_fns, W, 0, n_branch)
-        g_timed = capture_pipelined(step_fns, args.steps, W, n_branch)
-        torch.cuda.synchronize()
-        g_warm.replay()
-        secs, t0, t1 = timed_loop([g_timed.replay], 1, 0, barrier)
-    if use_dist:
-        tt = torch.tensor([secs], device=dev, dtype=torch.float64)
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        secs = float(tt.item())
-    value = world * B * args.steps / secs
+        value_serial = value
 
     # ---- dominant kernel alone at this launch size ----------------------------------------------
-    fit_secs, _, _ = timed_loop(fit_calls, max(args.steps, 200), 10)
-    fit_us = fit_secs / max(args.steps, 200) * 1e6
+    n_alone = max(K, 200)
+    fit_secs, _, _ = timed_loop(fit_calls, n_alone, 10)
+    fit_us = fit_secs / n_alone * 1e6
     peak, peak_src = measured_peak_gbs()
     achieved = fit_bytes(B, N) / (fit_us * 1e-6) / 1e9
     sms = torch.cuda.get_device_properties(dev).multi_processor_count
     small = B <= (6 if N * 20 <= 28 * 1024 else 2) * sms and N * 20 <= 56 * 1024      # fepe_fit.cu: fit_fwd_impl
     fit_kernel = "fepe_fit_fwd_small_kernel<POSE>" if small else "fepe_fit_fwd_kernel + fepe_pose_fwd_kernel"
+    traffic = ncu_traffic(B, N)
     roofline = {"bound": "hbm", "kernel": fit_kernel, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": ncu_traffic(B, N), "launch_us": fit_us,
+                "frac": achieved / peak, "traffic": traffic,
+                "traffic_source": None if traffic is None else
+                "static: profiles/traffic.json (dram__bytes of the same launch from the committed ncu --set full capture; "
+                "not re-measured in this run)",
+                "launch_us": fit_us,
                 "algorithmic_bytes_per_launch": fit_bytes(B, N), "peak_source": peak_src,
                 "note": "ONE launch of the timed step alone, single stream (batches of <= 6 pairs per SM go to the "
                         "one-CTA-per-pair latency kernel with the pose head fused into it, fepe_fit_pose_fwd); "
-                        "roofline_saturating is the split pipeline the same entry point uses for batches that fill "
-                        "the 148 SMs many times over"}
+                        "roofline_saturating is the same entry point at a batch that fills the 148 SMs many times over"}
 
     line = {
-        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-        "warmup": W, "ms_per_step": secs / args.steps * 1e3, "higher_is_better": True,
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K,
+        "warmup": W, "ms_per_step": secs / n_timed * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32 (Gram / eigen / SVD in f64)", "data": "synthetic",
-        "config": {"workload": f"C2: batch={B} pairs x N={N} corr, 30% outliers, Fit + epi residual + F-loss + E->R,t",
-                   "batch_per_gpu": B, "ncorr": N, "parallelism": f"pairs sharded over {world} GPU(s), no collective",
-                   "l2_policy": f"ring of {ring_n} distinct batches ({ring_n * per_batch_bytes / 2**20:.0f} MiB) > 126 MiB L2",
-                   "launch": "eager" if args.no_graph else
-                   f"one CUDA graph of the K step launches on {n_branch} parallel branch(es) (independent batches)"},
-        "gpu_launches": args.steps * (1 if small else 2),
+        "config": bench_config(label, B, N),
+        "replays": replays, "timed_steps": n_timed, "timed_region_ms": secs * 1e3,
+        "value_serial": value_serial,
+        "run": {"parallelism": f"pairs sharded over {world} GPU(s), no collective",
+                "l2_policy": f"ring of {ring_n} distinct batches ({ring_n * per_batch_bytes / 2**20:.0f} MiB) > 126 MiB L2, "
+                             "walked across the graph replays",
+                "launch": "eager" if args.no_graph else
+                f"value: CUDA graphs of K step launches on {n_branch} parallel branches (independent batches), replayed "
+                f"{replays}x; value_serial: the same on 1 branch"},
+        "gpu_launches": n_timed * (1 if small else 2),
         "roofline": roofline,
     }
+
+    if not args.no_extras:
+        # ---- forward + backward of the same step ("fwd and fwd+bwd") --------------------
+        for i, db in enumerate(ring):
+            db.enable_backward(777 + i)
+        step_fwd_bwd(ring[0], aff)
+        torch.cuda.synchronize()
+        bwd_fns = [(lambda db=db: step_fwd_bwd(db, aff)) for db in ring]
+        bsecs, bn, brep, _, _ = measure_steps(bwd_fns, K, W, n_branch, args.min_ms, barrier, reduce_max, args.no_graph)
+        bsecs = reduce_max(bsecs)
+        if args.no_graph:
+            b_alone = bwd_fns
+        else:
+            with torch.cuda.stream(torch.cuda.Stream()):
+                b_graphs = [capture(fn) for fn in bwd_fns[:max(8, min(len(bwd_fns), 48))]]
+            torch.cuda.synchronize()
+            b_alone = [g.replay for g in b_graphs]
+        b_secs1, _, _ = timed_loop(b_alone, 200, 10)
+        b_us = b_secs1 / 200 * 1e6
+        b_ach = bwd_bytes(B, N) / (b_us * 1e-6) / 1e9
+        line["bwd"] = {"value": world * B * bn / bsecs, "unit": UNIT, "ms_per_step": bsecs / bn * 1e3, "replays": brep,
+                       "what": "forward (fit saving its state + fused loss head) + fepe_pose_bwd + fepe_fit_bwd, same "
+                               "batches, same graph / branch structure as `value`",
+                       "kernels": ("fepe_fit_fwd_small_kernel<POSE>" if small else "fepe_fit_fwd_kernel + fepe_pose_fwd_kernel")
+                       + " + fepe_pose_bwd_kernel + fepe_fit_bwd_kernel<0>",
+                       "gpu_launches_per_step": (1 if small else 2) + 2,
+                       "roofline": {"bound": "hbm", "achieved": b_ach, "peak": peak, "unit": "GB/s", "frac": b_ach / peak,
+                                    "launch_us": b_us, "algorithmic_bytes_per_step": bwd_bytes(B, N),
+                                    "note": "one forward + backward step alone on one stream; bytes: forward 28 N + 548, "
+                                            "backward 32 N + 548 per pair"}}
 
     if not args.no_extras:
         # ---- end to end through the host API: pinned host -> device -> results on host ------------
@@ -435,7 +607,7 @@ def run_ours(args):
             else:
                 stages[j].replay()
 
-        e2e_steps = max(50, min(args.steps, 400))
+        e2e_steps = max(200, min(args.steps, 400))
         # the PCIe ceiling of THIS box at this moment: the same pinned buffers copied with nothing else, issued exactly like
         # the e2e steps (one captured graph per slot, round-robin over the slots' streams)
         copy_graphs = []
@@ -477,10 +649,7 @@ def run_ours(args):
         e1.record()
         torch.cuda.synchronize()
         e2e_secs = max(e0.elapsed_time(e1) * 1e-3, time.perf_counter() - tw0)
-        if use_dist:
-            tt = torch.tensor([e2e_secs], device=dev, dtype=torch.float64)
-            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-            e2e_secs = float(tt.item())
+        e2e_secs = reduce_max(e2e_secs)
         line["e2e"] = {"value": world * B * e2e_steps / e2e_secs, "unit": UNIT, "h2d_bytes_per_step": h2d,
                        "d2h_bytes_per_step": d2h, "steps": e2e_steps, "ms_per_step": e2e_secs / e2e_steps * 1e3,
                        "h2d_only_ms_per_step": h2d_only_us * 1e-3,
@@ -525,13 +694,18 @@ def run_ours(args):
             reference_step(sample[n_done % 2])
             n_done += 1
         cpu_secs = time.perf_counter() - tc0
+        kind, how = reference_kind()
         line["cpu_baseline"] = {"value": sample[0]["matches_xy_ori"].shape[0] * n_done / cpu_secs, "unit": UNIT,
-                                "cores": torch.get_num_threads(), "kind": "port", "host_cores": os.cpu_count(),
+                                "cores": torch.get_num_threads(), "kind": kind, "host_cores": os.cpu_count(),
                                 "sample": f"{n_done} x {sample[0]['matches_xy_ori'].shape[0]} pairs x N={N} of the same "
-                                          "workload through oracle/fepe_oracle.py (per-pair torch.svd loop, "
-                                          "deepFEPE/models/DeepFNet.py:232-240) in {:.1f} s".format(cpu_secs)}
+                                          f"workload through {how} in {cpu_secs:.1f} s"}
     if "e2e" not in line:
         line["e2e"] = None
+    if use_dist and not args.no_extras:
+        # the one collective north_star names: the training step (C5, 16 pairs per GPU) with its gradient all-reduce
+        del ring
+        torch.cuda.empty_cache()
+        line["training_step"] = c5_measure(args, dev, rank, world, steps=10, warm=3, mlp=args.mlp)
 
     sampler.stop_flag = True
     sampler.join(timeout=1.0)
@@ -557,15 +731,24 @@ def run_c4(args):
     B, N = (512 if args.batch == 256 else args.batch), args.ncorr
     torch.manual_seed(0)
     net = DeepFNet(depth=5, image_size=list(synth.KITTI_IMAGE_SIZE), if_quality=False).cuda().eval()
-    net.enable_tensor_core_mlp(True)
     host = make_host_batches(2, min(B, 128), N, seed0=77)
     batches = [{"matches_xy_ori": torch.from_numpy(d["matches_xy_ori"]).to(dev).repeat((B + 127) // 128, 1, 1)[:B].contiguous()}
                for d in host]
     steps, warm = min(args.steps, 50), max(3, min(args.warmup, 10))
+    sampler = ClockSampler(local)
+    sampler.start()
+    res = {}
     with torch.no_grad():
-        secs, t0, t1 = timed_loop([(lambda b=b: net(b)) for b in batches], steps, warm)
-        net.enable_tensor_core_mlp(False, False)
-        secs32, _, _ = timed_loop([(lambda b=b: net(b)) for b in batches], max(3, steps // 10), 2)
+        for path in dict.fromkeys([args.mlp, "tc32", "bf16"]):
+            net.set_mlp_path(path)
+            secs, t0, t1 = timed_loop([(lambda b=b: net(b)) for b in batches], steps, warm)
+            res[path] = (secs, t0, t1)
+        net.set_mlp_path("torch")
+        n32 = max(3, steps // 10)
+        secs32, _, _ = timed_loop([(lambda b=b: net(b)) for b in batches], n32, 2)
+    secs, t0, t1 = res[args.mlp]
+    sampler.stop_flag = True
+    sampler.join(timeout=1.0)
     flop_per_pt = lambda cin: 2 * (cin * 64 + 64 * 128 + 128 * 1024 + 1024 * 512 + 512 * 256 + 256)
     flops = B * N * (flop_per_pt(4) + 4 * flop_per_pt(7))
     try:
@@ -573,34 +756,41 @@ def run_c4(args):
             peak_tf = float(json.load(f)["bf16_tflops_sustained"])
     except Exception:
         peak_tf = 1400.0
+    mma_per_flop = {"tc32": 3.0, "bf16": 1.0, "torch": 0.0}[args.mlp]
+    dtype = {"tc32": "MLP: split-fp16 (hi + lo) operands, 3 x tcgen05 kind::f16 MMAs per product, fp32 accumulate, fp32 "
+                     "activations, fp64 statistics = fp32 parity; solver f32 / f64",
+             "bf16": "bf16 MLP (fp32 accumulate) + f32/f64 solver", "torch": "fp32 library MLP + f32/f64 solver"}[args.mlp]
+    ach = flops / (secs / steps) / 1e12
     line = {"metric": METRIC, "value": world * B * steps / secs, "unit": UNIT, "n_gpus": world, "steps": steps,
             "warmup": warm, "ms_per_step": secs / steps * 1e3, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "bf16 MLP (fp32 accumulate) + f32/f64 solver", "data": "synthetic",
+            "vs_baseline": None, "dtype": dtype, "data": "synthetic",
             "config": {"workload": f"C4: DeepFNet forward depth 5 (5 ErrorEstimator evaluations on tcgen05 + 5 fused fits), "
                                    f"batch={B} x N={N}, inference", "batch_per_gpu": B, "ncorr": N},
-            "roofline": {"bound": "tensor", "kernel": "fepe_mlp_gemm_persist_kernel (whole step counted)",
-                         "achieved": flops / (secs / steps) / 1e12, "peak": peak_tf, "unit": "TFLOP/s",
-                         "frac": flops / (secs / steps) / 1e12 / peak_tf, "traffic": None,
-                         "note": "MLP flops of the step / step time: includes the memory-bound norm kernels and the fits"},
-            "fp32_cudnn_mlp_pairs_per_sec": world * B * max(3, steps // 10) / secs32,
-            # per ErrorEstimator evaluation: first, 4 x scale_shift, 3 x gemm_norm, norm + gemm (the 128 -> 1024 layer
-            # keeps its norm kernel), last_norm = 11 launches; one fit launch per DeepFNet iteration
-            "gpu_launches": steps * (5 * 11 + 5)}
+            "mlp_path": args.mlp,
+            "roofline": {"bound": "tensor", "kernel": "fepe_mlp32_gemm_kernel (whole step counted)" if args.mlp == "tc32"
+                         else "fepe_mlp_gemm_persist_kernel (whole step counted)",
+                         "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach / peak_tf, "traffic": None,
+                         "executed_tensor_tflops": ach * mma_per_flop, "executed_frac": ach * mma_per_flop / peak_tf,
+                         "note": "achieved = ALGORITHMIC MLP flops of the step (1.59 MFLOP per correspondence and "
+                                 "evaluation) / step time, against the measured bf16 cuBLAS rate; the fp32-parity path "
+                                 "executes 3 fp16 MMAs per product (executed_*), so its ceiling on this scale is 1/3; "
+                                 "the step also contains the first / last layers, the statistics and the 5 fits"},
+            "pairs_per_sec_by_mlp_path": {k: world * B * steps / v[0] for k, v in res.items()} |
+                                         {"torch": world * B * n32 / secs32},
+            # per ErrorEstimator evaluation (tc32): first, 5 x scale_shift, 4 x gemm, last = 11 launches; one fit launch
+            # per DeepFNet iteration
+            "gpu_launches": steps * (5 * 11 + 5),
+            "clocks": sampler.summary(t0, t1)}
     if rank == 0:
         print(json.dumps(line), flush=True)
 
 
-def run_c5(args):
-    """Config 5 of BASELINE.json: end-to-end training step (random keypoints stand in for SuperPoint), batch 128
-    over 8 GPUs = 16 pairs per GPU; the only collective is the flattened gradient all-reduce."""
-    rank, world, local = dist_env()
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
+def c5_measure(args, dev, rank, world, steps: int, warm: int, mlp: str) -> dict:
+    """Config 5 of BASELINE.json: end-to-end training step (random keypoints / descriptors stand in for SuperPoint),
+    16 pairs per GPU (batch 128 over 8 GPUs); the only collective is ONE all-reduce of the flat gradient buffer
+    (fepe_b200.dist.FlatGradients; the reference: nn.DataParallel, deepFEPE/train_good.py:309-314).  The process group
+    must already exist when world > 1."""
     import torch.distributed as dist
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
-    import __graft_entry__ as entry
-    entry.build()
     from fepe_b200 import synth, dist as fdist
     from fepe_b200.models import DeepFNet
     from fepe_b200.matching import get_matches_from_descriptors
@@ -610,7 +800,9 @@ def run_c5(args):
     torch.manual_seed(0)
     # with_quality (configs/kitti_corr_baseline.yaml): the match score is the one quality channel
     net = DeepFNet(depth=5, image_size=list(synth.KITTI_IMAGE_SIZE), if_quality=True, quality_size=1).cuda()
+    net.set_mlp_path(mlp)
     opt = torch.optim.Adam(net.parameters(), lr=1e-4)          # configs/kitti_corr_baseline.yaml:62
+    flat = fdist.FlatGradients(net.parameters())
     # "SuperPoint frozen / random desc": a synthetic two-view scene gives NKP corresponding keypoints; image 2's are
     # shuffled and carry noisy copies of image 1's random unit descriptors.  The step starts from keypoints + descriptors.
     d = synth.make_batch(B, NKP, seed=500 + rank)
@@ -632,12 +824,11 @@ def run_c5(args):
         dist_ = dd.abs() * (1 / (l1[:, :, :2].norm(2, 2) + 1e-6) + 1 / (l2[:, :, :2].norm(2, 2) + 1e-6))
         return torch.clamp(dist_, max=clamp)
 
-    times = {"match": 0.0, "fwd": 0.0, "bwd": 0.0, "allreduce": 0.0}
     n_matches = []
 
     def step():
-        ev = [torch.cuda.Event(enable_timing=True) for _ in range(5)]
-        opt.zero_grad(set_to_none=True)
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(6)]
+        flat.zero_()
         ev[0].record()
         # train_good_utils.py:649-724: mutual-NN matches -> [B,N,4] + quality (fepe_nn_match, on the device)
         mt = get_matches_from_descriptors(kp1, kp2, desc1, desc2, 1.0, out_num_points=N, generator=gen)
@@ -657,48 +848,75 @@ def run_c5(args):
         ev[2].record()
         loss.backward()
         ev[3].record()
-        fdist.allreduce_mean_grads_(list(net.parameters()))
+        flat.allreduce_mean_()
         ev[4].record()
         opt.step()
+        ev[5].record()
         return ev
 
+    names = ("match", "fwd", "bwd", "allreduce", "adam")
+    for _ in range(warm):
+        step()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    evs = [step() for _ in range(steps)]
+    e1.record()
+    torch.cuda.synchronize()
+    secs = fdist.max_over_ranks(e0.elapsed_time(e1) * 1e-3, dev)
+    br = {k: sum(ev[i].elapsed_time(ev[i + 1]) for ev in evs) / steps for i, k in enumerate(names)}
+    # the collective alone, back to back (device time, max over ranks): the step's own interval also contains the wait
+    # for the slowest rank's backward
+    ar_us = None
+    gbytes = flat.flat.numel() * 4
+    if world > 1:
+        for _ in range(3):
+            dist.all_reduce(flat.flat)
+        torch.cuda.synchronize()
+        dist.barrier()
+        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a0.record()
+        for _ in range(20):
+            dist.all_reduce(flat.flat)
+        a1.record()
+        torch.cuda.synchronize()
+        ar_us = fdist.max_over_ranks(a0.elapsed_time(a1) / 20 * 1e3, dev)
+    out = {"metric": "training_pairs_per_sec", "value": world * B * steps / secs, "unit": UNIT, "n_gpus": world,
+           "steps": steps, "warmup": warm, "ms_per_step": secs / steps * 1e3, "mlp_path": mlp,
+           "workload": f"C5: training step from keypoints + random descriptors ({NKP} per image, {DESC}-d): mutual-NN "
+                       f"matching -> {N} matches + quality, DeepFNet depth 5, {B} pairs/GPU, F-loss + q/t pose loss "
+                       "(device get_Rt_loss), one all-reduce of the flat gradient buffer (NCCL), Adam",
+           "global_batch": world * B,
+           "mean_matches_per_pair": float(torch.stack(n_matches[-steps:]).float().mean()),
+           "ms_breakdown": br, "grad_bytes_allreduced": gbytes,
+           "allreduce_alone_us": ar_us,
+           "allreduce_busbw_gbs": None if not ar_us else gbytes * 2 * (world - 1) / world / (ar_us * 1e-6) / 1e9}
+    del net, opt, flat
+    return out
+
+
+def run_c5(args):
+    rank, world, local = dist_env()
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    import torch.distributed as dist
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    import __graft_entry__ as entry
+    entry.build()
     steps, warm = min(args.steps, 30), max(3, min(args.warmup, 5))
-
-    def run(tc: bool):
-        net.enable_tensor_core_mlp(inference=False, training=tc)
-        for k in times:
-            times[k] = 0.0
-        for _ in range(warm):
-            step()
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        evs = [step() for _ in range(steps)]
-        e1.record()
-        torch.cuda.synchronize()
-        secs_ = fdist.max_over_ranks(e0.elapsed_time(e1) * 1e-3, dev)
-        for ev in evs:
-            times["match"] += ev[0].elapsed_time(ev[1]); times["fwd"] += ev[1].elapsed_time(ev[2])
-            times["bwd"] += ev[2].elapsed_time(ev[3]); times["allreduce"] += ev[3].elapsed_time(ev[4])
-        return secs_, {k: v / steps for k, v in times.items()}
-
-    secs32, br32 = run(False)
-    secs, br = run(True)
-    line = {"metric": "training_pairs_per_sec", "value": world * B * steps / secs, "unit": UNIT, "n_gpus": world,
-            "steps": steps, "warmup": warm, "ms_per_step": secs / steps * 1e3, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "bf16 MLP forward+backward on tcgen05 (fp32 accumulate) + f32/f64 solver kernels",
-            "data": "synthetic",
-            "config": {"workload": f"C5: training step from keypoints + random descriptors ({NKP} per image, {DESC}-d): mutual-NN "
-                                   f"matching -> {N} matches + quality, DeepFNet depth 5, {B} pairs/GPU, F-loss + q/t pose "
-                                   "loss (device get_Rt_loss), Adam, one flattened gradient all-reduce (NCCL)",
-                       "global_batch": world * B,
-                       "mean_matches_per_pair": float(torch.stack(n_matches[-steps:]).float().mean())},
-            "ms_breakdown": br,
-            "fp32_autograd_mlp": {"value": world * B * steps / secs32, "ms_per_step": secs32 / steps * 1e3,
-                                  "ms_breakdown": br32},
-            "grad_bytes_allreduced": sum(p.numel() for p in net.parameters()) * 4}
+    res = c5_measure(args, dev, rank, world, steps, warm, args.mlp)
+    ref = c5_measure(args, dev, rank, world, max(3, steps // 3), 2, "torch") if args.mlp != "torch" else None
+    line = {"metric": "training_pairs_per_sec", "value": res["value"], "unit": UNIT, "n_gpus": world,
+            "steps": steps, "warmup": warm, "ms_per_step": res["ms_per_step"], "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None,
+            "dtype": {"tc32": "MLP: split-fp16 (3 x tcgen05 kind::f16, fp32 accumulate, fp32 activations) = fp32 parity; "
+                              "solver f32 / f64", "bf16": "bf16 MLP forward + backward on tcgen05 (fp32 accumulate) + f32/f64 "
+                                                         "solver kernels", "torch": "fp32 library MLP + f32/f64 solver kernels"}[args.mlp],
+            "data": "synthetic", "config": {"workload": res["workload"], "global_batch": res["global_batch"]},
+            "training_step": res, "fp32_library_mlp": ref}
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

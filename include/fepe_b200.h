@@ -41,6 +41,21 @@ extern "C" {
 /* library / build identification: returns e.g. "fepe_b200 0.1 sm_100a" (host pointer, static). */
 const char* fepe_version(void);
 
+/* Test / tuning hook (host call, process-wide, thread-safe; no environment variable is ever read): force a kernel
+ * variant the library otherwise picks from the problem size, so that every path can be exercised at small sizes.
+ *   FEPE_DISPATCH_FIT        0 by size | 1 one-CTA-per-pair latency kernel | 2 persistent pair ring | 3 split pipeline
+ *   FEPE_DISPATCH_GRAM_TEAM  0 by size | 1, 2, 3 = teams of 1, 2, 4 warps per pair in the split pipeline's Gram kernel
+ *   FEPE_DISPATCH_MLP_GEMM   0 by size | 1 one tile per CTA | 2 persistent kernel with 128-column tiles (bf16 path)
+ *   FEPE_DISPATCH_MLP_FUSE   0 default | 2 fused-norm variant with 8 transform warps (bf16 path)
+ * A forced variant that cannot run the problem falls back to the automatic choice.  Returns the previous value, or
+ * FEPE_E_BADARG. */
+#define FEPE_DISPATCH_FIT       0
+#define FEPE_DISPATCH_GRAM_TEAM 1
+#define FEPE_DISPATCH_MLP_GEMM  2
+#define FEPE_DISPATCH_MLP_FUSE  3
+#define FEPE_DISPATCH_COUNT     4
+int fepe_set_dispatch(int which, int value);
+
 /* Largest N one launch can stage (depends on the device's opt-in shared memory). Host call. */
 int fepe_max_correspondences(void);
 
@@ -179,6 +194,40 @@ int fepe_mlp_last_bwd(const float* dlogits, const void* X, const float* W, void*
                       int Npad, int Ci, void* stream);
 int fepe_mlp_first_bwd(const void* dY, const float* X0, const float* W, float* dX0, float* dW, int B, int N, int Npad,
                        int Ci, int Co, void* stream);
+
+/* ---- the same MLP at the reference's fp32 accuracy, still on tensor cores (the DEFAULT path of the modules) ----------
+ * Replaces ErrorEstimator.forward (deepFEPE/models/ErrorEstimators.py:46-68, fp32 in the reference) and the softmax
+ * (DeepFNet.py:443,512).  tcgen05 has no fp32 operands: every operand is split into two fp16 numbers (hi + lo, 22
+ * significant bits) and a product is three kind::f16 MMAs accumulated in fp32 (x w ~= hi hi + lo hi + hi lo), which
+ * keeps the logits within ~1e-5 of an fp32 evaluation.  Activations are fp32 row-major [B*Npad, C] in memory
+ * (Npad = N rounded up to 128; padded rows are zero and excluded from the statistics); every GEMM applies the previous
+ * block's InstanceNorm + LeakyReLU to its operand on the fly, so normalised activations are never stored.
+ *   fepe_mlp32_prepare_weights  W [Co,K] fp32 -> Whi, Wlo [Co,K] fp16 of W * s and wscale [4] = (s, 1/s, scratch, -),
+ *                               s = the power of two that puts max |W| into [2^13, 2^14)
+ *   fepe_mlp32_first            layer 1 straight from the model's inputs (DeepFNet.get_input :359-404 and the torch.cat
+ *                               of :487 are folded in): channels = [((ax x1+bx)+1)/2, ((ay y1+by)+1)/2, same for x2,y2]
+ *                               when matches [B,N,4] != NULL, then extra0..3, each [B,N,c_i] fp32 or NULL; at most 16
+ *                               channels in total; W [64,Ci] fp32, bias [64] or NULL -> Y [B*Npad,64] + stats
+ *   fepe_mlp32_scale_shift      stats [B,Co,2] fp64 (sum, sum of squares; zeroed by the caller before the producing
+ *                               launch) -> ss [B,Co,2] fp32 = (a, d), x' = LeakyReLU(a y + d); biased variance, eps
+ *   fepe_mlp32_gemm             Y = LeakyReLU(a Yprev + d) W^T (+ bias) with K % 64 == 0, Co % 64 == 0 -> Y [B*Npad,Co] +
+ *                               stats (or NULL).  ss == NULL: Yprev is used as is (data-gradient GEMM dX = dY W with
+ *                               Whi/Wlo of W^T, Nvalid = Npad)
+ *   fepe_mlp32_last             logits [B,Co,N] = LeakyReLU(a Y + d) W[Co,256]^T + bias for Co = 1 (then weights [B,N] =
+ *                               softmax over N, or NULL) or Co = 4 (the offsets network, DeepFNet.py:341-342)
+ */
+int fepe_mlp32_prepare_weights(const float* W, void* Whi, void* Wlo, float* wscale, int Co, int K, void* stream);
+int fepe_mlp32_first(const float* matches, float ax, float bx, float ay, float by, const float* extra0, int c0,
+                     const float* extra1, int c1, const float* extra2, int c2, const float* extra3, int c3,
+                     const float* W, const float* bias, float* Y, double* stats, int B, int N, int Npad, int Co,
+                     void* stream);
+int fepe_mlp32_scale_shift(double* stats, const float* gamma, const float* beta, float* ss, int B, int Co, int Nvalid,
+                           float eps, int clear_stats, void* stream);
+int fepe_mlp32_gemm(const float* Yprev, const float* ss, float slope, const void* Whi, const void* Wlo,
+                    const float* wscale, const float* bias, float* Y, double* stats, int B, int Npad, int Nvalid, int K,
+                    int Co, void* stream);
+int fepe_mlp32_last(const float* Y, const float* ss, float slope, const float* W, const float* bias, float* logits,
+                    float* weights, int B, int N, int Npad, int Ci, int Co, void* stream);
 
 /* ---- validation pose recovery ----------------------------------------------------
  * Replaces, per (layer, pair), the host work of deepFEPE/dsac_tools/utils_F.py:909-954 goodCorr_eval_nondecompose

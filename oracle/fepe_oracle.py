@@ -87,14 +87,18 @@ def constraint_rows(pts1n: torch.Tensor, pts2n: torch.Tensor) -> torch.Tensor:
     return F_.normalize(p, dim=2)
 
 
-def fit_weighted_svd(pts1: torch.Tensor, pts2: torch.Tensor, weights: torch.Tensor
-                     ) -> Tuple[torch.Tensor, torch.Tensor]:
+def fit_weighted_svd(pts1: torch.Tensor, pts2: torch.Tensor, weights: torch.Tensor,
+                     canonical_sign: bool = False) -> Tuple[torch.Tensor, torch.Tensor]:
     """Fit.forward / weighted_svd (DeepFNet.py:181-257).
 
     pts1, pts2 [B,N,3] homogeneous, weights [B,1,N].  Returns out [B,3,3] (de-normalised,
     rank-2) and the signed residual X @ f [B,N].  The per-pair torch.svd loop of the
     reference (:232-240) is kept: the smallest right singular vector of X = w * p_hat gives
-    f; the 3x3 SVD zeroes the last singular value; out = T2^T F_ T1 (:256)."""
+    f; the 3x3 SVD zeroes the last singular value; out = T2^T F_ T1 (:256).
+
+    canonical_sign: LAPACK's sign of V[:,-1] is arbitrary; with True the vector is flipped so that its
+    largest-magnitude entry is positive -- the convention of the CUDA kernel (include/fepe_b200.h: fepe_fit_fwd).
+    Any sign is a valid SVD; F and the signed residual follow it."""
     w = weights.squeeze(1).unsqueeze(2)                          # [B,N,1]
     pts1n, T1 = hartley(pts1)
     pts2n, T2 = hartley(pts2)
@@ -104,6 +108,8 @@ def fit_weighted_svd(pts1: torch.Tensor, pts2: torch.Tensor, weights: torch.Tens
     for b in range(X.shape[0]):
         _, _, V = torch.svd(X[b])
         v = V[:, -1]
+        if canonical_sign:
+            v = v * torch.sign(v.detach()[v.detach().abs().argmax()])
         fvecs.append(v / v.norm())
         U3, S3, V3 = torch.svd(v.view(3, 3))
         Fs.append(U3 @ torch.diag(S3 * mask) @ V3.t())
@@ -251,10 +257,11 @@ def build_error_estimator(input_size: int, output_size: int = 1) -> nn.Sequentia
 # ----------------------------------------------------------------------------- a8
 def deepf_forward(matches_xy: torch.Tensor, image_size, net_init: nn.Module, net_update: nn.Module,
                   depth: int = 5, quality: Optional[torch.Tensor] = None,
-                  weights_im: Optional[torch.Tensor] = None) -> dict:
+                  weights_im: Optional[torch.Tensor] = None, canonical_sign: bool = False) -> dict:
     """DeepFNet.forward (DeepFNet.py:429-554) for the live option set (no offsets / des / tri).
 
-    Returns the same dict keys the reference returns (:534-548)."""
+    Returns the same dict keys the reference returns (:534-548).  canonical_sign: see fit_weighted_svd -- the signed
+    residual is an input channel of the next layer's network (:487), so layers >= 1 depend on the convention."""
     pts1, pts2, T = norm_hw(matches_xy, image_size)
     feats = [(pts1[:, :, :2] + 1) / 2, (pts2[:, :, :2] + 1) / 2]
     if quality is not None:
@@ -266,7 +273,7 @@ def deepf_forward(matches_xy: torch.Tensor, image_size, net_init: nn.Module, net
         w = w * weights_im
     out_layers, epi_layers, res_layers, w_layers, logit_layers = [], [], [], [w], [logits]
     for _ in range(depth - 1):
-        out, res = fit_weighted_svd(pts1, pts2, w)
+        out, res = fit_weighted_svd(pts1, pts2, w, canonical_sign)
         out_layers.append(out)
         res_layers.append(res)
         epi = epi_residual(pts1, pts2, out).unsqueeze(1)
@@ -277,7 +284,7 @@ def deepf_forward(matches_xy: torch.Tensor, image_size, net_init: nn.Module, net
             w = w * weights_im
         w_layers.append(w)
         logit_layers.append(logits)
-    out, res = fit_weighted_svd(pts1, pts2, w)
+    out, res = fit_weighted_svd(pts1, pts2, w, canonical_sign)
     out_layers.append(out)
     res_layers.append(res)
     return {"logits": logits.squeeze(1), "logits_layers": logit_layers, "F_est": out,

@@ -14,9 +14,11 @@
 // products of fp32 values).  The 9x9 eigenproblem and the 3x3 SVD are fp64 (fepe_math.cuh).  The
 // streaming passes (Hartley sums, residuals, epipolar distances) are fp32 like the reference.
 #include <cuda_runtime.h>
+#include <atomic>
 #include <stdint.h>
 #include <stdlib.h>
 
+#include "fepe_dispatch.cuh"
 #include "fepe_fit.cuh"
 #include "fepe_fit_passes.cuh"
 #include "fepe_pose_head.cuh"
@@ -559,9 +561,19 @@ __global__ void __launch_bounds__(kSmallThreads, FEPE_SMALL_MINBLOCKS) fepe_fit_
 
 }  // namespace fepe
 
+namespace fepe {
+static std::atomic<int> g_dispatch[FEPE_DISPATCH_COUNT];
+int dispatch_get(int which) { return g_dispatch[which].load(std::memory_order_relaxed); }
+}  // namespace fepe
+
 extern "C" {
 
-const char* fepe_version(void) { return "fepe_b200 0.1 sm_100a"; }
+const char* fepe_version(void) { return "fepe_b200 0.2 sm_100a"; }
+
+int fepe_set_dispatch(int which, int value) {
+    if (which < 0 || which >= FEPE_DISPATCH_COUNT || value < 0 || value > 3) return FEPE_E_BADARG;
+    return fepe::g_dispatch[which].exchange(value);
+}
 
 int fepe_max_correspondences(void) {
     fepe::DeviceInfo& d = fepe::device_info();
@@ -594,15 +606,15 @@ static int fit_fwd_impl(const float* matches, const float* weights, int B, int N
     }
     // Small batches are bound by the latency of one pair: spread each pair over a CTA of 4 warps.
     const int small_bytes = ((N * 20 + 127) / 128) * 128;
-    const char* force = getenv("FEPE_FIT_KERNEL");     // "ring" | "small": development override
+    const int force = fepe::dispatch_get(FEPE_DISPATCH_FIT);   // 0 = by size (default); tests force each path
     // one wave of the latency kernel: 6 CTAs per SM while a pair's stage is <= 28 KB (N <= 1400), else 2 (measured
     // crossovers against the ring kernel, profiles/r1_kernel_crossover.txt)
     const int small_ctas_per_sm = (small_bytes <= 28 * 1024) ? 6 : 2;
     bool use_small = (B <= small_ctas_per_sm * d.sms) && (small_bytes <= 56 * 1024);
-    if (force != nullptr) use_small = (force[0] == 's') && (force[1] == 'm') && (small_bytes <= 56 * 1024);
+    if (force != 0) use_small = (force == 1) && (small_bytes <= 56 * 1024);
     // Batches that fill the machine several times over go through the split pipeline (fepe_fit_split.cu).
     bool use_split = !use_small && (B >= fepe::kSplitMinPairsPerSM * d.sms) && fepe::split_path_supported(p, d);
-    if (force != nullptr) use_split = (force[0] == 's') && (force[1] == 'p') && fepe::split_path_supported(p, d);
+    if (force != 0) use_split = (force == 3) && fepe::split_path_supported(p, d);
     if (use_small && pose != nullptr) {
         if (!d.small_pose_configured) {
             e = cudaFuncSetAttribute(fepe::fepe_fit_fwd_small_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -617,8 +629,8 @@ static int fit_fwd_impl(const float* matches, const float* weights, int B, int N
         const int st = fit_fwd_impl(matches, weights, B, N, ax, bx, ay, by, clamp_at, F_out, resid, epi, saved, nullptr,
                                     stream);
         if (st != 0) return st;
-        return fepe_pose_fwd(F_out, pose->K, 1, B, ax, bx, ay, by, pose->q_gt, pose->t_gt, pose->Rt, pose->virt1,
-                             pose->virt2, pose->V, pose->clamp_at, pose->out, stream);
+        // the predecessor on the stream is our own fit kernel (writes F / residual / epi only): the head may start early
+        return fepe::launch_pose_fwd(*pose, static_cast<cudaStream_t>(stream), /*pdl=*/true);
     }
     if (use_split) return fepe::launch_split(p, d, static_cast<cudaStream_t>(stream));
     if (use_small) {

@@ -23,6 +23,7 @@
 #include <stdint.h>
 #include <stdlib.h>
 
+#include "fepe_dispatch.cuh"
 #include "fepe_fit.cuh"
 #include "fepe_fit_passes.cuh"
 
@@ -378,10 +379,10 @@ int launch_split(FitParams p, const DeviceInfo& d, cudaStream_t stream) {
     int T = 1;
     while (T < 4 && kGramConsumerWarps / T > S - 2) T *= 2;
     if (kGramConsumerWarps / T > S - 1) return FEPE_E_TOOLARGE;
-    const char* force = getenv("FEPE_GRAM_TEAM");
-    if (force != nullptr) {
-        const int t = atoi(force);
-        if ((t == 1 || t == 2 || t == 4) && kGramConsumerWarps / t <= S - 1) T = t;
+    const int force = dispatch_get(FEPE_DISPATCH_GRAM_TEAM);     // 0 = automatic; 1 / 2 / 3 = teams of 1 / 2 / 4 warps
+    if (force != 0) {
+        const int t = (force == 3) ? 4 : force;
+        if (kGramConsumerWarps / t <= S - 1) T = t;
     }
     p.ring.stages = S;
     p.ring.consumers = kGramConsumerWarps / T;

@@ -28,64 +28,14 @@
 
 #include "../../include/fepe_b200.h"
 #include "fepe_common.cuh"
+#include "fepe_dispatch.cuh"
+#include "fepe_umma.cuh"
 
 namespace fepe {
 
 constexpr int kGemmBM = 128;
 constexpr int kGemmBK = 64;          // 64 bf16 = 128 B = one swizzle atom
 constexpr int kGemmThreads = 256;
-
-__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
-    asm volatile(
-        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
-            smem_u32(dst)),
-        "l"(map), "r"(c0), "r"(c1), "r"(smem_u32(bar))
-        : "memory");
-}
-__device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tcgen05_commit(uint64_t* bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
-                 : "memory");
-}
-__device__ __forceinline__ bool elect_one() {
-    uint32_t pred = 0;
-    asm volatile(
-        "{\n\t.reg .pred P;\n\t"
-        "elect.sync _|P, 0xffffffff;\n\t"
-        "selp.u32 %0, 1, 0, P;\n\t}"
-        : "=r"(pred));
-    return pred != 0;
-}
-// K-major operand tile in shared memory, 128-byte swizzle (what a TMA box of 64 bf16 x rows produces):
-// start address >> 4, stride-byte-offset = 8 rows * 128 B, descriptor version 1, layout SWIZZLE_128B
-// (cute/arch/mma_sm100_desc.hpp: SmemDescriptor).
-__device__ __forceinline__ uint64_t umma_desc_k_sw128(const void* smem_ptr) {
-    const uint64_t addr = static_cast<uint64_t>(smem_u32(smem_ptr));
-    // leading-byte-offset field = 1 (unused for swizzled K-major, CUTLASS sets the canonical value 1)
-    return ((addr >> 4) & 0x3FFFull) | (1ull << 16) | (static_cast<uint64_t>(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
-}
-__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
-                                          uint32_t accumulate) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
-        "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
-        : "memory");
-}
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
-          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
-          "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
-          "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
-        : "r"(taddr));
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-}
 
 struct GemmParams {
     int M, K, Co;          // M = B * Npad
@@ -1116,22 +1066,6 @@ fepe_mlp_wgrad_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_c
 }
 
 // ------------------------------------------------------------------------------------------------
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
-                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
-                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-static EncodeTiledFn get_encode() {
-    static EncodeTiledFn fn = nullptr;
-    if (fn == nullptr) {
-        void* sym = nullptr;
-        cudaDriverEntryPointQueryResult q;
-        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &q) == cudaSuccess &&
-            q == cudaDriverEntryPointSuccess)
-            fn = reinterpret_cast<EncodeTiledFn>(sym);
-    }
-    return fn;
-}
-
 // 2-D bf16 row-major [rows, K] tensor, box = 64 (contiguous dim) x box_rows, 128-byte swizzle
 static bool make_map(CUtensorMap* map, const void* ptr, int rows, int K, int box_rows) {
     EncodeTiledFn enc = get_encode();
@@ -1268,18 +1202,17 @@ int fepe_mlp_gemm(const void* X, const void* W, const float* bias, void* Y, floa
     fepe::GemmParams p{B * Npad, K, Co, Npad, Nvalid, bias, static_cast<__nv_bfloat16*>(Y), stats, nullptr, 0.f};
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     // 2 stages / 2 CTAs per SM: the epilogue of one CTA overlaps the main loop of the other.  Measured faster
-    // than 4 stages / 1 CTA per SM on every layer (profiles/r1_mlp_timing.txt).  FEPE_MLP_STAGES=2|4 overrides.
+    // than 4 stages / 1 CTA per SM on every layer (profiles/r1_mlp_timing.txt).  
     // Default for Co % 128 == 0: the persistent kernel (double-buffered TMEM accumulator, 128 x 256 tiles when Co
     // allows).  FEPE_MLP_GEMM=tile selects the one-tile-per-CTA kernel, FEPE_MLP_GEMM=persist128 forces BN = 128.
-    const char* mode = getenv("FEPE_MLP_GEMM");
-    const bool tile_mode = mode != nullptr && strcmp(mode, "tile") == 0;
+    const int mode = fepe::dispatch_get(FEPE_DISPATCH_MLP_GEMM);   // 0 = automatic; 1 = one tile per CTA; 2 = persistent, BN = 128
+    const bool tile_mode = mode == 1;
     if (!tile_mode && Co % 128 == 0) {
-        const bool force128 = mode != nullptr && strcmp(mode, "persist128") == 0;
+        const bool force128 = mode == 2;
         if (Co % 256 == 0 && !force128) return fepe::launch_gemm_persist<256, 4, 0>(X, W, p, st);
         return fepe::launch_gemm_persist<128, 6, 0>(X, W, p, st);
     }
-    int stages = 2;
-    if (const char* ev = getenv("FEPE_MLP_STAGES")) stages = (ev[0] == '2') ? 2 : 4;
+    const int stages = 2;
     if (Co % 128 == 0)
         return stages == 2 ? fepe::launch_gemm<128, 2>(X, W, p, st) : fepe::launch_gemm<128, 4>(X, W, p, st);
     return stages == 2 ? fepe::launch_gemm<64, 2>(X, W, p, st) : fepe::launch_gemm<64, 4>(X, W, p, st);
@@ -1299,8 +1232,7 @@ int fepe_mlp_gemm_norm(const void* Yprev, const float* ss, float slope, const vo
     // selects variant 2 (4 epilogue + 8 transform warps, (a, d) through a shared-memory slot of the stage): measured
     // equal or slower on every layer (profiles/r1_mlp_fused_norm.md) -- the fused layers are bound by the bytes in flight
     // through the L2 and by shared-memory bandwidth, not by the transform's latency -- kept as the tested alternative.
-    const char* fv = getenv("FEPE_MLP_FUSE");
-    if (fv != nullptr && fv[0] == '2') {
+    if (fepe::dispatch_get(FEPE_DISPATCH_MLP_FUSE) == 2) {
         if (Co % 256 == 0) return fepe::launch_gemm_persist<256, 4, 2>(Yprev, W, p, st);
         return fepe::launch_gemm_persist<128, 6, 2>(Yprev, W, p, st);
     }

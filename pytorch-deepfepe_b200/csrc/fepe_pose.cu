@@ -198,6 +198,29 @@ extern "C" int fepe_pose_bwd(const float* F, const float* K, int L, int B, float
     return static_cast<int>(cudaGetLastError());
 }
 
+namespace fepe {
+// `pdl`: programmatic dependent launch -- the grid may be scheduled while the preceding kernel of the stream is still
+// running; the kernel fetches everything that does not depend on F and then blocks in griddepcontrol.wait until that
+// kernel has completed.  ONLY safe when the predecessor is known to write nothing but F / residual / epi, i.e. on the
+// internal two-launch path of fit_fwd_impl (fepe_fit.cu).  The public entry point launches with ordinary stream
+// serialization: there the preceding kernel may be the producer of K, q_gt, t_gt, Rt or the virtual points, which this
+// kernel reads BEFORE its griddepcontrol.wait.
+int launch_pose_fwd(const PoseParams& p, cudaStream_t stream, bool pdl) {
+    const int n = p.L * p.B;
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((n + 3) / 4);
+    cfg.blockDim = dim3(128);
+    cfg.dynamicSmemBytes = 0;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl ? 1 : 0;
+    return static_cast<int>(cudaLaunchKernelEx(&cfg, fepe_pose_fwd_kernel, p));
+}
+}  // namespace fepe
+
 extern "C" int fepe_pose_fwd(const float* F, const float* K, int L, int B, float ax, float bx, float ay, float by,
                              const float* q_gt, const float* t_gt, const float* Rt_scene, const float* virt1,
                              const float* virt2, int V, float clamp_at, float* out, void* stream) {
@@ -205,21 +228,5 @@ extern "C" int fepe_pose_fwd(const float* F, const float* K, int L, int B, float
     if (!F || !K || !q_gt || !t_gt || !out || L < 0 || B < 0 || V < 0) return FEPE_E_BADARG;
     if ((virt1 == nullptr) != (virt2 == nullptr)) return FEPE_E_BADARG;
     fepe::PoseParams p{F, K, q_gt, t_gt, Rt_scene, virt1, virt2, L, B, V, ax, bx, ay, by, clamp_at, out};
-    const int n = L * B;
-    // Programmatic dependent launch: the grid may be scheduled while the preceding kernel of the stream (normally
-    // fepe_fit_fwd, which produces F) is still running; the kernel fetches everything that does not depend on F and
-    // then blocks in griddepcontrol.wait until that kernel has completed and its writes are visible.  Disable with
-    // FEPE_POSE_PDL=0.
-    static const bool pdl = []() { const char* e = getenv("FEPE_POSE_PDL"); return e == nullptr || e[0] != '0'; }();
-    cudaLaunchConfig_t cfg{};
-    cfg.gridDim = dim3((n + 3) / 4);
-    cfg.blockDim = dim3(128);
-    cfg.dynamicSmemBytes = 0;
-    cfg.stream = static_cast<cudaStream_t>(stream);
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    attr[0].val.programmaticStreamSerializationAllowed = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = pdl ? 1 : 0;
-    return static_cast<int>(cudaLaunchKernelEx(&cfg, fepe::fepe_pose_fwd_kernel, p));
+    return fepe::launch_pose_fwd(p, static_cast<cudaStream_t>(stream), /*pdl=*/false);
 }

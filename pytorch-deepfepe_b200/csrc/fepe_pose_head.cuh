@@ -24,6 +24,10 @@ struct PoseParams {
     float* out;           // [L,B,FEPE_POSE_OUT_FLOATS]
 };
 
+// fepe_pose.cu; `pdl` = programmatic dependent launch, only for a predecessor that writes nothing this kernel reads
+// before its griddepcontrol.wait (the internal fit -> head pair of fepe_fit_pose_fwd)
+int launch_pose_fwd(const PoseParams& p, cudaStream_t stream, bool pdl);
+
 constexpr int kVirtPerLane = 4;     // virtual correspondences held in registers per lane (V <= 128 in one trip)
 
 __device__ __forceinline__ float virt_term(const float (&Ff)[9], float ax, float bx, float ay, float by, float clamp_at,

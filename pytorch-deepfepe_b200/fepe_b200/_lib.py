@@ -17,6 +17,8 @@ POSE_OUT_FLOATS = 32        # FEPE_POSE_OUT_FLOATS
 RECOVER_OUT_FLOATS = 24     # FEPE_RECOVER_OUT_FLOATS
 GT_FLOATS = 32              # FEPE_GT_FLOATS
 
+DISPATCH_FIT, DISPATCH_GRAM_TEAM, DISPATCH_MLP_GEMM, DISPATCH_MLP_FUSE = 0, 1, 2, 3   # FEPE_DISPATCH_*
+
 _lib = None
 
 _c_f = ctypes.c_float
@@ -26,6 +28,7 @@ _c_p = ctypes.c_void_p
 _SIGNATURES = {
     "fepe_version": (ctypes.c_char_p, []),
     "fepe_max_correspondences": (_c_i, []),
+    "fepe_set_dispatch": (_c_i, [_c_i, _c_i]),
     "fepe_fit_fwd": (_c_i, [_c_p, _c_p, _c_i, _c_i, _c_f, _c_f, _c_f, _c_f, _c_f,
                             _c_p, _c_p, _c_p, _c_p, _c_p]),
     "fepe_fit_bwd": (_c_i, [_c_p, _c_p, _c_i, _c_i, _c_f, _c_f, _c_f, _c_f, _c_f,
@@ -53,6 +56,12 @@ _SIGNATURES = {
     "fepe_mlp_normbwd": (_c_i, [_c_p, _c_p, _c_p, _c_p, _c_p, _c_p, _c_p, _c_i, _c_i, _c_i, _c_i, _c_f, _c_f, _c_p]),
     "fepe_mlp_last_bwd": (_c_i, [_c_p, _c_p, _c_p, _c_p, _c_p, _c_p, _c_i, _c_i, _c_i, _c_i, _c_p]),
     "fepe_mlp_first_bwd": (_c_i, [_c_p, _c_p, _c_p, _c_p, _c_p, _c_i, _c_i, _c_i, _c_i, _c_i, _c_p]),
+    "fepe_mlp32_prepare_weights": (_c_i, [_c_p, _c_p, _c_p, _c_p, _c_i, _c_i, _c_p]),
+    "fepe_mlp32_first": (_c_i, [_c_p, _c_f, _c_f, _c_f, _c_f, _c_p, _c_i, _c_p, _c_i, _c_p, _c_i, _c_p, _c_i,
+                                _c_p, _c_p, _c_p, _c_p, _c_i, _c_i, _c_i, _c_i, _c_p]),
+    "fepe_mlp32_scale_shift": (_c_i, [_c_p, _c_p, _c_p, _c_p, _c_i, _c_i, _c_i, _c_f, _c_i, _c_p]),
+    "fepe_mlp32_gemm": (_c_i, [_c_p, _c_p, _c_f, _c_p, _c_p, _c_p, _c_p, _c_p, _c_p, _c_i, _c_i, _c_i, _c_i, _c_i, _c_p]),
+    "fepe_mlp32_last": (_c_i, [_c_p, _c_p, _c_f, _c_p, _c_p, _c_p, _c_p, _c_i, _c_i, _c_i, _c_i, _c_i, _c_p]),
 }
 
 _ERRORS = {-1: "FEPE_E_BADARG (null pointer, misaligned buffer or non-positive size)",

@@ -75,7 +75,7 @@ class TensorCoreMLP:
         Npad = (N + 127) // 128 * 128
         dev = x.device
         lib = _lib.lib()
-        st = torch.cuda.current_stream().cuda_stream
+        st = torch.cuda.current_stream(dev).cuda_stream
         x0 = x.permute(0, 2, 1).contiguous()
         (ya, xa), stats = self._buffers(B, Npad, dev)
         slope = 0.01
@@ -153,7 +153,7 @@ class TensorCoreMLPFunction(torch.autograd.Function):
         B, Cin, N = x.shape
         Npad = (N + 127) // 128 * 128
         dev = x.device
-        st = torch.cuda.current_stream().cuda_stream
+        st = torch.cuda.current_stream(dev).cuda_stream
         M = B * Npad
         convw = [params[4 * i] for i in range(5)] + [params[20]]
         convb = [params[4 * i + 1] for i in range(5)] + [params[21]]
@@ -193,7 +193,7 @@ class TensorCoreMLPFunction(torch.autograd.Function):
         B, Cin, N, Npad = ctx.dims
         x0, w0, wb, w_last, gam, Ys, Xs, stats = ctx.saved
         dev = x0.device
-        st = torch.cuda.current_stream().cuda_stream
+        st = torch.cuda.current_stream(dev).cuda_stream
         M = B * Npad
         eps, slope = 1e-5, 0.01
         dl = dlogits.detach().reshape(B, N).float().contiguous()

@@ -99,12 +99,18 @@ class DeepFNet(nn.Module):
         self.fit = Fit(is_cuda, is_test, if_cpu_svd)
 
     def enable_tensor_core_mlp(self, inference: bool = True, training: bool = False):
-        """Run both weight networks on the tcgen05 bf16 path: under torch.no_grad() (`inference`) and / or under
-        autograd with the tensor-core backward (`training`).  fp32 PyTorch kernels remain the default."""
-        for net in (self.input_weights, self.update_weights):
+        """Round-1 switch, kept for callers: the opt-in bf16 tcgen05 path (faster, outside the reference's fp32
+        tolerance).  `set_mlp_path("tc32")` -- fp32-parity tensor cores -- is the default."""
+        return self.set_mlp_path("bf16" if (inference or training) else "tc32")
+
+    def set_mlp_path(self, path: str):
+        """Select the arithmetic of every weight network: "tc32" (split-fp16 tcgen05 GEMMs at fp32 parity, the default),
+        "bf16" (the faster bf16 tcgen05 path; opt-in, outside the reference's fp32 tolerance) or "torch" (PyTorch's fp32
+        library kernels; A/B baseline only)."""
+        for name in ("input_weights", "update_weights", "update_offsets"):
+            net = getattr(self, name, None)
             if isinstance(net, ErrorEstimator):
-                net.tensor_cores = bool(inference)
-                net.tensor_cores_training = bool(training)
+                net.set_path(path)
         return self
 
     def get_input(self, data_batch, offsets=None, iter=None):
@@ -122,9 +128,17 @@ class DeepFNet(nn.Module):
 
     @staticmethod
     def _softmax(net, logits):
-        # the tensor-core path computes the softmax over N in its last kernel
+        # the kernel paths compute the softmax over N in their last kernel
         sm = getattr(net, "last_softmax", None)
         return sm if sm is not None else F.softmax(logits, dim=2)
+
+    @staticmethod
+    def _net(net, matches, aff, extras, B, N):
+        """Evaluate a weight network on [the 4 normalised coordinates of `matches`] + `extras` (channel groups in the
+        order of the reference's torch.cat).  ErrorEstimator reads them in place (no cat / permute on its kernel paths)."""
+        if isinstance(net, ErrorEstimator):
+            return net.forward_parts(matches, aff, extras, B, N)
+        return net(ErrorEstimator._features(matches, aff, extras))
 
     def forward(self, data_batch):
         matches = data_batch['matches_xy_ori']
@@ -133,9 +147,10 @@ class DeepFNet(nn.Module):
         matches = matches.float().contiguous()
         B, N = matches.shape[0], matches.shape[1]
         aff = self.norm_HW.affine()
-        pts_normalized_in, pts1, pts2, T1, T2 = self.get_input(data_batch)
+        _, pts1, pts2, T1, T2 = self.get_input(data_batch)        # returned to the caller (outs['pts1'], ['T1'], ...)
+        base = [data_batch['quality'].float()] if self.if_quality else []      # DeepFNet.py:385-389
 
-        logits = self.input_weights(pts_normalized_in)
+        logits = self._net(self.input_weights, matches, aff, base, B, N)
         weights_pts = self._softmax(self.input_weights, logits)
         weights_prod = weights_pts * data_batch['weights_im'] if self.if_img_w else weights_pts
         _ = data_batch.get('matches_good_unique_nums'), data_batch.get('t_scene_scale')   # read, unused (:449,:453)
@@ -147,15 +162,14 @@ class DeepFNet(nn.Module):
             out, residual, epi = ops.FitFunction.apply(matches, weights_prod.reshape(B, N), *aff, 0.5)
             out_layers.append(out)
             residual_layers.append(residual)
-            epi_res = epi.unsqueeze(1)
-            epi_res_layers.append(epi_res)
-            net_in = torch.cat((pts_normalized_in, weights_prod, epi_res, residual.unsqueeze(1)), 1)
+            epi_res_layers.append(epi.unsqueeze(1))
+            # net_in = cat(pts_normalized_in, weights_prod, epi_res, residual) (:487), read in place by the first layer
+            extras = base + [weights_prod.reshape(B, N), epi, residual]
             if self.if_learn_offsets:                 # DeepFNet.py:489-505: offsets replace (not accumulate)
-                offsets_accu = self.update_offsets(net_in)
-                pts_normalized_in, pts1, pts2, T1, T2 = self.get_input(data_batch, offsets_accu, _it)
+                offsets_accu = self._net(self.update_offsets, matches, aff, extras, B, N)
+                _, pts1, pts2, T1, T2 = self.get_input(data_batch, offsets_accu, _it)
                 matches = (data_batch['matches_xy_ori'].float() + offsets_accu.permute(0, 2, 1)).contiguous()
-                net_in = torch.cat((pts_normalized_in, weights_prod, epi_res, residual.unsqueeze(1)), 1)
-            logits = self.update_weights(net_in)
+            logits = self._net(self.update_weights, matches, aff, extras, B, N)
             weights_pts = self._softmax(self.update_weights, logits)
             weights_prod = weights_pts * data_batch['weights_im'] if self.if_img_w else weights_pts
             weights_layers.append(weights_prod)

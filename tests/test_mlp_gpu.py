@@ -14,11 +14,11 @@ pytestmark = pytest.mark.gpu
 @pytest.mark.parametrize("mode", ["persist", "persist128", "tile"])
 @pytest.mark.parametrize("B,N,K,Co", [(1, 128, 64, 64), (2, 100, 64, 128), (3, 1000, 128, 1024), (2, 1000, 1024, 512),
                                       (2, 333, 512, 256), (40, 1000, 128, 256), (37, 900, 192, 384)])
-def test_gemm_against_torch_fp32(B, N, K, Co, mode, monkeypatch):
+def test_gemm_against_torch_fp32(B, N, K, Co, mode, dispatch):
     # mode: the persistent kernel (default; 128 x 256 tiles when Co allows), the same with 128 x 128 tiles, and the
-    # one-tile-per-CTA kernel (FEPE_MLP_GEMM is read by the library on every call).  The two larger cases give every
+    # one-tile-per-CTA kernel (forced through fepe_set_dispatch).  The two larger cases give every
     # persistent CTA several tiles (both TMEM accumulator buffers and the operand ring wrap around).
-    monkeypatch.setenv("FEPE_MLP_GEMM", mode)
+    dispatch("mlp_gemm", mode)
     lib = _lib.lib()
     torch.manual_seed(0)
     Npad = (N + 127) // 128 * 128
@@ -67,13 +67,13 @@ def test_error_estimator_tensor_core_path(cin, B, N):
 @pytest.mark.parametrize("variant", ["1", "2"])
 @pytest.mark.parametrize("B,N,K,Co", [(2, 100, 64, 128), (3, 1000, 128, 1024), (40, 1000, 1024, 512), (37, 900, 192, 384),
                                       (300, 1000, 64, 128), (150, 1000, 512, 256)])
-def test_gemm_norm_fused_equals_norm_then_gemm(B, N, K, Co, variant, monkeypatch):
+def test_gemm_norm_fused_equals_norm_then_gemm(B, N, K, Co, variant, dispatch):
     """fepe_mlp_gemm_norm (InstanceNorm + LeakyReLU applied to the operand tiles in shared memory) against
     fepe_mlp_norm followed by fepe_mlp_gemm: the same arithmetic, so Y is bit-identical and the statistics agree to
     fp32 summation order."""
     # variant 1 (default): (a, d) from global memory, 4 transform warps; variant 2: through a shared-memory slot of the
-    # stage, 8 transform warps (FEPE_MLP_FUSE is read by the library on every call)
-    monkeypatch.setenv("FEPE_MLP_FUSE", variant)
+    # stage, 8 transform warps (forced through fepe_set_dispatch)
+    dispatch("mlp_fuse", variant)
     lib = _lib.lib()
     torch.manual_seed(2)
     st = torch.cuda.current_stream().cuda_stream
