@@ -295,7 +295,7 @@ def measure_steps(step_fns, K: int, W: int, n_branch: int, min_ms: float, barrie
     n = len(step_fns)
     if no_graph:
         one, _, _ = timed_loop(step_fns, K, W)
-        R = int(reduce_max(max(1, int(np.ceil(min_ms * 1e-3 / max(one, 1e-9))))))
+        R = int(reduce_max(max(1, int(np.ceil(1.3 * min_ms * 1e-3 / max(one, 1e-9))))))
         secs, t0, t1 = timed_loop(step_fns, K * R, 0, barrier)
         return secs, K * R, R, t0, t1
     G = 1 if K >= n else max(1, n // K)
@@ -304,7 +304,7 @@ def measure_steps(step_fns, K: int, W: int, n_branch: int, min_ms: float, barrie
     torch.cuda.synchronize()
     g_warm.replay()
     one, _, _ = timed_loop([graphs[-1].replay], 1, 0)
-    R = int(reduce_max(max(1, int(np.ceil(min_ms * 1e-3 / max(one, 1e-9))))))
+    R = int(reduce_max(max(1, int(np.ceil(1.3 * min_ms * 1e-3 / max(one, 1e-9))))))
     secs, t0, t1 = timed_loop([g.replay for g in graphs], R, 0, barrier)
     return secs, K * R, R, t0, t1
 

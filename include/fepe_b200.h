@@ -217,17 +217,42 @@ int fepe_mlp_first_bwd(const void* dY, const float* X0, const float* W, float* d
  *                               softmax over N, or NULL) or Co = 4 (the offsets network, DeepFNet.py:341-342)
  */
 int fepe_mlp32_prepare_weights(const float* W, void* Whi, void* Wlo, float* wscale, int Co, int K, void* stream);
+/* X0_out [B,N,Ci] or NULL: the assembled input features, kept for fepe_mlp32_first_bwd */
 int fepe_mlp32_first(const float* matches, float ax, float bx, float ay, float by, const float* extra0, int c0,
                      const float* extra1, int c1, const float* extra2, int c2, const float* extra3, int c3,
-                     const float* W, const float* bias, float* Y, double* stats, int B, int N, int Npad, int Co,
-                     void* stream);
-int fepe_mlp32_scale_shift(double* stats, const float* gamma, const float* beta, float* ss, int B, int Co, int Nvalid,
-                           float eps, int clear_stats, void* stream);
-int fepe_mlp32_gemm(const float* Yprev, const float* ss, float slope, const void* Whi, const void* Wlo,
-                    const float* wscale, const float* bias, float* Y, double* stats, int B, int Npad, int Nvalid, int K,
-                    int Co, void* stream);
+                     const float* W, const float* bias, float* Y, double* stats, float* X0_out, int B, int N, int Npad,
+                     int Co, void* stream);
+/* mean_rstd [B,Co,2] fp32 or NULL: (mean, 1/sqrt(var + eps)) per (pair, channel), kept for fepe_mlp32_normbwd */
+int fepe_mlp32_scale_shift(double* stats, const float* gamma, const float* beta, float* ss, float* mean_rstd, int B, int Co,
+                           int Nvalid, float eps, int clear_stats, void* stream);
+/* a_amax (ss == NULL only; device pointer or NULL): bit pattern of max |Yprev| -- the operand is multiplied by the power
+ * of two that brings it to 2^13..2^14 before the fp16 split (gradients can lie far below fp16's range) and the result is
+ * divided by it again */
+int fepe_mlp32_gemm(const float* Yprev, const float* ss, float slope, const unsigned* a_amax, const void* Whi,
+                    const void* Wlo, const float* wscale, const float* bias, float* Y, double* stats, int B, int Npad,
+                    int Nvalid, int K, int Co, void* stream);
 int fepe_mlp32_last(const float* Y, const float* ss, float slope, const float* W, const float* bias, float* logits,
                     float* weights, int B, int N, int Npad, int Ci, int Co, void* stream);
+/* ---- backward of the same (training: what autograd does at Train_model_pipeline.py:595 for ErrorEstimators.py:46-64) --
+ * Everything fp32 in memory; the block outputs x' = LeakyReLU(a y + d) are recomputed from the saved pre-norm y.
+ *   fepe_mlp32_last_bwd   dlogits [B,Co,N] -> dX [B*Npad,Ci] (gradient of the last block's output), dW [Co,Ci] and db [Co]
+ *                         (accumulated: zero them first)
+ *   fepe_mlp32_normbwd    dX -> dY [B*Npad,C] through LeakyReLU + InstanceNorm(affine); A [B,C,2] fp64 = (sum dZ, sum dZ
+ *                         yhat) (zeroed by the caller; dbeta = sum_b A[..,0], dgamma = sum_b A[..,1]); dy_amax = bit
+ *                         pattern of max |dY| (zeroed by the caller).  C / 4 a power of two <= 256 or a multiple of 256.
+ *   fepe_mlp32_wgrad      dW [Co,Ci] += dY^T LeakyReLU(a Yprev + d) on tcgen05 (Co % 128 == 0, Ci % 64 == 0; dW zeroed by
+ *                         the caller); the data gradient dX = dY W is fepe_mlp32_gemm(dY, NULL, 1, dy_amax, (W^T)hi/lo, ...)
+ *   fepe_mlp32_first_bwd  layer 1: dW [64,Ci] += dY^T X0 and, when dX0 != NULL, dX0 [B,N,Ci] = dY W
+ */
+int fepe_mlp32_last_bwd(const float* dlogits, const float* Y, const float* ss, float slope, const float* W, float* dX,
+                        float* dW, float* db, int B, int N, int Npad, int Ci, int Co, void* stream);
+int fepe_mlp32_normbwd(const float* dX, const float* Y, const float* ss, const float* mean_rstd, const float* gamma,
+                       float slope, double* A, float* dY, unsigned* dy_amax, int B, int Npad, int Nvalid, int C,
+                       void* stream);
+int fepe_mlp32_wgrad(const float* dY, const unsigned* dy_amax, const float* Yprev, const float* ss_prev, float slope,
+                     float* dW, int M, int Npad, int Co, int Ci, void* stream);
+int fepe_mlp32_first_bwd(const float* dY, const float* X0, const float* W, float* dX0, float* dW, int B, int N, int Npad,
+                         int Ci, int Co, void* stream);
 
 /* ---- validation pose recovery ----------------------------------------------------
  * Replaces, per (layer, pair), the host work of deepFEPE/dsac_tools/utils_F.py:909-954 goodCorr_eval_nondecompose

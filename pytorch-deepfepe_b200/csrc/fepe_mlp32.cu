@@ -36,6 +36,7 @@
 
 #include "../../include/fepe_b200.h"
 #include "fepe_common.cuh"
+#include "fepe_split.cuh"
 #include "fepe_umma.cuh"
 
 namespace fepe {
@@ -59,14 +60,9 @@ struct GemmParams {
     const float* bias;       // [Co] or null (a bias in front of an InstanceNorm cancels in the normalisation)
     float* Y;                // [M, Co]
     double* stats;           // [B, Co, 2] (sum, sum of squares), zeroed by the caller; or null
+    const unsigned* a_amax;  // ss == null only: bits of max |A| (device), the operand is pre-multiplied by the power of
+                             // two that puts it at 2^13..2^14 (gradients can be far below fp16's range); or null
 };
-
-// x = hi + lo in fp16 (round to nearest, saturating): the low half of each result holds the first element
-__device__ __forceinline__ void split2(float x0, float x1, uint32_t& hi, uint32_t& lo) {
-    asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(hi) : "f"(x1), "f"(x0));
-    const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&hi));
-    asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(lo) : "f"(x1 - f.y), "f"(x0 - f.x));
-}
 
 __device__ __forceinline__ void group_sync(int g) { asm volatile("bar.sync %0, %1;" ::"r"(g + 1), "r"(128) : "memory"); }
 
@@ -250,6 +246,7 @@ fepe_mlp32_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
         const int row = static_cast<int>(threadIdx.x) - 384;
         const int sw = row & 7;
         const float slope = p.slope;
+        const float a_scale = (!has_ss && p.a_amax != nullptr) ? pow2_scale(__ldg(p.a_amax)) : 1.f;
         uint32_t it = 0;
         for (int j = 0; j < n_local; ++j) {
             for (int kb = 0; kb < num_kb; ++kb, ++it) {
@@ -275,6 +272,9 @@ fepe_mlp32_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
                         v[2 * q] = fmaxf(t0, slope * t0);
                         v[2 * q + 1] = fmaxf(t1, slope * t1);
                     }
+                } else if (a_scale != 1.f) {
+#pragma unroll
+                    for (int q = 0; q < kBK; ++q) v[q] *= a_scale;
                 }
 #pragma unroll
                 for (int c = 0; c < 8; ++c) {                                 // fp16 chunk c = channels 8c .. 8c+7
@@ -298,7 +298,7 @@ fepe_mlp32_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
         const int et = wq * 32 + lane;                        // thread inside the group
         unsigned char* tile = epi_tiles + g * kTileBytes;
         const bool has_bias = p.bias != nullptr;
-        const float inv_scale = __ldg(p.wscale + 1);
+        const float inv_scale = __ldg(p.wscale + 1) / ((!has_ss && p.a_amax != nullptr) ? pow2_scale(__ldg(p.a_amax)) : 1.f);
         for (int j = 0; j < n_local; ++j) {
             const int t = static_cast<int>(blockIdx.x) + j * static_cast<int>(gridDim.x);
             const int m0 = (t / n_tiles) * kBM, n0 = (t % n_tiles) * BN;
@@ -365,15 +365,7 @@ __global__ void __launch_bounds__(256) absmax_kernel(const float* __restrict__ W
 
 __global__ void __launch_bounds__(256) split_weights_kernel(const float* __restrict__ W, size_t n, __half* __restrict__ Whi,
                                                             __half* __restrict__ Wlo, float* __restrict__ wsc) {
-    const float amax = __uint_as_float(reinterpret_cast<const unsigned int*>(wsc)[2]);
-    float s = 1.f;
-    if (amax > 0.f) {
-        int ex;
-        frexpf(amax, &ex);                                 // amax in [2^(ex-1), 2^ex)
-        int e = 14 - ex;
-        e = e > 100 ? 100 : (e < -100 ? -100 : e);
-        s = ldexpf(1.f, e);
-    }
+    const float s = pow2_scale(reinterpret_cast<const unsigned int*>(wsc)[2]);
     if (blockIdx.x == 0 && threadIdx.x == 0) { wsc[0] = s; wsc[1] = 1.f / s; }
     for (size_t i = (blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x) * 2; i < n; i += static_cast<size_t>(gridDim.x) * blockDim.x * 2) {
         const float x0 = W[i] * s, x1 = (i + 1 < n) ? W[i + 1] * s : 0.f;
@@ -393,8 +385,9 @@ __global__ void __launch_bounds__(256) split_weights_kernel(const float* __restr
 // (biased variance like InstanceNorm1d).  One thread per (pair, channel); ss[b][c] = (a_c, d_c).  With `clear` the
 // statistics are zeroed for the next accumulation.
 __global__ void __launch_bounds__(256) scale_shift_kernel(double* __restrict__ stats, const float* __restrict__ gamma,
-                                                          const float* __restrict__ beta, float2* __restrict__ ss, int total,
-                                                          int Co, int Nvalid, float eps, int clear) {
+                                                          const float* __restrict__ beta, float2* __restrict__ ss,
+                                                          float2* __restrict__ mr, int total, int Co, int Nvalid, float eps,
+                                                          int clear) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= total) return;
     const int c = i % Co;
@@ -404,8 +397,10 @@ __global__ void __launch_bounds__(256) scale_shift_kernel(double* __restrict__ s
     const double mean = v.x * invN;
     double var = v.y * invN - mean * mean;
     var = var > 0.0 ? var : 0.0;
-    const double a = static_cast<double>(gamma[c]) / sqrt(var + static_cast<double>(eps));
+    const double rstd = 1.0 / sqrt(var + static_cast<double>(eps));
+    const double a = static_cast<double>(gamma[c]) * rstd;
     ss[i] = make_float2(static_cast<float>(a), static_cast<float>(static_cast<double>(beta[c]) - mean * a));
+    if (mr != nullptr) mr[i] = make_float2(static_cast<float>(mean), static_cast<float>(rstd));   // for the backward pass
     if (clear) *sp = make_double2(0.0, 0.0);
 }
 
@@ -426,6 +421,7 @@ struct FirstParams {
     const float* bias;         // [64] or null
     float* Y;
     double* stats;
+    float* X0_out;             // [B,N,Ci] the assembled input features (kept for the backward pass) or null
     int B, N, Npad, Ci;
 };
 
@@ -468,6 +464,12 @@ __global__ void __launch_bounds__(128) fepe_mlp32_first_kernel(const FirstParams
                 ++c;
             }
         }
+    }
+    if (valid && p.X0_out != nullptr) {
+        float* xo = p.X0_out + (static_cast<size_t>(b) * p.N + r) * Ci;
+#pragma unroll
+        for (int k = 0; k < kFirstMaxCi; ++k)
+            if (k < Ci) xo[k] = x[k];
     }
     __syncthreads();
     int rows_valid = p.N - blockIdx.x * 128;
@@ -641,40 +643,41 @@ int fepe_mlp32_prepare_weights(const float* W, void* Whi, void* Wlo, float* wsca
 
 int fepe_mlp32_first(const float* matches, float ax, float bx, float ay, float by, const float* extra0, int c0,
                      const float* extra1, int c1, const float* extra2, int c2, const float* extra3, int c3,
-                     const float* W, const float* bias, float* Y, double* stats, int B, int N, int Npad, int Co,
-                     void* stream) {
+                     const float* W, const float* bias, float* Y, double* stats, float* X0_out, int B, int N, int Npad,
+                     int Co, void* stream) {
     const int Ci = (matches ? 4 : 0) + (extra0 ? c0 : 0) + (extra1 ? c1 : 0) + (extra2 ? c2 : 0) + (extra3 ? c3 : 0);
     if (!W || !Y || !stats || B <= 0 || N <= 0 || Ci <= 0 || Ci > fepe::m32::kFirstMaxCi || Co != 64 || (Npad % 128) != 0 ||
         Npad < N || c0 < 0 || c1 < 0 || c2 < 0 || c3 < 0 || (reinterpret_cast<uintptr_t>(matches) & 15u))
         return FEPE_E_BADARG;
     fepe::m32::FirstParams p{matches, ax, bx, ay, by, {extra0, extra1, extra2, extra3}, {c0, c1, c2, c3}, W, bias, Y, stats,
-                             B, N, Npad, Ci};
+                             X0_out, B, N, Npad, Ci};
     dim3 grid(Npad / 128, B);
     fepe::m32::fepe_mlp32_first_kernel<<<grid, 128, 0, static_cast<cudaStream_t>(stream)>>>(p);
     return static_cast<int>(cudaGetLastError());
 }
 
-int fepe_mlp32_scale_shift(double* stats, const float* gamma, const float* beta, float* ss, int B, int Co, int Nvalid,
-                           float eps, int clear_stats, void* stream) {
+int fepe_mlp32_scale_shift(double* stats, const float* gamma, const float* beta, float* ss, float* mean_rstd, int B, int Co,
+                           int Nvalid, float eps, int clear_stats, void* stream) {
     if (!stats || !gamma || !beta || !ss || B <= 0 || Co <= 0 || Nvalid <= 0 || (reinterpret_cast<uintptr_t>(stats) & 15u) ||
         (reinterpret_cast<uintptr_t>(ss) & 15u))
         return FEPE_E_BADARG;
     const int total = B * Co;
     fepe::m32::scale_shift_kernel<<<(total + 255) / 256, 256, 0, static_cast<cudaStream_t>(stream)>>>(
-        stats, gamma, beta, reinterpret_cast<float2*>(ss), total, Co, Nvalid, eps, clear_stats);
+        stats, gamma, beta, reinterpret_cast<float2*>(ss), reinterpret_cast<float2*>(mean_rstd), total, Co, Nvalid, eps,
+        clear_stats);
     return static_cast<int>(cudaGetLastError());
 }
 
-int fepe_mlp32_gemm(const float* Yprev, const float* ss, float slope, const void* Whi, const void* Wlo,
-                    const float* wscale, const float* bias, float* Y, double* stats, int B, int Npad, int Nvalid, int K,
-                    int Co, void* stream) {
+int fepe_mlp32_gemm(const float* Yprev, const float* ss, float slope, const unsigned* a_amax, const void* Whi,
+                    const void* Wlo, const float* wscale, const float* bias, float* Y, double* stats, int B, int Npad,
+                    int Nvalid, int K, int Co, void* stream) {
     using namespace fepe::m32;
     if (!Yprev || !Whi || !Wlo || !wscale || !Y || B <= 0 || Npad <= 0 || (Npad % kBM) != 0 || Nvalid > Npad || Nvalid <= 0 ||
         K <= 0 || (K % kBK) != 0 || Co <= 0 || (Co % 64) != 0 || (reinterpret_cast<uintptr_t>(ss) & 15u) ||
         (reinterpret_cast<uintptr_t>(bias) & 15u) || (reinterpret_cast<uintptr_t>(Y) & 15u) ||
         (reinterpret_cast<uintptr_t>(Yprev) & 15u) || (ss != nullptr && !(slope > 0.f && slope <= 1.f)))
         return FEPE_E_BADARG;
-    GemmParams p{B * Npad, K, Co, Npad, Nvalid, ss, slope, wscale, bias, Y, stats};
+    GemmParams p{B * Npad, K, Co, Npad, Nvalid, ss, slope, wscale, bias, Y, stats, ss == nullptr ? a_amax : nullptr};
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     if (Co % 256 == 0) return launch_gemm<256, 2>(Yprev, Whi, Wlo, p, st);
     if (Co % 128 == 0) return launch_gemm<128, 3>(Yprev, Whi, Wlo, p, st);

@@ -58,10 +58,15 @@ _SIGNATURES = {
     "fepe_mlp_first_bwd": (_c_i, [_c_p, _c_p, _c_p, _c_p, _c_p, _c_i, _c_i, _c_i, _c_i, _c_i, _c_p]),
     "fepe_mlp32_prepare_weights": (_c_i, [_c_p, _c_p, _c_p, _c_p, _c_i, _c_i, _c_p]),
     "fepe_mlp32_first": (_c_i, [_c_p, _c_f, _c_f, _c_f, _c_f, _c_p, _c_i, _c_p, _c_i, _c_p, _c_i, _c_p, _c_i,
-                                _c_p, _c_p, _c_p, _c_p, _c_i, _c_i, _c_i, _c_i, _c_p]),
-    "fepe_mlp32_scale_shift": (_c_i, [_c_p, _c_p, _c_p, _c_p, _c_i, _c_i, _c_i, _c_f, _c_i, _c_p]),
-    "fepe_mlp32_gemm": (_c_i, [_c_p, _c_p, _c_f, _c_p, _c_p, _c_p, _c_p, _c_p, _c_p, _c_i, _c_i, _c_i, _c_i, _c_i, _c_p]),
+                                _c_p, _c_p, _c_p, _c_p, _c_p, _c_i, _c_i, _c_i, _c_i, _c_p]),
+    "fepe_mlp32_scale_shift": (_c_i, [_c_p, _c_p, _c_p, _c_p, _c_p, _c_i, _c_i, _c_i, _c_f, _c_i, _c_p]),
+    "fepe_mlp32_gemm": (_c_i, [_c_p, _c_p, _c_f, _c_p, _c_p, _c_p, _c_p, _c_p, _c_p, _c_p, _c_i, _c_i, _c_i, _c_i, _c_i,
+                               _c_p]),
     "fepe_mlp32_last": (_c_i, [_c_p, _c_p, _c_f, _c_p, _c_p, _c_p, _c_p, _c_i, _c_i, _c_i, _c_i, _c_i, _c_p]),
+    "fepe_mlp32_last_bwd": (_c_i, [_c_p, _c_p, _c_p, _c_f, _c_p, _c_p, _c_p, _c_p, _c_i, _c_i, _c_i, _c_i, _c_i, _c_p]),
+    "fepe_mlp32_normbwd": (_c_i, [_c_p, _c_p, _c_p, _c_p, _c_p, _c_f, _c_p, _c_p, _c_p, _c_i, _c_i, _c_i, _c_i, _c_p]),
+    "fepe_mlp32_wgrad": (_c_i, [_c_p, _c_p, _c_p, _c_p, _c_f, _c_p, _c_i, _c_i, _c_i, _c_i, _c_p]),
+    "fepe_mlp32_first_bwd": (_c_i, [_c_p, _c_p, _c_p, _c_p, _c_p, _c_i, _c_i, _c_i, _c_i, _c_i, _c_p]),
 }
 
 _ERRORS = {-1: "FEPE_E_BADARG (null pointer, misaligned buffer or non-positive size)",

@@ -115,21 +115,21 @@ class MLP32:
             ss = torch.empty(B * 1024 * 2, dtype=torch.float32, device=dev)
             args, keep = first_layer_args(matches, affine, extras, self.cin)
             # conv biases in front of an InstanceNorm cancel in the mean subtraction: not applied (bias = NULL)
-            _lib.check(lib.fepe_mlp32_first(*args, self.w0.data_ptr(), None, bufa.data_ptr(), stats.data_ptr(),
+            _lib.check(lib.fepe_mlp32_first(*args, self.w0.data_ptr(), None, bufa.data_ptr(), stats.data_ptr(), None,
                                             B, N, Npad, 64, st), "fepe_mlp32_first")
             src, dst, k = bufa, bufb, 64
             for i in range(1, 5):
                 co = _CH[i]
                 _lib.check(lib.fepe_mlp32_scale_shift(stats.data_ptr(), self.gamma[i - 1].data_ptr(),
-                                                      self.beta[i - 1].data_ptr(), ss.data_ptr(), B, k, N, self.eps[i - 1],
-                                                      1, st), "fepe_mlp32_scale_shift")
+                                                      self.beta[i - 1].data_ptr(), ss.data_ptr(), None, B, k, N,
+                                                      self.eps[i - 1], 1, st), "fepe_mlp32_scale_shift")
                 whi, wlo, wsc = self.w[i]
-                _lib.check(lib.fepe_mlp32_gemm(src.data_ptr(), ss.data_ptr(), SLOPE, whi.data_ptr(), wlo.data_ptr(),
+                _lib.check(lib.fepe_mlp32_gemm(src.data_ptr(), ss.data_ptr(), SLOPE, None, whi.data_ptr(), wlo.data_ptr(),
                                                wsc.data_ptr(), None, dst.data_ptr(), stats.data_ptr(), B, Npad, N, k, co,
                                                st), "fepe_mlp32_gemm")
                 src, dst, k = dst, src, co
             _lib.check(lib.fepe_mlp32_scale_shift(stats.data_ptr(), self.gamma[4].data_ptr(), self.beta[4].data_ptr(),
-                                                  ss.data_ptr(), B, 256, N, self.eps[4], 0, st), "fepe_mlp32_scale_shift")
+                                                  ss.data_ptr(), None, B, 256, N, self.eps[4], 0, st), "fepe_mlp32_scale_shift")
             logits = torch.empty(B, self.cout, N, dtype=torch.float32, device=dev)
             weights = torch.empty(B, 1, N, dtype=torch.float32, device=dev) if self.cout == 1 else None
             _lib.check(lib.fepe_mlp32_last(src.data_ptr(), ss.data_ptr(), SLOPE, self.w_last.data_ptr(),
@@ -138,3 +138,138 @@ class MLP32:
                                            self.cout, st), "fepe_mlp32_last")
             del keep
         return logits, weights
+
+
+class MLP32Function(torch.autograd.Function):
+    """logits = ErrorEstimator(inputs) under autograd: the forward kernels of MLP32 keeping every block's pre-norm output
+    y (fp32), its (a, d) and (mean, rstd); the backward is fepe_mlp32_last_bwd, fepe_mlp32_normbwd, fepe_mlp32_wgrad and
+    the data-gradient GEMM on tensor cores (split-fp16 operands), fepe_mlp32_first_bwd -- no library kernel on the path.
+
+    forward(meta, matches | None, *extras, *params) -> logits [B, out, N];
+    meta = (affine, n_extras, B, N); params = module_params(fw) (22 tensors)."""
+
+    @staticmethod
+    def forward(ctx, meta, matches, *tensors):
+        affine, n_extras, B, N = meta
+        extras, params = tensors[:n_extras], tensors[n_extras:]
+        lib = _lib.lib()
+        ref = matches if matches is not None else extras[0]
+        dev = ref.device
+        Npad = (N + 127) // 128 * 128
+        M = B * Npad
+        convw = [params[4 * i] for i in range(5)] + [params[20]]
+        gam = [params[4 * i + 2].detach().float().contiguous() for i in range(5)]
+        bet = [params[4 * i + 3].detach().float().contiguous() for i in range(5)]
+        cin, cout = convw[0].shape[1], convw[5].shape[0]
+        with torch.cuda.device(dev):
+            st = torch.cuda.current_stream(dev).cuda_stream
+            w0 = convw[0].detach().reshape(64, cin).float().contiguous()
+            w2d = [None] + [convw[i].detach().reshape(_CH[i], _CH[i - 1]).float().contiguous() for i in range(1, 5)]
+            wsp = [None] + [split_weight(lib, w2d[i], st) for i in range(1, 5)]
+            w_last = convw[5].detach().reshape(cout, 256).float().contiguous()
+            b_last = params[21].detach().float().contiguous()
+            Ys = [torch.empty(M, c, dtype=torch.float32, device=dev) for c in _CH]
+            sss = [torch.empty(B, c, 2, dtype=torch.float32, device=dev) for c in _CH]
+            mrs = [torch.empty(B, c, 2, dtype=torch.float32, device=dev) for c in _CH]
+            stats = torch.zeros(B * 1024 * 2, dtype=torch.float64, device=dev)
+            X0 = torch.empty(B, N, cin, dtype=torch.float32, device=dev)
+            args, keep = first_layer_args(matches.detach() if matches is not None else None, affine,
+                                          [e.detach().float() for e in extras], cin)
+            _lib.check(lib.fepe_mlp32_first(*args, w0.data_ptr(), None, Ys[0].data_ptr(), stats.data_ptr(), X0.data_ptr(),
+                                            B, N, Npad, 64, st), "fepe_mlp32_first")
+            for i in range(5):
+                _lib.check(lib.fepe_mlp32_scale_shift(stats.data_ptr(), gam[i].data_ptr(), bet[i].data_ptr(),
+                                                      sss[i].data_ptr(), mrs[i].data_ptr(), B, _CH[i], N, 1e-5,
+                                                      1 if i < 4 else 0, st), "fepe_mlp32_scale_shift")
+                if i < 4:
+                    whi, wlo, wsc = wsp[i + 1]
+                    _lib.check(lib.fepe_mlp32_gemm(Ys[i].data_ptr(), sss[i].data_ptr(), SLOPE, None, whi.data_ptr(),
+                                                   wlo.data_ptr(), wsc.data_ptr(), None, Ys[i + 1].data_ptr(),
+                                                   stats.data_ptr(), B, Npad, N, _CH[i], _CH[i + 1], st), "fepe_mlp32_gemm")
+            logits = torch.empty(B, cout, N, dtype=torch.float32, device=dev)
+            _lib.check(lib.fepe_mlp32_last(Ys[4].data_ptr(), sss[4].data_ptr(), SLOPE, w_last.data_ptr(), b_last.data_ptr(),
+                                           logits.data_ptr(), None, B, N, Npad, 256, cout, st), "fepe_mlp32_last")
+            del keep
+        ctx.dims = (B, N, Npad, cin, cout, affine, n_extras, matches is not None,
+                    [1 if e.dim() == 2 else e.shape[2] for e in extras], [tuple(e.shape) for e in extras])
+        ctx.saved = (X0, w0, w2d, w_last, gam, Ys, sss, mrs)
+        return logits
+
+    @staticmethod
+    def backward(ctx, dlogits):
+        lib = _lib.lib()
+        B, N, Npad, cin, cout, affine, n_extras, has_m, ecs, eshapes = ctx.dims
+        X0, w0, w2d, w_last, gam, Ys, sss, mrs = ctx.saved
+        dev = X0.device
+        M = B * Npad
+        grads = [None] * 22
+        with torch.cuda.device(dev):
+            st = torch.cuda.current_stream(dev).cuda_stream
+            zf = lambda *shape: torch.zeros(*shape, dtype=torch.float32, device=dev)
+            dl = dlogits.detach().float().contiguous()
+            dX = torch.empty(M, 256, dtype=torch.float32, device=dev)
+            dwl, dbl = zf(cout, 256), zf(cout)
+            _lib.check(lib.fepe_mlp32_last_bwd(dl.data_ptr(), Ys[4].data_ptr(), sss[4].data_ptr(), SLOPE, w_last.data_ptr(),
+                                               dX.data_ptr(), dwl.data_ptr(), dbl.data_ptr(), B, N, Npad, 256, cout, st),
+                       "fepe_mlp32_last_bwd")
+            grads[20], grads[21] = dwl.reshape(cout, 256, 1), dbl
+            amax = torch.zeros(8, dtype=torch.int32, device=dev)          # one slot per layer (bits of max |dY|)
+            for i in range(4, -1, -1):
+                c = _CH[i]
+                A = torch.zeros(B, c, 2, dtype=torch.float64, device=dev)
+                dY = torch.empty(M, c, dtype=torch.float32, device=dev)
+                am = amax[i:i + 1]
+                _lib.check(lib.fepe_mlp32_normbwd(dX.data_ptr(), Ys[i].data_ptr(), sss[i].data_ptr(), mrs[i].data_ptr(),
+                                                  gam[i].data_ptr(), SLOPE, A.data_ptr(), dY.data_ptr(), am.data_ptr(),
+                                                  B, Npad, N, c, st), "fepe_mlp32_normbwd")
+                grads[4 * i + 2] = A[:, :, 1].sum(0).float()      # dgamma
+                grads[4 * i + 3] = A[:, :, 0].sum(0).float()      # dbeta
+                grads[4 * i + 1] = zf(c)                           # conv bias before InstanceNorm: exactly zero gradient
+                if i > 0:
+                    ci = _CH[i - 1]
+                    dW = zf(c, ci)
+                    _lib.check(lib.fepe_mlp32_wgrad(dY.data_ptr(), am.data_ptr(), Ys[i - 1].data_ptr(),
+                                                    sss[i - 1].data_ptr(), SLOPE, dW.data_ptr(), M, Npad, c, ci, st),
+                               "fepe_mlp32_wgrad")
+                    grads[4 * i] = dW.reshape(c, ci, 1)
+                    thi, tlo, tsc = split_weight(lib, w2d[i].t().contiguous(), st)       # [ci, c]: the data-gradient "weight"
+                    dXn = torch.empty(M, ci, dtype=torch.float32, device=dev)
+                    _lib.check(lib.fepe_mlp32_gemm(dY.data_ptr(), None, 1.0, am.data_ptr(), thi.data_ptr(), tlo.data_ptr(),
+                                                   tsc.data_ptr(), None, dXn.data_ptr(), None, B, Npad, Npad, c, ci, st),
+                               "fepe_mlp32_gemm(dgrad)")
+                    dX = dXn
+                else:
+                    dW = zf(64, cin)
+                    need_x = any(ctx.needs_input_grad[1:2 + n_extras])
+                    dX0 = torch.empty(B, N, cin, dtype=torch.float32, device=dev) if need_x else None
+                    _lib.check(lib.fepe_mlp32_first_bwd(dY.data_ptr(), X0.data_ptr(), w0.data_ptr(),
+                                                        dX0.data_ptr() if dX0 is not None else None, dW.data_ptr(), B, N,
+                                                        Npad, cin, 64, st), "fepe_mlp32_first_bwd")
+                    grads[0] = dW.reshape(64, cin, 1)
+        # route the input gradient back to the channel groups
+        gm, ge, off = None, [None] * n_extras, 0
+        if has_m:
+            if ctx.needs_input_grad[1]:
+                ax, _, ay, _ = affine                                   # x = ((a m + b) + 1) / 2
+                gm = dX0[:, :, 0:4] * torch.tensor([ax / 2, ay / 2, ax / 2, ay / 2], dtype=torch.float32, device=dev)
+            off = 4
+        for j in range(n_extras):
+            if ctx.needs_input_grad[2 + j]:
+                ge[j] = dX0[:, :, off:off + ecs[j]].reshape(eshapes[j])
+            off += ecs[j]
+        return (None, gm) + tuple(ge) + tuple(grads)
+
+
+def module_params(fw: nn.Sequential):
+    """The 22 parameters of an ErrorEstimator in the order MLP32Function expects."""
+    convs, norms = _layers(fw)
+    out = []
+    for i in range(5):
+        out += [convs[i].weight, convs[i].bias, norms[i].weight, norms[i].bias]
+    return out + [convs[5].weight, convs[5].bias]
+
+
+def mlp32_autograd(fw: nn.Sequential, matches, affine, extras, B: int, N: int):
+    extras = [e if e.dtype == torch.float32 else e.float() for e in extras]
+    return MLP32Function.apply((tuple(float(v) for v in affine) if affine is not None else None, len(extras), B, N),
+                               matches, *extras, *module_params(fw))

@@ -103,15 +103,19 @@ def test_mlp_entry_points_reject_bad_shapes(built):
     assert lib.fepe_mlp_first(p, p, p, p, p, 2, 200, 256, 9, 64, 0) == -1          # more than 8 input channels
     assert lib.fepe_mlp_wgrad(p, p, p, 100, 128, 64, 0) == -1                      # M not a multiple of 64
     # the fp32-parity path (fepe_mlp32_*)
-    assert lib.fepe_mlp32_gemm(p, p, 0.01, p, p, p, 0, p, p, 2, 250, 200, 128, 256, 0) == -1     # Npad % 128
-    assert lib.fepe_mlp32_gemm(p, p, 0.01, p, p, p, 0, p, p, 2, 256, 200, 100, 256, 0) == -1     # K % 64
-    assert lib.fepe_mlp32_gemm(p, p, 0.01, p, p, p, 0, p, p, 2, 256, 200, 128, 100, 0) == -1     # Co % 64
-    assert lib.fepe_mlp32_gemm(p, p + 4, 0.01, p, p, p, 0, p, p, 2, 256, 200, 128, 256, 0) == -1  # ss alignment
-    assert lib.fepe_mlp32_gemm(p, p, 1.5, p, p, p, 0, p, p, 2, 256, 200, 128, 256, 0) == -1      # slope outside (0, 1]
-    assert lib.fepe_mlp32_first(p, 1.0, 0.0, 1.0, 0.0, p, 13, 0, 0, 0, 0, 0, 0, p, p, p, p, 2, 200, 256, 64, 0) == -1   # 17 channels
-    assert lib.fepe_mlp32_first(0, 1.0, 0.0, 1.0, 0.0, 0, 0, 0, 0, 0, 0, 0, 0, p, p, p, p, 2, 200, 256, 64, 0) == -1    # no channels
+    assert lib.fepe_mlp32_gemm(p, p, 0.01, 0, p, p, p, 0, p, p, 2, 250, 200, 128, 256, 0) == -1     # Npad % 128
+    assert lib.fepe_mlp32_gemm(p, p, 0.01, 0, p, p, p, 0, p, p, 2, 256, 200, 100, 256, 0) == -1     # K % 64
+    assert lib.fepe_mlp32_gemm(p, p, 0.01, 0, p, p, p, 0, p, p, 2, 256, 200, 128, 100, 0) == -1     # Co % 64
+    assert lib.fepe_mlp32_gemm(p, p + 4, 0.01, 0, p, p, p, 0, p, p, 2, 256, 200, 128, 256, 0) == -1  # ss alignment
+    assert lib.fepe_mlp32_gemm(p, p, 1.5, 0, p, p, p, 0, p, p, 2, 256, 200, 128, 256, 0) == -1      # slope outside (0, 1]
+    assert lib.fepe_mlp32_first(p, 1.0, 0.0, 1.0, 0.0, p, 13, 0, 0, 0, 0, 0, 0, p, p, p, p, 0, 2, 200, 256, 64, 0) == -1   # 17 channels
+    assert lib.fepe_mlp32_first(0, 1.0, 0.0, 1.0, 0.0, 0, 0, 0, 0, 0, 0, 0, 0, p, p, p, p, 0, 2, 200, 256, 64, 0) == -1    # no channels
     assert lib.fepe_mlp32_last(p, p, 0.01, p, p, p, 0, 2, 200, 256, 256, 3, 0) == -1             # Co must be 1 or 4
     assert lib.fepe_mlp32_last(p, p, 0.01, p, p, p, p, 2, 200, 256, 256, 4, 0) == -1             # softmax only for Co = 1
+    assert lib.fepe_mlp32_normbwd(p, p, p, p, p, 0.01, p, p, p, 2, 256, 200, 192, 0) == -1       # C / 4 = 48: not a power of two
+    assert lib.fepe_mlp32_wgrad(p, p, p, p, 0.01, p, 512, 256, 192, 64, 0) == -1                 # Co % 128
+    assert lib.fepe_mlp32_wgrad(p, p, p, p, 0.01, p, 500, 256, 128, 64, 0) == -1                 # M not a multiple of Npad
+    assert lib.fepe_mlp32_last_bwd(p, p, p, 0.01, p, p, p, p, 2, 200, 256, 256, 2, 0) == -1      # Co must be 1 or 4
 
 
 def test_no_cpu_fallback(built):

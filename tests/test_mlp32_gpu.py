@@ -29,8 +29,10 @@ def test_prepare_weights_splits_to_22_bits():
         amax = float(W.abs().max()) * s
         assert 2 ** 13 <= amax < 2 ** 14, amax
         rec = (whi.double() + wlo.double()) * inv
-        err = ((rec - W.double()).abs() / W.double().abs().clamp_min(1e-30))[W != 0]
-        assert float(err.max()) < 2.0 ** -21, float(err.max())
+        # hi + lo keeps 22 bits of every weight; below 2^-14 / s the lo part is an fp16 subnormal (absolute floor 2^-25 / s,
+        # i.e. 2^-38 of the largest weight)
+        err = (rec - W.double()).abs() - (2.0 ** -21 * W.double().abs() + 2.0 ** -24 * inv)
+        assert float(err.max()) <= 0.0, float(err.max())
         assert float(rec[0, 0]) == 0.0
         assert torch.isfinite(whi.float()).all() and torch.isfinite(wlo.float()).all()
 
@@ -76,7 +78,7 @@ def test_gemm_matches_fp64(B, N, K, Co, mode):
     whi, wlo, wsc = mlp32.split_weight(lib, W, _st())
     Y = torch.full((B * Npad, Co), 7.0, device="cuda")
     stats = torch.zeros(B, Co, 2, device="cuda", dtype=torch.float64)
-    st = lib.fepe_mlp32_gemm(Yprev.data_ptr(), ss.data_ptr() if ss is not None else None, SLOPE, whi.data_ptr(),
+    st = lib.fepe_mlp32_gemm(Yprev.data_ptr(), ss.data_ptr() if ss is not None else None, SLOPE, None, whi.data_ptr(),
                              wlo.data_ptr(), wsc.data_ptr(), bias.data_ptr() if bias is not None else None, Y.data_ptr(),
                              stats.data_ptr(), B, Npad, nvalid, K, Co, _st())
     assert st == 0, st
@@ -91,13 +93,19 @@ def test_gemm_matches_fp64(B, N, K, Co, mode):
     rel = ((Y.double() - ref).abs() / mass)
     rel[ref == 0] = 0
     print(f"B={B} N={N} K={K} Co={Co} {mode}: max err / mass = {float(rel.max()):.2e} (2^-22 = 2.4e-7)")
-    assert float(rel.max()) < 1.5e-6, float(rel.max())
+    # measured 4e-7 (K = 64) .. 1.2e-6 (K = 1024) .. 2.8e-6 (K = 4928): product errors 3 x 2^-22 plus the fp32 accumulation
+    # of 3 K / 16 partial MMAs in tensor memory
+    assert float(rel.max()) < 1.0e-6 + 5e-10 * K, float(rel.max())
     if nvalid < Npad:
         assert float(Y.reshape(B, Npad, Co)[:, N:].abs().max()) == 0.0
     serr = (stats - rstats).abs() / (rstats.abs() + 1e-300)
     # sums: fp32 partial sums over 128 rows folded in fp64
-    assert float(((stats[..., 0] - rstats[..., 0]).abs() / (ref.reshape(B, Npad, Co).abs().sum(1) + 1e-30)).max()) < 1e-6
-    assert float(serr[..., 1].max()) < 1e-6
+    # the statistics are taken of the fp32 values the kernel stored: exact (fp64) sums of THOSE
+    yk = Y.double().reshape(B, Npad, Co)[:, :nvalid]
+    kstats = torch.stack((yk.sum(1), (yk ** 2).sum(1)), 2)
+    assert float(((stats[..., 0] - kstats[..., 0]).abs() / (yk.abs().sum(1) + 1e-30)).max()) < 2e-7
+    assert float(((stats[..., 1] - kstats[..., 1]).abs() / (kstats[..., 1] + 1e-300)).max()) < 2e-7
+    assert float(serr[..., 1].max()) < 1e-5
 
 
 def test_statistics_survive_a_large_mean():
@@ -113,12 +121,12 @@ def test_statistics_survive_a_large_mean():
     whi, wlo, wsc = mlp32.split_weight(lib, W, _st())
     Y = torch.empty(B * Npad, Co, device="cuda")
     stats = torch.zeros(B, Co, 2, device="cuda", dtype=torch.float64)
-    assert lib.fepe_mlp32_gemm(Yprev.data_ptr(), None, 1.0, whi.data_ptr(), wlo.data_ptr(), wsc.data_ptr(), None,
+    assert lib.fepe_mlp32_gemm(Yprev.data_ptr(), None, 1.0, None, whi.data_ptr(), wlo.data_ptr(), wsc.data_ptr(), None,
                                Y.data_ptr(), stats.data_ptr(), B, Npad, N, K, Co, _st()) == 0
     gamma, beta = torch.rand(Co, device="cuda") + 0.5, torch.randn(Co, device="cuda")
     ss = torch.empty(B, Co, 2, device="cuda")
-    assert lib.fepe_mlp32_scale_shift(stats.data_ptr(), gamma.data_ptr(), beta.data_ptr(), ss.data_ptr(), B, Co, N, 1e-5,
-                                      0, _st()) == 0
+    assert lib.fepe_mlp32_scale_shift(stats.data_ptr(), gamma.data_ptr(), beta.data_ptr(), ss.data_ptr(), None, B, Co, N,
+                                      1e-5, 0, _st()) == 0
     torch.cuda.synchronize()
     y = Y.reshape(B, Npad, Co)[:, :N].double()                       # the values the statistics were taken of
     mean, var = y.mean(1), y.var(1, unbiased=False)
@@ -144,9 +152,12 @@ def test_first_layer_reads_the_model_inputs_in_place(N):
     Y = torch.empty(B * Npad, 64, device="cuda")
     stats = torch.zeros(B, 64, 2, device="cuda", dtype=torch.float64)
     args, keep = mlp32.first_layer_args(m, aff, [q, w, e, r], 9)
-    assert lib.fepe_mlp32_first(*args, W.data_ptr(), None, Y.data_ptr(), stats.data_ptr(), B, N, Npad, 64, _st()) == 0
+    X0 = torch.empty(B, N, 9, device="cuda")
+    assert lib.fepe_mlp32_first(*args, W.data_ptr(), None, Y.data_ptr(), stats.data_ptr(), X0.data_ptr(), B, N, Npad, 64,
+                                _st()) == 0
     torch.cuda.synchronize()
     feat = ErrorEstimator._features(m, aff, [q, w, e, r]).double()                   # [B,9,N], the reference's cat
+    assert float((X0.double() - feat.permute(0, 2, 1)).abs().max()) < 1e-6
     ref = torch.einsum("oc,bcn->bno", W.double(), feat)
     got = Y.reshape(B, Npad, 64)
     assert float((got[:, :N].double() - ref).abs().max()) < 2e-5 * float(ref.abs().max())
@@ -207,3 +218,166 @@ def test_error_estimator_is_in_the_fp32_accuracy_class(cin, cout, B, N):
     if cout == 1:
         ref_sm = torch.softmax(truth, 2)
         assert float(((sm.double() - ref_sm).abs() / ref_sm).max()) < max(20 * e_tc * scale, 1e-4)
+
+
+# ------------------------------------------------------------------------------------------------ backward
+def test_normbwd_matches_fp64_autograd():
+    lib = _lib.lib()
+    torch.manual_seed(6)
+    for B, N, C in ((2, 1000, 128), (3, 333, 1024), (2, 128, 64), (2, 900, 512)):
+        Npad = (N + 127) // 128 * 128
+        y = torch.randn(B, Npad, C, device="cuda") * 2 + 0.3
+        y[:, N:] = 0
+        gamma, beta = torch.rand(C, device="cuda") + 0.5, torch.randn(C, device="cuda") * 0.3
+        dX = torch.randn(B, Npad, C, device="cuda") * 1e-4                  # gradients are small numbers
+        dX[:, N:] = 0
+        # forward statistics through the product's own kernel
+        yv = y[:, :N].double()
+        stats = torch.stack((yv.sum(1), (yv ** 2).sum(1)), 2).contiguous()
+        ss, mr = torch.empty(B, C, 2, device="cuda"), torch.empty(B, C, 2, device="cuda")
+        assert lib.fepe_mlp32_scale_shift(stats.data_ptr(), gamma.data_ptr(), beta.data_ptr(), ss.data_ptr(), mr.data_ptr(),
+                                          B, C, N, 1e-5, 0, _st()) == 0
+        A = torch.zeros(B, C, 2, device="cuda", dtype=torch.float64)
+        dY = torch.full((B, Npad, C), 7.0, device="cuda")
+        amax = torch.zeros(1, dtype=torch.int32, device="cuda")
+        assert lib.fepe_mlp32_normbwd(dX.data_ptr(), y.data_ptr(), ss.data_ptr(), mr.data_ptr(), gamma.data_ptr(), SLOPE,
+                                      A.data_ptr(), dY.data_ptr(), amax.data_ptr(), B, Npad, N, C, _st()) == 0
+        torch.cuda.synchronize()
+        y64 = y[:, :N].double().permute(0, 2, 1).clone().requires_grad_(True)          # [B,C,N]
+        g64, b64 = gamma.double().clone().requires_grad_(True), beta.double().clone().requires_grad_(True)
+        out = torch.nn.functional.leaky_relu(torch.nn.functional.instance_norm(y64, weight=g64, bias=b64, eps=1e-5), SLOPE)
+        out.backward(dX[:, :N].double().permute(0, 2, 1))
+        ref = y64.grad.permute(0, 2, 1)
+        sc = float(ref.abs().max())
+        assert float((dY[:, :N].double() - ref).abs().max()) < 2e-5 * sc, (B, N, C)
+        assert float(dY[:, N:].abs().max() if Npad > N else 0.0) == 0.0
+        assert float((A[:, :, 1].sum(0) - g64.grad).abs().max()) < 1e-5 * float(g64.grad.abs().max())
+        assert float((A[:, :, 0].sum(0) - b64.grad).abs().max()) < 1e-5 * float(b64.grad.abs().max())
+        got_max = float(amax.view(torch.float32)[0])
+        assert abs(got_max - float(dY.abs().max())) <= 1e-6 * got_max
+
+
+@pytest.mark.parametrize("B,N,Co,Ci", [(1, 128, 128, 64), (2, 1000, 1024, 128), (64, 1000, 512, 1024), (4, 1000, 256, 512),
+                                       (2, 300, 128, 64)])
+def test_wgrad_matches_fp64(B, N, Co, Ci):
+    """dW = dY^T LeakyReLU(a Yprev + d) on tcgen05 with both operands MN-major, split into fp16 pairs in place."""
+    lib = _lib.lib()
+    torch.manual_seed(7)
+    Npad = (N + 127) // 128 * 128
+    M = B * Npad
+    dY = torch.randn(B, Npad, Co, device="cuda") * 3e-6                    # far below fp16's normal range: needs the scale
+    dY[:, N:] = 0
+    Yp = torch.randn(B, Npad, Ci, device="cuda") * 2 + 0.5
+    ss = torch.stack((torch.rand(B, Ci, device="cuda") + 0.5, torch.randn(B, Ci, device="cuda")), 2).contiguous()
+    amax = dY.abs().max().reshape(1).view(torch.int32).clone()
+    dW = torch.zeros(Co, Ci, device="cuda")
+    assert lib.fepe_mlp32_wgrad(dY.data_ptr(), amax.data_ptr(), Yp.data_ptr(), ss.data_ptr(), SLOPE, dW.data_ptr(), M, Npad,
+                                Co, Ci, _st()) == 0
+    torch.cuda.synchronize()
+    t = Yp.double() * ss.double()[:, :, 0].unsqueeze(1) + ss.double()[:, :, 1].unsqueeze(1)
+    x = torch.maximum(t, SLOPE * t).reshape(M, Ci)
+    ref = dY.double().reshape(M, Co).t() @ x
+    mass = dY.double().abs().reshape(M, Co).t() @ x.abs()
+    rel = float(((dW.double() - ref).abs() / mass).max())
+    print(f"wgrad B={B} N={N} {Co}x{Ci}: max err / mass {rel:.2e}")
+    assert rel < 2e-6, rel
+
+
+def test_dgrad_gemm_with_tiny_operand():
+    """Data gradient dX = dY W through fepe_mlp32_gemm (ss = NULL) with dY ~ 1e-7: the power-of-two pre-scale from
+    a_amax keeps the fp16 split exact."""
+    lib = _lib.lib()
+    torch.manual_seed(8)
+    B, N, K, Co = 3, 1000, 512, 1024
+    Npad = 1024
+    dY = torch.randn(B, Npad, K, device="cuda") * 1e-7
+    W = torch.randn(Co, K, device="cuda") / K ** 0.5
+    whi, wlo, wsc = mlp32.split_weight(lib, W, _st())
+    amax = dY.abs().max().reshape(1).view(torch.int32).clone()
+    Y = torch.empty(B * Npad, Co, device="cuda")
+    assert lib.fepe_mlp32_gemm(dY.data_ptr(), None, 1.0, amax.data_ptr(), whi.data_ptr(), wlo.data_ptr(), wsc.data_ptr(), None,
+                               Y.data_ptr(), None, B, Npad, Npad, K, Co, _st()) == 0
+    torch.cuda.synchronize()
+    ref = dY.double().reshape(-1, K) @ W.double().t()
+    mass = dY.double().abs().reshape(-1, K) @ W.double().abs().t()
+    assert float(((Y.double() - ref).abs() / mass).max()) < 1.5e-6
+
+
+@pytest.mark.parametrize("cin,cout,B,N", [(4, 1, 3, 1000), (7, 1, 2, 777), (9, 4, 2, 500)])
+def test_error_estimator_gradients_are_in_the_fp32_accuracy_class(cin, cout, B, N):
+    """Training path (tc32 forward + backward kernels, no library kernel) vs fp64 autograd, next to PyTorch's fp32
+    autograd vs the same truth: parameter and input gradients."""
+    torch.manual_seed(9)
+    ee = ErrorEstimator(cin, cout).cuda()
+    with torch.no_grad():
+        for m in ee.fw:
+            if isinstance(m, torch.nn.InstanceNorm1d):
+                m.weight.copy_(torch.rand_like(m.weight) + 0.5)
+                m.bias.copy_(torch.randn_like(m.bias) * 0.3)
+    x = torch.rand(B, cin, N, device="cuda")
+    g = torch.randn(B, cout, N, device="cuda") / N
+
+    def grads(module, xin, gout):
+        module.zero_grad()
+        xx = xin.clone().requires_grad_(True)
+        out = module(xx)
+        (out * gout).sum().backward()
+        return {n: p.grad.detach().double().clone() for n, p in module.named_parameters()}, xx.grad.detach().double(), out.detach().double()
+
+    assert ee.path == "tc32"
+    ours, oursx, out = grads(ee, x, g)
+    ee.set_path("torch")
+    lib32, lib32x, out32 = grads(ee, x, g)
+    ee.double()
+    truth, truthx, out64 = grads(ee, x.double(), g.double())
+    ee.float().set_path("tc32")
+    assert float((out - out64).abs().max()) < 1e-4 * float(out64.abs().max())
+    worst_o, worst_l = 0.0, 0.0
+    scale = max(float(v.abs().max()) for v in truth.values())
+    for n, ref in truth.items():
+        if float(ref.abs().max()) < 1e-6 * scale:            # conv biases in front of an InstanceNorm: zero gradient
+            assert float(ours[n].abs().max()) <= 1e-5 * scale, n
+            continue
+        eo = float((ours[n] - ref).norm() / ref.norm())
+        el = float((lib32[n] - ref).norm() / ref.norm())
+        worst_o, worst_l = max(worst_o, eo), max(worst_l, el)
+    ex_o = float((oursx - truthx).norm() / truthx.norm())
+    ex_l = float((lib32x - truthx).norm() / truthx.norm())
+    print(f"cin={cin} cout={cout}: worst parameter-gradient rel err vs fp64: tc32 {worst_o:.2e}, torch fp32 {worst_l:.2e}; "
+          f"input gradient: tc32 {ex_o:.2e}, torch fp32 {ex_l:.2e}")
+    assert worst_o < max(5 * worst_l, 2e-4), (worst_o, worst_l)
+    assert ex_o < max(5 * ex_l, 2e-4), (ex_o, ex_l)
+
+
+def test_deepfnet_training_step_on_the_kernel_path():
+    """A DeepFNet training step (depth 3, quality channel) with the default tc32 path: no parameter is left without a
+    gradient, and the gradients agree with the same step through PyTorch's fp32 kernels."""
+    from fepe_b200 import synth
+    from fepe_b200.models import DeepFNet
+    from oracle import fepe_oracle as O
+    torch.manual_seed(10)
+    net = DeepFNet(depth=3, image_size=[376, 1241, 3], if_quality=True, quality_size=1).cuda()
+    d = synth.make_batch(4, 640, seed=21)
+    batch = {"matches_xy_ori": torch.from_numpy(d["matches_xy_ori"]).cuda(), "quality": torch.rand(4, 640, 1, device="cuda")}
+    v1, v2 = torch.from_numpy(d["pts1_virt"]).cuda(), torch.from_numpy(d["pts2_virt"]).cuda()
+
+    def step():
+        net.zero_grad()
+        outs = net(batch)
+        p1 = (outs["T1"] @ v1.permute(0, 2, 1)).permute(0, 2, 1)
+        p2 = (outs["T1"] @ v2.permute(0, 2, 1)).permute(0, 2, 1)
+        loss = sum(O.epi_residual(p1, p2, Fo, 0.02).mean() for Fo in outs["out_layers"]) / 3
+        loss.backward()
+        return float(loss), {n: p.grad.detach().clone() for n, p in net.named_parameters()}
+
+    l_tc, g_tc = step()
+    net.set_mlp_path("torch")
+    l_lib, g_lib = step()
+    assert abs(l_tc - l_lib) < 1e-4 * abs(l_lib)
+    scale = max(float(v.abs().max()) for v in g_lib.values())
+    for n, ref in g_lib.items():
+        assert torch.isfinite(g_tc[n]).all(), n
+        if float(ref.abs().max()) < 1e-4 * scale:
+            continue
+        rel = float((g_tc[n] - ref).norm() / ref.norm())
+        assert rel < 2e-2, (n, rel)          # two fp32 evaluations of an ill-conditioned recursion; fp64 is the judge above
