@@ -121,6 +121,6 @@ def test_product_reproduces_reference_at_every_layer(case, layers):
     _check(tag, got, layers, planar, tolF=1e-4)
     # the same under autograd (training forward): identical arithmetic contract
     o2 = net(batch)
-    e = float(O.sign_aligned_rel_err(o2["F_est"].detach().cpu(), T(layers[f"{tag}_F_est"])).max())
+    e = O.sign_aligned_rel_err(o2["F_est"].detach().cpu(), T(layers[f"{tag}_F_est"]))
     if not planar:
-        assert e < 1e-4, e
+        assert bool((e < torch.clamp(4.0 * T(layers[f"{tag}_F_ref_vs_fp64"][4]).double(), min=1e-4)).all()), e.tolist()
