@@ -675,7 +675,7 @@ int fepe_mlp32_gemm(const float* Yprev, const float* ss, float slope, const unsi
     if (!Yprev || !Whi || !Wlo || !wscale || !Y || B <= 0 || Npad <= 0 || (Npad % kBM) != 0 || Nvalid > Npad || Nvalid <= 0 ||
         K <= 0 || (K % kBK) != 0 || Co <= 0 || (Co % 64) != 0 || (reinterpret_cast<uintptr_t>(ss) & 15u) ||
         (reinterpret_cast<uintptr_t>(bias) & 15u) || (reinterpret_cast<uintptr_t>(Y) & 15u) ||
-        (reinterpret_cast<uintptr_t>(Yprev) & 15u) || (ss != nullptr && !(slope > 0.f && slope <= 1.f)))
+        (reinterpret_cast<uintptr_t>(Yprev) & 15u) || (ss != nullptr && !(slope >= 0.f && slope <= 1.f)))
         return FEPE_E_BADARG;
     GemmParams p{B * Npad, K, Co, Npad, Nvalid, ss, slope, wscale, bias, Y, stats, ss == nullptr ? a_amax : nullptr};
     cudaStream_t st = static_cast<cudaStream_t>(stream);
@@ -687,7 +687,7 @@ int fepe_mlp32_gemm(const float* Yprev, const float* ss, float slope, const unsi
 int fepe_mlp32_last(const float* Y, const float* ss, float slope, const float* W, const float* bias, float* logits,
                     float* weights, int B, int N, int Npad, int Ci, int Co, void* stream) {
     if (!Y || !ss || !W || !logits || B <= 0 || N <= 0 || Npad < N || Ci != 256 || (Co != 1 && Co != 4) ||
-        (Co != 1 && weights != nullptr) || (reinterpret_cast<uintptr_t>(Y) & 15u) || !(slope > 0.f && slope <= 1.f))
+        (Co != 1 && weights != nullptr) || (reinterpret_cast<uintptr_t>(Y) & 15u) || !(slope >= 0.f && slope <= 1.f))
         return FEPE_E_BADARG;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const float2* s2 = reinterpret_cast<const float2*>(ss);

@@ -475,7 +475,7 @@ int fepe_mlp32_wgrad(const float* dY, const unsigned* dy_amax, const float* Ypre
                      float* dW, int M, int Npad, int Co, int Ci, void* stream) {
     if (!dY || !dy_amax || !Yprev || !ss_prev || !dW || M <= 0 || Npad <= 0 || (Npad % 128) != 0 || (M % Npad) != 0 ||
         (Co % 128) != 0 || (Ci % 64) != 0 || Co <= 0 || Ci <= 0 || (reinterpret_cast<uintptr_t>(ss_prev) & 15u) ||
-        (reinterpret_cast<uintptr_t>(dY) & 15u) || (reinterpret_cast<uintptr_t>(Yprev) & 15u) || !(slope > 0.f && slope <= 1.f))
+        (reinterpret_cast<uintptr_t>(dY) & 15u) || (reinterpret_cast<uintptr_t>(Yprev) & 15u) || !(slope >= 0.f && slope <= 1.f))
         return FEPE_E_BADARG;
     const int bn = (Ci % 128 == 0) ? 128 : 64;
     const int tiles = (Co / 128) * (Ci / bn);

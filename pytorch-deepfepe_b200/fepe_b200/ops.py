@@ -358,3 +358,59 @@ class PoseLossFunction(torch.autograd.Function):
         dF = pose_backward(F, K, ctx.aff, q_gt, t_gt, virt1 if has_v else None, virt2 if has_v else None,
                            ctx.clamp_at, out, g_q, g_t, g_loss)
         return (dF,) + (None,) * 11
+
+
+class LinearTC32(torch.autograd.Function):
+    """y [M,Co] = x [M,K] @ W[Co,K]^T on tcgen05 at fp32 accuracy (split-fp16 operands, three MMAs per product, fp32
+    accumulation; csrc/fepe_mlp32.cu), with the data gradient (the same GEMM with W^T) and the weight gradient
+    (fepe_mlp32_wgrad, both operands read in place as MN-major tiles) on tensor cores as well.
+    M % 128 == 0, K % 64 == 0, Co % 128 == 0 (use torch for thinner layers)."""
+
+    @staticmethod
+    def forward(ctx, x, W):
+        from . import mlp32
+        x = _check_cuda_f32(x, "x")
+        W2 = _check_cuda_f32(W, "W")
+        M, K = x.shape
+        Co = W2.shape[0]
+        if M % 128 or K % 64 or Co % 128 or W2.shape[1] != K:
+            raise RuntimeError("fepe_b200.LinearTC32: need M % 128 == 0, K % 64 == 0, Co % 128 == 0")
+        lib = _lib.lib()
+        with torch.cuda.device(x.device):
+            st = _stream_ptr()
+            whi, wlo, wsc = mlp32.split_weight(lib, W2, st)
+            y = torch.empty(M, Co, dtype=torch.float32, device=x.device)
+            _lib.check(lib.fepe_mlp32_gemm(x.data_ptr(), None, 1.0, None, whi.data_ptr(), wlo.data_ptr(), wsc.data_ptr(),
+                                           None, y.data_ptr(), None, 1, M, M, K, Co, st), "fepe_mlp32_gemm")
+        ctx.save_for_backward(x, W2)
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        from . import mlp32
+        x, W2 = ctx.saved_tensors
+        M, K = x.shape
+        Co = W2.shape[0]
+        gy = _check_cuda_f32(gy, "gy")
+        lib = _lib.lib()
+        gx = gw = None
+        with torch.cuda.device(x.device):
+            st = _stream_ptr()
+            amax = gy.abs().max().reshape(1).view(torch.int32)          # bit pattern of max |gy| (stays on the device)
+            if ctx.needs_input_grad[0]:
+                thi, tlo, tsc = mlp32.split_weight(lib, W2.t().contiguous(), st)
+                gx = torch.empty(M, K, dtype=torch.float32, device=x.device)
+                _lib.check(lib.fepe_mlp32_gemm(gy.data_ptr(), None, 1.0, amax.data_ptr(), thi.data_ptr(), tlo.data_ptr(),
+                                               tsc.data_ptr(), None, gx.data_ptr(), None, 1, M, M, Co, K, st),
+                           "fepe_mlp32_gemm(dgrad)")
+            if ctx.needs_input_grad[1]:
+                ident = torch.tensor([1.0, 0.0], device=x.device).repeat(K).reshape(1, K, 2).contiguous()
+                gw = torch.zeros(Co, K, dtype=torch.float32, device=x.device)
+                _lib.check(lib.fepe_mlp32_wgrad(gy.data_ptr(), amax.data_ptr(), x.data_ptr(), ident.data_ptr(), 1.0,
+                                                gw.data_ptr(), M, M, Co, K, st), "fepe_mlp32_wgrad")
+        return gx, gw
+
+
+def linear_tc32(x: torch.Tensor, W: torch.Tensor) -> torch.Tensor:
+    """x [M,K] @ W[Co,K]^T at fp32 accuracy on tensor cores (see LinearTC32)."""
+    return LinearTC32.apply(x, W)
