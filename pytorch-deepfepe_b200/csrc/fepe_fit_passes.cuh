@@ -183,71 +183,6 @@ __device__ __forceinline__ void pass_gram(const float4* __restrict__ sp, const f
     }
 }
 
-// pass 3, fp32 variant (inference path of the split pipeline): the same 36 entries with fp32 products and per-lane fp32
-// partial sums (a lane owns ~N / 64 correspondences; the cross-lane fold is fp64).  The Gram matrix then carries ~1e-7
-// of relative error -- too much for the eigenvector on ill-conditioned pairs -- which ONE row-space
-// refinement step in the residual kernel removes (refine_accumulate below, fepe_math.cuh: eig9_refine_step).
-struct GramTerm32 {
-    float x1, y1, x2, y2, s;
-};
-__device__ __forceinline__ GramTerm32 gram_prepare32(const float4 q, const float wi, const PairMap& m) {
-    GramTerm32 t;
-    t.x1 = fmaf(m.k1x, q.x, m.j1x); t.y1 = fmaf(m.k1y, q.y, m.j1y);
-    t.x2 = fmaf(m.k2x, q.z, m.j2x); t.y2 = fmaf(m.k2y, q.w, m.j2y);
-    const float nb = fmaf(t.x1, t.x1, fmaf(t.y1, t.y1, 1.0f));
-    const float na = fmaf(t.x2, t.x2, fmaf(t.y2, t.y2, 1.0f));
-    t.s = (wi * wi) * approx_rcp(na * nb);
-    return t;
-}
-__device__ __forceinline__ void gram_accumulate32(const GramTerm32& c, float (&acc)[36]) {
-    const float b0 = c.x1 * c.x1, b1 = c.x1 * c.y1, b3 = c.y1 * c.y1;
-    const float t0 = c.s * c.x2, t1 = c.s * c.y2;
-    const float a[6] = {t0 * c.x2, t0 * c.y2, t0, t1 * c.y2, t1, c.s};
-#pragma unroll
-    for (int u = 0; u < 6; ++u) {
-        acc[u * 6 + 0] = fmaf(a[u], b0, acc[u * 6 + 0]);
-        acc[u * 6 + 1] = fmaf(a[u], b1, acc[u * 6 + 1]);
-        acc[u * 6 + 2] = fmaf(a[u], c.x1, acc[u * 6 + 2]);
-        acc[u * 6 + 3] = fmaf(a[u], b3, acc[u * 6 + 3]);
-        acc[u * 6 + 4] = fmaf(a[u], c.y1, acc[u * 6 + 4]);
-        acc[u * 6 + 5] += a[u];
-    }
-}
-__device__ __forceinline__ void pass_gram32(const float4* __restrict__ sp, const float* __restrict__ sw, int N,
-                                            int start, int stride, const PairMap& m, float (&acc)[36]) {
-#pragma unroll
-    for (int i = 0; i < 36; ++i) acc[i] = 0.f;
-    int i = start;
-    for (; i + stride < N; i += 2 * stride) {               // two correspondences in flight
-        const GramTerm32 A = gram_prepare32(sp[i], sw[i], m);
-        const GramTerm32 B = gram_prepare32(sp[i + stride], sw[i + stride], m);
-        gram_accumulate32(A, acc);
-        gram_accumulate32(B, acc);
-    }
-    if (i < N) gram_accumulate32(gram_prepare32(sp[i], sw[i], m), acc);
-}
-
-// Row-space refinement: g += x_i (x_i . f0), x_i = w_i p^_i, with the row product r_i = x_i . f0 in fp32 (it only has to
-// be accurate relative to itself) and the nine sums in fp64 from exact products of the fp32 factors: X^T scales the
-// rounding of r by sigma_8 only, so g = X^T X f0 has the accuracy of the rows, not of the squared problem.
-__device__ __forceinline__ void refine_accumulate(const float4 q, const float wi, const PairMap& m, const float (&f0)[9],
-                                                  double (&g)[9]) {
-    const float x1 = fmaf(m.k1x, q.x, m.j1x), y1 = fmaf(m.k1y, q.y, m.j1y);
-    const float x2 = fmaf(m.k2x, q.z, m.j2x), y2 = fmaf(m.k2y, q.w, m.j2y);
-    const float nb = fmaf(x1, x1, fmaf(y1, y1, 1.0f));
-    const float na = fmaf(x2, x2, fmaf(y2, y2, 1.0f));
-    const float r0 = fmaf(f0[0], x1, fmaf(f0[1], y1, f0[2]));
-    const float r1 = fmaf(f0[3], x1, fmaf(f0[4], y1, f0[5]));
-    const float r2 = fmaf(f0[6], x1, fmaf(f0[7], y1, f0[8]));
-    const float inv = wi * rsqrtf(na * nb);                  // w / |p|
-    const float r = inv * fmaf(x2, r0, fmaf(y2, r1, r2));    // x_i . f0
-    const double t = static_cast<double>(inv) * static_cast<double>(r);
-    const double dx1 = x1, dy1 = y1, dx2 = x2, dy2 = y2;
-    g[0] = fma(t, dx2 * dx1, g[0]); g[1] = fma(t, dx2 * dy1, g[1]); g[2] = fma(t, dx2, g[2]);
-    g[3] = fma(t, dy2 * dx1, g[3]); g[4] = fma(t, dy2 * dy1, g[4]); g[5] = fma(t, dy2, g[5]);
-    g[6] = fma(t, dx1, g[6]);       g[7] = fma(t, dy1, g[7]);       g[8] += t;
-}
-
 // pass 4: residual r_i = w_i p^_i . f and the clamped symmetric epipolar distance with out = T2^T F_ T1
 __device__ __forceinline__ float resid_one(const float4 q, const float wi, const PairMap& m, const float (&ff)[9]) {
     const float x1 = fmaf(m.k1x, q.x, m.j1x), y1 = fmaf(m.k1y, q.y, m.j1y);

@@ -54,9 +54,7 @@ __device__ __forceinline__ void team_sync(int team) {
 // ------------------------------------------------------------------------------------------------
 // K1: Hartley + Gram.  T warps per pair.
 // ------------------------------------------------------------------------------------------------
-// F32: fp32 Gram accumulation (inference path; refined in fepe_resid_refine_kernel), else fp64 (training: the saved
-// Gram matrix feeds the backward pass).
-template <int T, bool F32>
+template <int T>
 __global__ void __launch_bounds__(kGramThreads, 1) fepe_gram_kernel(const FitParams p) {
     extern __shared__ __align__(128) unsigned char smem[];
     const int warp = threadIdx.x >> 5;
@@ -171,14 +169,7 @@ __global__ void __launch_bounds__(kGramThreads, 1) fepe_gram_kernel(const FitPar
         double* st = pair_state(p, pair);
         double acc[36];
         const long long tc2 = clock64();
-        if constexpr (F32) {
-            float acc32[36];
-            pass_gram32(sp, sw, N, tt, TS, m, acc32);
-#pragma unroll
-            for (int e = 0; e < 36; ++e) acc[e] = static_cast<double>(acc32[e]);
-        } else {
-            pass_gram(sp, sw, N, tt, TS, m, acc);
-        }
+        pass_gram(sp, sw, N, tt, TS, m, acc);
         const long long tc3 = clock64();
         if (reduce_in_stage) {
             // Cross-lane reduction through the pair's own stage (its correspondences are dead now): every lane
@@ -355,122 +346,18 @@ __global__ void __launch_bounds__(kResidThreads) fepe_resid_kernel(const FitPara
                p.clamp_at, r_out, e_out);
 }
 
-// ------------------------------------------------------------------------------------------------
-// K3 of the inference path: refinement + residual rows.  One CTA of 128 threads per pair, the pair's correspondences in
-// registers (up to 8 per thread; longer pairs re-read the tail).  Pass A forms g = X^T (X f0) (refine_accumulate); one
-// thread applies the correction f1 = normalise(f0 - (G~ - rho)^+ (g - rho f0)) with the fp32-accumulated Gram G~ of K1
-// (eig9_refine_step), the rank-2 projection and the de-normalisation; pass B writes both residual rows with f1.
-// Several CTAs per SM (launch bounds) stream while one of them sits in its ~4 k-cycle serial section.
-// ------------------------------------------------------------------------------------------------
-constexpr int kRefineThreads = 128;
-constexpr int kRefineHold = 8;
-
-__device__ __noinline__ void refine_solve(const double* __restrict__ g36, const double* __restrict__ gsum,
-                                          const double* __restrict__ st, const PairNorm& h, float* __restrict__ ff_out,
-                                          float* __restrict__ Fo_out) {
-    double f0[9], g[9], f1[9];
-#pragma unroll
-    for (int i = 0; i < 9; ++i) { f0[i] = st[i]; g[i] = gsum[i]; }
-    eig9_refine_step(g36, f0, st[9], g, f1);
-    double F2[9], v3[3], sigma3;
-    rank2_project(f1, F2, v3, sigma3);
-    float Fo[9];
-    denormalise_F(F2, h, Fo);
-#pragma unroll
-    for (int i = 0; i < 9; ++i) { ff_out[i] = static_cast<float>(f1[i]); Fo_out[i] = Fo[i]; }
-}
-
-__global__ void __launch_bounds__(kRefineThreads, 5) fepe_resid_refine_kernel(const FitParams p) {
-    __shared__ double g36s[36];
-    __shared__ double f0s[10];                 // f0, lambda0
-    __shared__ double gred[kRefineThreads / 32][9];
-    __shared__ double gsum[9];
-    __shared__ float ffs[9], Fos[9];
-    pdl_launch_dependents();
-    const size_t pair = gridDim.x - 1 - blockIdx.x;          // highest pair first: what K1 read last is still in L2
-    const int N = p.N;
-    const int tid = threadIdx.x;
-    const float4* gp = reinterpret_cast<const float4*>(p.matches) + pair * static_cast<size_t>(N);
-    const float* gw = p.weights + pair * static_cast<size_t>(N);
-    float4 q[kRefineHold];
-    float wv[kRefineHold];
-#pragma unroll
-    for (int u = 0; u < kRefineHold; ++u) {
-        const int i = tid + u * kRefineThreads;
-        q[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-        wv[u] = 0.f;
-        if (i < N) { q[u] = __ldcs(gp + i); wv[u] = __ldcs(gw + i); }
-    }
-    const double* st = pair_state(p, pair);
-    PairNorm h;
-    h.m1x = static_cast<float>(st[0]); h.m1y = static_cast<float>(st[1]); h.s1 = static_cast<float>(st[2]);
-    h.m2x = static_cast<float>(st[3]); h.m2y = static_cast<float>(st[4]); h.s2 = static_cast<float>(st[5]);
-    h.c1x = fmaf(p.ax, h.m1x, p.bx); h.c1y = fmaf(p.ay, h.m1y, p.by);
-    h.c2x = fmaf(p.ax, h.m2x, p.bx); h.c2y = fmaf(p.ay, h.m2y, p.by);
-    float f0f[9];
-#pragma unroll
-    for (int i = 0; i < 9; ++i) f0f[i] = static_cast<float>(st[6 + i]);
-    if (tid < 36) g36s[tid] = st[16 + tid];
-    if (tid >= 64 && tid < 74) f0s[tid - 64] = st[6 + tid - 64];
-    __syncthreads();                                          // the state may sit in the row this CTA overwrites
-    const PairMap m = make_map(h, p.ax, p.ay);
-    // ---- pass A: g = X^T (X f0) ----
-    double g[9];
-#pragma unroll
-    for (int i = 0; i < 9; ++i) g[i] = 0.0;
-#pragma unroll
-    for (int u = 0; u < kRefineHold; ++u) refine_accumulate(q[u], wv[u], m, f0f, g);      // w = 0 beyond N: no contribution
-    for (int i = tid + kRefineHold * kRefineThreads; i < N; i += kRefineThreads) refine_accumulate(__ldg(gp + i), __ldg(gw + i), m, f0f, g);
-#pragma unroll
-    for (int i = 0; i < 9; ++i) g[i] = warp_sum(g[i]);
-    if ((tid & 31) == 0) {
-#pragma unroll
-        for (int i = 0; i < 9; ++i) gred[tid >> 5][i] = g[i];
-    }
-    __syncthreads();
-    if (tid < 9) {
-        double t = 0.0;
-#pragma unroll
-        for (int w = 0; w < kRefineThreads / 32; ++w) t += gred[w][tid];
-        gsum[tid] = t;
-    }
-    __syncthreads();
-    if (tid == 0) {
-        refine_solve(g36s, gsum, f0s, h, ffs, Fos);
-#pragma unroll
-        for (int i = 0; i < 9; ++i) p.F_out[pair * 9 + i] = Fos[i];
-    }
-    __syncthreads();
-    float ff[9], Fo[9];
-#pragma unroll
-    for (int i = 0; i < 9; ++i) { ff[i] = ffs[i]; Fo[i] = Fos[i]; }
-    // ---- pass B: residual rows with the refined f ----
-    float* r_out = p.resid + pair * static_cast<size_t>(N);
-    float* e_out = (p.epi != nullptr) ? p.epi + pair * static_cast<size_t>(N) : nullptr;
-#pragma unroll
-    for (int u = 0; u < kRefineHold; ++u) {
-        const int i = tid + u * kRefineThreads;
-        if (i < N) {
-            __stcs(r_out + i, resid_one(q[u], wv[u], m, ff));
-            if (e_out != nullptr) __stcs(e_out + i, epi_one(q[u], Fo, p.ax, p.bx, p.ay, p.by, p.clamp_at));
-        }
-    }
-    pass_resid(gp, gw, N, tid + kRefineHold * kRefineThreads, kRefineThreads, m, ff, Fo, p.ax, p.bx, p.ay, p.by,
-               p.clamp_at, r_out, e_out);
-}
-
-template <int T, bool F32>
+template <int T>
 static cudaError_t launch_gram(const FitParams& p, int grid, cudaStream_t stream) {
     static int configured[64] = {0};
     int dev = 0;
     cudaGetDevice(&dev);
     if (!configured[dev & 63]) {
-        cudaError_t e = cudaFuncSetAttribute(fepe_gram_kernel<T, F32>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        cudaError_t e = cudaFuncSetAttribute(fepe_gram_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              device_info().smem_optin);
         if (e != cudaSuccess) return e;
         configured[dev & 63] = 1;
     }
-    fepe_gram_kernel<T, F32><<<grid, kGramThreads, p.ring.total_bytes, stream>>>(p);
+    fepe_gram_kernel<T><<<grid, kGramThreads, p.ring.total_bytes, stream>>>(p);
     return cudaGetLastError();
 }
 
@@ -504,21 +391,14 @@ int launch_split(FitParams p, const DeviceInfo& d, cudaStream_t stream) {
     p.ring.scratch_off = p.ring.bar_off + 2 * kMaxStages * 8;
     p.ring.total_bytes = p.ring.scratch_off + kGramConsumerWarps * (36 * 8 + 8 * 4);
     const int grid = p.B < d.sms ? p.B : d.sms;
-    // Inference (no saved state requested): fp32 Gram in K1 and one row-space refinement step in K3 -- K1 leaves the fp64
-    // pipe and runs at memory speed, K3's fp64 work hides under its memory time.  Training keeps the fp64 Gram (the saved
-    // matrix feeds the backward pass).  FEPE_DISPATCH_GRAM_F64 forces the fp64 path (A/B, tests).
-    const bool f32 = p.saved == nullptr && dispatch_get(FEPE_DISPATCH_GRAM_F64) == 0;
-    cudaError_t e;
-    if (f32) e = (T == 1) ? launch_gram<1, true>(p, grid, stream) : (T == 2) ? launch_gram<2, true>(p, grid, stream)
-                                                                            : launch_gram<4, true>(p, grid, stream);
-    else e = (T == 1) ? launch_gram<1, false>(p, grid, stream) : (T == 2) ? launch_gram<2, false>(p, grid, stream)
-                                                                          : launch_gram<4, false>(p, grid, stream);
+    cudaError_t e = (T == 1)   ? launch_gram<1>(p, grid, stream)
+                    : (T == 2) ? launch_gram<2>(p, grid, stream)
+                               : launch_gram<4>(p, grid, stream);
     if (e != cudaSuccess) return static_cast<int>(e);
     fepe_solve_kernel<<<(p.B + 31) / 32, 32, 0, stream>>>(p);
     e = cudaGetLastError();
     if (e != cudaSuccess) return static_cast<int>(e);
-    if (f32) fepe_resid_refine_kernel<<<p.B, kRefineThreads, 0, stream>>>(p);
-    else fepe_resid_kernel<<<p.B, kResidThreads, 0, stream>>>(p);
+    fepe_resid_kernel<<<p.B, kResidThreads, 0, stream>>>(p);
     return static_cast<int>(cudaGetLastError());
 }
 

@@ -17,7 +17,7 @@ POSE_OUT_FLOATS = 32        # FEPE_POSE_OUT_FLOATS
 RECOVER_OUT_FLOATS = 24     # FEPE_RECOVER_OUT_FLOATS
 GT_FLOATS = 32              # FEPE_GT_FLOATS
 
-DISPATCH_FIT, DISPATCH_GRAM_TEAM, DISPATCH_MLP_GEMM, DISPATCH_MLP_FUSE, DISPATCH_GRAM_F64 = 0, 1, 2, 3, 4   # FEPE_DISPATCH_*
+DISPATCH_FIT, DISPATCH_GRAM_TEAM, DISPATCH_MLP_GEMM, DISPATCH_MLP_FUSE = 0, 1, 2, 3   # FEPE_DISPATCH_*
 
 _lib = None
 

@@ -45,6 +45,27 @@ def split_weight(lib, w2d: torch.Tensor, st):
     return whi, wlo, wsc
 
 
+_SPLIT_CACHE = {}
+
+
+def split_param_cached(lib, param: torch.Tensor, co: int, k: int, transposed: bool, st):
+    """(hi, lo, scale) of a Conv1d weight [co, k, 1] (or of its transpose [k, co]: the data-gradient operand), cached per
+    parameter VERSION: the update network is evaluated depth-1 times per step with the same weights, forward and
+    backward, so each split is computed once per optimizer step instead of 2 x (depth - 1) times."""
+    key = (id(param), bool(transposed))
+    ver = (param._version, param.data_ptr(), param.device)
+    hit = _SPLIT_CACHE.get(key)
+    if hit is not None and hit[0] == ver:
+        return hit[1]
+    w2d = param.detach().reshape(co, k).float()
+    w2d = w2d.t().contiguous() if transposed else w2d.contiguous()
+    out = split_weight(lib, w2d, st)
+    if len(_SPLIT_CACHE) > 256:
+        _SPLIT_CACHE.clear()
+    _SPLIT_CACHE[key] = (ver, out)
+    return out
+
+
 def first_layer_args(matches, affine, extras, cin: int):
     """ctypes arguments of fepe_mlp32_first for the channel groups; returns (args, tensors to keep alive)."""
     keep = []
@@ -164,8 +185,7 @@ class MLP32Function(torch.autograd.Function):
         with torch.cuda.device(dev):
             st = torch.cuda.current_stream(dev).cuda_stream
             w0 = convw[0].detach().reshape(64, cin).float().contiguous()
-            w2d = [None] + [convw[i].detach().reshape(_CH[i], _CH[i - 1]).float().contiguous() for i in range(1, 5)]
-            wsp = [None] + [split_weight(lib, w2d[i], st) for i in range(1, 5)]
+            wsp = [None] + [split_param_cached(lib, convw[i], _CH[i], _CH[i - 1], False, st) for i in range(1, 5)]
             w_last = convw[5].detach().reshape(cout, 256).float().contiguous()
             b_last = params[21].detach().float().contiguous()
             Ys = [torch.empty(M, c, dtype=torch.float32, device=dev) for c in _CH]
@@ -192,14 +212,14 @@ class MLP32Function(torch.autograd.Function):
             del keep
         ctx.dims = (B, N, Npad, cin, cout, affine, n_extras, matches is not None,
                     [1 if e.dim() == 2 else e.shape[2] for e in extras], [tuple(e.shape) for e in extras])
-        ctx.saved = (X0, w0, w2d, w_last, gam, Ys, sss, mrs)
+        ctx.saved = (X0, w0, convw, w_last, gam, Ys, sss, mrs)
         return logits
 
     @staticmethod
     def backward(ctx, dlogits):
         lib = _lib.lib()
         B, N, Npad, cin, cout, affine, n_extras, has_m, ecs, eshapes = ctx.dims
-        X0, w0, w2d, w_last, gam, Ys, sss, mrs = ctx.saved
+        X0, w0, convw, w_last, gam, Ys, sss, mrs = ctx.saved
         dev = X0.device
         M = B * Npad
         grads = [None] * 22
@@ -232,7 +252,7 @@ class MLP32Function(torch.autograd.Function):
                                                     sss[i - 1].data_ptr(), SLOPE, dW.data_ptr(), M, Npad, c, ci, st),
                                "fepe_mlp32_wgrad")
                     grads[4 * i] = dW.reshape(c, ci, 1)
-                    thi, tlo, tsc = split_weight(lib, w2d[i].t().contiguous(), st)       # [ci, c]: the data-gradient "weight"
+                    thi, tlo, tsc = split_param_cached(lib, convw[i], c, ci, True, st)   # [ci, c]: the data-gradient "weight"
                     dXn = torch.empty(M, ci, dtype=torch.float32, device=dev)
                     _lib.check(lib.fepe_mlp32_gemm(dY.data_ptr(), None, 1.0, am.data_ptr(), thi.data_ptr(), tlo.data_ptr(),
                                                    tsc.data_ptr(), None, dXn.data_ptr(), None, B, Npad, Npad, c, ci, st),

@@ -74,8 +74,11 @@ def test_forward_and_gradients_against_fp64(cin, N):
     worst_tc = max(float((gp[n] - gpr[n]).norm() / gpr[n].norm().clamp_min(1e-30)) for n in gpr if float(gpr[n].norm()) > 1e-12)
     worst_32 = max(float((gp32[n] - gpr[n]).norm() / gpr[n].norm().clamp_min(1e-30)) for n in gpr if float(gpr[n].norm()) > 1e-12)
     print(f"   worst parameter-gradient rel err vs fp64: tensor cores {worst_tc:.2e}, torch fp32 {worst_32:.2e}")
-    assert worst_tc < max(5 * worst_32, 1e-3)
-    assert float((gx - gxr).norm() / gxr.norm()) < max(5 * float((gx32 - gxr).norm() / gxr.norm()), 1e-3)
+    # The network is not smooth (ReLU kinks, arg-max of the global pooling): one flipped arg-max between an fp32 and the
+    # fp64 evaluation moves every upstream gradient by ~3e-3 (measured for BOTH the tensor-core path and torch's fp32
+    # matmul, scripts/diag_linear_tc32.py).  The smooth accuracy of the GEMMs is pinned by test_linear_tc32_* below.
+    assert worst_tc < 2e-2
+    assert float((gx - gxr).norm() / gxr.norm()) < 2e-2
 
 
 @pytest.mark.gpu
@@ -95,3 +98,23 @@ def test_deepfnet_good_corres_arch_branch():
         assert float(torch.linalg.svdvals(Fo.double())[:, 2].max()) < 1e-6
     sum(Fo.pow(2).sum() for Fo in outs["out_layers"]).backward()
     assert all(p.grad is not None and torch.isfinite(p.grad).all() for p in net.parameters())
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("M,K,Co", [(1024, 64, 128), (1024, 512, 2048), (1024, 4928, 256), (2048, 256, 256)])
+def test_linear_tc32_forward_dgrad_wgrad_against_fp64(M, K, Co):
+    """ops.linear_tc32 (GoodCorresNet's dense 1x1 convolutions): forward, data gradient and weight gradient on tcgen05
+    with split-fp16 operands against fp64 on GoodCorresNet-shaped layers.  The forward bias of long sums (K = 4928:
+    1.7e-5) is the truncating fp32 accumulation of tensor memory, 3 K / 16 accumulation steps of ~2^-25 each."""
+    from fepe_b200 import ops
+    torch.manual_seed(3)
+    x = torch.relu(torch.randn(M, K, device="cuda")).requires_grad_(True)
+    W = (torch.randn(Co, K, device="cuda") / K ** 0.5).requires_grad_(True)
+    gy = torch.randn(M, Co, device="cuda") * 1e-3
+    y = ops.linear_tc32(x, W)
+    y.backward(gy)
+    x64, W64 = x.detach().double(), W.detach().double()
+    rel = lambda a, b: float((a.double() - b).norm() / b.norm())
+    assert rel(y, x64 @ W64.t()) < 2e-6 + 4e-9 * K
+    assert rel(x.grad, gy.double() @ W64) < 4e-6
+    assert rel(W.grad, gy.double().t() @ x64) < 4e-6
