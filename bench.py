@@ -552,6 +552,14 @@ def run_ours(args):
                 f"{replays}x; value_serial: the same on 1 branch"},
         "gpu_launches": n_timed * (1 if small else 2),
         "roofline": roofline,
+        # the same kernel inside the timed region: launches of independent batches overlap on the parallel branches, so
+        # the AVERAGE time per launch (region / launches) is shorter than one launch alone
+        "roofline_timed_region": {"bound": "hbm", "kernel": fit_kernel, "unit": "GB/s", "peak": peak,
+                                  "achieved": fit_bytes(B, N) * n_timed / secs / 1e9,
+                                  "frac": fit_bytes(B, N) * n_timed / secs / 1e9 / peak,
+                                  "avg_launch_us": secs / n_timed * 1e6,
+                                  "note": "algorithmic bytes of all launches of the timed region / its CUDA-event time "
+                                          f"({n_branch} concurrent branches on this rank)"},
     }
 
     if not args.no_extras:
