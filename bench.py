@@ -54,6 +54,15 @@ CLAMP_EPI = 0.5      # in-model epipolar clamp (DeepFNet.py:479 default)
 CLAMP_LOSS = 0.02    # configs/kitti_corr_baseline.yaml:36
 
 
+_OUT = None
+
+
+def emit(line: dict) -> None:
+    out = _OUT if _OUT is not None else sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -443,7 +452,7 @@ def run_reference(args):
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -723,7 +732,7 @@ def run_ours(args):
         dist.barrier()
         dist.destroy_process_group()
     if rank == 0:
-        print(json.dumps(line), flush=True)
+        emit(line)
 
 
 def run_c4(args):
@@ -790,7 +799,7 @@ def run_c4(args):
             "gpu_launches": steps * (5 * 11 + 5),
             "clocks": sampler.summary(t0, t1)}
     if rank == 0:
-        print(json.dumps(line), flush=True)
+        emit(line)
 
 
 def c5_measure(args, dev, rank, world, steps: int, warm: int, mlp: str) -> dict:
@@ -929,10 +938,15 @@ def run_c5(args):
         dist.barrier()
         dist.destroy_process_group()
     if rank == 0:
-        print(json.dumps(line), flush=True)
+        emit(line)
 
 
 def main():
+    # stdout must carry exactly ONE JSON line: libraries (NCCL's version banner, torchrun notices) write to file
+    # descriptor 1 as well, so fd 1 is pointed at stderr for the whole run and the line goes out through a private copy
+    global _OUT
+    _OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     args = parse_args()
     if args.impl == "reference":
         run_reference(args)

