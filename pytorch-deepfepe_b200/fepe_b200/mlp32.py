@@ -10,6 +10,7 @@ feature tensor.  Output: logits [B, out, N] and, for a one-logit network, the so
 """
 from __future__ import annotations
 
+import weakref
 from typing import Optional, Sequence
 
 import torch
@@ -55,14 +56,15 @@ def split_param_cached(lib, param: torch.Tensor, co: int, k: int, transposed: bo
     key = (id(param), bool(transposed))
     ver = (param._version, param.data_ptr(), param.device)
     hit = _SPLIT_CACHE.get(key)
-    if hit is not None and hit[0] == ver:
+    # id() values are reused once an object dies: the entry must belong to THIS parameter object (weak reference)
+    if hit is not None and hit[0] == ver and hit[2]() is param:
         return hit[1]
     w2d = param.detach().reshape(co, k).float()
     w2d = w2d.t().contiguous() if transposed else w2d.contiguous()
     out = split_weight(lib, w2d, st)
     if len(_SPLIT_CACHE) > 256:
         _SPLIT_CACHE.clear()
-    _SPLIT_CACHE[key] = (ver, out)
+    _SPLIT_CACHE[key] = (ver, out, weakref.ref(param))
     return out
 
 

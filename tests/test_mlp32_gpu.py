@@ -382,3 +382,22 @@ def test_deepfnet_training_step_on_the_kernel_path():
             continue
         rel = float((g_tc[n] - ref).norm() / ref.norm())
         assert rel < 2e-2, (n, rel)          # two fp32 evaluations of an ill-conditioned recursion; fp64 is the judge above
+
+
+def test_weight_split_cache_does_not_survive_the_parameter():
+    """The per-parameter cache of split weights is keyed by id(): a NEW model whose parameters land on the addresses of a
+    dead one (same id, same data pointer, same version) must not be served the old model's weights."""
+    import gc
+    x = torch.rand(2, 4, 256, device="cuda", requires_grad=True)
+    outs = []
+    for seed in (1, 2, 3, 4):
+        torch.manual_seed(seed)
+        ee = ErrorEstimator(4).cuda()
+        y_train = ee(x)                                   # autograd path: fills the cache
+        with torch.no_grad():
+            y_inf = ee(x)                                 # inference path: its own per-instance copies
+        assert float((y_train - y_inf).abs().max()) < 1e-5 * float(y_inf.abs().max()), seed
+        outs.append(y_inf)
+        del ee, y_train
+        gc.collect()
+    assert float((outs[0] - outs[1]).abs().max()) > 1e-3      # different seeds do give different networks
