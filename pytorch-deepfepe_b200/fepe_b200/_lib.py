@@ -97,6 +97,22 @@ def lib() -> ctypes.CDLL:
     return _lib
 
 
+_DISPATCH_KEYS = {"fit": (DISPATCH_FIT, {"auto": 0, "small": 1, "ring": 2, "split": 3}),
+                  "gram_team": (DISPATCH_GRAM_TEAM, {"auto": 0, "1": 1, "2": 2, "4": 3}),
+                  "mlp_gemm": (DISPATCH_MLP_GEMM, {"auto": 0, "persist": 0, "tile": 1, "persist128": 2}),
+                  "mlp_fuse": (DISPATCH_MLP_FUSE, {"auto": 0, "1": 0, "2": 2})}
+
+
+def set_dispatch(key: str, value) -> int:
+    """Force a kernel variant by name (tests, development scripts): set_dispatch("fit", "split"), ("fit", "auto"), ...
+    -- a thin wrapper of fepe_set_dispatch (include/fepe_b200.h).  Returns the previous raw value."""
+    which, values = _DISPATCH_KEYS[key]
+    st = lib().fepe_set_dispatch(which, values[str(value)])
+    if st < 0:
+        raise RuntimeError(f"fepe_set_dispatch({key}, {value}) failed: {st}")
+    return st
+
+
 def check(status: int, what: str) -> None:
     if status == 0:
         return

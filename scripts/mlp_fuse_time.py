@@ -5,6 +5,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path[:0] = [ROOT, os.path.join(ROOT, "pytorch-deepfepe_b200")]
 import torch
 from fepe_b200 import synth, _lib
+from fepe_b200 import _lib as _fepe_lib
 import fepe_b200.mlp_tc as mt
 from fepe_b200.models import DeepFNet, ErrorEstimator
 
@@ -37,12 +38,12 @@ for B in ((512,) if "--ncu" in sys.argv else (64, 512)):
         if "--ncu" in sys.argv:
             fus(); fus(); torch.cuda.synchronize(); sys.exit(0)
         tu = ev(unf)
-        os.environ["FEPE_MLP_FUSE"] = "1"; tf1 = ev(fus)
-        os.environ["FEPE_MLP_FUSE"] = "2"; tf = ev(fus)
+        _fepe_lib.set_dispatch("mlp_fuse", "1"); tf1 = ev(fus)
+        _fepe_lib.set_dispatch("mlp_fuse", "2"); tf = ev(fus)
         print(f"B={B} K={K} Co={Co}: norm + gemm {tu*1e3:7.1f} us | fused v1 {tf1*1e3:7.1f} us | fused v2 {tf*1e3:7.1f} us ({2*B*Npad*K*Co/tf/1e9:7.1f} TFLOP/s)", flush=True)
 for fuse, fv in ((False, "2"), (True, "1"), (True, "2")):
-    os.environ["FEPE_MLP_FUSE"] = fv
-    print(f"-- FEPE_MLP_FUSE={fv}")
+    _fepe_lib.set_dispatch("mlp_fuse", fv)
+    print(f"-- mlp_fuse dispatch={fv}")
     for B in (64, 512):
         ee = ErrorEstimator(4).cuda(); ee.tensor_cores = True
         x = torch.rand(B, 4, N, device="cuda")

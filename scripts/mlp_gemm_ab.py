@@ -1,10 +1,11 @@
-"""A/B timing of the MLP GEMM variants (FEPE_MLP_GEMM = tile | persist128 | persist) on the ErrorEstimator's
+"""A/B timing of the MLP GEMM variants (fepe_set_dispatch: mlp_gemm = tile | persist128 | persist) on the ErrorEstimator's
 layer shapes, of the whole ErrorEstimator and of a DeepFNet forward.  Development aid."""
 import sys, os
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path[:0] = [ROOT, os.path.join(ROOT, "pytorch-deepfepe_b200")]
 import torch
 from fepe_b200 import synth, _lib
+from fepe_b200 import _lib as _fepe_lib
 from fepe_b200.models import DeepFNet, ErrorEstimator
 
 def ev(fn, iters=10, warm=3):
@@ -26,7 +27,7 @@ for B in (64, 512):
         stats = torch.zeros(B, Co, 2, device="cuda")
         ref = None
         for mode in ("tile", "persist128", "persist"):
-            os.environ["FEPE_MLP_GEMM"] = mode
+            _fepe_lib.set_dispatch("mlp_gemm", mode)
             call = lambda: lib.fepe_mlp_gemm(X.data_ptr(), W.data_ptr(), 0, Y.data_ptr(), stats.data_ptr(), B, Npad, N, K, Co, torch.cuda.current_stream().cuda_stream)
             stats.zero_(); Y.fill_(7.0)
             assert call() == 0
@@ -36,7 +37,7 @@ for B in (64, 512):
             t = ev(call)
             print(f"B={B} gemm K={K} Co={Co} {mode:10s}: {t*1e3:7.1f} us  {2*B*Npad*K*Co/t/1e9:7.1f} TFLOP/s  {(B*Npad*(K+Co)*2)/t/1e6:6.0f} GB/s  |dY| vs tile {dy:.3g}  rel dstats {ds:.2g}", flush=True)
 # fused norm -> GEMM against norm kernel + GEMM, per layer
-os.environ["FEPE_MLP_GEMM"] = "persist"
+_fepe_lib.set_dispatch("mlp_gemm", "persist")
 for B in (64, 512):
     for K, Co in [(64, 128), (128, 1024), (1024, 512), (512, 256)]:
         Yp = torch.randn(B * Npad, K, device="cuda").bfloat16(); W = (torch.randn(Co, K, device="cuda") / K ** 0.5).bfloat16()
@@ -54,7 +55,7 @@ for B in (64, 512):
         print(f"B={B} K={K} Co={Co}: norm + gemm {tu*1e3:7.1f} us | fused {tf*1e3:7.1f} us ({2*B*Npad*K*Co/tf/1e9:7.1f} TFLOP/s)", flush=True)
 import fepe_b200.mlp_tc as _mt
 for mode, fuse in (("tile", False), ("persist128", False), ("persist", False), ("persist", True)):
-    os.environ["FEPE_MLP_GEMM"] = mode
+    _fepe_lib.set_dispatch("mlp_gemm", mode)
     _orig = _mt.TensorCoreMLP.__init__
     def _init(self, fw, _o=_orig, _f=fuse):
         _o(self, fw); self.fuse_norm = _f

@@ -3,7 +3,7 @@ import sys, os, time
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path[:0] = [ROOT, os.path.join(ROOT, "pytorch-deepfepe_b200")]
 import torch
-from fepe_b200 import ops, synth
+from fepe_b200 import ops, synth, _lib
 
 def timeit(B, N, iters=20, epi=True, saved=False):
     base = synth.make_batch(min(B, 512), N, seed=1, weight_mode="softmax")
@@ -27,12 +27,12 @@ def timeit(B, N, iters=20, epi=True, saved=False):
 
 if __name__ == "__main__":
     for kern in ("ring", "small"):
-        os.environ["FEPE_FIT_KERNEL"] = kern
+        _lib.set_dispatch("fit", kern)
         print("kernel", kern)
         timeit(256, 1000)
         timeit(64, 2000)
         timeit(148, 1000)
-    del os.environ["FEPE_FIT_KERNEL"]
+    _lib.set_dispatch("fit", "auto")
     for B, N in [(256, 1000), (32768, 1000), (64, 2000), (16384, 2000)]:
         timeit(B, N)
 

@@ -4,10 +4,11 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path[:0] = [ROOT, os.path.join(ROOT, "pytorch-deepfepe_b200")]
 import torch
 from fepe_b200 import ops, synth
+from fepe_b200 import _lib as _fepe_lib
 from fepe_b200.models import ErrorEstimator
 shapes = [(5, 333), (3, 37), (4, 1000)] if len(sys.argv) < 2 else [tuple(int(v) for v in a.split("x")) for a in sys.argv[1:]]
 for kern in ("ring", "small"):
-    os.environ["FEPE_FIT_KERNEL"] = kern
+    _fepe_lib.set_dispatch("fit", kern)
     for B, N in shapes:
         d = synth.make_batch(B, N, seed=1)
         aff = ops.hw_affine(d["image_size"])

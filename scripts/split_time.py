@@ -4,12 +4,13 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path[:0] = [ROOT, os.path.join(ROOT, "pytorch-deepfepe_b200")]
 import torch
 from fepe_b200 import ops, synth
+from fepe_b200 import _lib as _fepe_lib
 
 
 def run(B, N, kern, iters=10, saved=False, env=None):
-    os.environ["FEPE_FIT_KERNEL"] = kern
+    _fepe_lib.set_dispatch("fit", kern)
     for k, v in (env or {}).items():
-        os.environ[k] = v
+        _fepe_lib.set_dispatch(k, v)
     base = synth.make_batch(512, N, seed=1, weight_mode="softmax")
     m = torch.from_numpy(base["matches_xy_ori"]).cuda()
     w = torch.from_numpy(base["weights"]).cuda().reshape(-1, N)
@@ -30,7 +31,7 @@ def run(B, N, kern, iters=10, saved=False, env=None):
     print(f"{kern:6s} {env or ''} B={B:6d} N={N:5d} saved={saved}: {ms*1e3:9.1f} us  {B/ms*1e3/1e6:7.2f} M pairs/s  "
           f"{by/ms/1e6:7.1f} GB/s ({by/ms/1e6/6574.5*100:4.1f}% of HBM peak)", flush=True)
     for k in (env or {}):
-        del os.environ[k]
+        _fepe_lib.set_dispatch(k, "auto")
     return out
 
 
@@ -40,7 +41,7 @@ if __name__ == "__main__":
         for t in ("1", "2", "4"):
             if N == 1000 and t == "1":
                 continue
-            b = run(B, N, "split", env={"FEPE_GRAM_TEAM": t})
+            b = run(B, N, "split", env={"gram_team": t})
         relF = ((a[0] - b[0]).flatten(1).norm(dim=1) / a[0].flatten(1).norm(dim=1)).max().item()
         print(f"   max rel F difference split vs ring: {relF:.2e}; resid {float((a[1]-b[1]).abs().max()):.2e}")
     run(32768, 1000, "split", saved=True)
