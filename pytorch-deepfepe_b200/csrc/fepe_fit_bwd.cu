@@ -21,6 +21,7 @@
 // the four partial gradients of correspondence i in the four dead row slots of the stage (weight, rbar, ebar and
 // one spare row: 32 B / correspondence staged) and accumulates the ten sums the adjoint of Fit.normalize needs;
 // pass 3 adds the mean / mean-distance terms and writes [N,4] once.  No read-modify-write of global memory.
+#include "fepe_dispatch.cuh"
 #include "fepe_fit.cuh"
 #include "fepe_fit_adjoint.cuh"
 
@@ -273,6 +274,180 @@ __global__ void __launch_bounds__(kThreads, 1) fepe_fit_bwd_kernel(const FitPara
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Latency variant for small batches (weights gradient only): ONE CTA of 4 warps per pair instead of one warp of a
+// persistent ring -- the same two passes spread over 128 threads with block reductions, the warp-uniform 9x9 algebra on
+// every thread (it is a serial fp64 chain: redundancy costs nothing and saves a broadcast).  The ring kernel walks a pair
+// with 32 lanes (2 x 31 trips): 33.5 us for a 256-pair launch (profiles/r2_bwd.md); this kernel needs 2 x 8 trips.
+// ------------------------------------------------------------------------------------------------
+constexpr int kBwdSmallThreads = 128;
+
+__global__ void __launch_bounds__(kBwdSmallThreads, 3) fepe_fit_bwd_small_kernel(const FitParams p) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    __shared__ uint64_t full_bar;
+    __shared__ float red[kBwdSmallThreads / 32][18];
+    __shared__ double gram[36];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, tid = threadIdx.x;
+    const int N = p.N;
+    const size_t pair = blockIdx.x;
+    const uint32_t pts_bytes = static_cast<uint32_t>(N) * 16u;
+    const uint32_t row_bytes = static_cast<uint32_t>(N) * 4u;
+    const float4* sp = reinterpret_cast<const float4*>(smem);
+    float* sw = reinterpret_cast<float*>(smem + pts_bytes);
+    float* sgr = reinterpret_cast<float*>(smem + pts_bytes + row_bytes);
+    float* sge = reinterpret_cast<float*>(smem + pts_bytes + 2 * row_bytes);
+    const bool has_gr = p.gresid != nullptr, has_ge = p.gepi != nullptr;
+    const float* rows[3] = {p.weights, p.gresid, p.gepi};
+    float* dsts[3] = {sw, sgr, sge};
+
+    if (tid == 0) {
+        mbar_init(&full_bar, 1);
+        fence_barrier_init();
+    }
+    __syncthreads();
+    if (tid == 0) {
+        uint32_t tx = pts_bytes;
+        for (int a = 0; a < 3; ++a)
+            if (ring_row_is_bulk(rows[a], pair, N)) tx += row_bytes;
+        mbar_arrive_expect_tx(&full_bar, tx);
+        bulk_g2s(smem, p.matches + pair * static_cast<size_t>(N) * 4, pts_bytes, &full_bar);
+        for (int a = 0; a < 3; ++a)
+            if (ring_row_is_bulk(rows[a], pair, N))
+                bulk_g2s(dsts[a], rows[a] + pair * static_cast<size_t>(N), row_bytes, &full_bar);
+    }
+    for (int a = 0; a < 3; ++a) {                           // ragged rows: plain loads by the CTA itself
+        if (rows[a] == nullptr || ring_row_is_bulk(rows[a], pair, N)) continue;
+        const float* g = rows[a] + pair * static_cast<size_t>(N);
+        for (int i = tid; i < N; i += kBwdSmallThreads) dsts[a][i] = __ldg(g + i);
+    }
+    // ---- per-pair state saved by the forward (uniform) -- fetched behind the bulk copy ----
+    const float ax = p.ax, bx = p.bx, ay = p.ay, by = p.by;
+    const double* sv = p.saved + pair * FEPE_SAVED_DOUBLES;
+    PairNorm h;
+    h.m1x = static_cast<float>(sv[0]); h.m1y = static_cast<float>(sv[1]); h.s1 = static_cast<float>(sv[2]);
+    h.m2x = static_cast<float>(sv[3]); h.m2y = static_cast<float>(sv[4]); h.s2 = static_cast<float>(sv[5]);
+    h.c1x = fmaf(ax, h.m1x, bx); h.c1y = fmaf(ay, h.m1y, by);
+    h.c2x = fmaf(ax, h.m2x, bx); h.c2y = fmaf(ay, h.m2y, by);
+    double f[9], v3[3];
+#pragma unroll
+    for (int i = 0; i < 9; ++i) f[i] = sv[6 + i];
+    const double lambda = sv[15];
+    v3[0] = sv[53]; v3[1] = sv[54]; v3[2] = sv[55];
+    if (tid < 36) gram[tid] = sv[16 + tid];
+    double F2[9];
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+        const double wv = f[3 * r] * v3[0] + f[3 * r + 1] * v3[1] + f[3 * r + 2] * v3[2];
+        F2[3 * r] = f[3 * r] - wv * v3[0]; F2[3 * r + 1] = f[3 * r + 1] - wv * v3[1]; F2[3 * r + 2] = f[3 * r + 2] - wv * v3[2];
+    }
+    float Fo[9], ff[9];
+    denormalise_F(F2, h, Fo);
+#pragma unroll
+    for (int i = 0; i < 9; ++i) ff[i] = static_cast<float>(f[i]);
+    const float k1x = h.s1 * ax, k1y = h.s1 * ay, k2x = h.s2 * ax, k2y = h.s2 * ay;
+    const float j1x = -k1x * h.m1x, j1y = -k1y * h.m1y, j2x = -k2x * h.m2x, j2y = -k2y * h.m2y;
+    const float clamp_at = p.clamp_at;
+    double gFv[9];
+#pragma unroll
+    for (int i = 0; i < 9; ++i) gFv[i] = static_cast<double>(p.gF[pair * 9 + i]);
+
+    mbar_wait(&full_bar, 0);
+    __syncthreads();                                         // also orders the hand-copied rows and gram[]
+
+    // ---- pass 1: hs = sum rbar_i x_i  and  ge = sum ebar_i d epi_i / d out ----
+    float hs[9], ge[9];
+#pragma unroll
+    for (int i = 0; i < 9; ++i) { hs[i] = 0.f; ge[i] = 0.f; }
+#pragma unroll 2
+    for (int i = tid; i < N; i += kBwdSmallThreads) {
+        const float4 q = sp[i];
+        if (has_gr) {
+            const float x1 = fmaf(k1x, q.x, j1x), y1 = fmaf(k1y, q.y, j1y);
+            const float x2 = fmaf(k2x, q.z, j2x), y2 = fmaf(k2y, q.w, j2y);
+            const float nb = fmaf(x1, x1, fmaf(y1, y1, 1.0f));
+            const float na = fmaf(x2, x2, fmaf(y2, y2, 1.0f));
+            const float c = sgr[i] * sw[i] * rsqrtf(na * nb);
+            const float c0 = c * x2, c1 = c * y2;
+            hs[0] = fmaf(c0, x1, hs[0]); hs[1] = fmaf(c0, y1, hs[1]); hs[2] += c0;
+            hs[3] = fmaf(c1, x1, hs[3]); hs[4] = fmaf(c1, y1, hs[4]); hs[5] += c1;
+            hs[6] = fmaf(c, x1, hs[6]);  hs[7] = fmaf(c, y1, hs[7]);  hs[8] += c;
+        }
+        if (has_ge) {
+            const float u1 = fmaf(ax, q.x, bx), v1 = fmaf(ay, q.y, by);
+            const float u2 = fmaf(ax, q.z, bx), v2 = fmaf(ay, q.w, by);
+            float cb_unused[4];
+            epi_adjoint<float>(u1, v1, u2, v2, Fo, clamp_at, sge[i], ge, cb_unused);
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 9; ++i) { hs[i] = warp_sum(hs[i]); ge[i] = warp_sum(ge[i]); }
+    if (lane == 0) {
+#pragma unroll
+        for (int i = 0; i < 9; ++i) { red[warp][i] = hs[i]; red[warp][9 + i] = ge[i]; }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < 9; ++i) {
+        float a = 0.f, b = 0.f;
+#pragma unroll
+        for (int w = 0; w < kBwdSmallThreads / 32; ++w) { a += red[w][i]; b += red[w][9 + i]; }
+        hs[i] = a; ge[i] = b;
+    }
+
+    // ---- small algebra (uniform, every thread) ----
+    double ob[9];
+#pragma unroll
+    for (int i = 0; i < 9; ++i) ob[i] = static_cast<double>(ge[i]) + gFv[i];
+    double Ab[9];
+    {
+        const double s1 = h.s1, s2 = h.s2;
+        const double t1x = -s1 * h.c1x, t1y = -s1 * h.c1y, t2x = -s2 * h.c2x, t2y = -s2 * h.c2y;
+        double X[9];   // T2 * outbar
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            X[k] = s2 * ob[k] + t2x * ob[6 + k];
+            X[3 + k] = s2 * ob[3 + k] + t2y * ob[6 + k];
+            X[6 + k] = ob[6 + k];
+        }
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {   // ... * T1^T
+            Ab[3 * r] = X[3 * r] * s1 + X[3 * r + 2] * t1x;
+            Ab[3 * r + 1] = X[3 * r + 1] * s1 + X[3 * r + 2] * t1y;
+            Ab[3 * r + 2] = X[3 * r + 2];
+        }
+    }
+    double fb[9], z[9];
+    rank2_project_adjoint(f, v3, Ab, fb);
+#pragma unroll
+    for (int i = 0; i < 9; ++i) fb[i] += static_cast<double>(hs[i]);
+    eig9_pinv_apply(gram, f, lambda, fb, z);
+    float zf[9];
+#pragma unroll
+    for (int i = 0; i < 9; ++i) zf[i] = static_cast<float>(z[i]);
+
+    // ---- pass 2: wbar_i ----
+    float* __restrict__ gw_out = p.gweights + pair * static_cast<size_t>(N);
+#pragma unroll 2
+    for (int i = tid; i < N; i += kBwdSmallThreads) {
+        const float4 q = sp[i];
+        const float x1 = fmaf(k1x, q.x, j1x), y1 = fmaf(k1y, q.y, j1y);
+        const float x2 = fmaf(k2x, q.z, j2x), y2 = fmaf(k2y, q.w, j2y);
+        const float nb = fmaf(x1, x1, fmaf(y1, y1, 1.0f));
+        const float na = fmaf(x2, x2, fmaf(y2, y2, 1.0f));
+        const float inv = rsqrtf(na * nb);
+        const float f0 = fmaf(ff[0], x1, fmaf(ff[1], y1, ff[2]));
+        const float f1 = fmaf(ff[3], x1, fmaf(ff[4], y1, ff[5]));
+        const float f2 = fmaf(ff[6], x1, fmaf(ff[7], y1, ff[8]));
+        const float pf = fmaf(x2, f0, fmaf(y2, f1, f2)) * inv;
+        const float z0 = fmaf(zf[0], x1, fmaf(zf[1], y1, zf[2]));
+        const float z1 = fmaf(zf[3], x1, fmaf(zf[4], y1, zf[5]));
+        const float z2 = fmaf(zf[6], x1, fmaf(zf[7], y1, zf[8]));
+        const float pz = fmaf(x2, z0, fmaf(y2, z1, z2)) * inv;
+        const float gr = has_gr ? sgr[i] : 0.f;
+        gw_out[i] = fmaf(-2.0f * sw[i] * pz, pf, gr * pf);
+    }
+}
+
 }  // namespace fepe
 
 extern "C" int fepe_fit_bwd(const float* matches, const float* weights, int B, int N, float ax, float bx, float ay,
@@ -307,6 +482,23 @@ extern "C" int fepe_fit_bwd_coords(const float* matches, const float* weights, i
                                  d.smem_optin);
         if (e != cudaSuccess) return static_cast<int>(e);
         d.bwd_configured = 1;
+    }
+    // small batches, weights gradient only: the one-CTA-per-pair latency kernel (3 CTAs of 28 KB per SM and wave)
+    const int small_bytes = ((N * 28 + 127) / 128) * 128;
+    const int force = fepe::dispatch_get(FEPE_DISPATCH_FIT);          // tests force each path (1 = small, 2 = ring)
+    bool use_small = gmatches == nullptr && small_bytes <= 64 * 1024 && B <= 3 * d.sms;
+    if (force != 0) use_small = (force == 1) && gmatches == nullptr && small_bytes <= 64 * 1024;
+    if (use_small) {
+        static int configured[64] = {0};
+        int dev = 0;
+        cudaGetDevice(&dev);
+        if (!configured[dev & 63]) {
+            e = cudaFuncSetAttribute(fepe::fepe_fit_bwd_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+            if (e != cudaSuccess) return static_cast<int>(e);
+            configured[dev & 63] = 1;
+        }
+        fepe::fepe_fit_bwd_small_kernel<<<B, fepe::kBwdSmallThreads, small_bytes, static_cast<cudaStream_t>(stream)>>>(p);
+        return static_cast<int>(cudaGetLastError());
     }
     const int grid = B < d.sms ? B : d.sms;
     if (gmatches != nullptr)

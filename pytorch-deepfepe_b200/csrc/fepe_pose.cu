@@ -15,6 +15,7 @@
 #include <stdint.h>
 #include <stdlib.h>
 
+#include "fepe_common.cuh"
 #include "fepe_pose_head.cuh"
 
 namespace fepe {
@@ -88,7 +89,9 @@ __global__ void __launch_bounds__(128) fepe_pose_fwd_kernel(const PoseParams p) 
 }
 
 // Backward of the head: dL/dF from the upstream gradients of (q L2 error, t L2 error, F-loss) of every (layer, pair).
-// One THREAD per (layer, pair): pure register math (3x3 SVD adjoint, quaternion adjoint), 32 pairs per warp.
+// One WARP per (layer, pair), like the forward: the 3x3 SVD / quaternion adjoint is a serial fp64 chain that every lane
+// runs redundantly (warp-uniform), the V virtual correspondences of the F-loss gradient are spread over the lanes and
+// folded with shuffles.  (Round 1 ran one thread per item: the 100-point loop alone was a ~6 k-instruction serial chain.)
 struct PoseBwdParams {
     const float* F;        // [L,B,9]
     const float* K;        // [B,9]
@@ -105,8 +108,9 @@ struct PoseBwdParams {
     float* dF;             // [L,B,9]
 };
 
-__global__ void __launch_bounds__(64) fepe_pose_bwd_kernel(const PoseBwdParams p) {
-    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+__global__ void __launch_bounds__(128) fepe_pose_bwd_kernel(const PoseBwdParams p) {
+    const int idx = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
     if (idx >= p.L * p.B) return;
     const int b = idx % p.B;
     double F[9], K[9], M[9];
@@ -152,7 +156,7 @@ __global__ void __launch_bounds__(64) fepe_pose_bwd_kernel(const PoseBwdParams p
         for (int i = 0; i < 9; ++i) { Ff[i] = static_cast<float>(F[i]); acc[i] = 0.f; }
         const float* v1 = p.virt1 + static_cast<size_t>(b) * p.V * 3;
         const float* v2 = p.virt2 + static_cast<size_t>(b) * p.V * 3;
-        for (int i = 0; i < p.V; ++i) {
+        for (int i = lane; i < p.V; i += 32) {
             const float z1 = v1[3 * i + 2], z2 = v2[3 * i + 2];
             const float u1 = fmaf(p.ax, v1[3 * i], p.bx * z1), w1 = fmaf(p.ay, v1[3 * i + 1], p.by * z1);
             const float u2 = fmaf(p.ax, v2[3 * i], p.bx * z2), w2 = fmaf(p.ay, v2[3 * i + 1], p.by * z2);
@@ -176,12 +180,18 @@ __global__ void __launch_bounds__(64) fepe_pose_bwd_kernel(const PoseBwdParams p
             acc[3] += w2 * uk0 + vj1 * u1; acc[4] += w2 * uk1 + vj1 * w1; acc[5] += w2 * uk2 + vj1 * z1;
             acc[6] += z2 * uk0;            acc[7] += z2 * uk1;            acc[8] += z2 * uk2;
         }
+#pragma unroll
+        for (int i = 0; i < 9; ++i) acc[i] = warp_sum(acc[i]);
         const double sc = static_cast<double>(gl) / static_cast<double>(p.V);
 #pragma unroll
         for (int i = 0; i < 9; ++i) dF[i] += sc * static_cast<double>(acc[i]);
     }
+    if (lane < 9) {
+        double out = 0.0;
 #pragma unroll
-    for (int i = 0; i < 9; ++i) p.dF[static_cast<size_t>(idx) * 9 + i] = static_cast<float>(dF[i]);
+        for (int i = 0; i < 9; ++i) out = (lane == i) ? dF[i] : out;
+        p.dF[static_cast<size_t>(idx) * 9 + lane] = static_cast<float>(out);
+    }
 }
 
 }  // namespace fepe
@@ -194,7 +204,7 @@ extern "C" int fepe_pose_bwd(const float* F, const float* K, int L, int B, float
     if (!F || !K || !q_gt || !t_gt || !pose_out || !dF || L < 0 || B < 0 || V < 0) return FEPE_E_BADARG;
     fepe::PoseBwdParams p{F, K, q_gt, t_gt, virt1, virt2, pose_out, g_q, g_t, g_loss, L, B, V, ax, bx, ay, by, clamp_at, dF};
     const int n = L * B;
-    fepe::fepe_pose_bwd_kernel<<<(n + 63) / 64, 64, 0, static_cast<cudaStream_t>(stream)>>>(p);
+    fepe::fepe_pose_bwd_kernel<<<(n + 3) / 4, 128, 0, static_cast<cudaStream_t>(stream)>>>(p);
     return static_cast<int>(cudaGetLastError());
 }
 

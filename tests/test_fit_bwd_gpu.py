@@ -46,7 +46,16 @@ def _check(gw_ours, gw_ref, tol=1e-3, gw_ref32=None):
         assert float(rel.max()) < tol, rel
 
 
-def test_against_reference_golden(golden):
+@pytest.fixture(params=["small", "ring"])
+def bwd_kernel(request, dispatch):
+    """Both backward kernels of the weights gradient: the one-CTA-per-pair latency kernel (small batches by default) and
+    the persistent pair ring (one warp per pair).  The dispatch hook also steers the forward; both forwards are tested
+    elsewhere and save the same state."""
+    dispatch("fit", request.param)
+    return request.param
+
+
+def test_against_reference_golden(golden, bwd_kernel):
     p1, p2 = T(golden["bwd_pts1"]), T(golden["bwd_pts2"])
     m = torch.cat((p1[:, :, :2], p2[:, :, :2]), 2).float().contiguous()
     w = T(golden["bwd_w"]).float()
@@ -64,7 +73,7 @@ def test_against_reference_golden(golden):
 
 @pytest.mark.parametrize("mode,B,N", [("softmax", 6, 1000), ("inlier", 4, 2000), ("uniform", 5, 333), ("softmax", 3, 37)])
 @pytest.mark.parametrize("which", ["all", "F_only", "res_only", "epi_only"])
-def test_against_oracle_autograd(mode, B, N, which):
+def test_against_oracle_autograd(mode, B, N, which, bwd_kernel):
     d = synth.make_batch(B, N, seed=200 + N, weight_mode=mode)
     aff = ops.hw_affine(d["image_size"])
     g = torch.Generator().manual_seed(N)
@@ -148,3 +157,36 @@ def test_fit_module_passes_coordinate_gradient():
     _check(b1.grad.cpu()[:, :, :2], a1.grad[:, :, :2], tol=2e-3)
     _check(b2.grad.cpu()[:, :, :2], a2.grad[:, :, :2], tol=2e-3)
     assert float(b1.grad[:, :, 2].abs().max()) == 0.0      # z = 1 is a constant of the boundary
+
+
+def test_config_batch_backward_small_kernel_equals_ring(dispatch):
+    """Config-size batch (C2: 256 x 1000): the latency kernel and the ring kernel give the same weights gradient (to fp32
+    summation order), and a sample of pairs agrees with fp64 autograd through the oracle."""
+    B, N = 256, 1000
+    d = synth.make_batch(B, N, seed=61, weight_mode="softmax")
+    m = T(d["matches_xy_ori"]).cuda()
+    w = T(d["weights"]).cuda().reshape(B, N)
+    aff = ops.hw_affine(d["image_size"])
+    g = torch.Generator(device="cuda").manual_seed(3)
+    gF = torch.randn(B, 3, 3, device="cuda", generator=g)
+    gr = torch.randn(B, N, device="cuda", generator=g) * 1e-2
+    ge = torch.randn(B, N, device="cuda", generator=g) * 1e-2
+    F, res, epi, saved = ops.fit_forward(m, w, aff, want_saved=True)
+    dispatch("fit", "small")
+    gw_s = ops.fit_backward(m, w, saved, gF, gr, ge, aff, 0.5)
+    dispatch("fit", "ring")
+    gw_r = ops.fit_backward(m, w, saved, gF, gr, ge, aff, 0.5)
+    torch.cuda.synchronize()
+    rel = (gw_s - gw_r).norm(dim=1) / gw_r.norm(dim=1)
+    assert float(rel.max()) < 1e-4, float(rel.max())
+    # fp64 autograd through the oracle on the first pairs
+    k = 6
+    p1, p2, _ = O.norm_hw(T(d["matches_xy_ori"][:k]).double(), d["image_size"])
+    wv = T(d["weights"][:k]).double().requires_grad_(True)
+    Fo, ro = O.fit_weighted_svd(p1, p2, wv, canonical_sign=True)
+    eo = O.epi_residual(p1, p2, Fo, 0.5)
+    ((Fo * gF[:k].cpu().double()).sum() + (ro * gr[:k].cpu().double()).sum() + (eo * ge[:k].cpu().double()).sum()).backward()
+    ref = wv.grad.reshape(k, N)
+    rel64 = (gw_s[:k].cpu().double() - ref).norm(dim=1) / ref.norm(dim=1)
+    print("config-batch backward vs fp64 autograd (6 pairs):", ["%.1e" % v for v in rel64.tolist()])
+    assert float(rel64.max()) < 1e-3
