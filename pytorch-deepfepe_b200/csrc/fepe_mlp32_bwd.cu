@@ -392,8 +392,14 @@ fepe_mlp32_wgrad_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid
         for (int c = 0; c < BN; c += 32) {
             uint32_t v[32];
             tmem_ld32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(c), v);
+            // vector reductions (REDG.ADD.F32x4): a quarter of the L2 transactions of scalar atomics -- with one row per
+            // lane every lane touches its own cache line, so the epilogue is bound by the number of requests
 #pragma unroll
-            for (int j = 0; j < 32; ++j) atomicAdd(out + c + j, __uint_as_float(v[j]) * inv);
+            for (int j = 0; j < 32; j += 4)
+                asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(out + c + j),
+                             "f"(__uint_as_float(v[j]) * inv), "f"(__uint_as_float(v[j + 1]) * inv),
+                             "f"(__uint_as_float(v[j + 2]) * inv), "f"(__uint_as_float(v[j + 3]) * inv)
+                             : "memory");
         }
         tcgen05_fence_before();
     }
@@ -475,11 +481,12 @@ int fepe_mlp32_wgrad(const float* dY, const unsigned* dy_amax, const float* Ypre
                      float* dW, int M, int Npad, int Co, int Ci, void* stream) {
     if (!dY || !dy_amax || !Yprev || !ss_prev || !dW || M <= 0 || Npad <= 0 || (Npad % 128) != 0 || (M % Npad) != 0 ||
         (Co % 128) != 0 || (Ci % 64) != 0 || Co <= 0 || Ci <= 0 || (reinterpret_cast<uintptr_t>(ss_prev) & 15u) ||
-        (reinterpret_cast<uintptr_t>(dY) & 15u) || (reinterpret_cast<uintptr_t>(Yprev) & 15u) || !(slope >= 0.f && slope <= 1.f))
+        (reinterpret_cast<uintptr_t>(dY) & 15u) || (reinterpret_cast<uintptr_t>(Yprev) & 15u) ||
+        (reinterpret_cast<uintptr_t>(dW) & 15u) || !(slope >= 0.f && slope <= 1.f))
         return FEPE_E_BADARG;
     const int bn = (Ci % 128 == 0) ? 128 : 64;
     const int tiles = (Co / 128) * (Ci / bn);
-    int slabs = (592 + tiles - 1) / tiles;                    // ~4 waves of 148 SMs
+    int slabs = (296 + tiles - 1) / tiles;                    // ~2 waves of 148 SMs: every slab pays a prologue and 128 x BN reductions
     const int max_slabs = M / 64;
     if (slabs > max_slabs) slabs = max_slabs;
     if (slabs < 1) slabs = 1;
