@@ -186,20 +186,6 @@ fepe_mlp32_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
     if (warp == 0) {
         // ---------------- TMA producer: the ring runs across tile boundaries ----------------
         if (lane == 0) {
-            // The A operand streams from HBM (the weights stay in L2): with two or three stages the DRAM round trip of
-            // a stage is on the critical loop (stage period = MMA + load + transform).  An L2 prefetch of the A boxes
-            // kPrefetch k-blocks ahead turns that load into an L2 hit.
-            constexpr int kPrefetch = 4;
-            const int total = n_local * num_kb;
-            auto prefetch_a = [&](int q) {
-                if (q >= total) return;
-                const int jq = q / num_kb, kq = q - jq * num_kb;
-                const int tq = static_cast<int>(blockIdx.x) + jq * static_cast<int>(gridDim.x);
-                const int mq = (tq / n_tiles) * kBM;
-                tma_prefetch_2d(&map_a, kq * kBK, mq);
-                tma_prefetch_2d(&map_a, kq * kBK + 32, mq);
-            };
-            for (int q = 0; q < kPrefetch; ++q) prefetch_a(q);
             uint32_t it = 0;
             for (int j = 0; j < n_local; ++j) {
                 const int t = static_cast<int>(blockIdx.x) + j * static_cast<int>(gridDim.x);
@@ -208,7 +194,6 @@ fepe_mlp32_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
                 for (int kb = 0; kb < num_kb; ++kb, ++it) {
                     const uint32_t s = it % STAGES;
                     const uint32_t ph = (it / STAGES) & 1u;
-                    prefetch_a(static_cast<int>(it) + kPrefetch);
                     mbar_wait(&empty[s], ph ^ 1u);
                     unsigned char* sa = smem + s * kStageBytes;
                     mbar_arrive_expect_tx(&full[s], kStageBytes + (has_ss ? kSsBytes : 0));

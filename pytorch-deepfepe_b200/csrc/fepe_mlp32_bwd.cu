@@ -288,21 +288,9 @@ fepe_mlp32_wgrad_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid
 
     if (warp == 0) {
         if (lane == 0) {
-            // both operands stream from HBM: L2 prefetch kPrefetch k-blocks ahead (see fepe_mlp32_gemm_kernel)
-            constexpr int kPrefetch = 4;
-            auto prefetch = [&](int kq) {
-                if (kq >= num_kb) return;
-                const int rq = row0 + kq * 64;
-#pragma unroll
-                for (int g = 0; g < 4; ++g) tma_prefetch_2d(&map_dy, co0 + g * 32, rq);
-#pragma unroll
-                for (int g = 0; g < BN / 32; ++g) tma_prefetch_2d(&map_x, ci0 + g * 32, rq);
-            };
-            for (int q = 0; q < kPrefetch; ++q) prefetch(q);
             for (int kb = 0; kb < num_kb; ++kb) {
                 const int s = kb % kWgStages;
                 const uint32_t ph = static_cast<uint32_t>(kb / kWgStages) & 1u;
-                prefetch(kb + kPrefetch);
                 mbar_wait(&empty[s], ph ^ 1u);
                 unsigned char* sa = smem + s * kStageBytes;
                 mbar_arrive_expect_tx(&full[s], kStageBytes + kSsBytes);
