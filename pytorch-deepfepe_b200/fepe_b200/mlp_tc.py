@@ -30,7 +30,6 @@ class TensorCoreMLP:
         if self.cin > 8:
             raise RuntimeError("TensorCoreMLP: the first layer supports at most 8 input channels")
         self._versions = None
-        self._buf_key = None
         # fuse_norm: InstanceNorm + LeakyReLU of layers 1-4 applied to the next GEMM's operand tiles in shared memory
         # (fepe_mlp_gemm_norm) instead of a separate pass over memory; same bf16 results as the unfused kernels.
         self.fuse_norm = True
@@ -57,13 +56,12 @@ class TensorCoreMLP:
         self._versions = vers
 
     def _buffers(self, B, Npad, dev):
-        key = (B, Npad, dev)
-        if key != self._buf_key:
-            self.act = [torch.empty(B * Npad, 1024, dtype=torch.bfloat16, device=dev) for _ in range(2)]
-            self.stats = torch.empty(B, 1024, 2, dtype=torch.float32, device=dev)
-            self.ss = torch.empty(B, 512, 4, dtype=torch.float32, device=dev)
-            self.xn = torch.empty(B * Npad, 128, dtype=torch.bfloat16, device=dev)   # normalised operand of an unfused layer
-            self._buf_key = key
+        # allocated per call through the caching allocator (stream ordered): a module evaluated from several streams or
+        # threads (nn.DataParallel replicas share nothing, but user code may) must not share scratch buffers
+        self.act = [torch.empty(B * Npad, 1024, dtype=torch.bfloat16, device=dev) for _ in range(2)]
+        self.stats = torch.empty(B, 1024, 2, dtype=torch.float32, device=dev)
+        self.ss = torch.empty(B, 512, 4, dtype=torch.float32, device=dev)
+        self.xn = torch.empty(B * Npad, 128, dtype=torch.bfloat16, device=dev)   # normalised operand of an unfused layer
         return self.act, self.stats
 
     def __call__(self, x: torch.Tensor):
