@@ -58,11 +58,11 @@ class TensorCoreMLP:
     def _buffers(self, B, Npad, dev):
         # allocated per call through the caching allocator (stream ordered): a module evaluated from several streams or
         # threads (nn.DataParallel replicas share nothing, but user code may) must not share scratch buffers
-        self.act = [torch.empty(B * Npad, 1024, dtype=torch.bfloat16, device=dev) for _ in range(2)]
-        self.stats = torch.empty(B, 1024, 2, dtype=torch.float32, device=dev)
-        self.ss = torch.empty(B, 512, 4, dtype=torch.float32, device=dev)
-        self.xn = torch.empty(B * Npad, 128, dtype=torch.bfloat16, device=dev)   # normalised operand of an unfused layer
-        return self.act, self.stats
+        act = [torch.empty(B * Npad, 1024, dtype=torch.bfloat16, device=dev) for _ in range(2)]
+        stats = torch.empty(B, 1024, 2, dtype=torch.float32, device=dev)
+        ss = torch.empty(B, 512, 4, dtype=torch.float32, device=dev)
+        xn = torch.empty(B * Npad, 128, dtype=torch.bfloat16, device=dev)   # normalised operand of an unfused layer
+        return act, stats, ss, xn
 
     def __call__(self, x: torch.Tensor):
         """x [B,Cin,N] fp32 cuda -> (logits [B,1,N], softmax weights [B,1,N]) fp32."""
@@ -75,7 +75,7 @@ class TensorCoreMLP:
         lib = _lib.lib()
         st = torch.cuda.current_stream(dev).cuda_stream
         x0 = x.permute(0, 2, 1).contiguous()
-        (ya, xa), stats = self._buffers(B, Npad, dev)
+        (ya, xa), stats, ss, xn = self._buffers(B, Npad, dev)
         slope = 0.01
         with torch.cuda.device(dev):
             stats.zero_()
@@ -84,7 +84,7 @@ class TensorCoreMLP:
             k = 64
             bias = [0 if self.drop_bias else b.data_ptr() for b in self.b]
             if self.fuse_norm:
-                return self._fused_tail(lib, st, ya, xa, stats, bias, B, N, Npad, dev, slope)
+                return self._fused_tail(lib, st, ya, xa, stats, ss, xn, bias, B, N, Npad, dev, slope)
             _lib.check(lib.fepe_mlp_norm(ya.data_ptr(), stats.data_ptr(), self.gamma[0].data_ptr(),
                                          self.beta[0].data_ptr(), xa.data_ptr(), B, Npad, N, 64, self.eps[0], slope, st),
                        "fepe_mlp_norm")
@@ -104,10 +104,9 @@ class TensorCoreMLP:
         return logits, weights
 
 
-    def _fused_tail(self, lib, st, src, dst, stats, bias, B, N, Npad, dev, slope):
+    def _fused_tail(self, lib, st, src, dst, stats, ss, xn, bias, B, N, Npad, dev, slope):
         """Layers 2-5 with the previous layer's norm fused into the GEMM operand path; `src` holds layer 1's pre-norm
         output and `stats` its statistics."""
-        ss = self.ss
         k = 64
         for i in range(1, 5):
             co = _CH[i]
@@ -115,10 +114,10 @@ class TensorCoreMLP:
                 # thin operand, wide output (128 -> 1024): the GEMM is bound by its epilogue, the operand would be
                 # transformed once per n-tile, and the norm pass over 128 channels is cheap -- measured faster unfused
                 _lib.check(lib.fepe_mlp_norm(src.data_ptr(), stats.data_ptr(), self.gamma[i - 1].data_ptr(),
-                                             self.beta[i - 1].data_ptr(), self.xn.data_ptr(), B, Npad, N, k,
+                                             self.beta[i - 1].data_ptr(), xn.data_ptr(), B, Npad, N, k,
                                              self.eps[i - 1], slope, st), "fepe_mlp_norm")
                 stats.zero_()
-                _lib.check(lib.fepe_mlp_gemm(self.xn.data_ptr(), self.w[i].data_ptr(), bias[i], dst.data_ptr(),
+                _lib.check(lib.fepe_mlp_gemm(xn.data_ptr(), self.w[i].data_ptr(), bias[i], dst.data_ptr(),
                                              stats.data_ptr(), B, Npad, N, k, co, st), "fepe_mlp_gemm")
             else:
                 _lib.check(lib.fepe_mlp_scale_shift(stats.data_ptr(), self.gamma[i - 1].data_ptr(),
