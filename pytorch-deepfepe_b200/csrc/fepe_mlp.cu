@@ -1204,7 +1204,7 @@ int fepe_mlp_gemm(const void* X, const void* W, const float* bias, void* Y, floa
     // 2 stages / 2 CTAs per SM: the epilogue of one CTA overlaps the main loop of the other.  Measured faster
     // than 4 stages / 1 CTA per SM on every layer (profiles/r1_mlp_timing.txt).  
     // Default for Co % 128 == 0: the persistent kernel (double-buffered TMEM accumulator, 128 x 256 tiles when Co
-    // allows).  FEPE_MLP_GEMM=tile selects the one-tile-per-CTA kernel, FEPE_MLP_GEMM=persist128 forces BN = 128.
+    // allows).  fepe_set_dispatch(FEPE_DISPATCH_MLP_GEMM, 1) selects the one-tile-per-CTA kernel, 2 forces BN = 128.
     const int mode = fepe::dispatch_get(FEPE_DISPATCH_MLP_GEMM);   // 0 = automatic; 1 = one tile per CTA; 2 = persistent, BN = 128
     const bool tile_mode = mode == 1;
     if (!tile_mode && Co % 128 == 0) {
@@ -1228,7 +1228,7 @@ int fepe_mlp_gemm_norm(const void* Yprev, const float* ss, float slope, const vo
         return FEPE_E_BADARG;
     fepe::GemmParams p{B * Npad, K, Co, Npad, Nvalid, bias, static_cast<__nv_bfloat16*>(Y), stats, ss, slope};
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    // Default: variant 1 (8 epilogue + 4 transform warps, (a, d) prefetched from global memory).  FEPE_MLP_FUSE=2
+    // Default: variant 1 (8 epilogue + 4 transform warps, (a, d) prefetched from global memory).  fepe_set_dispatch(FEPE_DISPATCH_MLP_FUSE, 2)
     // selects variant 2 (4 epilogue + 8 transform warps, (a, d) through a shared-memory slot of the stage): measured
     // equal or slower on every layer (profiles/r1_mlp_fused_norm.md) -- the fused layers are bound by the bytes in flight
     // through the L2 and by shared-memory bandwidth, not by the transform's latency -- kept as the tested alternative.

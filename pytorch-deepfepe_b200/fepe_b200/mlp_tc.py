@@ -5,9 +5,8 @@ Inference (torch.no_grad()): ``TensorCoreMLP.__call__`` -- ping-pong activation 
 Training: ``TensorCoreMLPFunction`` (torch.autograd.Function) -- the same forward kernels keeping every
 layer's pre-norm output Y and block output X', and a backward made of fepe_mlp_last_bwd, fepe_mlp_normbwd
 (InstanceNorm + LeakyReLU adjoint), fepe_mlp_wgrad (MN-major tcgen05 GEMM, dW = dY^T X), the data-gradient
-GEMM (fepe_mlp_gemm with W^T) and fepe_mlp_first_bwd.  Both are opt-in:
-``DeepFNet.enable_tensor_core_mlp(inference=True, training=False)``; fp32 PyTorch kernels stay the default
-and the parity reference.
+GEMM (fepe_mlp_gemm with W^T) and fepe_mlp_first_bwd.  Both are opt-in (``DeepFNet.set_mlp_path("bf16")``): the default
+is the fp32-parity tensor-core path of fepe_b200/mlp32.py.
 """
 from __future__ import annotations
 
