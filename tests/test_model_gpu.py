@@ -44,10 +44,12 @@ def test_forward_matches_oracle_and_reference_layer0(golden):
         assert key in outs
     assert len(outs["out_layers"]) == 5 and len(outs["epi_res_layers"]) == 4
     # layer 0 is independent of the arbitrary sign of f: compare with the reference's own output
-    np.testing.assert_allclose(outs["weights_layers"][0].cpu().numpy(), golden["c1b_w_layers"][0], rtol=2e-3, atol=1e-7)
+    # (round 2: the weight network runs on the fp32-parity tensor-core path; measured 1.4e-5 on the weights, 1.6e-6 on F.
+    # All five layers are compared in tests/test_all_layers.py.)
+    np.testing.assert_allclose(outs["weights_layers"][0].cpu().numpy(), golden["c1b_w_layers"][0], rtol=3e-4, atol=1e-8)
     err0 = O.sign_aligned_rel_err(outs["out_layers"][0].cpu(), T(golden["c1b_F_layers"][0]))
-    assert float(err0.max()) < 1e-3          # weights come from cuDNN vs CPU convs: ~1e-4 relative
-    np.testing.assert_allclose(outs["epi_res_layers"][0].cpu().numpy(), golden["c1b_epi_layers"][0], atol=2e-3)
+    assert float(err0.max()) < 1e-4
+    np.testing.assert_allclose(outs["epi_res_layers"][0].cpu().numpy(), golden["c1b_epi_layers"][0], atol=2e-4)
     assert outs["pts1"].shape == (2, 160, 3) and outs["T1"].shape == (2, 3, 3)
     np.testing.assert_allclose(outs["pts1"].cpu().numpy(), ref["pts1"].numpy(), atol=1e-6)
     for l in range(5):
@@ -88,7 +90,7 @@ def test_error_estimator_matches_reference_output(golden):
     ee = ErrorEstimator(4).cuda()
     with torch.no_grad():
         y = ee(T(golden["ee_x"]).cuda())
-    np.testing.assert_allclose(y.cpu().numpy(), golden["ee_y"], rtol=1e-3, atol=1e-4)
+    np.testing.assert_allclose(y.cpu().numpy(), golden["ee_y"], rtol=1e-4, atol=2e-5)
 
 
 def test_learn_offsets_matches_reference_forward_and_backward():
