@@ -87,7 +87,8 @@ class ErrorEstimator(nn.Module):
         if self.path == "tc32":
             from .. import mlp32
             if not grad:
-                if self._tc32 is None:
+                # (nn.DataParallel replicas are shallow copies: a cached evaluator must belong to THIS replica's layers)
+                if self._tc32 is None or self._tc32.fw is not self.fw:
                     self._tc32 = mlp32.MLP32(self.fw)
                 logits, self.last_softmax = self._tc32(matches, affine, [t.float() for t in extras], B, N)
                 return logits
@@ -97,7 +98,7 @@ class ErrorEstimator(nn.Module):
         if self.path == "bf16" and self.output_size == 1 and data.shape[1] <= 8:
             from ..mlp_tc import TensorCoreMLP, TensorCoreMLPFunction, module_params
             if not grad:
-                if self._tc is None:
+                if self._tc is None or self._tc.fw is not self.fw:
                     self._tc = TensorCoreMLP(self.fw)
                 logits, self.last_softmax = self._tc(data.float().contiguous())
                 return logits
