@@ -132,3 +132,27 @@ def test_learn_offsets_matches_reference_forward_and_backward():
         worst = max(worst, rel)
     assert float(params["update_offsets.fw.15.weight"].grad.abs().sum()) > 0
     assert worst < 5e-2, worst
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs")
+def test_data_parallel_replicas_match_single_device():
+    """The reference's multi-GPU mode (nn.DataParallel, deepFEPE/train_good.py:309-314): the dict input is scattered along
+    dim 0, the module replicated; every replica must launch on its own device / stream and use its own weights -- in
+    inference and under autograd."""
+    torch.manual_seed(5)
+    net = DeepFNet(**MODEL_KW).cuda(0)
+    d = synth.make_batch(4, 512, seed=12)
+    batch = {"matches_xy_ori": T(d["matches_xy_ori"]).cuda(0), "matches_good_unique_nums": T(d["matches_good_unique_nums"]).cuda(0),
+             "t_scene_scale": torch.ones(4, 1, 1).cuda(0)}
+    with torch.no_grad():
+        single = net(batch)
+        dp = torch.nn.DataParallel(net, device_ids=[0, 1])
+        multi = dp(batch)
+        again = dp(batch)                                       # replicas are rebuilt every call
+    for a, b, c in zip(single["out_layers"], multi["out_layers"], again["out_layers"]):
+        assert b.device.index == 0 and b.shape == a.shape
+        assert float(O.sign_aligned_rel_err(b.cpu(), a.cpu()).max()) < 1e-5
+        assert float(O.sign_aligned_rel_err(c.cpu(), a.cpu()).max()) < 1e-5
+    outs = dp(batch)
+    sum(Fo.pow(2).sum() for Fo in outs["out_layers"]).backward()
+    assert all(p.grad is not None and torch.isfinite(p.grad).all() for p in net.parameters())
