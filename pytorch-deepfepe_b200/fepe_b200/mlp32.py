@@ -62,8 +62,11 @@ def split_param_cached(lib, param: torch.Tensor, co: int, k: int, transposed: bo
     w2d = param.detach().reshape(co, k).float()
     w2d = w2d.t().contiguous() if transposed else w2d.contiguous()
     out = split_weight(lib, w2d, st)
-    if len(_SPLIT_CACHE) > 256:
-        _SPLIT_CACHE.clear()
+    if len(_SPLIT_CACHE) >= 32:                        # drop the entries of dead parameters (e.g. DataParallel replicas)
+        for k in [k for k, v in _SPLIT_CACHE.items() if v[2]() is None]:
+            del _SPLIT_CACHE[k]
+        if len(_SPLIT_CACHE) > 256:
+            _SPLIT_CACHE.clear()
     _SPLIT_CACHE[key] = (ver, out, weakref.ref(param))
     return out
 
