@@ -108,7 +108,9 @@ class MLP32:
         self._versions = None
 
     def _refresh(self, lib, st):
-        vers = tuple(p._version for p in self.fw.parameters()) + (next(self.fw.parameters()).device,)
+        # (the layers' own tensors, not fw.parameters(): nn.DataParallel replicas carry no registered parameters)
+        tensors = [t for m in self.convs + self.norms for t in (m.weight, m.bias)]
+        vers = tuple((t._version, t.data_ptr()) for t in tensors) + (tensors[0].device,)
         if vers == self._versions:
             return
         c, n = self.convs, self.norms

@@ -39,7 +39,8 @@ class TensorCoreMLP:
 
     # -- parameters in the layouts the kernels want (refreshed when the module's parameters change) --
     def _refresh(self):
-        vers = tuple(p._version for p in self.fw.parameters()) + (next(self.fw.parameters()).device,)
+        tensors = [t for m in self.convs + self.norms for t in (m.weight, m.bias)]       # (DataParallel replicas: see mlp32)
+        vers = tuple((t._version, t.data_ptr()) for t in tensors) + (tensors[0].device,)
         if vers == self._versions:
             return
         c, n = self.convs, self.norms

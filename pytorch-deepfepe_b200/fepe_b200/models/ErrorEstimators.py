@@ -81,7 +81,9 @@ class ErrorEstimator(nn.Module):
         if not ref.is_cuda:
             raise RuntimeError("fepe_b200.ErrorEstimator needs CUDA tensors: there is no CPU path")
         self.last_softmax = None
-        grad = torch.is_grad_enabled() and (any(p.requires_grad for p in self.fw.parameters())
+        # (m.weight / m.bias, not fw.parameters(): nn.DataParallel replicas carry no registered parameters)
+        grad = torch.is_grad_enabled() and (any(t.requires_grad for m in self.fw if hasattr(m, "weight")
+                                                for t in (m.weight, m.bias))
                                             or any(t.requires_grad for t in extras)
                                             or (matches is not None and matches.requires_grad))
         if self.path == "tc32":
