@@ -843,16 +843,9 @@ def c5_measure(args, dev, rank, world, steps: int, warm: int, mlp: str) -> dict:
 
     n_matches = []
 
-    def step():
-        ev = [torch.cuda.Event(enable_timing=True) for _ in range(6)]
-        flat.zero_()
-        ev[0].record()
-        # train_good_utils.py:649-724: mutual-NN matches -> [B,N,4] + quality (fepe_nn_match, on the device)
-        mt = get_matches_from_descriptors(kp1, kp2, desc1, desc2, 1.0, out_num_points=N, generator=gen)
-        batch = {"matches_xy_ori": mt["xs"], "quality": mt["quality"]}
-        n_matches.append(mt["num_matches"])
-        ev[1].record()
-        outs = net(batch)
+    def fwd_bwd(xs, quality):
+        """Forward + losses + backward of one batch; the gradients accumulate into the flat buffer."""
+        outs = net({"matches_xy_ori": xs, "quality": quality})
         T1 = outs["T1"]
         p1 = (T1 @ v1.transpose(1, 2)).transpose(1, 2)
         p2 = (T1 @ v2.transpose(1, 2)).transpose(1, 2)
@@ -860,10 +853,32 @@ def c5_measure(args, dev, rank, world, steps: int, warm: int, mlp: str) -> dict:
         # get_all_loss_DeepF: E_i = K^T T2^T F_i T1 K (train_good_utils.py:356-358); get_Rt_loss (:64-295) on the device
         TK = T1 @ Ks
         E_layers = [TK.transpose(1, 2) @ Fo @ TK for Fo in outs["out_layers"]]
-        rt = get_Rt_loss(E_layers, None, None, None, Rt, q_cam, t_cam)
+        rt = get_Rt_loss(E_layers, None, None, None, Rt, q_cam, t_cam, metrics_on_host=False)
         loss = loss_F + pose_loss_from_Rt_loss(rt)            # Train_model_pipeline.py:580-592 (if_qt_loss)
-        ev[2].record()
+        mid = torch.cuda.Event(enable_timing=True) if not capturing[0] else None
+        if mid is not None:
+            mid.record()
         loss.backward()
+        return loss.detach(), torch.stack(rt["R_angle_error_layers_list"]), torch.stack(rt["t_angle_error_layers_list"]), mid
+
+    capturing = [False]
+    graphed = [None]
+
+    def step():
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(6)]
+        flat.zero_()
+        ev[0].record()
+        # train_good_utils.py:649-724: mutual-NN matches -> [B,N,4] + quality (fepe_nn_match, on the device)
+        mt = get_matches_from_descriptors(kp1, kp2, desc1, desc2, 1.0, out_num_points=N, generator=gen)
+        n_matches.append(mt["num_matches"])
+        ev[1].record()
+        if graphed[0] is not None:
+            loss, r_ang, t_ang, _ = graphed[0].replay(mt["xs"], mt["quality"])
+            ev[2] = None                                      # forward / backward are one graph launch
+        else:
+            loss, r_ang, t_ang, mid = fwd_bwd(mt["xs"], mt["quality"])
+            ev[2] = mid
+        metrics = (r_ang.cpu(), t_ang.cpu())                  # the angular metrics the reference logs every step (one D2H each)
         ev[3].record()
         flat.allreduce_mean_()
         ev[4].record()
@@ -871,10 +886,26 @@ def c5_measure(args, dev, rank, world, steps: int, warm: int, mlp: str) -> dict:
         ev[5].record()
         return ev
 
-    names = ("match", "fwd", "bwd", "allreduce", "adam")
     for _ in range(warm):
         step()
     torch.cuda.synchronize()
+    launch = "eager"
+    if not args.no_graph:
+        # the forward + losses + backward of the step as ONE CUDA graph (the step is launch-bound at 16 pairs per GPU)
+        try:
+            from fepe_b200.graphs import GraphedStep
+            mt0 = get_matches_from_descriptors(kp1, kp2, desc1, desc2, 1.0, out_num_points=N, generator=gen)
+            flat.zero_()
+            capturing[0] = True
+            graphed[0] = GraphedStep(fwd_bwd, (mt0["xs"], mt0["quality"]))
+            launch = "forward + losses + backward replayed as one CUDA graph (fepe_b200.graphs.GraphedStep); matcher, all-reduce, Adam eager"
+        except Exception as e:                                 # noqa: BLE001
+            graphed[0] = None
+            launch = f"eager (graph capture failed: {type(e).__name__}: {str(e)[:120]})"
+        capturing[0] = False
+        for _ in range(2):
+            step()
+        torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -883,7 +914,14 @@ def c5_measure(args, dev, rank, world, steps: int, warm: int, mlp: str) -> dict:
     e1.record()
     torch.cuda.synchronize()
     secs = fdist.max_over_ranks(e0.elapsed_time(e1) * 1e-3, dev)
-    br = {k: sum(ev[i].elapsed_time(ev[i + 1]) for ev in evs) / steps for i, k in enumerate(names)}
+    br = {"match": sum(ev[0].elapsed_time(ev[1]) for ev in evs) / steps,
+          "allreduce": sum(ev[3].elapsed_time(ev[4]) for ev in evs) / steps,
+          "adam": sum(ev[4].elapsed_time(ev[5]) for ev in evs) / steps}
+    if evs[0][2] is not None:
+        br["fwd"] = sum(ev[1].elapsed_time(ev[2]) for ev in evs) / steps
+        br["bwd"] = sum(ev[2].elapsed_time(ev[3]) for ev in evs) / steps
+    else:
+        br["fwd_bwd_graph"] = sum(ev[1].elapsed_time(ev[3]) for ev in evs) / steps
     # the collective alone, back to back (device time, max over ranks): the step's own interval also contains the wait
     # for the slowest rank's backward
     ar_us = None
@@ -907,7 +945,7 @@ def c5_measure(args, dev, rank, world, steps: int, warm: int, mlp: str) -> dict:
                        "(device get_Rt_loss), one all-reduce of the flat gradient buffer (NCCL), Adam",
            "global_batch": world * B,
            "mean_matches_per_pair": float(torch.stack(n_matches[-steps:]).float().mean()),
-           "ms_breakdown": br, "grad_bytes_allreduced": gbytes,
+           "ms_breakdown": br, "launch": launch, "grad_bytes_allreduced": gbytes,
            "allreduce_alone_us": ar_us,
            "allreduce_busbw_gbs": None if not ar_us else gbytes * 2 * (world - 1) / world / (ar_us * 1e-6) / 1e9}
     del net, opt, flat

@@ -23,7 +23,7 @@ from . import ops
 
 
 def get_Rt_loss(E_ests_layers: Sequence[torch.Tensor], Ks_cpu, x1_cpu, x2_cpu, delta_Rtijs_4_4_cpu: torch.Tensor,
-                qs_cam: torch.Tensor, ts_cam: torch.Tensor, device="cuda"):
+                qs_cam: torch.Tensor, ts_cam: torch.Tensor, device="cuda", metrics_on_host: bool = True):
     """E_ests_layers: list (depth) of [B,3,3] CUDA tensors WITH autograd history; delta_Rtijs_4_4_cpu [B,4,4];
     qs_cam [B,4(,1)], ts_cam [B,3(,1)].  Ks_cpu, x1_cpu, x2_cpu are accepted and unused, exactly as in the reference
     (its docstring says "no use"; they only fed commented-out code).  Returns the reference's dict:
@@ -33,6 +33,8 @@ def get_Rt_loss(E_ests_layers: Sequence[torch.Tensor], Ks_cpu, x1_cpu, x2_cpu, d
       R_angle_error_mean / _list, t_angle_error_mean / _list      floats / numpy [depth]
       R_angle_error_layers_list, t_angle_error_layers_list        list of numpy [B]
       t_l2_error_layers_list, q_l2_error_layers_list              list of [B] tensors (differentiable)
+    metrics_on_host=False keeps the angular metrics on the device (CUDA tensors under the same keys, no device-to-host
+    copy inside the call) -- for callers that capture the step in a CUDA graph and fetch the metrics afterwards.
     """
     E = torch.stack(list(E_ests_layers))                          # [L,B,3,3]
     if not E.is_cuda:
@@ -45,7 +47,10 @@ def get_Rt_loss(E_ests_layers: Sequence[torch.Tensor], Ks_cpu, x1_cpu, x2_cpu, d
     t = ts_cam.to(dev, torch.float32).reshape(B, 3)
     # K = I and the identity affine make the head's E = (TK)^T F (TK) equal to its input
     q_l2, t_l2, _, out = ops.PoseLossFunction.apply(E.float(), eye, q, t, Rt, None, None, *ops.IDENTITY_AFFINE, 0.02)
-    ang = out[..., 23:25].detach().cpu().numpy().astype(np.float64)         # the one D2H copy: [L,B,2]
+    if metrics_on_host:
+        ang = out[..., 23:25].detach().cpu().numpy().astype(np.float64)     # the one D2H copy: [L,B,2]
+    else:
+        ang = out[..., 23:25].detach()
     R_ang, t_ang = ang[..., 0], ang[..., 1]
     t_l2_mean_layers = t_l2.mean(1)
     q_l2_mean_layers = q_l2.mean(1)
@@ -54,9 +59,9 @@ def get_Rt_loss(E_ests_layers: Sequence[torch.Tensor], Ks_cpu, x1_cpu, x2_cpu, d
         "q_l2_error_mean": q_l2_mean_layers.mean(),
         "t_l2_error_list": t_l2_mean_layers,
         "q_l2_error_list": t_l2_mean_layers,                      # sic (train_good_utils.py:270)
-        "R_angle_error_mean": float(R_ang.mean(1).mean()),
+        "R_angle_error_mean": float(R_ang.mean(1).mean()) if metrics_on_host else R_ang.mean(),
         "R_angle_error_list": R_ang.mean(1),
-        "t_angle_error_mean": float(t_ang.mean(1).mean()),
+        "t_angle_error_mean": float(t_ang.mean(1).mean()) if metrics_on_host else t_ang.mean(),
         "t_angle_error_list": t_ang.mean(1),
         "R_angle_error_layers_list": [R_ang[l] for l in range(L)],
         "t_angle_error_layers_list": [t_ang[l] for l in range(L)],

@@ -30,13 +30,23 @@ class NormalizeAndExpand_HW(nn.Module):
     def __init__(self, image_size, is_cuda=True, is_test=False):
         super().__init__()
         self.H, self.W = image_size[0], image_size[1]
+        self._T_cache = {}
 
     def affine(self):
         return ops.hw_affine((self.H, self.W))
 
+    def _T(self, device, dtype):
+        # cached per device: building it from a Python list is a blocking host-to-device copy, which would also make
+        # the forward impossible to capture in a CUDA graph
+        key = (device, dtype)
+        T = self._T_cache.get(key)
+        if T is None:
+            T = torch.tensor([[2. / self.W, 0., -1.], [0., 2. / self.H, -1.], [0., 0., 1.]], device=device, dtype=dtype)
+            self._T_cache[key] = T
+        return T
+
     def normalize(self, pts):
-        T = torch.tensor([[2. / self.W, 0., -1.], [0., 2. / self.H, -1.], [0., 0., 1.]],
-                         device=pts.device, dtype=pts.dtype).unsqueeze(0).expand(pts.size(0), -1, -1)
+        T = self._T(pts.device, pts.dtype).unsqueeze(0).expand(pts.size(0), -1, -1)
         ones = torch.ones(pts.size(0), pts.size(1), 1, device=pts.device, dtype=pts.dtype)
         return T @ torch.cat((pts, ones), 2).permute(0, 2, 1), T
 

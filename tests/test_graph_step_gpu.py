@@ -1,0 +1,60 @@
+"""The whole DeepFNet training step (forward + F-loss + backward into a flat gradient buffer) recorded as one CUDA graph
+by fepe_b200.graphs.GraphedStep and replayed on NEW inputs must give the eager step's loss and gradients: this holds only
+if every library launch goes to the capturing stream, nothing synchronises and no launch depends on host-side state
+that changes between steps (weight versions, cached splits)."""
+import pytest
+import torch
+
+from oracle import fepe_oracle as O
+from fepe_b200 import synth
+from fepe_b200.dist import FlatGradients
+from fepe_b200.graphs import GraphedStep
+from fepe_b200.models import DeepFNet
+
+pytestmark = pytest.mark.gpu
+T = torch.from_numpy
+MODEL_KW = dict(depth=3, image_size=[376, 1241, 3], quality_size=0, if_quality=False, if_img_des_to_pointnet=False,
+                if_goodCorresArch=False, if_img_feat=False, if_cpu_svd=True, if_learn_offsets=False,
+                if_tri_depth=False, if_sample_loss=False)
+
+
+@pytest.mark.parametrize("path", ["tc32", "bf16"])
+def test_graphed_training_step_matches_eager(path):
+    torch.manual_seed(3)
+    net = DeepFNet(**MODEL_KW).cuda()
+    net.set_mlp_path(path)
+    flat = FlatGradients(net.parameters())
+    B, N = 4, 512
+    batches = [synth.make_batch(B, N, seed=s) for s in (11, 12, 13)]
+    xs = [T(d["matches_xy_ori"]).cuda() for d in batches]
+    v1 = torch.stack([T(d["pts1_virt"]).cuda() for d in batches])     # [3,B,V,3]
+    v2 = torch.stack([T(d["pts2_virt"]).cuda() for d in batches])
+
+    def fwd_bwd(x, p1v, p2v):
+        outs = net({"matches_xy_ori": x})
+        T1 = outs["T1"]
+        p1 = (T1 @ p1v.transpose(1, 2)).transpose(1, 2)
+        p2 = (T1 @ p2v.transpose(1, 2)).transpose(1, 2)
+        loss = sum(O.epi_residual(p1, p2, Fo, 0.02).mean() for Fo in outs["out_layers"]) / len(outs["out_layers"])
+        loss.backward()
+        return loss.detach(), outs["out_layers"][-1].detach()
+
+    flat.zero_()
+    g = GraphedStep(fwd_bwd, (xs[0], v1[0], v2[0]))
+    opt = torch.optim.SGD(net.parameters(), lr=1e-3)
+    for i in (1, 2):
+        # the weights change between replays (the optimiser runs outside the graph): the split weights must follow
+        flat.zero_()
+        loss_g, F_g = g.replay(xs[i], v1[i], v2[i])
+        grad_g, loss_g, F_g = flat.flat.clone(), loss_g.clone(), F_g.clone()
+        flat.zero_()
+        loss_e, F_e = fwd_bwd(xs[i], v1[i], v2[i])
+        grad_e = flat.flat.clone()
+        assert flat.check_views()
+        assert torch.isfinite(grad_g).all() and float(grad_g.abs().sum()) > 0
+        # same kernels on the same inputs: equal up to the order of the fp32 / fp64 atomics
+        assert float((loss_g - loss_e).abs()) <= 1e-6 * float(loss_e.abs()) + 1e-9
+        assert float((F_g - F_e).abs().max()) <= 1e-5 * float(F_e.abs().max())
+        rel = float((grad_g - grad_e).norm() / grad_e.norm())
+        assert rel < (1e-4 if path == "tc32" else 1e-3), rel
+        opt.step()
