@@ -47,13 +47,18 @@ const char* fepe_version(void);
  *   FEPE_DISPATCH_GRAM_TEAM  0 by size | 1, 2, 3 = teams of 1, 2, 4 warps per pair in the split pipeline's Gram kernel
  *   FEPE_DISPATCH_MLP_GEMM   0 by size | 1 one tile per CTA | 2 persistent kernel with 128-column tiles (bf16 path)
  *   FEPE_DISPATCH_MLP_FUSE   0 default | 2 fused-norm variant with 8 transform warps (bf16 path)
+ *   FEPE_DISPATCH_SPLIT_PIPE   0 default | 1 split pipeline over the whole batch at once | 2 in L2-sized chunks |
+ *                              3 chunks, solve + residual kernels of a chunk on a second stream under the next Gram kernel
+ *   FEPE_DISPATCH_SPLIT_ROUNDS 0 default | 1..15 pairs per Gram team per chunk (modes 2 / 3)
  * A forced variant that cannot run the problem falls back to the automatic choice.  Returns the previous value, or
  * FEPE_E_BADARG. */
 #define FEPE_DISPATCH_FIT       0
 #define FEPE_DISPATCH_GRAM_TEAM 1
 #define FEPE_DISPATCH_MLP_GEMM  2
 #define FEPE_DISPATCH_MLP_FUSE  3
-#define FEPE_DISPATCH_COUNT     4
+#define FEPE_DISPATCH_SPLIT_PIPE   4
+#define FEPE_DISPATCH_SPLIT_ROUNDS 5
+#define FEPE_DISPATCH_COUNT     6
 int fepe_set_dispatch(int which, int value);
 
 /* Largest N one launch can stage (depends on the device's opt-in shared memory). Host call. */

@@ -29,12 +29,16 @@ class GraphedStep:
                 fn(*self.static_in)
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
+        # The split (hi / lo fp16) copies of the weights are cached per parameter version.  The capture must RECORD the
+        # kernels that make them (a hit on a warm-up entry would bake pointers to memory the graph does not own, holding
+        # weights that are stale after the first optimiser step), so the cache is emptied first; entries made during
+        # the capture live in the graph's private pool, are rewritten by every replay, and must not be served to eager
+        # callers afterwards, so it is emptied again.
+        from . import mlp32
+        mlp32._SPLIT_CACHE.clear()
         self.graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.graph):
             self.static_out = fn(*self.static_in)
-        # split weights cached DURING capture live in the graph's private pool: they are recomputed by every replay and
-        # must not be served to eager callers
-        from . import mlp32
         mlp32._SPLIT_CACHE.clear()
 
     def replay(self, *inputs: torch.Tensor):

@@ -177,8 +177,11 @@ class TensorCoreMLPFunction(torch.autograd.Function):
                                              Xs[i].data_ptr(), B, Npad, N, _CH[i], eps, slope, st), "fepe_mlp_norm")
             logits = torch.empty(B, 1, N, dtype=torch.float32, device=dev)
             scratch = torch.empty(B, 1, N, dtype=torch.float32, device=dev)
-            _lib.check(lib.fepe_mlp_last(Xs[4].data_ptr(), w_last.data_ptr(), float(bias[5].item()), logits.data_ptr(),
+            # the bias of the last layer is added on the device (the ABI takes it as a scalar: reading it here would
+            # synchronise with the host every step and bake a stale value into a captured graph)
+            _lib.check(lib.fepe_mlp_last(Xs[4].data_ptr(), w_last.data_ptr(), 0.0, logits.data_ptr(),
                                          scratch.data_ptr(), B, N, Npad, 256, st), "fepe_mlp_last")
+            logits.add_(bias[5].reshape(1, 1, 1))
         ctx.dims = (B, Cin, N, Npad)
         ctx.saved = (x0, w0, wb, w_last, gam, Ys, Xs, stats)
         ctx.param_shapes = [p.shape for p in params]

@@ -53,7 +53,7 @@ def test_graphed_training_step_matches_eager(path):
         assert flat.check_views()
         assert torch.isfinite(grad_g).all() and float(grad_g.abs().sum()) > 0
         # same kernels on the same inputs: equal up to the order of the fp32 / fp64 atomics
-        assert float((loss_g - loss_e).abs()) <= 1e-6 * float(loss_e.abs()) + 1e-9
+        assert float((loss_g - loss_e).abs()) <= 1e-5 * float(loss_e.abs()) + 1e-9
         assert float((F_g - F_e).abs().max()) <= 1e-5 * float(F_e.abs().max())
         rel = float((grad_g - grad_e).norm() / grad_e.norm())
         assert rel < (1e-4 if path == "tc32" else 1e-3), rel
