@@ -47,19 +47,21 @@ const char* fepe_version(void);
  *   FEPE_DISPATCH_GRAM_TEAM  0 by size | 1, 2, 3 = teams of 1, 2, 4 warps per pair in the split pipeline's Gram kernel
  *   FEPE_DISPATCH_MLP_GEMM   0 by size | 1 one tile per CTA | 2 persistent kernel with 128-column tiles (bf16 path)
  *   FEPE_DISPATCH_MLP_FUSE   0 default | 2 fused-norm variant with 8 transform warps (bf16 path)
- *   FEPE_DISPATCH_SPLIT_PIPE   0 default | 1 split pipeline over the whole batch at once | 2 in L2-sized chunks |
- *                              3 chunks, solve + residual kernels of a chunk on a second stream under the next Gram kernel
- *   FEPE_DISPATCH_SPLIT_ROUNDS 0 default | 1..15 pairs per Gram team per chunk (modes 2 / 3)
  * A forced variant that cannot run the problem falls back to the automatic choice.  Returns the previous value, or
  * FEPE_E_BADARG. */
 #define FEPE_DISPATCH_FIT       0
 #define FEPE_DISPATCH_GRAM_TEAM 1
 #define FEPE_DISPATCH_MLP_GEMM  2
 #define FEPE_DISPATCH_MLP_FUSE  3
-#define FEPE_DISPATCH_SPLIT_PIPE   4
-#define FEPE_DISPATCH_SPLIT_ROUNDS 5
-#define FEPE_DISPATCH_COUNT     6
+#define FEPE_DISPATCH_COUNT     4
 int fepe_set_dispatch(int which, int value);
+
+/* Diagnostics of the split pipeline (throughput path of fepe_fit_fwd): while `buf` (device memory, 32 bytes per record)
+ * is set, every CTA of its three kernels appends {kernel 1 Gram | 2 solve | 3 residual, SM id, start ns, end ns} as four
+ * u64 (globaltimer); pass NULL to stop.  fepe_debug_trace_count returns the number of records requested so far (may
+ * exceed the capacity; the surplus was dropped).  Host calls, synchronous with the device; not for production use. */
+int fepe_debug_trace(void* buf, unsigned int capacity_records);
+int fepe_debug_trace_count(void);
 
 /* Largest N one launch can stage (depends on the device's opt-in shared memory). Host call. */
 int fepe_max_correspondences(void);

@@ -571,7 +571,7 @@ extern "C" {
 const char* fepe_version(void) { return "fepe_b200 0.2 sm_100a"; }
 
 int fepe_set_dispatch(int which, int value) {
-    if (which < 0 || which >= FEPE_DISPATCH_COUNT || value < 0 || value > 15) return FEPE_E_BADARG;
+    if (which < 0 || which >= FEPE_DISPATCH_COUNT || value < 0 || value > 3) return FEPE_E_BADARG;
     return fepe::g_dispatch[which].exchange(value);
 }
 

@@ -42,6 +42,27 @@ __device__ __forceinline__ double* pair_state(const FitParams& p, size_t pair) {
                                 : reinterpret_cast<double*>(p.resid + pair * static_cast<size_t>(p.N));
 }
 
+// Diagnostics (fepe_debug_trace): one record {kernel id, SM, start ns, end ns} per CTA of the three kernels, to see on
+// which SMs and when they run (and, for experiments with several streams, whether kernels really share an SM).  Costs one
+// global load per CTA while no buffer is set.
+__device__ unsigned long long* g_trace = nullptr;
+__device__ unsigned int g_trace_cap = 0;
+__device__ unsigned int g_trace_n = 0;
+__device__ __forceinline__ unsigned long long trace_now() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+__device__ __forceinline__ void trace_cta(unsigned long long kid, unsigned long long t0) {
+    unsigned long long* buf = g_trace;
+    if (buf == nullptr) return;
+    const unsigned int i = atomicAdd(&g_trace_n, 1u);
+    if (i >= g_trace_cap) return;
+    unsigned int sm;
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(sm));
+    buf[i * 4 + 0] = kid; buf[i * 4 + 1] = sm; buf[i * 4 + 2] = t0; buf[i * 4 + 3] = trace_now();
+}
+
 template <int T>
 __device__ __forceinline__ void team_sync(int team) {
     if constexpr (T == 1) {
@@ -54,13 +75,14 @@ __device__ __forceinline__ void team_sync(int team) {
 // ------------------------------------------------------------------------------------------------
 // K1: Hartley + Gram.  T warps per pair.
 // ------------------------------------------------------------------------------------------------
-template <int T, int W>
-__device__ __forceinline__ void gram_body(const FitParams& p) {
+template <int T>
+__global__ void __launch_bounds__(kGramThreads, 1) fepe_gram_kernel(const FitParams p) {
     extern __shared__ __align__(128) unsigned char smem[];
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
     const int S = p.ring.stages;
-    constexpr int G = W / T;                               // teams (= ring consumers)
+    constexpr int G = kGramConsumerWarps / T;              // teams (= ring consumers)
+    const unsigned long long t_begin = trace_now();
     uint64_t* full = reinterpret_cast<uint64_t*>(smem + p.ring.bar_off);
     double* gram_w = reinterpret_cast<double*>(smem + p.ring.scratch_off);             // [16][36]
     float* red = reinterpret_cast<float*>(gram_w + kGramConsumerWarps * 36);           // [16][8]
@@ -246,21 +268,10 @@ __device__ __forceinline__ void gram_body(const FitParams& p) {
             st[60] = 0.0; st[61] = 0.0; st[62] = 0.0;
         }
     }
-}
-
-// 16 warps: the whole register file (128 registers per thread), nothing else fits beside the CTA.
-template <int T>
-__global__ void __launch_bounds__(kGramThreads, 1) fepe_gram_kernel(const FitParams p) {
-    gram_body<T, kGramConsumerWarps>(p);
-}
-
-// 12 warps at the same 128 registers: a quarter of the register file (and, with one stage fewer, ~26 KB of shared
-// memory) stays free, so the solve / residual CTAs of the PREVIOUS chunk run on the same SMs while this kernel's teams
-// are in their issue- and fp64-bound passes (launch_split, overlapped mode).
-constexpr int kGramOverlapWarps = 12;
-template <int T>
-__global__ void __maxnreg__(128) fepe_gram_overlap_kernel(const FitParams p) {
-    gram_body<T, kGramOverlapWarps>(p);
+    if (g_trace != nullptr) {
+        __syncthreads();
+        if (threadIdx.x == 0) trace_cta(1, t_begin);
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -270,6 +281,7 @@ constexpr int kSolveStride = 33;
 
 __global__ void __launch_bounds__(32) fepe_solve_kernel(const FitParams p) {
     __shared__ double g[36 * kSolveStride];
+    const unsigned long long t_begin = trace_now();
     const int lane = threadIdx.x;
     const size_t pair0 = static_cast<size_t>(blockIdx.x) * 32;
     const int n_here = min(32, p.B - static_cast<int>(pair0));
@@ -313,6 +325,7 @@ __global__ void __launch_bounds__(32) fepe_solve_kernel(const FitParams p) {
     st[52] = static_cast<double>(its);
     st[53] = v3[0]; st[54] = v3[1]; st[55] = v3[2];
     st[63] = sigma3;
+    if (lane == 0) trace_cta(2, t_begin);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -323,6 +336,7 @@ constexpr int kResidPrefetch = 4;
 
 __global__ void __launch_bounds__(kResidThreads) fepe_resid_kernel(const FitParams p) {
     pdl_launch_dependents();
+    const unsigned long long t_begin = trace_now();
     // Highest pair first: K1 walks the batch upwards, so the pairs it read last are the ones still in the 126 MB L2.
     const size_t pair = gridDim.x - 1 - blockIdx.x;
     const int N = p.N;
@@ -359,20 +373,21 @@ __global__ void __launch_bounds__(kResidThreads) fepe_resid_kernel(const FitPara
     }
     pass_resid(gp, gw, N, tid + kResidPrefetch * kResidThreads, kResidThreads, m, ff, Fo, p.ax, p.bx, p.ay, p.by,
                p.clamp_at, r_out, e_out);
+    if (tid == 0) trace_cta(3, t_begin);
 }
 
-template <int T, bool OVERLAP>
+template <int T>
 static cudaError_t launch_gram(const FitParams& p, int grid, cudaStream_t stream) {
     static int configured[64] = {0};
     int dev = 0;
     cudaGetDevice(&dev);
-    auto kern = OVERLAP ? fepe_gram_overlap_kernel<T> : fepe_gram_kernel<T>;
     if (!configured[dev & 63]) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, device_info().smem_optin);
+        cudaError_t e = cudaFuncSetAttribute(fepe_gram_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             device_info().smem_optin);
         if (e != cudaSuccess) return e;
         configured[dev & 63] = 1;
     }
-    kern<<<grid, (OVERLAP ? kGramOverlapWarps : kGramConsumerWarps) * 32, p.ring.total_bytes, stream>>>(p);
+    fepe_gram_kernel<T><<<grid, kGramThreads, p.ring.total_bytes, stream>>>(p);
     return cudaGetLastError();
 }
 
@@ -385,116 +400,50 @@ bool split_path_supported(const FitParams& p, const DeviceInfo& d) {
     return (d.smem_optin - kGramFixedBytes) / stage >= 5;     // 4 teams of 4 warps + one stage of prefetch
 }
 
-// A second stream per device for the overlapped mode, created on first use (never inside a capture: the first call
-// of a process is a warm-up call, and creation is not a stream operation).
-struct SplitAux {
-    cudaStream_t stream = nullptr;
-    cudaEvent_t fork = nullptr, join = nullptr;
-    int ok = 0;
-};
-static SplitAux& split_aux() {
-    static SplitAux aux[64];
-    int dev = 0;
-    cudaGetDevice(&dev);
-    SplitAux& a = aux[dev & 63];
-    if (!a.ok) {
-        if (cudaStreamCreateWithFlags(&a.stream, cudaStreamNonBlocking) == cudaSuccess &&
-            cudaEventCreateWithFlags(&a.fork, cudaEventDisableTiming) == cudaSuccess &&
-            cudaEventCreateWithFlags(&a.join, cudaEventDisableTiming) == cudaSuccess)
-            a.ok = 1;
-        else
-            a.ok = -1;
-    }
-    return a;
-}
-
-static FitParams chunk_of(const FitParams& p, int c0, int nb) {
-    FitParams q = p;
-    const size_t o = static_cast<size_t>(c0);
-    q.matches = p.matches + o * p.N * 4;
-    q.weights = p.weights + o * p.N;
-    q.F_out = p.F_out + o * 9;
-    q.resid = p.resid + o * p.N;
-    if (p.epi != nullptr) q.epi = p.epi + o * p.N;
-    if (p.saved != nullptr) q.saved = p.saved + o * FEPE_SAVED_DOUBLES;
-    q.B = nb;
-    return q;
-}
-
-template <bool OVERLAP>
-static cudaError_t launch_gram_t(int T, const FitParams& p, int grid, cudaStream_t stream) {
-    return (T == 1) ? launch_gram<1, OVERLAP>(p, grid, stream)
-         : (T == 2) ? launch_gram<2, OVERLAP>(p, grid, stream)
-                    : launch_gram<4, OVERLAP>(p, grid, stream);
-}
-
 int launch_split(FitParams p, const DeviceInfo& d, cudaStream_t stream) {
     const int stage = ((p.N * 20 + 127) / 128) * 128;
     int S = (d.smem_optin - kGramFixedBytes) / stage;
     if (S > kMaxStages) S = kMaxStages;
     if (S < 5) return FEPE_E_TOOLARGE;
-    // Mode.  1: the three kernels once over the whole batch.  2: the batch in chunks that fit the L2 (the residual
-    // kernel re-reads its chunk from there).  3: chunks, with the solve + residual kernels of chunk c on a second
-    // stream underneath the Gram kernel of chunk c+1 (12-warp Gram CTAs leave them room on every SM).
-    int mode = dispatch_get(FEPE_DISPATCH_SPLIT_PIPE);
-    if (mode == 0) mode = 1;
-    if (mode == 3) {
-        // leave >= 24 KB of shared memory for the co-resident CTAs
-        while (S > 5 && S * stage + kGramFixedBytes + 24 * 1024 > d.smem_optin) --S;
-        if (split_aux().ok != 1) mode = 2;
-    }
-    const int W = (mode == 3) ? kGramOverlapWarps : kGramConsumerWarps;
     // largest number of teams that still leaves >= 2 stages of prefetch
     int T = 1;
-    while (T < 4 && W / T > S - 2) T *= 2;
-    if (W / T > S - 1) return FEPE_E_TOOLARGE;
+    while (T < 4 && kGramConsumerWarps / T > S - 2) T *= 2;
+    if (kGramConsumerWarps / T > S - 1) return FEPE_E_TOOLARGE;
     const int force = dispatch_get(FEPE_DISPATCH_GRAM_TEAM);     // 0 = automatic; 1 / 2 / 3 = teams of 1 / 2 / 4 warps
     if (force != 0) {
         const int t = (force == 3) ? 4 : force;
-        if (W / t <= S - 1) T = t;
+        if (kGramConsumerWarps / t <= S - 1) T = t;
     }
     p.ring.stages = S;
-    p.ring.consumers = W / T;
+    p.ring.consumers = kGramConsumerWarps / T;
     p.ring.stage_bytes = stage;
     p.ring.bar_off = S * stage;
     p.ring.scratch_off = p.ring.bar_off + 2 * kMaxStages * 8;
     p.ring.total_bytes = p.ring.scratch_off + kGramConsumerWarps * (36 * 8 + 8 * 4);
-    cudaError_t e;
-    if (mode == 1) {
-        const int grid = p.B < d.sms ? p.B : d.sms;
-        e = launch_gram_t<false>(T, p, grid, stream);
-        if (e != cudaSuccess) return static_cast<int>(e);
-        fepe_solve_kernel<<<(p.B + 31) / 32, 32, 0, stream>>>(p);
-        e = cudaGetLastError();
-        if (e != cudaSuccess) return static_cast<int>(e);
-        fepe_resid_kernel<<<p.B, kResidThreads, 0, stream>>>(p);
-        return static_cast<int>(cudaGetLastError());
-    }
-    int rounds = dispatch_get(FEPE_DISPATCH_SPLIT_ROUNDS);       // pairs per team per chunk
-    if (rounds == 0) rounds = 2;
-    const int chunk = (W / T) * d.sms * rounds;
-    SplitAux& aux = split_aux();
-    cudaStream_t s2 = (mode == 3) ? aux.stream : stream;
-    for (int c0 = 0; c0 < p.B; c0 += chunk) {
-        const int nb = (p.B - c0 < chunk) ? p.B - c0 : chunk;
-        const FitParams q = chunk_of(p, c0, nb);
-        const int grid = nb < d.sms ? nb : d.sms;
-        e = (mode == 3) ? launch_gram_t<true>(T, q, grid, stream) : launch_gram_t<false>(T, q, grid, stream);
-        if (e != cudaSuccess) return static_cast<int>(e);
-        if (mode == 3) {
-            if ((e = cudaEventRecord(aux.fork, stream)) != cudaSuccess) return static_cast<int>(e);
-            if ((e = cudaStreamWaitEvent(s2, aux.fork, 0)) != cudaSuccess) return static_cast<int>(e);
-        }
-        fepe_solve_kernel<<<(nb + 31) / 32, 32, 0, s2>>>(q);
-        if ((e = cudaGetLastError()) != cudaSuccess) return static_cast<int>(e);
-        fepe_resid_kernel<<<nb, kResidThreads, 0, s2>>>(q);
-        if ((e = cudaGetLastError()) != cudaSuccess) return static_cast<int>(e);
-    }
-    if (mode == 3) {
-        if ((e = cudaEventRecord(aux.join, s2)) != cudaSuccess) return static_cast<int>(e);
-        if ((e = cudaStreamWaitEvent(stream, aux.join, 0)) != cudaSuccess) return static_cast<int>(e);
-    }
-    return 0;
+    const int grid = p.B < d.sms ? p.B : d.sms;
+    cudaError_t e = (T == 1)   ? launch_gram<1>(p, grid, stream)
+                    : (T == 2) ? launch_gram<2>(p, grid, stream)
+                               : launch_gram<4>(p, grid, stream);
+    if (e != cudaSuccess) return static_cast<int>(e);
+    fepe_solve_kernel<<<(p.B + 31) / 32, 32, 0, stream>>>(p);
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return static_cast<int>(e);
+    fepe_resid_kernel<<<p.B, kResidThreads, 0, stream>>>(p);
+    return static_cast<int>(cudaGetLastError());
 }
 
 }  // namespace fepe
+
+extern "C" int fepe_debug_trace(void* buf, unsigned int capacity_records) {
+    unsigned long long* b = static_cast<unsigned long long*>(buf);
+    unsigned int zero = 0;
+    cudaError_t e = cudaMemcpyToSymbol(fepe::g_trace, &b, sizeof(b));
+    if (e == cudaSuccess) e = cudaMemcpyToSymbol(fepe::g_trace_cap, &capacity_records, sizeof(capacity_records));
+    if (e == cudaSuccess) e = cudaMemcpyToSymbol(fepe::g_trace_n, &zero, sizeof(zero));
+    return static_cast<int>(e);
+}
+extern "C" int fepe_debug_trace_count(void) {
+    unsigned int n = 0;
+    if (cudaMemcpyFromSymbol(&n, fepe::g_trace_n, sizeof(n)) != cudaSuccess) return -1;
+    return static_cast<int>(n);
+}

@@ -18,7 +18,6 @@ RECOVER_OUT_FLOATS = 24     # FEPE_RECOVER_OUT_FLOATS
 GT_FLOATS = 32              # FEPE_GT_FLOATS
 
 DISPATCH_FIT, DISPATCH_GRAM_TEAM, DISPATCH_MLP_GEMM, DISPATCH_MLP_FUSE = 0, 1, 2, 3   # FEPE_DISPATCH_*
-DISPATCH_SPLIT_PIPE, DISPATCH_SPLIT_ROUNDS = 4, 5
 
 _lib = None
 
@@ -30,6 +29,8 @@ _SIGNATURES = {
     "fepe_version": (ctypes.c_char_p, []),
     "fepe_max_correspondences": (_c_i, []),
     "fepe_set_dispatch": (_c_i, [_c_i, _c_i]),
+    "fepe_debug_trace": (_c_i, [_c_p, ctypes.c_uint]),
+    "fepe_debug_trace_count": (_c_i, []),
     "fepe_fit_fwd": (_c_i, [_c_p, _c_p, _c_i, _c_i, _c_f, _c_f, _c_f, _c_f, _c_f,
                             _c_p, _c_p, _c_p, _c_p, _c_p]),
     "fepe_fit_bwd": (_c_i, [_c_p, _c_p, _c_i, _c_i, _c_f, _c_f, _c_f, _c_f, _c_f,
@@ -101,9 +102,7 @@ def lib() -> ctypes.CDLL:
 _DISPATCH_KEYS = {"fit": (DISPATCH_FIT, {"auto": 0, "small": 1, "ring": 2, "split": 3}),
                   "gram_team": (DISPATCH_GRAM_TEAM, {"auto": 0, "1": 1, "2": 2, "4": 3}),
                   "mlp_gemm": (DISPATCH_MLP_GEMM, {"auto": 0, "persist": 0, "tile": 1, "persist128": 2}),
-                  "mlp_fuse": (DISPATCH_MLP_FUSE, {"auto": 0, "1": 0, "2": 2}),
-                  "split_pipe": (DISPATCH_SPLIT_PIPE, {"auto": 0, "whole": 1, "chunks": 2, "overlap": 3}),
-                  "split_rounds": (DISPATCH_SPLIT_ROUNDS, dict({"auto": 0}, **{str(i): i for i in range(1, 16)}))}
+                  "mlp_fuse": (DISPATCH_MLP_FUSE, {"auto": 0, "1": 0, "2": 2})}
 
 
 def set_dispatch(key: str, value) -> int:

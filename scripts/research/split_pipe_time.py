@@ -40,12 +40,10 @@ def run(B, N, pipe, rounds="auto", team="auto", iters=10, saved=False, ref=None)
 
 
 if __name__ == "__main__":
-    for B, N in [(32768, 1000), (8192, 1000), (16384, 2000)]:
+    for B, N in [(32768, 1000)]:
         ref = run(B, N, "whole")
-        for r in ("1", "2", "3", "4", "6"):
+        for r in ("2", "4", "6", "8", "12"):
             run(B, N, "chunks", r, ref=ref)
-        for r in ("1", "2", "3", "4", "6"):
+        for r in ("1", "2", "3", "4", "6", "8", "12"):
             run(B, N, "overlap", r, ref=ref)
-        run(B, N, "overlap", "2", team="4", ref=ref)
-    ref = run(32768, 1000, "whole", saved=True)
-    run(32768, 1000, "overlap", "2", saved=True, ref=ref)
+        ref = run(B, N, "whole")
