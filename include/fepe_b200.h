@@ -60,7 +60,7 @@ int fepe_set_dispatch(int which, int value);
  * is set, every CTA of its three kernels appends {kernel 1 Gram | 2 solve | 3 residual, SM id, start ns, end ns} as four
  * u64 (globaltimer); pass NULL to stop.  fepe_debug_trace_count returns the number of records requested so far (may
  * exceed the capacity; the surplus was dropped).  Host calls, synchronous with the device; not for production use. */
-int fepe_debug_trace(void* buf, unsigned int capacity_records);
+int fepe_debug_trace(void* buf, int capacity_records);
 int fepe_debug_trace_count(void);
 
 /* Largest N one launch can stage (depends on the device's opt-in shared memory). Host call. */

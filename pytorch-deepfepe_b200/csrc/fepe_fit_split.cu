@@ -434,7 +434,9 @@ int launch_split(FitParams p, const DeviceInfo& d, cudaStream_t stream) {
 
 }  // namespace fepe
 
-extern "C" int fepe_debug_trace(void* buf, unsigned int capacity_records) {
+extern "C" int fepe_debug_trace(void* buf, int capacity_records_in) {
+    if (capacity_records_in < 0) return FEPE_E_BADARG;
+    const unsigned int capacity_records = (buf != nullptr) ? static_cast<unsigned int>(capacity_records_in) : 0u;
     unsigned long long* b = static_cast<unsigned long long*>(buf);
     unsigned int zero = 0;
     cudaError_t e = cudaMemcpyToSymbol(fepe::g_trace, &b, sizeof(b));

@@ -29,7 +29,7 @@ _SIGNATURES = {
     "fepe_version": (ctypes.c_char_p, []),
     "fepe_max_correspondences": (_c_i, []),
     "fepe_set_dispatch": (_c_i, [_c_i, _c_i]),
-    "fepe_debug_trace": (_c_i, [_c_p, ctypes.c_uint]),
+    "fepe_debug_trace": (_c_i, [_c_p, _c_i]),
     "fepe_debug_trace_count": (_c_i, []),
     "fepe_fit_fwd": (_c_i, [_c_p, _c_p, _c_i, _c_i, _c_f, _c_f, _c_f, _c_f, _c_f,
                             _c_p, _c_p, _c_p, _c_p, _c_p]),

@@ -64,7 +64,8 @@ def test_ctypes_signatures_match_the_header(built):
         assert got == want_args, f"{name}: ctypes {''.join(got)} vs header {''.join(want_args)}"
 
 
-_INFO_ONLY = ("fepe_version", "fepe_max_correspondences", "fepe_nn_match_workspace_bytes")
+_INFO_ONLY = ("fepe_version", "fepe_max_correspondences", "fepe_nn_match_workspace_bytes",
+              "fepe_debug_trace", "fepe_debug_trace_count")      # diagnostics: NULL is a valid argument (stop tracing)
 
 
 def test_entry_points_reject_null_pointers_before_touching_cuda(built):
