@@ -294,7 +294,9 @@ class MLP32Function(torch.autograd.Function):
         if has_m:
             if ctx.needs_input_grad[1]:
                 ax, _, ay, _ = affine                                   # x = ((a m + b) + 1) / 2
-                gm = dX0[:, :, 0:4] * torch.tensor([ax / 2, ay / 2, ax / 2, ay / 2], dtype=torch.float32, device=dev)
+                gm = dX0[:, :, 0:4].clone()                             # scalar multiplies: nothing is copied from the
+                gm[:, :, 0::2] *= ax / 2                                # host, so the step stays capturable in a graph
+                gm[:, :, 1::2] *= ay / 2
             off = 4
         for j in range(n_extras):
             if ctx.needs_input_grad[2 + j]:

@@ -404,7 +404,8 @@ class LinearTC32(torch.autograd.Function):
                                                tsc.data_ptr(), None, gx.data_ptr(), None, 1, M, M, Co, K, st),
                            "fepe_mlp32_gemm(dgrad)")
             if ctx.needs_input_grad[1]:
-                ident = torch.tensor([1.0, 0.0], device=x.device).repeat(K).reshape(1, K, 2).contiguous()
+                ident = torch.zeros(1, K, 2, dtype=torch.float32, device=x.device)     # (scale 1, shift 0) per channel
+                ident[:, :, 0] = 1.0
                 gw = torch.zeros(Co, K, dtype=torch.float32, device=x.device)
                 _lib.check(lib.fepe_mlp32_wgrad(gy.data_ptr(), amax.data_ptr(), x.data_ptr(), ident.data_ptr(), 1.0,
                                                 gw.data_ptr(), M, M, Co, K, st), "fepe_mlp32_wgrad")

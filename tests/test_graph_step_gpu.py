@@ -58,7 +58,16 @@ def test_graphed_training_step_matches_eager(path):
         assert float((loss_g - loss_e).abs()) <= tol_loss * float(loss_e.abs()) + 1e-9
         assert float((F_g - F_e).abs().max()) <= tol_F * float(F_e.abs().max())
         rel = float((grad_g - grad_e).norm() / grad_e.norm())
-        assert rel < tol_grad, rel
+        if path == "bf16":
+            # yardstick: the eager step against itself (the bf16 path is not run-to-run reproducible: fp32 atomics in
+            # the statistics move single bf16 activations, and the gradient through three eigen-solves amplifies that)
+            flat.zero_()
+            fwd_bwd(xs[i], v1[i], v2[i])
+            noise = float((flat.flat - grad_e).norm() / grad_e.norm())
+            print(f"bf16 replay {i}: graph vs eager {rel:.3e}, eager vs eager {noise:.3e}")
+            assert rel < max(tol_grad, 4 * noise), (rel, noise)
+        else:
+            assert rel < tol_grad, rel
         # the weights change between replays outside the graph (here by 5 %, far above either tolerance): a graph that
         # had baked split / converted weights in would now disagree with the eager step
         with torch.no_grad():
