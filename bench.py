@@ -811,7 +811,8 @@ def c5_measure(args, dev, rank, world, steps: int, warm: int, mlp: str) -> dict:
     from fepe_b200 import synth, dist as fdist
     from fepe_b200.models import DeepFNet
     from fepe_b200.matching import get_matches_from_descriptors
-    from fepe_b200.losses import get_Rt_loss, pose_loss_from_Rt_loss
+    from fepe_b200.losses import deepf_training_loss
+    from fepe_b200 import ops as fops
     B, N = 16, args.ncorr
     NKP, DESC = 1200, 256                    # keypoints per image and descriptor size (SuperPoint: 256)
     torch.manual_seed(0)
@@ -819,7 +820,9 @@ def c5_measure(args, dev, rank, world, steps: int, warm: int, mlp: str) -> dict:
     net = DeepFNet(depth=5, image_size=list(synth.KITTI_IMAGE_SIZE), if_quality=True, quality_size=1).cuda()
     net.set_mlp_path(mlp)
     opt = torch.optim.Adam(net.parameters(), lr=1e-4)          # configs/kitti_corr_baseline.yaml:62
-    flat = fdist.FlatGradients(net.parameters())
+    # gradients of all parameters are views of ONE buffer, and the MLP's weight-gradient kernels add straight into them
+    flat = fdist.FlatGradients(net.parameters(), fuse_accumulation=True)
+    aff = fops.hw_affine(synth.KITTI_IMAGE_SIZE)
     # "SuperPoint frozen / random desc": a synthetic two-view scene gives NKP corresponding keypoints; image 2's are
     # shuffled and carry noisy copies of image 1's random unit descriptors.  The step starts from keypoints + descriptors.
     d = synth.make_batch(B, NKP, seed=500 + rank)
@@ -835,31 +838,20 @@ def c5_measure(args, dev, rank, world, steps: int, warm: int, mlp: str) -> dict:
     v1, v2 = T("pts1_virt"), T("pts2_virt")
     Ks, Rt, q_cam, t_cam = T("Ks"), T("delta_Rtijs_4_4"), T("q_cam"), T("t_cam")
 
-    def epi(p1, p2, Fm, clamp):            # utils_F.compute_epi_residual with torch ops (loss glue stays the reference's)
-        l1, l2 = p2 @ Fm, p1 @ Fm.transpose(1, 2)
-        dd = (p1 * l1).sum(2)
-        dist_ = dd.abs() * (1 / (l1[:, :, :2].norm(2, 2) + 1e-6) + 1 / (l2[:, :, :2].norm(2, 2) + 1e-6))
-        return torch.clamp(dist_, max=clamp)
-
     n_matches = []
 
     def fwd_bwd(xs, quality):
         """Forward + losses + backward of one batch; the gradients accumulate into the flat buffer."""
         outs = net({"matches_xy_ori": xs, "quality": quality})
-        T1 = outs["T1"]
-        p1 = (T1 @ v1.transpose(1, 2)).transpose(1, 2)
-        p2 = (T1 @ v2.transpose(1, 2)).transpose(1, 2)
-        loss_F = sum(epi(p1, p2, Fo, CLAMP_LOSS).mean() for Fo in outs["out_layers"]) / len(outs["out_layers"])
-        # get_all_loss_DeepF: E_i = K^T T2^T F_i T1 K (train_good_utils.py:356-358); get_Rt_loss (:64-295) on the device
-        TK = T1 @ Ks
-        E_layers = [TK.transpose(1, 2) @ Fo @ TK for Fo in outs["out_layers"]]
-        rt = get_Rt_loss(E_layers, None, None, None, Rt, q_cam, t_cam, metrics_on_host=False)
-        loss = loss_F + pose_loss_from_Rt_loss(rt)            # Train_model_pipeline.py:580-592 (if_qt_loss)
+        # get_all_loss_DeepF (F-loss on the virtual points, E_i = K^T T2^T F_i T1 K: train_good_utils.py:325-364) +
+        # get_Rt_loss (:64-295) + their combination (Train_model_pipeline.py:580-592, if_qt_loss): one launch of the
+        # fused head over all (layer, pair) items, one in the backward
+        loss, parts = deepf_training_loss(outs["out_layers"], Ks, v1, v2, Rt, q_cam, t_cam, aff, clamp_at=CLAMP_LOSS)
         mid = torch.cuda.Event(enable_timing=True) if not capturing[0] else None
         if mid is not None:
             mid.record()
         loss.backward()
-        return loss.detach(), torch.stack(rt["R_angle_error_layers_list"]), torch.stack(rt["t_angle_error_layers_list"]), mid
+        return loss.detach(), parts["R_angle"], parts["t_angle"], mid
 
     capturing = [False]
     graphed = [None]
@@ -942,7 +934,8 @@ def c5_measure(args, dev, rank, world, steps: int, warm: int, mlp: str) -> dict:
            "steps": steps, "warmup": warm, "ms_per_step": secs / steps * 1e3, "mlp_path": mlp,
            "workload": f"C5: training step from keypoints + random descriptors ({NKP} per image, {DESC}-d): mutual-NN "
                        f"matching -> {N} matches + quality, DeepFNet depth 5, {B} pairs/GPU, F-loss + q/t pose loss "
-                       "(device get_Rt_loss), one all-reduce of the flat gradient buffer (NCCL), Adam",
+                       "(one fused device head: fepe_b200.losses.deepf_training_loss), MLP weight gradients accumulated in "
+                       "place into ONE flat buffer, one all-reduce of it (NCCL), Adam",
            "global_batch": world * B,
            "mean_matches_per_pair": float(torch.stack(n_matches[-steps:]).float().mean()),
            "ms_breakdown": br, "launch": launch, "grad_bytes_allreduced": gbytes,

@@ -250,6 +250,10 @@ int fepe_mlp32_last(const float* Y, const float* ss, float slope, const float* W
  *   fepe_mlp32_wgrad      dW [Co,Ci] += dY^T LeakyReLU(a Yprev + d) on tcgen05 (Co % 128 == 0, Ci % 64 == 0; dW zeroed by
  *                         the caller); the data gradient dX = dY W is fepe_mlp32_gemm(dY, NULL, 1, dy_amax, (W^T)hi/lo, ...)
  *   fepe_mlp32_first_bwd  layer 1: dW [64,Ci] += dY^T X0 and, when dX0 != NULL, dX0 [B,N,Ci] = dY W
+ *   fepe_mlp32_affine_grads  dgamma_s[c] += sum_b A_s[b,c,1], dbeta_s[c] += sum_b A_s[b,c,0] for nseg <= 8 blocks whose A
+ *                         arrays [B,C_s,2] lie back to back at A (C, dgamma, dbeta: HOST arrays of nseg entries; the
+ *                         device pointers in them are accumulated into) -- one launch for a whole estimator
+ * All d* outputs are ACCUMULATED, so a caller may hand in its gradient buffers directly (fepe_b200.dist.FlatGradients).
  */
 int fepe_mlp32_last_bwd(const float* dlogits, const float* Y, const float* ss, float slope, const float* W, float* dX,
                         float* dW, float* db, int B, int N, int Npad, int Ci, int Co, void* stream);
@@ -258,6 +262,8 @@ int fepe_mlp32_normbwd(const float* dX, const float* Y, const float* ss, const f
                        void* stream);
 int fepe_mlp32_wgrad(const float* dY, const unsigned* dy_amax, const float* Yprev, const float* ss_prev, float slope,
                      float* dW, int M, int Npad, int Co, int Ci, void* stream);
+int fepe_mlp32_affine_grads(const double* A, int B, int nseg, const int* C, float* const* dgamma, float* const* dbeta,
+                            void* stream);
 int fepe_mlp32_first_bwd(const float* dY, const float* X0, const float* W, float* dX0, float* dW, int B, int N, int Npad,
                          int Ci, int Co, void* stream);
 

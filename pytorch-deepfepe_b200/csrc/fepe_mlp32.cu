@@ -31,6 +31,7 @@
 // written as zeros and excluded from the statistics.
 #include <cuda.h>
 #include <cuda_fp16.h>
+#include <cooperative_groups.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -499,18 +500,26 @@ __global__ void __launch_bounds__(128) fepe_mlp32_first_kernel(const FirstParams
 
 // ------------------------------------------------------------------------------------------------
 // Last block: x' = LeakyReLU(a y + d) of the PRE-norm output Y [B*Npad, Ci] (fp32), logits[b, o, n] = x' . W[o, :] + bias[o]
-// for CO outputs, and for CO == 1 the softmax over the N rows of the pair (DeepFNet.py:443,512).  One CTA per pair; a
-// warp per row, lane = 4 consecutive channels of every 128 (coalesced 512-byte reads), (a, d) and W of the lane's
-// channels live in registers for the whole pair.
+// for CO outputs, and for CO == 1 the softmax over the N rows of the pair (DeepFNet.py:443,512).  A pair is spread over the
+// S = gridDim.x CTAs of one thread-block cluster (S = 1 for batches that fill the machine on their own, up to 8 for the 16
+// pairs of a training step): every CTA owns a contiguous range of rows -- a warp per row, lane = 4 consecutive channels
+// of every 128 (coalesced 512-byte reads), (a, d) and W of the lane's channels in registers -- keeps its logits in shared
+// memory, and the softmax's max and sum are exchanged through distributed shared memory (two cluster barriers).
 template <int CO, int CI>
 __global__ void __launch_bounds__(256) fepe_mlp32_last_kernel(const float* __restrict__ Y, const float2* __restrict__ ss,
                                                               float slope, const float* __restrict__ W,
                                                               const float* __restrict__ bias, float* __restrict__ logits,
                                                               float* __restrict__ weights, int N, int Npad) {
-    extern __shared__ float sh[];            // [Npad] logits (CO == 1)
+    namespace cg = cooperative_groups;
+    extern __shared__ float sh[];            // [rows of this CTA] logits (CO == 1)
     __shared__ float red[8];
+    __shared__ float part[2];                // this CTA's max / sum of exponentials, read by the whole cluster
     constexpr int KPL = CI / 128;            // channel groups of 4 per lane
-    const int b = blockIdx.x;
+    const int b = blockIdx.y;
+    const int S = gridDim.x;
+    const int chunk = (((N + S - 1) / S) + 1) & ~1;
+    const int n0 = blockIdx.x * chunk;
+    const int n1 = (n0 + chunk < N) ? n0 + chunk : N;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarp = blockDim.x >> 5;
     float a[KPL][4], d[KPL][4], w[CO][KPL][4];
 #pragma unroll
@@ -528,14 +537,14 @@ __global__ void __launch_bounds__(256) fepe_mlp32_last_kernel(const float* __res
 #pragma unroll
     for (int o = 0; o < CO; ++o) bs[o] = bias != nullptr ? __ldg(bias + o) : 0.f;
     const float* yb = Y + static_cast<size_t>(b) * Npad * CI;
-    for (int r0 = warp * 2; r0 < N; r0 += nwarp * 2) {
+    for (int r0 = n0 + warp * 2; r0 < n1; r0 += nwarp * 2) {
         float4 in[2][KPL];
 #pragma unroll
         for (int u = 0; u < 2; ++u) {
 #pragma unroll
             for (int g = 0; g < KPL; ++g) {
                 in[u][g] = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (r0 + u < N) in[u][g] = __ldcs(reinterpret_cast<const float4*>(yb + static_cast<size_t>(r0 + u) * CI + g * 128 + lane * 4));
+                if (r0 + u < n1) in[u][g] = __ldcs(reinterpret_cast<const float4*>(yb + static_cast<size_t>(r0 + u) * CI + g * 128 + lane * 4));
             }
         }
 #pragma unroll
@@ -559,29 +568,36 @@ __global__ void __launch_bounds__(256) fepe_mlp32_last_kernel(const float* __res
 #pragma unroll
                 for (int off = 16; off > 0; off >>= 1) acc[o] += __shfl_xor_sync(0xffffffffu, acc[o], off);
             }
-            if (lane == 0 && r0 + u < N) {
+            if (lane == 0 && r0 + u < n1) {
 #pragma unroll
                 for (int o = 0; o < CO; ++o) {
                     const float val = acc[o] + bs[o];
                     logits[(static_cast<size_t>(b) * CO + o) * N + r0 + u] = val;
-                    if (CO == 1) sh[r0 + u] = val;
+                    if (CO == 1) sh[r0 + u - n0] = val;
                 }
             }
         }
     }
-    if (CO != 1 || weights == nullptr) return;
+    if (CO != 1 || weights == nullptr) return;          // uniform over the grid: no CTA waits for one that left
+    cg::cluster_group cluster = cg::this_cluster();
+    const int rows = n1 > n0 ? n1 - n0 : 0;
     __syncthreads();
     float mx = -3.4e38f;
-    for (int r = threadIdx.x; r < N; r += blockDim.x) mx = fmaxf(mx, sh[r]);
+    for (int r = threadIdx.x; r < rows; r += blockDim.x) mx = fmaxf(mx, sh[r]);
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
     if (lane == 0) red[warp] = mx;
     __syncthreads();
-    mx = red[0];
-    for (int i = 1; i < nwarp; ++i) mx = fmaxf(mx, red[i]);
-    __syncthreads();
+    if (threadIdx.x == 0) {
+        mx = red[0];
+        for (int i = 1; i < nwarp; ++i) mx = fmaxf(mx, red[i]);
+        part[0] = mx;
+    }
+    cluster.sync();
+    mx = -3.4e38f;
+    for (int r = 0; r < S; ++r) mx = fmaxf(mx, *cluster.map_shared_rank(&part[0], r));
     float sum = 0.f;
-    for (int r = threadIdx.x; r < N; r += blockDim.x) {
+    for (int r = threadIdx.x; r < rows; r += blockDim.x) {
         const float e = expf(sh[r] - mx);
         sh[r] = e;
         sum += e;
@@ -589,10 +605,17 @@ __global__ void __launch_bounds__(256) fepe_mlp32_last_kernel(const float* __res
     sum = warp_sum(sum);
     if (lane == 0) red[warp] = sum;
     __syncthreads();
+    if (threadIdx.x == 0) {
+        sum = 0.f;
+        for (int i = 0; i < nwarp; ++i) sum += red[i];
+        part[1] = sum;
+    }
+    cluster.sync();
     sum = 0.f;
-    for (int i = 0; i < nwarp; ++i) sum += red[i];
+    for (int r = 0; r < S; ++r) sum += *cluster.map_shared_rank(&part[1], r);
     const float inv = 1.0f / sum;
-    for (int r = threadIdx.x; r < N; r += blockDim.x) weights[static_cast<size_t>(b) * N + r] = sh[r] * inv;
+    for (int r = threadIdx.x; r < rows; r += blockDim.x) weights[static_cast<size_t>(b) * N + n0 + r] = sh[r] * inv;
+    cluster.sync();                                      // nobody's shared memory goes away while a peer still reads it
 }
 
 template <int BN, int STAGES>
@@ -691,11 +714,32 @@ int fepe_mlp32_last(const float* Y, const float* ss, float slope, const float* W
         return FEPE_E_BADARG;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const float2* s2 = reinterpret_cast<const float2*>(ss);
-    if (Co == 1)
-        fepe::m32::fepe_mlp32_last_kernel<1, 256><<<B, 256, Npad * sizeof(float), st>>>(Y, s2, slope, W, bias, logits, weights, N, Npad);
-    else
-        fepe::m32::fepe_mlp32_last_kernel<4, 256><<<B, 256, 0, st>>>(Y, s2, slope, W, bias, logits, nullptr, N, Npad);
-    return static_cast<int>(cudaGetLastError());
+    int S = 1;                                           // CTAs (= cluster size) per pair: ~2 CTAs per SM, at most 8
+    while (S < 8 && B * S < 2 * 148) S *= 2;
+    const int chunk = (((N + S - 1) / S) + 1) & ~1;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(S, B);
+    cfg.blockDim = dim3(256);
+    cfg.dynamicSmemBytes = (Co == 1) ? chunk * sizeof(float) : 0;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = S; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    float* no_weights = nullptr;
+    cudaError_t e;
+    if (Co == 1) {
+        if (cfg.dynamicSmemBytes > 48 * 1024) {
+            e = cudaFuncSetAttribute(fepe::m32::fepe_mlp32_last_kernel<1, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     static_cast<int>(cfg.dynamicSmemBytes));
+            if (e != cudaSuccess) return static_cast<int>(e);
+        }
+        e = cudaLaunchKernelEx(&cfg, fepe::m32::fepe_mlp32_last_kernel<1, 256>, Y, s2, slope, W, bias, logits, weights, N, Npad);
+    } else {
+        e = cudaLaunchKernelEx(&cfg, fepe::m32::fepe_mlp32_last_kernel<4, 256>, Y, s2, slope, W, bias, logits, no_weights, N, Npad);
+    }
+    return static_cast<int>(e);
 }
 
 }  // extern "C"

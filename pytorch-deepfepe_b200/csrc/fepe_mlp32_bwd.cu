@@ -31,19 +31,19 @@ namespace fepe {
 namespace m32 {
 
 // ------------------------------------------------------------------------------------------------
-// last layer: logits[b,o,n] = x'[m,:] . W[o,:] + bias[o], x' = LeakyReLU(a y + d).  One CTA per (128-row slab, pair),
-// thread = channel (Ci = 256).
+// last layer: logits[b,o,n] = x'[m,:] . W[o,:] + bias[o], x' = LeakyReLU(a y + d).  One CTA per (`rows`-row slab, pair),
+// thread = channel (Ci = 256); rows = 128, or less for batches that would not fill the machine with 128-row slabs.
 template <int CO>
 __global__ void __launch_bounds__(256) last_bwd_kernel(const float* __restrict__ dlogits, const float* __restrict__ Y,
                                                        const float2* __restrict__ ss, float slope,
                                                        const float* __restrict__ W, float* __restrict__ dX,
                                                        float* __restrict__ dW, float* __restrict__ db, int N, int Npad,
-                                                       int Ci) {
+                                                       int Ci, int rows) {
     __shared__ float dl[CO][128];
-    const int b = blockIdx.y, r0 = blockIdx.x * 128;
+    const int b = blockIdx.y, r0 = blockIdx.x * rows;
     for (int i = threadIdx.x; i < CO * 128; i += 256) {
         const int o = i >> 7, r = i & 127;
-        dl[o][r] = (r0 + r < N) ? dlogits[(static_cast<size_t>(b) * CO + o) * N + r0 + r] : 0.f;
+        dl[o][r] = (r < rows && r0 + r < N) ? dlogits[(static_cast<size_t>(b) * CO + o) * N + r0 + r] : 0.f;
     }
     __syncthreads();
     for (int k = threadIdx.x; k < Ci; k += 256) {
@@ -52,8 +52,8 @@ __global__ void __launch_bounds__(256) last_bwd_kernel(const float* __restrict__
 #pragma unroll
         for (int o = 0; o < CO; ++o) { wk[o] = __ldg(W + o * Ci + k); acc[o] = 0.f; }
         const size_t base = (static_cast<size_t>(b) * Npad + r0) * Ci + k;
-#pragma unroll 4
-        for (int r = 0; r < 128; ++r) {
+#pragma unroll 8
+        for (int r = 0; r < rows; ++r) {
             const float t = fmaf(Y[base + static_cast<size_t>(r) * Ci], ad.x, ad.y);
             const float x = fmaxf(t, slope * t);
             float g = 0.f;
@@ -69,8 +69,39 @@ __global__ void __launch_bounds__(256) last_bwd_kernel(const float* __restrict__
     }
     if (threadIdx.x < CO) {
         float s = 0.f;
-        for (int r = 0; r < 128; ++r) s += dl[threadIdx.x][r];
+        for (int r = 0; r < rows; ++r) s += dl[threadIdx.x][r];
         atomicAdd(db + threadIdx.x, s);
+    }
+}
+
+// dgamma[c] += sum_b A[b,c,1], dbeta[c] += sum_b A[b,c,0] for up to kAffineMaxSeg blocks whose A arrays lie back to back
+// ([B,C_0,2], [B,C_1,2], ...): ONE launch for the affine gradients of a whole estimator, accumulating straight into the
+// caller's gradient buffers (a thread per channel; launches on one stream are serial, so a plain read-modify-write).
+constexpr int kAffineMaxSeg = 8;
+struct AffineGradParams {
+    const double* A;
+    int B, nseg;
+    int C[kAffineMaxSeg];
+    float* dgamma[kAffineMaxSeg];
+    float* dbeta[kAffineMaxSeg];
+};
+__global__ void __launch_bounds__(128) affine_grads_kernel(const AffineGradParams p) {
+    int c = blockIdx.x * 128 + threadIdx.x;
+    const double* A = p.A;
+    for (int s = 0; s < p.nseg; ++s) {
+        const int C = p.C[s];
+        if (c < C) {
+            double s1 = 0.0, s2 = 0.0;
+            for (int b = 0; b < p.B; ++b) {
+                const double2 v = *reinterpret_cast<const double2*>(A + (static_cast<size_t>(b) * C + c) * 2);
+                s1 += v.x; s2 += v.y;
+            }
+            p.dbeta[s][c] += static_cast<float>(s1);
+            p.dgamma[s][c] += static_cast<float>(s2);
+            return;
+        }
+        c -= C;
+        A += static_cast<size_t>(p.B) * C * 2;
     }
 }
 
@@ -88,18 +119,20 @@ struct NormBwdParams {
     unsigned* amax;         // bits of max |dY|, zeroed by the caller
     int C, Npad, Nvalid;
     float slope;
+    int rows;               // rows of a pair per CTA: 128, or less when B * Npad / 128 CTAs would not fill the machine
 };
 
 __global__ void __launch_bounds__(256) normbwd_reduce_kernel(const NormBwdParams p) {
     extern __shared__ float acc[];           // [2*C]
-    const int b = blockIdx.y, r0 = blockIdx.x * 128;
+    const int b = blockIdx.y, r0 = blockIdx.x * p.rows;
     const int C = p.C, vpr = C / 4;
     for (int i = threadIdx.x; i < 2 * C; i += 256) acc[i] = 0.f;
     __syncthreads();
     const int cols = vpr < 256 ? vpr : 256;              // channel vectors handled side by side
     const int nrg = 256 / cols, rg = threadIdx.x / cols;
     int rows = p.Nvalid - r0;
-    rows = rows > 128 ? 128 : rows;
+    rows = rows > p.rows ? p.rows : rows;
+    if (rows <= 0) return;                               // a tile of padding rows only: nothing to add
     for (int v = threadIdx.x % cols; v < vpr; v += cols) {
         const int c0 = v * 4;
         float a[4], d[4], mu[4], rs[4], a1[4], a2[4];
@@ -110,6 +143,7 @@ __global__ void __launch_bounds__(256) normbwd_reduce_kernel(const NormBwdParams
             a[k] = s2.x; d[k] = s2.y; mu[k] = m2.x; rs[k] = m2.y; a1[k] = 0.f; a2[k] = 0.f;
         }
         const size_t base = (static_cast<size_t>(b) * p.Npad + r0) * C + c0;
+#pragma unroll 4
         for (int r = rg; r < rows; r += nrg) {
             const float4 g4 = __ldg(reinterpret_cast<const float4*>(p.dX + base + static_cast<size_t>(r) * C));
             const float4 y4 = __ldg(reinterpret_cast<const float4*>(p.Y + base + static_cast<size_t>(r) * C));
@@ -130,12 +164,12 @@ __global__ void __launch_bounds__(256) normbwd_reduce_kernel(const NormBwdParams
 }
 
 __global__ void __launch_bounds__(256) normbwd_apply_kernel(const NormBwdParams p) {
-    const int b = blockIdx.y, r0 = blockIdx.x * 128;
+    const int b = blockIdx.y, r0 = blockIdx.x * p.rows;
     const int C = p.C, vpr = C / 4;
     const int cols = vpr < 256 ? vpr : 256;
     const int nrg = 256 / cols, rg = threadIdx.x / cols;
     int rows = p.Nvalid - r0;
-    rows = rows > 128 ? 128 : (rows < 0 ? 0 : rows);
+    rows = rows > p.rows ? p.rows : (rows < 0 ? 0 : rows);
     const double invN = 1.0 / static_cast<double>(p.Nvalid);
     float amax = 0.f;
     for (int v = threadIdx.x % cols; v < vpr; v += cols) {
@@ -152,7 +186,8 @@ __global__ void __launch_bounds__(256) normbwd_apply_kernel(const NormBwdParams 
             k2[k] = static_cast<float>(p.A[ch * 2 + 1] * invN);
         }
         const size_t base = (static_cast<size_t>(b) * p.Npad + r0) * C + c0;
-        for (int r = rg; r < 128; r += nrg) {
+#pragma unroll 4
+        for (int r = rg; r < p.rows; r += nrg) {
             float4 out = make_float4(0.f, 0.f, 0.f, 0.f);                    // padded rows stay zero
             if (r < rows) {
                 const float4 g4 = __ldg(reinterpret_cast<const float4*>(p.dX + base + static_cast<size_t>(r) * C));
@@ -441,11 +476,13 @@ int fepe_mlp32_last_bwd(const float* dlogits, const float* Y, const float* ss, f
     if (!dlogits || !Y || !ss || !W || !dX || !dW || !db || B <= 0 || N <= 0 || Npad < N || (Npad % 128) != 0 || Ci <= 0 ||
         (Co != 1 && Co != 4))
         return FEPE_E_BADARG;
-    dim3 grid(Npad / 128, B);
+    int rows = 128;
+    while (rows > 16 && (Npad / rows) * B < 4 * 148) rows >>= 1;
+    dim3 grid(Npad / rows, B);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const float2* s2 = reinterpret_cast<const float2*>(ss);
-    if (Co == 1) fepe::m32::last_bwd_kernel<1><<<grid, 256, 0, st>>>(dlogits, Y, s2, slope, W, dX, dW, db, N, Npad, Ci);
-    else fepe::m32::last_bwd_kernel<4><<<grid, 256, 0, st>>>(dlogits, Y, s2, slope, W, dX, dW, db, N, Npad, Ci);
+    if (Co == 1) fepe::m32::last_bwd_kernel<1><<<grid, 256, 0, st>>>(dlogits, Y, s2, slope, W, dX, dW, db, N, Npad, Ci, rows);
+    else fepe::m32::last_bwd_kernel<4><<<grid, 256, 0, st>>>(dlogits, Y, s2, slope, W, dX, dW, db, N, Npad, Ci, rows);
     return static_cast<int>(cudaGetLastError());
 }
 
@@ -459,11 +496,30 @@ int fepe_mlp32_normbwd(const float* dX, const float* Y, const float* ss, const f
         (reinterpret_cast<uintptr_t>(dY) & 15u))
         return FEPE_E_BADARG;
     fepe::m32::NormBwdParams p{dX, Y, reinterpret_cast<const float2*>(ss), reinterpret_cast<const float2*>(mean_rstd), gamma,
-                               A, dY, dy_amax, C, Npad, Nvalid, slope};
+                               A, dY, dy_amax, C, Npad, Nvalid, slope, 128};
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    dim3 grid(Npad / 128, B);
+    // Small batches (a training step has 16 pairs per GPU): 128-row CTAs would leave most SMs without work and every
+    // thread with one pair of loads in flight; shrink the row tile until ~4 CTAs per SM exist (>= 32 rows: every CTA
+    // also pays 2 C shared + 2 C global atomics for the statistics).
+    while (p.rows > 32 && (Npad / p.rows) * B < 4 * 148) p.rows >>= 1;
+    dim3 grid(Npad / p.rows, B);
     fepe::m32::normbwd_reduce_kernel<<<grid, 256, 2 * C * sizeof(float), st>>>(p);
     fepe::m32::normbwd_apply_kernel<<<grid, 256, 0, st>>>(p);
+    return static_cast<int>(cudaGetLastError());
+}
+
+int fepe_mlp32_affine_grads(const double* A, int B, int nseg, const int* C, float* const* dgamma, float* const* dbeta,
+                            void* stream) {
+    if (!A || !C || !dgamma || !dbeta || B <= 0 || nseg <= 0 || nseg > fepe::m32::kAffineMaxSeg) return FEPE_E_BADARG;
+    fepe::m32::AffineGradParams p{};
+    p.A = A; p.B = B; p.nseg = nseg;
+    int total = 0;
+    for (int i = 0; i < nseg; ++i) {
+        if (C[i] <= 0 || !dgamma[i] || !dbeta[i]) return FEPE_E_BADARG;
+        p.C[i] = C[i]; p.dgamma[i] = dgamma[i]; p.dbeta[i] = dbeta[i];
+        total += C[i];
+    }
+    fepe::m32::affine_grads_kernel<<<(total + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(p);
     return static_cast<int>(cudaGetLastError());
 }
 

@@ -69,6 +69,7 @@ _SIGNATURES = {
     "fepe_mlp32_normbwd": (_c_i, [_c_p, _c_p, _c_p, _c_p, _c_p, _c_f, _c_p, _c_p, _c_p, _c_i, _c_i, _c_i, _c_i, _c_p]),
     "fepe_mlp32_wgrad": (_c_i, [_c_p, _c_p, _c_p, _c_p, _c_f, _c_p, _c_i, _c_i, _c_i, _c_i, _c_p]),
     "fepe_mlp32_first_bwd": (_c_i, [_c_p, _c_p, _c_p, _c_p, _c_p, _c_i, _c_i, _c_i, _c_i, _c_i, _c_p]),
+    "fepe_mlp32_affine_grads": (_c_i, [_c_p, _c_i, _c_i, _c_p, _c_p, _c_p, _c_p]),
 }
 
 _ERRORS = {-1: "FEPE_E_BADARG (null pointer, misaligned buffer or non-positive size)",

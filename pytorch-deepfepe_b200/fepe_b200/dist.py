@@ -36,19 +36,29 @@ class FlatGradients:
     ``set_to_none=False`` is fine too).  Reference behaviour replaced: nn.DataParallel's reduce of the replica
     gradients onto GPU 0 (deepFEPE/train_good.py:309-314)."""
 
-    def __init__(self, params: Iterable[torch.nn.Parameter], extra_numel: int = 0):
+    ALIGN = 32          # floats: every view starts on a 128-byte boundary (the weight-gradient kernels store 16-byte vectors)
+
+    def __init__(self, params: Iterable[torch.nn.Parameter], extra_numel: int = 0, fuse_accumulation: bool = False):
+        """fuse_accumulation=True additionally marks the parameters as gradient SINKS: backward kernels of the library
+        that accumulate anyway (the weight gradients of the tensor-core MLP: fepe_mlp32_wgrad / _first_bwd / _last_bwd /
+        _affine_grads) then add straight into these views and hand autograd no gradient for them -- no temporary, no
+        `grad += g` kernel per parameter and use (110 of them in a depth-5 DeepFNet step).  Only for training loops that
+        read gradients from .grad after backward() (not torch.autograd.grad, no per-parameter hooks)."""
         self.params = [p for p in params if p.requires_grad]
         if not self.params:
             raise ValueError("FlatGradients: no trainable parameters")
         dev = self.params[0].device
-        n = sum(p.numel() for p in self.params)
-        self.flat = torch.zeros(n + extra_numel, dtype=torch.float32, device=dev)
-        off = 0
+        offs, n = [], 0
         for p in self.params:
             if p.dtype != torch.float32 or p.device != dev:
                 raise ValueError("FlatGradients: parameters must be fp32 on one device")
+            offs.append(n)
+            n += (p.numel() + self.ALIGN - 1) // self.ALIGN * self.ALIGN
+        self.flat = torch.zeros(n + extra_numel, dtype=torch.float32, device=dev)
+        for p, off in zip(self.params, offs):
             p.grad = self.flat[off:off + p.numel()].view_as(p)
-            off += p.numel()
+            if fuse_accumulation:
+                p._fepe_grad_sink = True
         self.extra = self.flat[n:]
         self.numel = n
 

@@ -77,3 +77,34 @@ def pose_loss_from_Rt_loss(Rt_loss: dict, clamp_q: float = 0.1, clamp_t: float =
     q = torch.stack(Rt_loss["q_l2_error_layers_list"])
     t = torch.stack(Rt_loss["t_l2_error_layers_list"])
     return torch.clamp(q, 0.0, clamp_q).mean() * balance_q + torch.clamp(t, 0.0, clamp_t).mean() * balance_t
+
+
+def deepf_training_loss(out_layers: Sequence[torch.Tensor], Ks: torch.Tensor, pts1_virt: torch.Tensor,
+                        pts2_virt: torch.Tensor, delta_Rtijs_4_4: torch.Tensor, qs_cam: torch.Tensor,
+                        ts_cam: torch.Tensor, affine, clamp_at: float = 0.02, clamp_q: float = 0.1,
+                        clamp_t: float = 0.5, balance_q: float = 1.0, balance_t: float = 0.1):
+    """The whole loss of a DeepF training step in ONE launch (and one in the backward pass):
+
+        loss_F   = mean over layers of mean(compute_epi_residual(T1 virt1, T1 virt2, F_i, clamp_at))
+                                                        -- get_all_loss_DeepF, train_good_utils.py:325-364
+        E_i      = K^T T2^T F_i T1 K                    -- :356-358
+        q/t loss = get_Rt_loss(E_layers, ...)           -- :64-295, combined as Train_model_pipeline.py:580-592
+
+    instead of the reference's (and `get_Rt_loss`'s + torch glue's) ~25 small kernels per layer: the head computes E
+    from F, K and the image affine itself (ops.PoseLossFunction / fepe_pose_fwd over every (layer, pair)).
+    out_layers: list (depth) of [B,3,3] (DeepFNet's `out_layers`); pts*_virt [B,V,3] homogeneous PIXEL coordinates;
+    affine = ops.hw_affine(image_size).  Returns (loss, dict) -- the dict holds per-(layer, pair) tensors on the device:
+    q_l2, t_l2, loss_F [L,B] (differentiable) and R_angle, t_angle [L,B] (metrics)."""
+    F = torch.stack(list(out_layers))
+    if not F.is_cuda:
+        raise RuntimeError("fepe_b200.deepf_training_loss needs CUDA tensors: there is no CPU path")
+    B = F.shape[1]
+    dev = F.device
+    q = qs_cam.to(dev, torch.float32).reshape(B, 4)
+    t = ts_cam.to(dev, torch.float32).reshape(B, 3)
+    Rt = delta_Rtijs_4_4.to(dev, torch.float32)
+    q_l2, t_l2, loss_F, out = ops.PoseLossFunction.apply(F.float(), Ks.to(dev, torch.float32), q, t, Rt,
+                                                         pts1_virt.contiguous(), pts2_virt.contiguous(), *affine, clamp_at)
+    loss = (loss_F.mean() + torch.clamp(q_l2, 0.0, clamp_q).mean() * balance_q
+            + torch.clamp(t_l2, 0.0, clamp_t).mean() * balance_t)
+    return loss, {"q_l2": q_l2, "t_l2": t_l2, "loss_F": loss_F, "R_angle": out[..., 23], "t_angle": out[..., 24]}

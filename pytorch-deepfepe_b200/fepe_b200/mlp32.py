@@ -10,6 +10,8 @@ feature tensor.  Output: logits [B, out, N] and, for a one-logit network, the so
 """
 from __future__ import annotations
 
+import ctypes
+
 import weakref
 from typing import Optional, Sequence
 
@@ -220,6 +222,7 @@ class MLP32Function(torch.autograd.Function):
         ctx.dims = (B, N, Npad, cin, cout, affine, n_extras, matches is not None,
                     [1 if e.dim() == 2 else e.shape[2] for e in extras], [tuple(e.shape) for e in extras])
         ctx.saved = (X0, w0, convw, w_last, gam, Ys, sss, mrs)
+        ctx.param_objs = params            # the Parameter objects themselves: the backward may add into their .grad
         return logits
 
     @staticmethod
@@ -235,12 +238,24 @@ class MLP32Function(torch.autograd.Function):
             # every accumulated output of the pass (dW of all layers, conv-bias zeros, A sums, max |dY|) comes out of TWO
             # zero-filled allocations: the step is launch-bound at training batch sizes
             wsz = [64 * cin] + [_CH[i] * _CH[i - 1] for i in range(1, 5)] + [cout * 256, cout]
-            fz = torch.zeros(sum(wsz) + sum(_CH), dtype=torch.float32, device=dev)
+            fz = torch.zeros(sum(wsz) + 3 * sum(_CH), dtype=torch.float32, device=dev)
             woff = [0]
             for n in wsz:
                 woff.append(woff[-1] + n)
-            dWs = [fz[woff[i]:woff[i + 1]] for i in range(7)]
-            bz, boff = fz[woff[7]:], 0
+
+            def sink(k):
+                """.grad of parameter k when its owner asked for fused accumulation (dist.FlatGradients), else None."""
+                prm = ctx.param_objs[k]
+                g = prm.grad if getattr(prm, "_fepe_grad_sink", False) else None
+                if g is None or g.dtype != torch.float32 or g.device != dev or not g.is_contiguous() or g.data_ptr() % 16:
+                    return None
+                return g
+
+            widx = [0, 4, 8, 12, 16, 20, 21]                          # parameter index of dWs[0..6]
+            wsink = [sink(k) for k in widx]
+            dWs = [wsink[i].view(-1) if wsink[i] is not None else fz[woff[i]:woff[i + 1]] for i in range(7)]
+            bz, boff = fz[woff[7]:woff[7] + sum(_CH)], 0
+            gz = fz[woff[7] + sum(_CH):]                              # dgamma | dbeta of the five blocks (no sink)
             Az = torch.zeros(2 * B * sum(_CH) + 8, dtype=torch.float64, device=dev)
             amax = Az[2 * B * sum(_CH):].view(torch.int32)            # 16 int32 slots (bits of max |dY| per layer)
             aoff = [0]
@@ -252,7 +267,8 @@ class MLP32Function(torch.autograd.Function):
             _lib.check(lib.fepe_mlp32_last_bwd(dl.data_ptr(), Ys[4].data_ptr(), sss[4].data_ptr(), SLOPE, w_last.data_ptr(),
                                                dX.data_ptr(), dwl.data_ptr(), dbl.data_ptr(), B, N, Npad, 256, cout, st),
                        "fepe_mlp32_last_bwd")
-            grads[20], grads[21] = dwl.reshape(cout, 256, 1), dbl
+            grads[20] = dwl.reshape(cout, 256, 1) if wsink[5] is None else None
+            grads[21] = dbl if wsink[6] is None else None
             dX0 = None
             for i in range(4, -1, -1):
                 c = _CH[i]
@@ -262,7 +278,8 @@ class MLP32Function(torch.autograd.Function):
                 _lib.check(lib.fepe_mlp32_normbwd(dX.data_ptr(), Ys[i].data_ptr(), sss[i].data_ptr(), mrs[i].data_ptr(),
                                                   gam[i].data_ptr(), SLOPE, A.data_ptr(), dY.data_ptr(), am.data_ptr(),
                                                   B, Npad, N, c, st), "fepe_mlp32_normbwd")
-                grads[4 * i + 1] = bz[boff:boff + c]               # conv bias before InstanceNorm: exactly zero gradient
+                if sink(4 * i + 1) is None:
+                    grads[4 * i + 1] = bz[boff:boff + c]           # conv bias before InstanceNorm: exactly zero gradient
                 boff += c
                 if i > 0:
                     ci = _CH[i - 1]
@@ -270,7 +287,7 @@ class MLP32Function(torch.autograd.Function):
                     _lib.check(lib.fepe_mlp32_wgrad(dY.data_ptr(), am.data_ptr(), Ys[i - 1].data_ptr(),
                                                     sss[i - 1].data_ptr(), SLOPE, dW.data_ptr(), M, Npad, c, ci, st),
                                "fepe_mlp32_wgrad")
-                    grads[4 * i] = dW.reshape(c, ci, 1)
+                    grads[4 * i] = dW.reshape(c, ci, 1) if wsink[i] is None else None
                     thi, tlo, tsc = split_param_cached(lib, convw[i], c, ci, True, st)   # [ci, c]: the data-gradient "weight"
                     dXn = torch.empty(M, ci, dtype=torch.float32, device=dev)
                     _lib.check(lib.fepe_mlp32_gemm(dY.data_ptr(), None, 1.0, am.data_ptr(), thi.data_ptr(), tlo.data_ptr(),
@@ -284,11 +301,21 @@ class MLP32Function(torch.autograd.Function):
                     _lib.check(lib.fepe_mlp32_first_bwd(dY.data_ptr(), X0.data_ptr(), w0.data_ptr(),
                                                         dX0.data_ptr() if dX0 is not None else None, dW.data_ptr(), B, N,
                                                         Npad, cin, 64, st), "fepe_mlp32_first_bwd")
-                    grads[0] = dW.reshape(64, cin, 1)
-            # dgamma = sum_b A2, dbeta = sum_b A1 for all five blocks
+                    grads[0] = dW.reshape(64, cin, 1) if wsink[0] is None else None
+            # dgamma = sum_b A2, dbeta = sum_b A1 for all five blocks: one launch, accumulating into the sinks or into fz
+            dgs, dbs, goff = [], [], 0
             for i in range(5):
-                Asum = Az[aoff[i]:aoff[i + 1]].view(B, _CH[i], 2).sum(0).float()
-                grads[4 * i + 2], grads[4 * i + 3] = Asum[:, 1], Asum[:, 0]
+                sg, sb = sink(4 * i + 2), sink(4 * i + 3)
+                dg = sg if sg is not None else gz[goff:goff + _CH[i]]
+                db_ = sb if sb is not None else gz[goff + _CH[i]:goff + 2 * _CH[i]]
+                goff += 2 * _CH[i]
+                dgs.append(dg); dbs.append(db_)
+                grads[4 * i + 2] = dg if sg is None else None
+                grads[4 * i + 3] = db_ if sb is None else None
+            _lib.check(lib.fepe_mlp32_affine_grads(Az.data_ptr(), B, 5, (ctypes.c_int * 5)(*_CH),
+                                                   (ctypes.c_void_p * 5)(*[t.data_ptr() for t in dgs]),
+                                                   (ctypes.c_void_p * 5)(*[t.data_ptr() for t in dbs]), st),
+                       "fepe_mlp32_affine_grads")
         # route the input gradient back to the channel groups
         gm, ge, off = None, [None] * n_extras, 0
         if has_m:

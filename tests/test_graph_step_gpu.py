@@ -73,3 +73,38 @@ def test_graphed_training_step_matches_eager(path):
         with torch.no_grad():
             for prm in net.parameters():
                 prm.mul_(1.05)
+
+
+def test_fused_gradient_accumulation_matches_autograd_accumulation():
+    """FlatGradients(fuse_accumulation=True): the MLP's weight-gradient kernels add straight into the .grad views (no
+    temporary, no `grad += g` per parameter and use).  Same gradients as the plain autograd accumulation, including for
+    the update network that is evaluated depth-1 times per step, and a second backward keeps accumulating."""
+    torch.manual_seed(5)
+    net = DeepFNet(**MODEL_KW).cuda()
+    d = synth.make_batch(4, 512, seed=21)
+    x, p1v, p2v = T(d["matches_xy_ori"]).cuda(), T(d["pts1_virt"]).cuda(), T(d["pts2_virt"]).cuda()
+
+    def run():
+        outs = net({"matches_xy_ori": x})
+        T1 = outs["T1"]
+        p1 = (T1 @ p1v.transpose(1, 2)).transpose(1, 2)
+        p2 = (T1 @ p2v.transpose(1, 2)).transpose(1, 2)
+        loss = sum(O.epi_residual(p1, p2, Fo, 0.02).mean() for Fo in outs["out_layers"]) / len(outs["out_layers"])
+        loss.backward()
+
+    plain = FlatGradients(net.parameters())
+    run()
+    g_plain = plain.flat.clone()
+    fused = FlatGradients(net.parameters(), fuse_accumulation=True)
+    assert all(getattr(p, "_fepe_grad_sink", False) for p in net.parameters())
+    run()
+    g_fused = fused.flat.clone()
+    assert fused.check_views()
+    assert float(g_fused.abs().sum()) > 0
+    rel = float((g_fused - g_plain).norm() / g_plain.norm())
+    assert rel < 1e-4, rel
+    run()                                                      # accumulation: twice the gradient
+    rel2 = float((fused.flat - 2 * g_plain).norm() / (2 * g_plain.norm()))
+    assert rel2 < 1e-4, rel2
+    for p in net.parameters():                                 # views start on 128-byte boundaries (16-byte vector stores)
+        assert p.grad.data_ptr() % 128 == 0

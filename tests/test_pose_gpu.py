@@ -166,3 +166,40 @@ def test_get_Rt_loss_mirror_matches_oracle_values_and_gradient(golden):
     for a, b in zip(ours, ref_in):
         rel = float((a.grad.cpu().double() - b.grad).norm() / b.grad.norm().clamp_min(1e-30))
         assert rel < 2e-3, rel
+
+
+def test_deepf_training_loss_equals_the_unfused_composition():
+    """losses.deepf_training_loss (one launch: F-loss on the virtual points + E = K^T T2^T F T1 K + q/t errors) against the
+    composition the reference's trainer makes of get_all_loss_DeepF / get_Rt_loss (torch glue + losses.get_Rt_loss):
+    same loss, same gradient w.r.t. every layer's F."""
+    import torch
+    from fepe_b200 import losses, ops, synth
+    from oracle import fepe_oracle as O
+    d = synth.make_batch(6, 300, seed=77)
+    Tn = lambda k: torch.from_numpy(d[k]).cuda()
+    aff = ops.hw_affine(d["image_size"])
+    torch.manual_seed(1)
+    ax, bx, ay, by = aff
+    Tinv = torch.linalg.inv(torch.tensor([[ax, 0, bx], [0, ay, by], [0, 0, 1]], device="cuda", dtype=torch.float64))
+    base = Tinv.T @ Tn("F_gt").double() @ Tinv                  # the pixel-space F_gt in DeepFNet's (H, W)-normalised frame
+    base = (base / base.flatten(1).norm(dim=1).view(-1, 1, 1)).float()
+    # small perturbations: most virtual points stay below the clamp, so the F-loss has a gradient
+    layers = [(base + 0.002 * (l + 1) * torch.randn_like(base)).requires_grad_(True) for l in range(3)]
+    Ks, Rt, q, t = Tn("Ks"), Tn("delta_Rtijs_4_4"), Tn("q_cam"), Tn("t_cam")
+    v1, v2 = Tn("pts1_virt"), Tn("pts2_virt")
+    loss_f, parts = losses.deepf_training_loss(layers, Ks, v1, v2, Rt, q, t, aff, clamp_at=0.02)
+    g_f = torch.autograd.grad(loss_f, layers)
+    # unfused: T1 = T2 = the image affine as a matrix
+    T1 = torch.tensor([[ax, 0, bx], [0, ay, by], [0, 0, 1]], device="cuda").expand(6, 3, 3)
+    p1 = (T1 @ v1.transpose(1, 2)).transpose(1, 2)
+    p2 = (T1 @ v2.transpose(1, 2)).transpose(1, 2)
+    loss_F = sum(O.epi_residual(p1, p2, Fo, 0.02).mean() for Fo in layers) / len(layers)
+    TK = T1 @ Ks
+    E_layers = [TK.transpose(1, 2) @ Fo @ TK for Fo in layers]
+    rt = losses.get_Rt_loss(E_layers, None, None, None, Rt, q, t)
+    loss_u = loss_F + losses.pose_loss_from_Rt_loss(rt)
+    g_u = torch.autograd.grad(loss_u, layers)
+    assert abs(float(loss_f) - float(loss_u)) < 2e-5 * abs(float(loss_u)) + 1e-7
+    for a, b in zip(g_f, g_u):
+        assert float((a - b).norm() / b.norm()) < 2e-3
+    assert parts["q_l2"].shape == (3, 6) and parts["R_angle"].shape == (3, 6)
