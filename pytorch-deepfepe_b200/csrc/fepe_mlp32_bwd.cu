@@ -542,7 +542,9 @@ int fepe_mlp32_wgrad(const float* dY, const unsigned* dy_amax, const float* Ypre
         return FEPE_E_BADARG;
     const int bn = (Ci % 128 == 0) ? 128 : 64;
     const int tiles = (Co / 128) * (Ci / bn);
-    int slabs = (296 + tiles - 1) / tiles;                    // ~2 waves of 148 SMs: every slab pays a prologue and 128 x BN reductions
+    // 2 waves of 148 SMs, never a CTA more (a third, nearly empty wave cost 1.4x on the 1024 -> 512 layer: 320 CTAs);
+    // every slab pays a prologue and 128 x BN reductions
+    int slabs = 296 / tiles;
     const int max_slabs = M / 64;
     if (slabs > max_slabs) slabs = max_slabs;
     if (slabs < 1) slabs = 1;
