@@ -24,6 +24,7 @@
 
 #include "../../include/fepe_b200.h"
 #include "fepe_common.cuh"
+#include "fepe_dispatch.cuh"
 #include "fepe_split.cuh"
 #include "fepe_umma.cuh"
 
@@ -263,7 +264,8 @@ __global__ void __launch_bounds__(128) first_bwd_kernel(const float* __restrict_
 // 16 warps: 0 = TMA producer, 1 = MMA issuer, 2 = TMEM allocator, 4-7 = epilogue, 8.. = transform (one thread per
 // (group, row)).
 constexpr int kWgThreads = 512;
-constexpr int kWgStages = 3;
+// pipeline depth by tile width: a stage is (2 + BN / 64) groups of 16 KB
+template <int BN> struct WgStages { static constexpr int value = (BN == 256) ? 2 : 3; };
 constexpr int kGroupBytes = 64 * 64 * 4;      // 16 KB
 
 __device__ __forceinline__ uint64_t umma_desc_mn_sw128_g(const void* smem_ptr) {
@@ -286,6 +288,7 @@ __global__ void __launch_bounds__(kWgThreads, 1)
 fepe_mlp32_wgrad_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_constant__ CUtensorMap map_x,
                         const WgradParams p) {
     constexpr int G = 2 + BN / 64;
+    constexpr int kWgStages = WgStages<BN>::value;
     constexpr int kStageBytes = G * kGroupBytes;
     constexpr int kSsBytes = BN * 8;
     extern __shared__ __align__(1024) unsigned char smem_raw[];
@@ -320,6 +323,56 @@ fepe_mlp32_wgrad_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid
     __syncthreads();
     tcgen05_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+
+    // ---------------- transform: one thread per (group, row) of a stage ----------------
+    // 2 G warps: warps 8..15 take groups 0..3; at BN = 256 the four epilogue warps (idle until the last k-block) take
+    // groups 4 and 5 before they turn to the accumulator.
+    auto transform = [&](const int tt) {
+        const int g = tt >> 6, row = tt & 63;
+        const int sw = row & 7;
+        const bool is_dy = g < 2;
+        const float dy_scale = pow2_scale(__ldg(p.dy_amax));
+        const float slope = p.slope;
+        for (int kb = 0; kb < num_kb; ++kb) {
+            const int s = kb % kWgStages;
+            const uint32_t ph = static_cast<uint32_t>(kb / kWgStages) & 1u;
+            mbar_wait(&full[s], ph);
+            unsigned char* a0 = smem + s * kStageBytes + g * kGroupBytes + row * 128;
+            unsigned char* a1 = a0 + kGroupBytes / 2;
+            float v[64];
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+                const float4 t0 = *reinterpret_cast<const float4*>(a0 + ((c ^ sw) << 4));
+                const float4 t1 = *reinterpret_cast<const float4*>(a1 + ((c ^ sw) << 4));
+                v[4 * c + 0] = t0.x; v[4 * c + 1] = t0.y; v[4 * c + 2] = t0.z; v[4 * c + 3] = t0.w;
+                v[32 + 4 * c + 0] = t1.x; v[32 + 4 * c + 1] = t1.y; v[32 + 4 * c + 2] = t1.z; v[32 + 4 * c + 3] = t1.w;
+            }
+            if (is_dy) {
+#pragma unroll
+                for (int q = 0; q < 64; ++q) v[q] *= dy_scale;
+            } else {
+                const float4* cf = reinterpret_cast<const float4*>(ss_ring + s * kSsBytes) + (g - 2) * 32;
+#pragma unroll
+                for (int q = 0; q < 32; ++q) {
+                    const float4 c4 = cf[q];
+                    const float t0 = fmaf(v[2 * q], c4.x, c4.y), t1 = fmaf(v[2 * q + 1], c4.z, c4.w);
+                    v[2 * q] = fmaxf(t0, slope * t0);
+                    v[2 * q + 1] = fmaxf(t1, slope * t1);
+                }
+            }
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+                uint32_t h[4], l[4];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) split2(v[8 * c + 2 * q], v[8 * c + 2 * q + 1], h[q], l[q]);
+                *reinterpret_cast<uint4*>(a0 + ((c ^ sw) << 4)) = make_uint4(h[0], h[1], h[2], h[3]);
+                *reinterpret_cast<uint4*>(a1 + ((c ^ sw) << 4)) = make_uint4(l[0], l[1], l[2], l[3]);
+            }
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&ready[s]);
+        }
+    };
 
     if (warp == 0) {
         if (lane == 0) {
@@ -369,54 +422,10 @@ fepe_mlp32_wgrad_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid
             }
             __syncwarp();
         }
-    } else if (warp >= 8 && warp < 8 + 2 * G) {
-        // ---------------- transform: one thread per (group, row) ----------------
-        const int tt = static_cast<int>(threadIdx.x) - 256;
-        const int g = tt >> 6, row = tt & 63;
-        const int sw = row & 7;
-        const bool is_dy = g < 2;
-        const float dy_scale = pow2_scale(__ldg(p.dy_amax));
-        const float slope = p.slope;
-        for (int kb = 0; kb < num_kb; ++kb) {
-            const int s = kb % kWgStages;
-            const uint32_t ph = static_cast<uint32_t>(kb / kWgStages) & 1u;
-            mbar_wait(&full[s], ph);
-            unsigned char* a0 = smem + s * kStageBytes + g * kGroupBytes + row * 128;
-            unsigned char* a1 = a0 + kGroupBytes / 2;
-            float v[64];
-#pragma unroll
-            for (int c = 0; c < 8; ++c) {
-                const float4 t0 = *reinterpret_cast<const float4*>(a0 + ((c ^ sw) << 4));
-                const float4 t1 = *reinterpret_cast<const float4*>(a1 + ((c ^ sw) << 4));
-                v[4 * c + 0] = t0.x; v[4 * c + 1] = t0.y; v[4 * c + 2] = t0.z; v[4 * c + 3] = t0.w;
-                v[32 + 4 * c + 0] = t1.x; v[32 + 4 * c + 1] = t1.y; v[32 + 4 * c + 2] = t1.z; v[32 + 4 * c + 3] = t1.w;
-            }
-            if (is_dy) {
-#pragma unroll
-                for (int q = 0; q < 64; ++q) v[q] *= dy_scale;
-            } else {
-                const float4* cf = reinterpret_cast<const float4*>(ss_ring + s * kSsBytes) + (g - 2) * 32;
-#pragma unroll
-                for (int q = 0; q < 32; ++q) {
-                    const float4 c4 = cf[q];
-                    const float t0 = fmaf(v[2 * q], c4.x, c4.y), t1 = fmaf(v[2 * q + 1], c4.z, c4.w);
-                    v[2 * q] = fmaxf(t0, slope * t0);
-                    v[2 * q + 1] = fmaxf(t1, slope * t1);
-                }
-            }
-#pragma unroll
-            for (int c = 0; c < 8; ++c) {
-                uint32_t h[4], l[4];
-#pragma unroll
-                for (int q = 0; q < 4; ++q) split2(v[8 * c + 2 * q], v[8 * c + 2 * q + 1], h[q], l[q]);
-                *reinterpret_cast<uint4*>(a0 + ((c ^ sw) << 4)) = make_uint4(h[0], h[1], h[2], h[3]);
-                *reinterpret_cast<uint4*>(a1 + ((c ^ sw) << 4)) = make_uint4(l[0], l[1], l[2], l[3]);
-            }
-            fence_proxy_async();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&ready[s]);
-        }
+    } else if (warp >= 8 && warp < 8 + (2 * G < 8 ? 2 * G : 8)) {
+        transform(static_cast<int>(threadIdx.x) - 256);
     } else if (warp >= 4 && warp < 8 && num_kb > 0) {
+        if constexpr (2 * G > 8) transform(256 + static_cast<int>(threadIdx.x) - 128);
         const int q = warp & 3;
         const int row = q * 32 + lane;                         // output row = channel co0 + row
         const float inv = 1.f / pow2_scale(__ldg(p.dy_amax));
@@ -451,7 +460,7 @@ static int launch_wgrad(const float* dY, const float* X, const WgradParams& p, i
     if (!make_map_2d(&my, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, dY, p.M, p.Co, 32, 64) ||
         !make_map_2d(&mx, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, X, p.M, p.Ci, 32, 64))
         return FEPE_E_NODEVICE;
-    constexpr int smem = kWgStages * ((2 + BN / 64) * kGroupBytes + BN * 8) + 256 + 1024;
+    constexpr int smem = WgStages<BN>::value * ((2 + BN / 64) * kGroupBytes + BN * 8) + 256 + 1024;
     static_assert(smem <= 232448, "stage ring does not fit");
     static bool configured[64] = {false};                 // the attribute is per device
     int dev = 0;
@@ -540,7 +549,10 @@ int fepe_mlp32_wgrad(const float* dY, const unsigned* dy_amax, const float* Ypre
         (reinterpret_cast<uintptr_t>(dY) & 15u) || (reinterpret_cast<uintptr_t>(Yprev) & 15u) ||
         (reinterpret_cast<uintptr_t>(dW) & 15u) || !(slope >= 0.f && slope <= 1.f))
         return FEPE_E_BADARG;
-    const int bn = (Ci % 128 == 0) ? 128 : 64;
+    // 128 x 256 tiles where the layer allows it: the dY tile is split once per 256 instead of 128 input channels, which
+    // takes the operand transform (both operands are fp32 in memory) off the critical path of the tensor pipe
+    const int wide = fepe::dispatch_get(FEPE_DISPATCH_WGRAD);                  // 0 automatic | 1 never | 2 whenever possible
+    const int bn = (Ci % 256 == 0 && wide != 1) ? 256 : (Ci % 128 == 0) ? 128 : 64;
     const int tiles = (Co / 128) * (Ci / bn);
     // 2 waves of 148 SMs, never a CTA more (a third, nearly empty wave cost 1.4x on the 1024 -> 512 layer: 320 CTAs);
     // every slab pays a prologue and 128 x BN reductions
@@ -552,7 +564,9 @@ int fepe_mlp32_wgrad(const float* dY, const unsigned* dy_amax, const float* Ypre
     slabs = (M + rows_per_slab - 1) / rows_per_slab;
     fepe::m32::WgradParams p{M, Co, Ci, Npad, rows_per_slab, ss_prev, slope, dy_amax, dW};
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    return bn == 128 ? fepe::m32::launch_wgrad<128>(dY, Yprev, p, slabs, st) : fepe::m32::launch_wgrad<64>(dY, Yprev, p, slabs, st);
+    return bn == 256   ? fepe::m32::launch_wgrad<256>(dY, Yprev, p, slabs, st)
+           : bn == 128 ? fepe::m32::launch_wgrad<128>(dY, Yprev, p, slabs, st)
+                       : fepe::m32::launch_wgrad<64>(dY, Yprev, p, slabs, st);
 }
 
 }  // extern "C"

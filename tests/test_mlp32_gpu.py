@@ -258,10 +258,15 @@ def test_normbwd_matches_fp64_autograd():
         assert abs(got_max - float(dY.abs().max())) <= 1e-6 * got_max
 
 
+@pytest.mark.parametrize("tile", ["128", "256"])
 @pytest.mark.parametrize("B,N,Co,Ci", [(1, 128, 128, 64), (2, 1000, 1024, 128), (64, 1000, 512, 1024), (4, 1000, 256, 512),
-                                       (2, 300, 128, 64)])
-def test_wgrad_matches_fp64(B, N, Co, Ci):
-    """dW = dY^T LeakyReLU(a Yprev + d) on tcgen05 with both operands MN-major, split into fp16 pairs in place."""
+                                       (2, 300, 128, 64), (16, 1000, 128, 256), (1, 128, 256, 768)])
+def test_wgrad_matches_fp64(B, N, Co, Ci, tile, dispatch):
+    """dW = dY^T LeakyReLU(a Yprev + d) on tcgen05 with both operands MN-major, split into fp16 pairs in place; 128 x 128
+    / 128 x 64 output tiles and, where Ci % 256 == 0, 128 x 256 (the automatic choice)."""
+    if tile == "256" and Ci % 256:
+        pytest.skip("128 x 256 tiles need Ci % 256 == 0")
+    dispatch("wgrad", tile)
     lib = _lib.lib()
     torch.manual_seed(7)
     Npad = (N + 127) // 128 * 128
