@@ -820,7 +820,9 @@ def c5_measure(args, dev, rank, world, steps: int, warm: int, mlp: str) -> dict:
     net = DeepFNet(depth=5, image_size=list(synth.KITTI_IMAGE_SIZE), if_quality=True, quality_size=1).cuda()
     net.set_mlp_path(mlp)
     # configs/kitti_corr_baseline.yaml:62; fused=True: torch's own single-kernel Adam over all 44 parameters
-    opt = torch.optim.Adam(net.parameters(), lr=1e-4, fused=True)
+    # (capturable: its step can be replayed as a CUDA graph as well, see below)
+    opt = torch.optim.Adam(net.parameters(), lr=1e-4, fused=True, capturable=not args.no_graph)
+    adam_graph = [None]
     # gradients of all parameters are views of ONE buffer, and the MLP's weight-gradient kernels add straight into them
     flat = fdist.FlatGradients(net.parameters(), fuse_accumulation=True)
     aff = fops.hw_affine(synth.KITTI_IMAGE_SIZE)
@@ -875,7 +877,10 @@ def c5_measure(args, dev, rank, world, steps: int, warm: int, mlp: str) -> dict:
         ev[3].record()
         flat.allreduce_mean_()
         ev[4].record()
-        opt.step()
+        if adam_graph[0] is not None:
+            adam_graph[0].replay()
+        else:
+            opt.step()
         ev[5].record()
         return ev
 
@@ -891,11 +896,23 @@ def c5_measure(args, dev, rank, world, steps: int, warm: int, mlp: str) -> dict:
             flat.zero_()
             capturing[0] = True
             graphed[0] = GraphedStep(fwd_bwd, (mt0["xs"], mt0["quality"]))
-            launch = "forward + losses + backward replayed as one CUDA graph (fepe_b200.graphs.GraphedStep); matcher, all-reduce, Adam eager"
+            launch = "forward + losses + backward replayed as one CUDA graph (fepe_b200.graphs.GraphedStep); matcher, all-reduce eager"
         except Exception as e:                                 # noqa: BLE001
             graphed[0] = None
             launch = f"eager (graph capture failed: {type(e).__name__}: {str(e)[:120]})"
         capturing[0] = False
+        if graphed[0] is not None:
+            # torch's own fused Adam step as a second graph (its state exists: the warm-up steps ran it eagerly)
+            try:
+                torch.cuda.synchronize()
+                ga = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(ga):
+                    opt.step()
+                adam_graph[0] = ga
+                launch += "; Adam (torch, fused + capturable) replayed as a second graph"
+            except Exception as e:                             # noqa: BLE001
+                adam_graph[0] = None
+                launch += f"; Adam eager ({type(e).__name__})"
         for _ in range(2):
             step()
         torch.cuda.synchronize()
