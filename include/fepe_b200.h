@@ -48,6 +48,7 @@ const char* fepe_version(void);
  *   FEPE_DISPATCH_MLP_GEMM   0 by size | 1 one tile per CTA | 2 persistent kernel with 128-column tiles (bf16 path)
  *   FEPE_DISPATCH_MLP_FUSE   0 default | 2 fused-norm variant with 8 transform warps (bf16 path)
  *   FEPE_DISPATCH_WGRAD      0 by shape | 1 weight-gradient GEMM tiles of at most 128 x 128 | 2 128 x 256 where Ci % 256 == 0
+ *   FEPE_DISPATCH_NN_DIST    0 by shape | 1 descriptor distances on CUDA cores (plain fp32) | 2 on tcgen05 (split fp16)
  * A forced variant that cannot run the problem falls back to the automatic choice.  Returns the previous value, or
  * FEPE_E_BADARG. */
 #define FEPE_DISPATCH_FIT       0
@@ -55,7 +56,8 @@ const char* fepe_version(void);
 #define FEPE_DISPATCH_MLP_GEMM  2
 #define FEPE_DISPATCH_MLP_FUSE  3
 #define FEPE_DISPATCH_WGRAD     4
-#define FEPE_DISPATCH_COUNT     5
+#define FEPE_DISPATCH_NN_DIST   5
+#define FEPE_DISPATCH_COUNT     6
 int fepe_set_dispatch(int which, int value);
 
 /* Diagnostics of the split pipeline (throughput path of fepe_fit_fwd): while `buf` (device memory, 32 bytes per record)

@@ -18,6 +18,7 @@ RECOVER_OUT_FLOATS = 24     # FEPE_RECOVER_OUT_FLOATS
 GT_FLOATS = 32              # FEPE_GT_FLOATS
 
 DISPATCH_FIT, DISPATCH_GRAM_TEAM, DISPATCH_MLP_GEMM, DISPATCH_MLP_FUSE, DISPATCH_WGRAD = 0, 1, 2, 3, 4   # FEPE_DISPATCH_*
+DISPATCH_NN_DIST = 5
 
 _lib = None
 
@@ -104,7 +105,8 @@ _DISPATCH_KEYS = {"fit": (DISPATCH_FIT, {"auto": 0, "small": 1, "ring": 2, "spli
                   "gram_team": (DISPATCH_GRAM_TEAM, {"auto": 0, "1": 1, "2": 2, "4": 3}),
                   "mlp_gemm": (DISPATCH_MLP_GEMM, {"auto": 0, "persist": 0, "tile": 1, "persist128": 2}),
                   "mlp_fuse": (DISPATCH_MLP_FUSE, {"auto": 0, "1": 0, "2": 2}),
-                  "wgrad": (DISPATCH_WGRAD, {"auto": 0, "128": 1, "256": 2})}
+                  "wgrad": (DISPATCH_WGRAD, {"auto": 0, "128": 1, "256": 2}),
+                  "nn_dist": (DISPATCH_NN_DIST, {"auto": 0, "simt": 1, "tc": 2})}
 
 
 def set_dispatch(key: str, value) -> int:

@@ -3,9 +3,10 @@ import os, sys, time
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path[:0] = [ROOT, os.path.join(ROOT, "pytorch-deepfepe_b200")]
 import numpy as np, torch
-from fepe_b200 import ops
+from fepe_b200 import ops, _lib
 from oracle import nn_match_oracle as NO
-for B, N in [(16, 1000), (128, 1000), (128, 2000)]:
+for kern, B, N in [(k, b, n) for (b, n) in [(16, 1000), (16, 1200), (128, 1000), (128, 2000)] for k in ("simt", "tc")]:
+    _lib.set_dispatch("nn_dist", kern)
     g = torch.Generator(device="cuda").manual_seed(0)
     d1 = torch.nn.functional.normalize(torch.randn(B, N, 256, device="cuda", generator=g), dim=2)
     d2 = torch.nn.functional.normalize(d1[:, torch.randperm(N, device="cuda")] + 0.02 * torch.randn(B, N, 256, device="cuda", generator=g), dim=2)
@@ -24,5 +25,5 @@ for B, N in [(16, 1000), (128, 1000), (128, 2000)]:
     for _ in range(3):
         NO.nn_match_two_way(a, b, 1.0)
     cpu = (time.perf_counter() - t0) / 3
-    print(f"fepe_nn_match B={B} N1=N2={N} D=256: {us:9.1f} us = {fl/us/1e6:6.1f} TFLOP/s fp32, {B/us*1e6:9.0f} pairs/s, "
+    print(f"fepe_nn_match[{kern}] B={B} N1=N2={N} D=256: {us:9.1f} us = {fl/us/1e6:6.1f} TFLOP/s algorithmic, {B/us*1e6:9.0f} pairs/s, "
           f"matches/pair {float(out[3].float().mean()):.0f} | numpy on the host: {cpu*1e3:7.2f} ms per pair", flush=True)

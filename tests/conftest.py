@@ -78,12 +78,13 @@ def dispatch():
     back on automatic when the test ends.  Usage: dispatch("fit", "split"), dispatch("mlp_gemm", "tile"), ..."""
     from fepe_b200 import _lib
     which = {"fit": _lib.DISPATCH_FIT, "gram_team": _lib.DISPATCH_GRAM_TEAM, "mlp_gemm": _lib.DISPATCH_MLP_GEMM,
-             "mlp_fuse": _lib.DISPATCH_MLP_FUSE, "wgrad": _lib.DISPATCH_WGRAD}
+             "mlp_fuse": _lib.DISPATCH_MLP_FUSE, "wgrad": _lib.DISPATCH_WGRAD, "nn_dist": _lib.DISPATCH_NN_DIST}
     values = {"fit": {"auto": 0, "small": 1, "ring": 2, "split": 3},
               "gram_team": {"auto": 0, "1": 1, "2": 2, "4": 3},
               "mlp_gemm": {"auto": 0, "persist": 0, "tile": 1, "persist128": 2},
               "mlp_fuse": {"auto": 0, "1": 0, "2": 2},
-              "wgrad": {"auto": 0, "128": 1, "256": 2}}
+              "wgrad": {"auto": 0, "128": 1, "256": 2},
+              "nn_dist": {"auto": 0, "simt": 1, "tc": 2}}
     touched = set()
 
     def force(key, value):
