@@ -62,9 +62,9 @@ def test_bit_exact_on_exactly_representable_descriptors(B, N1, N2, thresh, dist_
 
 def test_generic_unit_descriptors_agree_up_to_rounding_ties(dist_kernel):
     # scores: fp32 CUDA cores differ from numpy by summation order only (2e-6 on the distance); the tensor-core kernel
-    # adds the split's 2^-22 per product and the tensor memory's truncating accumulation (~1.5e-6 on a dot product near
-    # 1, i.e. 3e-6 on a distance of 0.45)
-    score_tol = 2e-6 if dist_kernel == "simt" else 8e-6
+    # adds the split's 3e-8 and the tensor memory's truncating accumulation (~1.5e-6 on a dot product near 1, which
+    # sqrt(2 - 2 dot) magnifies to ~7e-6 on a distance of 0.3: CPU emulation of the arithmetic)
+    score_tol = 2e-6 if dist_kernel == "simt" else 2e-5
     rng = np.random.default_rng(5)
     B, N1, N2, D = 2, 800, 900, 256
     d1 = rng.normal(size=(B, N1, D)).astype(np.float32)
