@@ -30,8 +30,6 @@ nature).
 from __future__ import annotations
 
 import argparse
-import contextlib
-import io
 import json
 import os
 import statistics
