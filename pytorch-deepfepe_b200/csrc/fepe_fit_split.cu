@@ -84,6 +84,10 @@ __global__ void __launch_bounds__(kGramThreads, 1) fepe_gram_kernel(const FitPar
     constexpr int G = kGramConsumerWarps / T;              // teams (= ring consumers)
     const unsigned long long t_begin = trace_now();
     uint64_t* full = reinterpret_cast<uint64_t*>(smem + p.ring.bar_off);
+    // use counter per stage (second half of the barrier block): the refilling team announces "use k of this stage is on
+    // its way" BEFORE the waiter may trust the barrier's parity -- a parity wait alone cannot tell use k from use k-2, and
+    // nothing else stops a fast team from reaching a stage two uses early (tests/test_gram_ring_protocol.py)
+    volatile int* use_cnt = reinterpret_cast<volatile int*>(full + kMaxStages);
     double* gram_w = reinterpret_cast<double*>(smem + p.ring.scratch_off);             // [16][36]
     float* red = reinterpret_cast<float*>(gram_w + kGramConsumerWarps * 36);           // [16][8]
     const int N = p.N;
@@ -97,12 +101,13 @@ __global__ void __launch_bounds__(kGramThreads, 1) fepe_gram_kernel(const FitPar
         const size_t pair = static_cast<size_t>(blockIdx.x) + static_cast<size_t>(j) * gridDim.x;
         unsigned char* sb = smem + static_cast<size_t>(stage) * p.ring.stage_bytes;
         const bool wb = ring_row_is_bulk(p.weights, pair, N);
+        use_cnt[stage] = j / S + 1;
         mbar_arrive_expect_tx(&full[stage], pts_bytes + (wb ? static_cast<uint32_t>(N) * 4u : 0u));
         bulk_g2s(sb, p.matches + pair * static_cast<size_t>(N) * 4, pts_bytes, &full[stage]);
         if (wb) bulk_g2s(sb + pts_bytes, p.weights + pair * static_cast<size_t>(N), static_cast<uint32_t>(N) * 4u, &full[stage]);
     };
     if (threadIdx.x == 0) {
-        for (int s = 0; s < S; ++s) mbar_init(&full[s], 1);
+        for (int s = 0; s < S; ++s) { mbar_init(&full[s], 1); use_cnt[s] = 0; }
         fence_barrier_init();
     }
     __syncthreads();
@@ -128,6 +133,8 @@ __global__ void __launch_bounds__(kGramThreads, 1) fepe_gram_kernel(const FitPar
         const float4* sp = reinterpret_cast<const float4*>(sb);
         float* sw = reinterpret_cast<float*>(sb + pts_bytes);
         const long long tc0 = clock64();
+        while (use_cnt[stage] != j / S + 1) {
+        }
         mbar_wait(&full[stage], phase);
         const long long tc1 = clock64();
         if (!ring_row_is_bulk(p.weights, pair, N)) {        // ragged weight row: the team copies it itself
